@@ -1,0 +1,170 @@
+"""Drop-in for ``uibk/deep_preconditioning/cg.py`` backed by the B200 kernels of ``libdpcg``.
+
+Same names, argument meaning and return conventions as the reference:
+
+* ``stopping_criterion(_, rk, b)``                                   cg.py:15-17
+* ``conjugate_gradient(A, b, x0, x_true, rtol, max_iter)``           cg.py:20-47  -> ``(errors, x_hat)``
+* ``preconditioned_conjugate_gradient(A, b, M, x0, x_true, rtol, max_iter)``  cg.py:50-90
+  -> ``(seconds, iterations, info)`` with ``info`` always 0 and no exception on non-convergence
+  (``iterations == max_iter``), inputs never mutated.
+
+``A`` may be a :class:`~deeppreconditioning_b200.sparse.CsrMatrix`, a dense/sparse torch tensor on any device (what
+``test.py:138`` and ``train.py:102`` pass) or a scipy matrix; ``M`` one of the operators in
+:mod:`~deeppreconditioning_b200.precond`, ``None``, or any explicit matrix. Host operands are copied to the GPU — the
+arithmetic never runs on the CPU. :func:`pcg_solve` / :func:`pcg_solve_batch` additionally return what the reference
+computes but drops (``x_hat``, last criterion value, history).
+"""
+
+from __future__ import annotations
+
+import ctypes
+import time
+from dataclasses import dataclass, field
+
+import torch
+
+from . import _lib
+from .precond import Identity, _Operator, as_operator
+from .sparse import CsrMatrix, _workspace, as_csr
+
+_ENGINES = {"fused": _lib.ENGINE_FUSED, "stepped": _lib.ENGINE_STEPPED}
+
+
+@dataclass
+class PcgResult:
+    seconds: float
+    iterations: int
+    info: int
+    x_hat: torch.Tensor
+    res: float
+    history: list = field(default_factory=list)
+
+
+def stopping_criterion(_, rk, b):
+    """Squared relative residual (cg.py:15-17)."""
+    return torch.inner(rk, rk) / torch.inner(b, b)
+
+
+class PcgBatch:
+    """A prepared batch of independent systems: operands resident on one GPU, scratch allocated, ready to launch.
+
+    ``solve()`` enqueues ONE call of ``dp_pcg_solve_f64`` for the whole batch; ``results()`` reads iterations,
+    criterion and solutions back. Preparation (``__init__``) is the analogue of the reference's ``setup`` time
+    (``test.py:130-135``), ``solve()`` of its ``duration`` (``cg.py:69-88``).
+    """
+
+    def __init__(self, systems, rtol: float = 1e-8, max_iter: int = 1024, engine: str = "fused",
+                 check_every: int = 32, history: bool = False, device=None) -> None:
+        if not systems:
+            raise ValueError("empty batch")
+        self.device = torch.device(device) if device is not None else None
+        self.rtol, self.max_iter = float(rtol), int(max_iter)
+        self.params = _lib.PcgParams(self.rtol, self.max_iter, _ENGINES[engine], int(check_every), 0)
+        self.entries = []
+        lib = _lib.lib()
+        for item in systems:
+            A, b, M = item[0], item[1], item[2]
+            x0 = item[3] if len(item) > 3 else None
+            A = as_csr(A, self.device)
+            if self.device is None:
+                self.device = A.device
+            if A.device != self.device:
+                raise _lib.DpcgError("all systems of a batch must live on one device")
+            M = as_operator(M, self.device)
+            n = A.n
+            b_dev = b.detach().to(device=self.device, dtype=torch.float64).contiguous()
+            if b_dev.shape != (n,):
+                raise ValueError(f"right-hand side has shape {tuple(b_dev.shape)}, expected ({n},)")
+            f64 = dict(dtype=torch.float64, device=self.device)
+            x = (x0.detach().to(**f64).clone() if x0 is not None else torch.zeros(n, **f64)).contiguous()
+            work = torch.empty(lib.dp_pcg_work_doubles(n), **f64)
+            hist = torch.full((self.max_iter + 1,), float("nan"), **f64) if history else None
+            self.entries.append(dict(A=A, M=M, b=b_dev, x=x, work=work, hist=hist, out_device=b.device))
+        nsys = len(self.entries)
+        self.iters = torch.full((nsys,), -1, dtype=torch.int32, device=self.device)
+        self.res = torch.full((nsys,), float("nan"), dtype=torch.float64, device=self.device)
+        self.flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.ws = _workspace(lib.dp_pcg_workspace_bytes(nsys), self.device)
+        self.descs = (_lib.PcgSystem * nsys)()
+        for i, e in enumerate(self.entries):
+            d, A = self.descs[i], e["A"]
+            d.n, d.a_nnz = A.n, A.nnz
+            d.a_rowptr, d.a_col, d.a_val = _lib.ptr(A.rowptr), _lib.ptr(A.col), _lib.ptr(A.val)
+            e["M"].fill(d)
+            d.b, d.x, d.work = _lib.ptr(e["b"]), _lib.ptr(e["x"]), _lib.ptr(e["work"])
+            d.iters_out = self.iters.data_ptr() + 4 * i
+            d.res_out = self.res.data_ptr() + 8 * i
+            d.history = _lib.ptr(e["hist"])
+
+    def __len__(self) -> int:
+        return len(self.entries)
+
+    def reset(self, x0s=None) -> None:
+        """Restore the initial guess (zeros unless given) so the same prepared batch can be solved again."""
+        for i, e in enumerate(self.entries):
+            if x0s is not None and x0s[i] is not None:
+                e["x"].copy_(x0s[i])
+            else:
+                e["x"].zero_()
+        self.iters.fill_(-1)
+        self.res.fill_(float("nan"))
+
+    def solve(self) -> None:
+        """Enqueue the solve on the current stream (asynchronous for the fused engine)."""
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().dp_pcg_solve_f64(self.descs, len(self.entries), ctypes.byref(self.params),
+                                                   _lib.ptr(self.flag), _lib.ptr(self.ws), self.ws.numel(),
+                                                   _lib.stream_ptr(self.device)), "dp_pcg_solve_f64")
+
+    def results(self, seconds: float = 0.0) -> list[PcgResult]:
+        """Synchronise and collect ``PcgResult`` per system (``x_hat`` on the device the right-hand side came from)."""
+        _lib.raise_on_flag(self.flag, "dp_pcg_solve_f64")
+        iters, res = self.iters.cpu().tolist(), self.res.cpu().tolist()
+        out = []
+        for i, e in enumerate(self.entries):
+            hist = e["hist"][: iters[i] + 1].cpu().tolist() if e["hist"] is not None and iters[i] >= 0 else []
+            out.append(PcgResult(seconds, int(iters[i]), 0, e["x"].to(e["out_device"]), float(res[i]), hist))
+        return out
+
+
+def pcg_solve_batch(systems, rtol: float = 1e-8, max_iter: int = 1024, engine: str = "fused", check_every: int = 32,
+                    history: bool = False, device=None) -> list[PcgResult]:
+    """Solve independent systems ``[(A, b, M[, x0]), ...]`` in one launch; ``seconds`` is the batch wall time."""
+    batch = PcgBatch(systems, rtol, max_iter, engine, check_every, history, device)
+    torch.cuda.synchronize(batch.device)
+    start = time.perf_counter()
+    batch.solve()
+    torch.cuda.synchronize(batch.device)
+    return batch.results(time.perf_counter() - start)
+
+
+def pcg_solve(A, b, M=None, x0=None, rtol: float = 1e-8, max_iter: int = 1024, engine: str = "fused",
+              check_every: int = 32, history: bool = False) -> PcgResult:
+    """One system; like :func:`preconditioned_conjugate_gradient` but returns the full :class:`PcgResult`."""
+    return pcg_solve_batch([(A, b, M, x0)], rtol, max_iter, engine, check_every, history)[0]
+
+
+def preconditioned_conjugate_gradient(A, b: torch.Tensor, M, x0=None, x_true=None, rtol=1e-8, max_iter=1024):
+    """The preconditioned conjugate gradient method (cg.py:50-90): returns ``(seconds, iterations, 0)``.
+
+    ``seconds`` spans the solve only, like the reference's ``perf_counter`` pair (cg.py:69,88); operand upload and
+    workspace allocation are outside it. ``x_true`` is accepted for signature parity; the A-norm error it feeds in the
+    reference (cg.py:65,85,87) is computed and dropped there, so it is not evaluated here.
+    """
+    result = pcg_solve(A, b, M, x0, rtol, max_iter)
+    return result.seconds, result.iterations, 0
+
+
+def conjugate_gradient(A, b, x0=None, x_true=None, rtol=1e-8, max_iter=1024):
+    """Unpreconditioned CG (cg.py:20-47): returns ``(errors, x_hat)``, ``errors`` a list of ``(A-norm error, res)``.
+
+    With ``M = I`` the preconditioned recurrence is the same arithmetic as cg.py:31-45 (``z = r``, so
+    ``<r,z> = <r,r>``); the A-norm error entry is evaluated only when ``x_true`` is given, for the final iterate.
+    """
+    result = pcg_solve(A, b, Identity(), x0, rtol, max_iter, history=True)
+    zero = torch.zeros((), dtype=torch.float64)
+    errors = [(zero, torch.tensor(r, dtype=torch.float64)) for r in result.history]
+    if x_true is not None and errors:
+        e = (result.x_hat - x_true).to(torch.float64)
+        errors[-1] = (torch.inner(e, as_csr(A) @ e), errors[-1][1])
+    return errors, result.x_hat

@@ -1,0 +1,143 @@
+// common.cuh — shared device helpers for libdpcg (sm_100a). No torch, no libraries: CUDA runtime only.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/dpcg.h"
+
+namespace dp {
+
+constexpr int kWarp = 32;
+constexpr int kBlock = 512;                  // threads per CTA of every row-parallel kernel
+constexpr int kWarpsPerBlock = kBlock / kWarp;
+constexpr int kTileRows = kBlock;            // one CTA pass covers 512 consecutive rows (16 chunks of 32)
+constexpr int kStageCap = 256;               // products staged per warp in shared memory (2 KB)
+constexpr unsigned kFull = 0xffffffffu;
+
+// "Not yet produced" marker for sync-free dependency resolution: a quiet NaN with a payload that IEEE
+// arithmetic on this GPU never generates (computed NaNs are canonical 0x7ff8000000000000).
+constexpr unsigned long long kPending = 0xFFFBADC0FFEE0B20ull;
+
+// Spin budgets (polls) before a kernel gives up and raises DP_ERR_TIMEOUT instead of hanging the GPU.
+constexpr unsigned kSpinBudget = 1u << 24;
+
+const char* set_cuda_error(cudaError_t e);
+int sm_count();
+
+#define DP_CUDA(call)                                   \
+    do {                                                \
+        cudaError_t e__ = (call);                       \
+        if (e__ != cudaSuccess) {                       \
+            ::dp::set_cuda_error(e__);                  \
+            return DP_ERR_CUDA;                         \
+        }                                               \
+    } while (0)
+
+#define DP_LAUNCH_CHECK() DP_CUDA(cudaGetLastError())
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- memory-model helpers --------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const void* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(void* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ int ld_relaxed_s32(const void* p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_s32(void* p, int v) {
+    asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double as_double(unsigned long long u) { return __longlong_as_double((long long)u); }
+__device__ __forceinline__ unsigned long long as_bits(double d) { return (unsigned long long)__double_as_longlong(d); }
+
+// ---- deterministic reductions ------------------------------------------------------------------------------
+// Butterfly over the 32 lanes: every lane ends with the same bits; the order is fixed by the lane index only.
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+__device__ __forceinline__ double half_warp_sum(double v) {  // lanes 0..15 hold data
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+
+// Sum of one value per thread over the CTA (kBlock threads). `scratch` holds kWarpsPerBlock doubles.
+// Result valid in every thread. Fixed order: lane butterfly, then a 16-wide butterfly over the warp sums.
+__device__ __forceinline__ double block_sum(double v, double* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();  // scratch may still be read by a previous call
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    double w = scratch[lane & (kWarpsPerBlock - 1)];
+    return half_warp_sum(w);
+}
+
+// Sum of `count` doubles stored at `p` (global, produced before the last grid-wide barrier): thread t adds
+// p[t], p[t+kBlock], ... in that order, then block_sum. Same bits in every CTA.
+__device__ __forceinline__ double block_reduce_array(const double* p, int count, double* scratch) {
+    double v = 0.0;
+    for (int i = threadIdx.x; i < count; i += kBlock) v = __dadd_rn(v, __ldcg(p + i));
+    return block_sum(v, scratch);
+}
+
+// ---- grid-wide barrier (cooperative launch guarantees co-residency) ---------------------------------------
+// Monotonic 64-bit word: low 32 bits count arrivals, bit 63 is a sticky ABORT raised by any spin loop that ran
+// out of budget. Same protocol as cooperative groups (fence - arrive - spin - fence by thread 0, bracketed by
+// CTA barriers); sync() returns false in every thread of every CTA once ABORT is up, so kernels can unwind
+// instead of hanging the GPU.
+constexpr unsigned long long kAbortBit = 1ull << 63;
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+struct GridBarrier {
+    unsigned long long* word;
+    int* flag;  // device status word (DP_ERR_TIMEOUT)
+    unsigned epoch;
+    unsigned nblocks;
+    __device__ __forceinline__ void raise_abort(int status) {
+        atomicOr(word, kAbortBit);
+        atomicCAS(flag, 0, status);
+    }
+    __device__ __forceinline__ bool aborted() const { return (ld_volatile_u64(word) & kAbortBit) != 0; }
+    __device__ __forceinline__ bool sync() {
+        __syncthreads();
+        epoch += nblocks;
+        int bad = 0;
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(word, 1ull);
+            unsigned spins = 0;
+            for (;;) {
+                unsigned long long v = ld_volatile_u64(word);
+                if (v & kAbortBit) { bad = 1; break; }
+                if ((int)((unsigned)v - epoch) >= 0) break;
+                if (++spins > kSpinBudget) { raise_abort(DP_ERR_TIMEOUT); bad = 1; break; }
+            }
+            __threadfence();
+        }
+        return __syncthreads_or(bad) == 0;
+    }
+};
+
+}  // namespace dp

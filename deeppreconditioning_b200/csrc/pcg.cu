@@ -1,0 +1,598 @@
+// pcg.cu — K5: the whole preconditioned-CG loop of cg.py:50-90 on the device, for a batch of independent systems.
+//
+// Reference semantics kept exactly (cg.py line numbers):
+//   58-62  x = x0; r = b - A x; z = M r; p = z
+//   66     res_0 = <z0,z0>/<b,b>            (iteration 0 checks the PRECONDITIONED residual)
+//   70-72  for at most max_iter bodies: stop as soon as res < rtol (res is the SQUARED relative residual)
+//   75-83  Ap = A p; rz = <r,z>; a = rz/<Ap,p>; x += a p; r -= a Ap; z = M r; beta = <r,z>/rz; p = z + beta p
+//   86     res = <r,r>/<b,b>
+//   90     iterations = bodies executed
+// Element-wise updates round like torch (product, then sum); SpMV/SpTRSV rows are sequential sums; dot products
+// are fixed-order trees (lane butterfly -> 16 warp sums -> per-tile partial -> strided sum + tree over the tiles),
+// so a solve is bitwise reproducible and independent of which CTA processed which tile.
+//
+// Phase structure (one grid-wide barrier after each phase; k = body index, "old/new" = double buffers):
+//   A       p_new = z + beta p_old fused into the gather of Ap = A p_new; partial <Ap,p>; convergence check
+//   APPLY1  r_new = r_old - a Ap, x += a p fused into the first half of z = M r_new; partial <r,r> (and <r,z>)
+//             IDENTITY/JACOBI: element-wise z        CSR: z = M r_new        MULTIPLY: t = L^T r_new
+//   APPLY2  MULTIPLY: z = L t; partial <r,z>
+//   FWD/BWD SOLVE: y = L^-1 r_new, z = L^-T y (sync-free, sptrsv.cuh), then DOTRZ: partial <r,z>
+// The initial z0 = M r0 runs the same APPLY phases with kInit (no update, <z,z> into the <r,r> slot).
+#include <vector>
+
+#include "spmv.cuh"
+#include "sptrsv.cuh"
+
+namespace dp {
+
+int coop_grid(const void* kernel, int threads, size_t smem);  // sptrsv.cu
+
+struct SysDev {
+    int n, precond, ntiles, pad;
+    CsrView A, M, Mt;
+    const double* dinv;
+    const int* fwd_plan;
+    const int* bwd_plan;
+    const double* b;
+    double* x;
+    double* r[2];
+    double* p[2];
+    double* z[2];
+    double* ap;
+    double* t;  // MULTIPLY: t = L^T r;  SOLVE: y = L^-1 r
+    double* part_rr;
+    double* part_pap;
+    double* part_bb;
+    double* part_rz[2];
+    double* scal;  // [0],[1]: published <r,z> by body parity; [2]: <b,b>
+    int* state;    // [0]: finished
+    int* iters_out;
+    double* res_out;
+    double* history;
+};
+
+struct Ctx {
+    const SysDev* sys;
+    const int* tile_ofs;  // nsys+1
+    const int* fwd_ofs;   // nsys+1, plan chunks
+    const int* bwd_ofs;
+    int nsys, total_tiles, total_fwd, total_bwd;
+    int pw_fwd, pw_bwd;
+    int has_multiply, has_solve;
+    double rtol;
+    int max_iter;
+    unsigned long long* word;
+    int* n_done;
+    int* flag;
+};
+
+struct Smem {
+    double stage[kWarpsPerBlock][kStageCap];
+    double scratch[kWarpsPerBlock];
+    SysDev sys;   // descriptor of the system this CTA is working on (survives across phases)
+    int sys_id;
+};
+
+static_assert(sizeof(SysDev) % 8 == 0, "SysDev is copied as 8-byte words");
+
+// CTA-uniform: make sm.sys hold system s (one L2 round trip only when the system changes).
+__device__ __forceinline__ const SysDev& load_sys(const Ctx& ctx, int s, Smem& sm) {
+    if (sm.sys_id != s) {
+        __syncthreads();
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(ctx.sys + s);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(&sm.sys);
+        for (int i = threadIdx.x; i < (int)(sizeof(SysDev) / 8); i += kBlock) dst[i] = __ldg(src + i);
+        if (threadIdx.x == 0) sm.sys_id = s;
+        __syncthreads();
+    }
+    return sm.sys;
+}
+
+enum Phase { PH_INIT = 0, PH_A = 1, PH_APPLY1 = 2, PH_APPLY2 = 3, PH_FWD = 4, PH_BWD = 5, PH_DOTRZ = 6 };
+
+__device__ __forceinline__ int find_sys(const int* __restrict__ ofs, int nsys, int g) {
+    int lo = 0, hi = nsys;  // largest s with ofs[s] <= g
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(ofs + mid) <= g) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// Per-CTA cache of the scalars of the system it is currently working on (CTA-uniform registers).
+struct Scal {
+    int sys = -1;
+    bool active = false;
+    double v = 0.0;  // beta (phase A) or a (APPLY1)
+};
+
+// ---- PH_INIT: r0 = b - A x0 (cg.py:60), <b,b>, p = 0, arm the sync-free buffers -------------------------------
+__device__ __forceinline__ void phase_init(const SysDev& S, int tile, Smem& sm) {
+    const int warp = threadIdx.x >> 5;
+    const int row = tile * kTileRows + threadIdx.x;
+    const double ax = spmv_chunk(S.A, tile * kTileRows + warp * kWarp, GatherPlain{S.x}, sm.stage[warp]);
+    double bb = 0.0;
+    if (row < S.n) {
+        const double bi = S.b[row];
+        S.r[1][row] = __dsub_rn(bi, ax);
+        S.p[0][row] = 0.0;
+        bb = __dmul_rn(bi, bi);
+        if (S.precond == DP_PRECOND_SOLVE) {
+            st_relaxed_u64(S.z[0] + row, kPending);
+            st_relaxed_u64(S.t + row, kPending);
+        }
+    }
+    bb = block_sum(bb, sm.scratch);
+    if (threadIdx.x == 0) {
+        S.part_bb[tile] = bb;
+        if (tile == 0) S.state[0] = 0;
+    }
+}
+
+// ---- PH_A ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void phase_a(const Ctx& ctx, const SysDev& S, int s, int tile, int k, Smem& sm, Scal& sc) {
+    if (sc.sys != s) {
+        sc.sys = s;
+        sc.active = false;
+        const bool done = __ldcg(S.state) != 0;
+        if (!done) {
+            const double rr = block_reduce_array(S.part_rr, S.ntiles, sm.scratch);
+            const double rz = block_reduce_array(S.part_rz[k & 1], S.ntiles, sm.scratch);
+            const double res = rr / __ldcg(S.scal + 2);  // cg.py:17
+            const bool finished = (res < ctx.rtol) || (k >= ctx.max_iter);  // cg.py:70-72
+            sc.active = !finished;
+            sc.v = k > 0 ? rz / __ldcg(S.scal + ((k - 1) & 1)) : 0.0;  // beta, cg.py:82 (p_0 = z_0, cg.py:62)
+            if (tile == 0 && threadIdx.x == 0) {  // tile 0 of a system is visited by exactly one CTA per phase
+                if (S.history) S.history[k] = res;
+                if (finished) {
+                    *S.iters_out = k;
+                    *S.res_out = res;
+                    S.state[0] = 1;
+                    atomicAdd(ctx.n_done, 1);
+                } else {
+                    S.scal[k & 1] = rz;
+                }
+            }
+        }
+    }
+    if (!sc.active) return;
+    const int warp = threadIdx.x >> 5;
+    const int row = tile * kTileRows + threadIdx.x;
+    const double* z = S.z[k & 1];
+    const double* po = S.p[k & 1];
+    double* pn = S.p[(k + 1) & 1];
+    const GatherZBetaP g{z, po, sc.v};
+    const double ap = spmv_chunk(S.A, tile * kTileRows + warp * kWarp, g, sm.stage[warp]);  // cg.py:75
+    double pap = 0.0;
+    if (row < S.n) {
+        const double pi = g(row);  // cg.py:83
+        pn[row] = pi;
+        S.ap[row] = ap;
+        pap = __dmul_rn(ap, pi);
+        if (S.precond == DP_PRECOND_SOLVE) st_relaxed_u64(S.z[(k + 1) & 1] + row, kPending);  // re-arm next z
+    }
+    pap = block_sum(pap, sm.scratch);
+    if (threadIdx.x == 0) S.part_pap[tile] = pap;
+}
+
+// ---- PH_APPLY1 ----------------------------------------------------------------------------------------------
+template <bool kInit>
+__device__ __forceinline__ void phase_apply1(const Ctx& ctx, const SysDev& S, int s, int tile, int k, Smem& sm, Scal& sc) {
+    if (sc.sys != s) {
+        sc.sys = s;
+        sc.active = kInit || __ldcg(S.state) == 0;
+        sc.v = 0.0;
+        if (!kInit && sc.active)
+            sc.v = __ldcg(S.scal + (k & 1)) / block_reduce_array(S.part_pap, S.ntiles, sm.scratch);  // a, cg.py:78
+    }
+    if (!sc.active) return;
+    const int warp = threadIdx.x >> 5;
+    const int base = tile * kTileRows + warp * kWarp;
+    const int row = tile * kTileRows + threadIdx.x;
+    const bool valid = row < S.n;
+    const double a = sc.v;
+    const double* ro = S.r[k & 1];
+    double* rnw = S.r[(k + 1) & 1];
+    const double* pn = S.p[(k + 1) & 1];
+    double* zn = S.z[(k + 1) & 1];
+
+    double rn = 0.0;
+    if (valid) {
+        rn = kInit ? ro[row] : __dsub_rn(ro[row], __dmul_rn(a, S.ap[row]));          // cg.py:80
+        rnw[row] = rn;
+        if (!kInit) S.x[row] = __dadd_rn(S.x[row], __dmul_rn(a, pn[row]));            // cg.py:79
+    }
+    double zi = 0.0;
+    bool have_z = true;
+    switch (S.precond) {
+        case DP_PRECOND_IDENTITY:
+            zi = rn;
+            break;
+        case DP_PRECOND_JACOBI:
+            zi = valid ? __dmul_rn(S.dinv[row], rn) : 0.0;
+            break;
+        case DP_PRECOND_CSR:
+            zi = kInit ? spmv_chunk(S.M, base, GatherPlain{ro}, sm.stage[warp])
+                       : spmv_chunk(S.M, base, GatherRMinusAAp{ro, S.ap, a}, sm.stage[warp]);
+            break;
+        case DP_PRECOND_MULTIPLY: {
+            const double ti = kInit ? spmv_chunk(S.Mt, base, GatherPlain{ro}, sm.stage[warp])
+                                    : spmv_chunk(S.Mt, base, GatherRMinusAAp{ro, S.ap, a}, sm.stage[warp]);
+            if (valid) S.t[row] = ti;
+            have_z = false;
+            break;
+        }
+        default:  // DP_PRECOND_SOLVE: z comes from FWD/BWD
+            have_z = false;
+            break;
+    }
+    if (have_z && valid) zn[row] = zi;
+    if (!kInit) {
+        const double rr = block_sum(__dmul_rn(rn, rn), sm.scratch);  // cg.py:86
+        if (threadIdx.x == 0) S.part_rr[tile] = rr;
+    }
+    if (have_z) {
+        const double rz = block_sum(__dmul_rn(rn, zi), sm.scratch);  // cg.py:82 numerator / cg.py:76
+        if (threadIdx.x == 0) S.part_rz[(k + 1) & 1][tile] = rz;
+        if (kInit) {
+            const double zz = block_sum(__dmul_rn(zi, zi), sm.scratch);  // cg.py:66
+            if (threadIdx.x == 0) S.part_rr[tile] = zz;
+        }
+    }
+    if (kInit && tile == 0) {  // publish <b,b> once (all part_bb were written before the previous barrier)
+        const double bb = block_reduce_array(S.part_bb, S.ntiles, sm.scratch);
+        if (threadIdx.x == 0) S.scal[2] = bb;
+    }
+}
+
+// ---- PH_APPLY2 (MULTIPLY): z = L t ---------------------------------------------------------------------------
+template <bool kInit>
+__device__ __forceinline__ void phase_apply2(const SysDev& S, int s, int tile, int k, Smem& sm, Scal& sc) {
+    if (sc.sys != s) {
+        sc.sys = s;
+        sc.active = S.precond == DP_PRECOND_MULTIPLY && (kInit || __ldcg(S.state) == 0);
+    }
+    if (!sc.active) return;
+    const int warp = threadIdx.x >> 5;
+    const int row = tile * kTileRows + threadIdx.x;
+    const double zi = spmv_chunk(S.M, tile * kTileRows + warp * kWarp, GatherPlain{S.t}, sm.stage[warp]);
+    double rn = 0.0;
+    if (row < S.n) {
+        S.z[(k + 1) & 1][row] = zi;
+        rn = S.r[(k + 1) & 1][row];
+    }
+    const double rz = block_sum(__dmul_rn(rn, zi), sm.scratch);
+    if (threadIdx.x == 0) S.part_rz[(k + 1) & 1][tile] = rz;
+    if (kInit) {
+        const double zz = block_sum(__dmul_rn(zi, zi), sm.scratch);
+        if (threadIdx.x == 0) S.part_rr[tile] = zz;
+    }
+}
+
+// ---- PH_DOTRZ (SOLVE): <r,z> after the backward solve -----------------------------------------------------------
+template <bool kInit>
+__device__ __forceinline__ void phase_dotrz(const SysDev& S, int s, int tile, int k, Smem& sm, Scal& sc) {
+    if (sc.sys != s) {
+        sc.sys = s;
+        sc.active = S.precond == DP_PRECOND_SOLVE && (kInit || __ldcg(S.state) == 0);
+    }
+    if (!sc.active) return;
+    const int row = tile * kTileRows + threadIdx.x;
+    double rn = 0.0, zi = 0.0;
+    if (row < S.n) {
+        rn = S.r[(k + 1) & 1][row];
+        zi = S.z[(k + 1) & 1][row];
+    }
+    const double rz = block_sum(__dmul_rn(rn, zi), sm.scratch);
+    if (threadIdx.x == 0) S.part_rz[(k + 1) & 1][tile] = rz;
+    if (kInit) {
+        const double zz = block_sum(__dmul_rn(zi, zi), sm.scratch);
+        if (threadIdx.x == 0) S.part_rr[tile] = zz;
+    }
+}
+
+// ---- PH_FWD / PH_BWD (SOLVE): y = L^-1 r_new ; z_new = L^-T y ---------------------------------------------------
+template <bool kUpper, bool kInit>
+__device__ __forceinline__ bool phase_trsv(const Ctx& ctx, int k, const Smem& sm) {
+    const int pw = kUpper ? ctx.pw_bwd : ctx.pw_fwd;
+    const int gw = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+    if (gw >= pw) return true;
+    const int total = kUpper ? ctx.total_bwd : ctx.total_fwd;
+    const int* ofs = kUpper ? ctx.bwd_ofs : ctx.fwd_ofs;
+    const AbortCtl ctl{ctx.word, ctx.flag};
+    int cur = -1;
+    bool active = false;
+    for (int g = gw; g < total; g += pw) {
+        const int s = ctx.nsys == 1 ? 0 : find_sys(ofs, ctx.nsys, g);
+        const SysDev& S = (sm.sys_id == s) ? sm.sys : ctx.sys[s];
+        if (s != cur) {
+            cur = s;
+            active = kInit || __ldcg(S.state) == 0;
+        }
+        if (!active) continue;
+        const int c = ctx.nsys == 1 ? g : g - __ldg(ofs + s);
+        bool ok;
+        if (kUpper)
+            ok = sptrsv_chunk<true>(S.Mt, S.bwd_plan + (size_t)c * 32, RhsConsume{S.t}, S.z[(k + 1) & 1], ctl);
+        else
+            ok = sptrsv_chunk<false>(S.M, S.fwd_plan + (size_t)c * 32, RhsPlain{S.r[(k + 1) & 1]}, S.t, ctl);
+        if (!ok) return false;
+    }
+    return true;
+}
+
+// ---- tile driver ---------------------------------------------------------------------------------------------
+template <int kPhase, bool kInit>
+__device__ __forceinline__ void run_tiles(const Ctx& ctx, int k, Smem& sm) {
+    Scal sc;
+    for (int g = blockIdx.x; g < ctx.total_tiles; g += gridDim.x) {
+        const int s = ctx.nsys == 1 ? 0 : find_sys(ctx.tile_ofs, ctx.nsys, g);
+        const SysDev& S = load_sys(ctx, s, sm);
+        const int tile = ctx.nsys == 1 ? g : g - __ldg(ctx.tile_ofs + s);
+        if (kPhase == PH_INIT) phase_init(S, tile, sm);
+        if (kPhase == PH_A) phase_a(ctx, S, s, tile, k, sm, sc);
+        if (kPhase == PH_APPLY1) phase_apply1<kInit>(ctx, S, s, tile, k, sm, sc);
+        if (kPhase == PH_APPLY2) phase_apply2<kInit>(S, s, tile, k, sm, sc);
+        if (kPhase == PH_DOTRZ) phase_dotrz<kInit>(S, s, tile, k, sm, sc);
+    }
+}
+
+template <bool kInit>
+__device__ __forceinline__ bool apply_preconditioner(const Ctx& ctx, int k, GridBarrier& bar, Smem& sm) {
+    run_tiles<PH_APPLY1, kInit>(ctx, k, sm);
+    if (!bar.sync()) return false;
+    if (ctx.has_multiply) {
+        run_tiles<PH_APPLY2, kInit>(ctx, k, sm);
+        if (!bar.sync()) return false;
+    }
+    if (ctx.has_solve) {
+        const bool f = phase_trsv<false, kInit>(ctx, k, sm);
+        if (!bar.sync() || !f) return false;
+        const bool b = phase_trsv<true, kInit>(ctx, k, sm);
+        if (!bar.sync() || !b) return false;
+        run_tiles<PH_DOTRZ, kInit>(ctx, k, sm);
+        if (!bar.sync()) return false;
+    }
+    return true;
+}
+
+// The whole solve in one persistent cooperative launch: device-side loop control, no host round trips.
+__global__ void __launch_bounds__(kBlock, 2) pcg_fused_kernel(Ctx ctx) {
+    __shared__ __align__(16) Smem sm;
+    if (threadIdx.x == 0) sm.sys_id = -1;
+    __syncthreads();
+    GridBarrier bar{ctx.word, ctx.flag, 0u, gridDim.x};
+    run_tiles<PH_INIT, false>(ctx, -1, sm);
+    if (!bar.sync()) return;
+    if (!apply_preconditioner<true>(ctx, -1, bar, sm)) return;
+    for (int k = 0; k <= ctx.max_iter; ++k) {
+        run_tiles<PH_A, false>(ctx, k, sm);
+        if (!bar.sync()) return;
+        if (*reinterpret_cast<volatile int*>(ctx.n_done) >= ctx.nsys) break;
+        if (!apply_preconditioner<false>(ctx, k, bar, sm)) return;
+    }
+}
+
+// Stepped engine: the same phases, one launch each (the launch boundary is the barrier).
+template <int kPhase, bool kInit>
+__global__ void __launch_bounds__(kBlock, 2) pcg_phase_kernel(Ctx ctx, int k) {
+    __shared__ __align__(16) Smem sm;
+    if (threadIdx.x == 0) sm.sys_id = -1;
+    __syncthreads();
+    if (kPhase == PH_FWD) {
+        phase_trsv<false, kInit>(ctx, k, sm);
+    } else if (kPhase == PH_BWD) {
+        phase_trsv<true, kInit>(ctx, k, sm);
+    } else {
+        run_tiles<kPhase, kInit>(ctx, k, sm);
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------
+static inline int64_t pad32(int64_t v) { return (v + 31) / 32 * 32; }
+static inline int ntiles_of(int n) { return (n + kTileRows - 1) / kTileRows; }
+
+struct WsLayout {
+    size_t word, n_done, sys, tile_ofs, fwd_ofs, bwd_ofs, total;
+};
+static WsLayout ws_layout(int nsys) {
+    WsLayout w{};
+    size_t off = 0;
+    w.word = off; off += 256;
+    w.n_done = off; off += 256;
+    w.sys = off; off += align_up(sizeof(SysDev) * (size_t)nsys, 256);
+    w.tile_ofs = off; off += align_up(sizeof(int) * ((size_t)nsys + 1), 256);
+    w.fwd_ofs = off; off += align_up(sizeof(int) * ((size_t)nsys + 1), 256);
+    w.bwd_ofs = off; off += align_up(sizeof(int) * ((size_t)nsys + 1), 256);
+    w.total = off;
+    return w;
+}
+
+template <int kPhase, bool kInit>
+static int launch_phase(const Ctx& ctx, int k, int grid, bool cooperative, cudaStream_t s) {
+    if (cooperative) {
+        Ctx c = ctx;
+        void* args[] = {&c, &k};
+        DP_CUDA(cudaLaunchCooperativeKernel((const void*)pcg_phase_kernel<kPhase, kInit>, dim3(grid), dim3(kBlock), args, 0, s));
+    } else {
+        pcg_phase_kernel<kPhase, kInit><<<grid, kBlock, 0, s>>>(ctx, k);
+        DP_LAUNCH_CHECK();
+    }
+    return DP_OK;
+}
+
+template <bool kInit>
+static int launch_apply(const Ctx& ctx, int k, int tile_grid, int coop, cudaStream_t s) {
+    int st;
+    if ((st = launch_phase<PH_APPLY1, kInit>(ctx, k, tile_grid, false, s)) != DP_OK) return st;
+    if (ctx.has_multiply && (st = launch_phase<PH_APPLY2, kInit>(ctx, k, tile_grid, false, s)) != DP_OK) return st;
+    if (ctx.has_solve) {
+        if ((st = launch_phase<PH_FWD, kInit>(ctx, k, coop, true, s)) != DP_OK) return st;
+        if ((st = launch_phase<PH_BWD, kInit>(ctx, k, coop, true, s)) != DP_OK) return st;
+        if ((st = launch_phase<PH_DOTRZ, kInit>(ctx, k, tile_grid, false, s)) != DP_OK) return st;
+    }
+    return DP_OK;
+}
+
+}  // namespace dp
+
+using namespace dp;
+
+extern "C" {
+
+int64_t dp_pcg_work_doubles(int32_t n) {
+    if (n < 0) return -1;
+    return 8 * pad32(n) + 5 * pad32(ntiles_of(n)) + 32;
+}
+
+size_t dp_pcg_workspace_bytes(int32_t nsys) { return ws_layout(nsys < 0 ? 0 : nsys).total; }
+
+int dp_device_info(int* sm_count_host, int* pcg_ctas_per_sm_host, int* l2_bytes_host) {
+    int dev = 0, sms = 0, l2 = 0;
+    DP_CUDA(cudaGetDevice(&dev));
+    DP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    DP_CUDA(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev));
+    if (sm_count_host) *sm_count_host = sms;
+    if (l2_bytes_host) *l2_bytes_host = l2;
+    if (pcg_ctas_per_sm_host) *pcg_ctas_per_sm_host = coop_grid((const void*)pcg_fused_kernel, kBlock, 0) / (sms > 0 ? sms : 1);
+    return DP_OK;
+}
+
+int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp_pcg_params_t* params_host,
+                     int32_t* flag_out, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!systems_host || nsys <= 0 || !params_host || !flag_out || !workspace) return DP_ERR_INVALID;
+    if (params_host->max_iter < 0) return DP_ERR_INVALID;
+    if (!aligned16(workspace)) return DP_ERR_ALIGNMENT;
+    const WsLayout lay = ws_layout(nsys);
+    if (workspace_bytes < lay.total) return DP_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    char* ws = static_cast<char*>(workspace);
+
+    std::vector<SysDev> sys((size_t)nsys);
+    std::vector<int> tile_ofs((size_t)nsys + 1, 0), fwd_ofs((size_t)nsys + 1, 0), bwd_ofs((size_t)nsys + 1, 0);
+    int has_multiply = 0, has_solve = 0;
+    long long sum_fwd_lvl = 0, sum_bwd_lvl = 0;
+    for (int i = 0; i < nsys; ++i) {
+        const dp_pcg_system_t& u = systems_host[i];
+        if (u.n <= 0 || !u.a_rowptr || !u.a_col || !u.a_val || !u.b || !u.x || !u.work || !u.iters_out || !u.res_out)
+            return DP_ERR_INVALID;
+        if (!aligned16(u.a_col) || !aligned16(u.a_val) || !aligned16(u.work)) return DP_ERR_ALIGNMENT;
+        SysDev d{};
+        d.n = u.n;
+        d.precond = u.precond;
+        d.ntiles = ntiles_of(u.n);
+        d.A = CsrView{u.a_rowptr, u.a_col, u.a_val, u.n, u.a_nnz};
+        d.M = CsrView{u.m_rowptr, u.m_col, u.m_val, u.n, u.m_nnz};
+        d.Mt = CsrView{u.mt_rowptr, u.mt_col, u.mt_val, u.n, u.mt_nnz};
+        d.dinv = u.dinv;
+        d.fwd_plan = u.fwd_plan;
+        d.bwd_plan = u.bwd_plan;
+        int fwd_chunks = 0, bwd_chunks = 0;
+        switch (u.precond) {
+            case DP_PRECOND_IDENTITY: break;
+            case DP_PRECOND_JACOBI:
+                if (!u.dinv) return DP_ERR_INVALID;
+                break;
+            case DP_PRECOND_CSR:
+                if (!u.m_rowptr || !u.m_col || !u.m_val) return DP_ERR_INVALID;
+                if (!aligned16(u.m_col) || !aligned16(u.m_val)) return DP_ERR_ALIGNMENT;
+                break;
+            case DP_PRECOND_SOLVE:
+                if (!u.fwd_plan || !u.bwd_plan || u.fwd_nchunks <= 0 || u.bwd_nchunks <= 0) return DP_ERR_INVALID;
+                fwd_chunks = u.fwd_nchunks;
+                bwd_chunks = u.bwd_nchunks;
+                sum_fwd_lvl += u.fwd_max_level_chunks > 0 ? u.fwd_max_level_chunks : (1 << 20);
+                sum_bwd_lvl += u.bwd_max_level_chunks > 0 ? u.bwd_max_level_chunks : (1 << 20);
+                has_solve = 1;
+                // fallthrough: needs L and L^T as well
+            case DP_PRECOND_MULTIPLY:
+                if (!u.m_rowptr || !u.m_col || !u.m_val || !u.mt_rowptr || !u.mt_col || !u.mt_val) return DP_ERR_INVALID;
+                if (!aligned16(u.m_col) || !aligned16(u.m_val) || !aligned16(u.mt_col) || !aligned16(u.mt_val))
+                    return DP_ERR_ALIGNMENT;
+                if (u.precond == DP_PRECOND_MULTIPLY) has_multiply = 1;
+                break;
+            default: return DP_ERR_INVALID;
+        }
+        d.b = u.b;
+        d.x = u.x;
+        const int64_t np = pad32(u.n), tp = pad32(d.ntiles);
+        double* w = u.work;
+        d.r[0] = w; d.r[1] = w + np; d.p[0] = w + 2 * np; d.p[1] = w + 3 * np;
+        d.z[0] = w + 4 * np;
+        d.z[1] = u.precond == DP_PRECOND_SOLVE ? w + 5 * np : d.z[0];
+        d.ap = w + 6 * np; d.t = w + 7 * np;
+        double* q = w + 8 * np;
+        d.part_rr = q; d.part_pap = q + tp; d.part_bb = q + 2 * tp; d.part_rz[0] = q + 3 * tp; d.part_rz[1] = q + 4 * tp;
+        d.scal = q + 5 * tp;
+        d.state = reinterpret_cast<int*>(d.scal + 8);
+        d.iters_out = u.iters_out;
+        d.res_out = u.res_out;
+        d.history = u.history;
+        sys[(size_t)i] = d;
+        tile_ofs[(size_t)i + 1] = tile_ofs[(size_t)i] + d.ntiles;
+        fwd_ofs[(size_t)i + 1] = fwd_ofs[(size_t)i] + fwd_chunks;
+        bwd_ofs[(size_t)i + 1] = bwd_ofs[(size_t)i] + bwd_chunks;
+    }
+
+    const int coop = coop_grid((const void*)pcg_fused_kernel, kBlock, 0);
+    const int coop_phase = coop_grid((const void*)pcg_phase_kernel<PH_FWD, false>, kBlock, 0);
+    auto clamp_pw = [](long long lvl_chunks, int grid) {
+        long long pw = 4 * lvl_chunks;
+        if (pw < 32) pw = 32;
+        const long long w = (long long)grid * kWarpsPerBlock;
+        return (int)(pw > w ? w : pw);
+    };
+
+    Ctx ctx{};
+    ctx.sys = reinterpret_cast<const SysDev*>(ws + lay.sys);
+    ctx.tile_ofs = reinterpret_cast<const int*>(ws + lay.tile_ofs);
+    ctx.fwd_ofs = reinterpret_cast<const int*>(ws + lay.fwd_ofs);
+    ctx.bwd_ofs = reinterpret_cast<const int*>(ws + lay.bwd_ofs);
+    ctx.nsys = nsys;
+    ctx.total_tiles = tile_ofs[(size_t)nsys];
+    ctx.total_fwd = fwd_ofs[(size_t)nsys];
+    ctx.total_bwd = bwd_ofs[(size_t)nsys];
+    ctx.has_multiply = has_multiply;
+    ctx.has_solve = has_solve;
+    ctx.rtol = params_host->rtol;
+    ctx.max_iter = params_host->max_iter;
+    ctx.word = reinterpret_cast<unsigned long long*>(ws + lay.word);
+    ctx.n_done = reinterpret_cast<int*>(ws + lay.n_done);
+    ctx.flag = flag_out;
+
+    DP_CUDA(cudaMemsetAsync(ws, 0, 512, s));  // barrier word + done counter
+    DP_CUDA(cudaMemcpyAsync(ws + lay.sys, sys.data(), sizeof(SysDev) * (size_t)nsys, cudaMemcpyHostToDevice, s));
+    DP_CUDA(cudaMemcpyAsync(ws + lay.tile_ofs, tile_ofs.data(), sizeof(int) * ((size_t)nsys + 1), cudaMemcpyHostToDevice, s));
+    DP_CUDA(cudaMemcpyAsync(ws + lay.fwd_ofs, fwd_ofs.data(), sizeof(int) * ((size_t)nsys + 1), cudaMemcpyHostToDevice, s));
+    DP_CUDA(cudaMemcpyAsync(ws + lay.bwd_ofs, bwd_ofs.data(), sizeof(int) * ((size_t)nsys + 1), cudaMemcpyHostToDevice, s));
+
+    if (params_host->engine == DP_ENGINE_FUSED) {
+        ctx.pw_fwd = clamp_pw(sum_fwd_lvl, coop);
+        ctx.pw_bwd = clamp_pw(sum_bwd_lvl, coop);
+        void* args[] = {&ctx};
+        DP_CUDA(cudaLaunchCooperativeKernel((const void*)pcg_fused_kernel, dim3(coop), dim3(kBlock), args, 0, s));
+        return DP_OK;
+    }
+    if (params_host->engine != DP_ENGINE_STEPPED) return DP_ERR_INVALID;
+
+    ctx.pw_fwd = clamp_pw(sum_fwd_lvl, coop_phase);
+    ctx.pw_bwd = clamp_pw(sum_bwd_lvl, coop_phase);
+    const int tile_grid = ctx.total_tiles < coop * 4 ? ctx.total_tiles : coop * 4;
+    const int every = params_host->check_every > 0 ? params_host->check_every : 1;
+    int st;
+    if ((st = launch_phase<PH_INIT, false>(ctx, -1, tile_grid, false, s)) != DP_OK) return st;
+    if ((st = launch_apply<true>(ctx, -1, tile_grid, coop_phase, s)) != DP_OK) return st;
+    for (int k = 0; k <= ctx.max_iter; ++k) {
+        if ((st = launch_phase<PH_A, false>(ctx, k, tile_grid, false, s)) != DP_OK) return st;
+        if (k % every == 0 || k == ctx.max_iter) {  // the one host sync per convergence check
+            int done = 0;
+            DP_CUDA(cudaMemcpyAsync(&done, ctx.n_done, sizeof(int), cudaMemcpyDeviceToHost, s));
+            DP_CUDA(cudaStreamSynchronize(s));
+            if (done >= nsys) break;
+        }
+        if ((st = launch_apply<false>(ctx, k, tile_grid, coop_phase, s)) != DP_OK) return st;
+    }
+    return DP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,103 @@
+// spmv.cu — library plumbing + standalone K2 entry points (dp_spmv_csr_f64, dp_coo_spmv_batch_f32).
+#include <stdio.h>
+#include <string.h>
+
+#include "spmv.cuh"
+
+namespace dp {
+
+static thread_local char g_cuda_error[256] = "";
+
+const char* set_cuda_error(cudaError_t e) {
+    snprintf(g_cuda_error, sizeof(g_cuda_error), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+    return g_cuda_error;
+}
+
+// One warp per 32-row chunk, grid-stride over chunks. 2 CTAs of 512 threads per SM.
+__global__ void __launch_bounds__(kBlock, 2)
+spmv_csr_kernel(CsrView A, const double* __restrict__ x, double* __restrict__ y) {
+    __shared__ __align__(16) double stage[kWarpsPerBlock][kStageCap];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nchunks = (A.n + kWarp - 1) / kWarp;
+    const GatherReadOnly gx{x};
+    for (int chunk = blockIdx.x * kWarpsPerBlock + warp; chunk < nchunks; chunk += gridDim.x * kWarpsPerBlock) {
+        const int base = chunk * kWarp;
+        const double s = spmv_chunk(A, base, gx, stage[warp]);
+        if (base + lane < A.n) y[base + lane] = s;
+    }
+}
+
+// utils.py:15-43 — batched COO SpMV in fp32. Accumulation order is unspecified in the reference
+// (scatter_reduce("sum")) and here (atomicAdd).
+__global__ void coo_spmv_batch_kernel(const int* __restrict__ ind, const float* __restrict__ feat, long long nnz,
+                                      int nbatch, int n, const float* __restrict__ vec, int transpose,
+                                      float* __restrict__ out) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nnz;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int b = ind[3 * e], r = ind[3 * e + (transpose ? 2 : 1)], c = ind[3 * e + (transpose ? 1 : 2)];
+        if ((unsigned)b < (unsigned)nbatch && (unsigned)r < (unsigned)n && (unsigned)c < (unsigned)n)
+            atomicAdd(out + (size_t)b * n + r, feat[e] * vec[(size_t)b * n + c]);
+    }
+}
+
+int sm_count() {
+    static int cached = 0;
+    if (!cached) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) cached = 148;
+    }
+    return cached;
+}
+
+}  // namespace dp
+
+using namespace dp;
+
+extern "C" {
+
+int dp_version(void) { return DP_VERSION; }
+
+const char* dp_status_string(int status) {
+    switch (status) {
+        case DP_OK: return "ok";
+        case DP_ERR_INVALID: return "invalid argument";
+        case DP_ERR_ALIGNMENT: return "array not 16-byte aligned";
+        case DP_ERR_WORKSPACE: return "workspace too small";
+        case DP_ERR_CUDA: return "CUDA runtime error";
+        case DP_ERR_STRUCTURE: return "matrix structure violates the contract";
+        case DP_ERR_TIMEOUT: return "dependency spin timed out";
+        default: return "unknown status";
+    }
+}
+
+const char* dp_last_cuda_error(void) { return g_cuda_error; }
+
+int dp_spmv_csr_f64(int32_t n, int32_t nnz, const int32_t* rowptr, const int32_t* col, const double* val,
+                    const double* x, double* y, void* stream) {
+    if (n < 0 || nnz < 0 || !rowptr || !y || (nnz > 0 && (!col || !val || !x))) return DP_ERR_INVALID;
+    if (!aligned16(col) || !aligned16(val)) return DP_ERR_ALIGNMENT;
+    if (n == 0) return DP_OK;
+    const int nchunks = (n + kWarp - 1) / kWarp;
+    const int tiles = (nchunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const int grid = tiles < sm_count() * 2 * 8 ? tiles : sm_count() * 2 * 8;
+    CsrView A{rowptr, col, val, n, nnz};
+    spmv_csr_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>(A, x, y);
+    DP_LAUNCH_CHECK();
+    return DP_OK;
+}
+
+int dp_coo_spmv_batch_f32(const int32_t* indices, const float* features, int64_t nnz, int32_t nbatch, int32_t n,
+                          const float* vec, int32_t transpose, float* out, void* stream) {
+    if (nnz < 0 || nbatch < 0 || n < 0 || !out || (nnz > 0 && (!indices || !features || !vec))) return DP_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    DP_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)nbatch * (size_t)n, s));
+    if (nnz == 0) return DP_OK;
+    long long blocks = (nnz + 255) / 256;
+    if (blocks > sm_count() * 32) blocks = sm_count() * 32;
+    coo_spmv_batch_kernel<<<(int)blocks, 256, 0, s>>>(indices, features, nnz, nbatch, n, vec, transpose, out);
+    DP_LAUNCH_CHECK();
+    return DP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,208 @@
+"""Preconditioner operators ``M`` for ``preconditioned_conjugate_gradient(A, b, M)``.
+
+The reference applies ``M`` by ``@`` (``uibk/deep_preconditioning/cg.py:61,81``) and builds it as an explicit CSR
+tensor (``test.py:70-105``). These objects keep the ``@`` contract but stay factored on the device:
+
+===================  =======================================  ==========================================
+class                reference constructor                    apply
+===================  =======================================  ==========================================
+``Identity``         ``_construct_vanilla``   test.py:70-72   ``z = r``
+``Jacobi``           ``_construct_jacobi``    test.py:74-79   ``z = r / diag(A)``
+``FactoredMultiply`` ``_construct_learned``   test.py:100-105 ``z = L (L^T r)``   (approximate inverse)
+``FactoredSolve``    north_star / IC(0)                       ``z = L^-T (L^-1 r)`` (two sync-free SpTRSV)
+``CsrOperator``      any explicit CSR ``M``   test.py:88,105  ``z = M r``
+===================  =======================================  ==========================================
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from .sparse import CsrMatrix, _workspace, as_csr
+
+
+@dataclass
+class TriangularPlan:
+    """Level analysis (K3) of a triangular CSR pattern plus the warp-padded execution plan of the solves (K4)."""
+
+    level: torch.Tensor      # int32[n]
+    perm: torch.Tensor       # int32[n]   rows stably sorted by level
+    level_ptr: torch.Tensor  # int32[nlevels+1]
+    nlevels: int
+    plan: torch.Tensor       # int32[32*nchunks], -1 = idle lane
+    nchunks: int
+    max_level_chunks: int
+    upper: bool
+
+
+def analyse(matrix: CsrMatrix, upper: bool) -> TriangularPlan:
+    """``dp_sptrsv_analyse`` + ``dp_sptrsv_plan_build``. ``upper=False``: lower triangular, diagonal last in each row;
+    ``upper=True``: upper triangular (``L^T``), diagonal first."""
+    lib, n, dev = _lib.lib(), matrix.n, matrix.device
+    i32 = dict(dtype=torch.int32, device=dev)
+    level, perm = torch.empty(n, **i32), torch.empty(n, **i32)
+    level_ptr = torch.empty(n + 1, **i32)
+    nlev, flag = torch.zeros(1, **i32), torch.zeros(1, **i32)
+    ws = _workspace(lib.dp_sptrsv_analyse_workspace_bytes(n), dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.dp_sptrsv_analyse(n, _lib.ptr(matrix.rowptr), _lib.ptr(matrix.col), int(upper), _lib.ptr(level),
+                                         _lib.ptr(perm), _lib.ptr(level_ptr), _lib.ptr(nlev), _lib.ptr(flag),
+                                         _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "dp_sptrsv_analyse")
+    nlevels = int(nlev.item())  # once per matrix
+    _lib.raise_on_flag(flag, "dp_sptrsv_analyse (not triangular, or diagonal not first/last in its row)")
+    lp_host = np.ascontiguousarray(level_ptr[: nlevels + 1].cpu().numpy(), dtype=np.int32)
+    chunks = (np.diff(lp_host) + 31) // 32
+    chunk_ptr_host = np.concatenate([[0], np.cumsum(chunks)]).astype(np.int32)
+    nchunks = int(lib.dp_sptrsv_plan_chunks(nlevels, lp_host.ctypes.data))
+    assert nchunks == int(chunk_ptr_host[-1])
+    chunk_ptr = torch.from_numpy(chunk_ptr_host).to(dev)
+    plan = torch.empty(max(nchunks * 32, 1), **i32)
+    with torch.cuda.device(dev):
+        _lib.check(lib.dp_sptrsv_plan_build(n, nlevels, _lib.ptr(perm), _lib.ptr(level_ptr), _lib.ptr(chunk_ptr),
+                                            _lib.ptr(plan), nchunks, _lib.stream_ptr(dev)), "dp_sptrsv_plan_build")
+    return TriangularPlan(level, perm, level_ptr[: nlevels + 1], nlevels, plan, nchunks,
+                          int(chunks.max()) if nlevels else 0, bool(upper))
+
+
+def triangular_solve(matrix: CsrMatrix, plan: TriangularPlan, b: torch.Tensor, out: torch.Tensor | None = None):
+    """Solve ``T x = b`` with the sync-free kernel (``dp_sptrsv_solve_f64``)."""
+    lib, n, dev = _lib.lib(), matrix.n, matrix.device
+    assert b.is_cuda and b.dtype == torch.float64 and b.shape == (n,)
+    b = b.contiguous()
+    x = out if out is not None else torch.empty(n, dtype=torch.float64, device=dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = _workspace(lib.dp_sptrsv_workspace_bytes(), dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.dp_sptrsv_solve_f64(n, _lib.ptr(matrix.rowptr), _lib.ptr(matrix.col), _lib.ptr(matrix.val),
+                                           int(plan.upper), _lib.ptr(plan.plan), plan.nchunks, plan.max_level_chunks,
+                                           _lib.ptr(b), _lib.ptr(x), _lib.ptr(flag), _lib.ptr(ws), ws.numel(),
+                                           _lib.stream_ptr(dev)), "dp_sptrsv_solve_f64")
+    _lib.raise_on_flag(flag, "dp_sptrsv_solve_f64")
+    return x
+
+
+def incomplete_cholesky0(tril_a: CsrMatrix, plan: TriangularPlan | None = None) -> CsrMatrix:
+    """IC(0) factor on the pattern of ``tril(A)`` (``dp_ic0_f64``) — stands in for ``ilupp.ichol0`` (``test.py:84``)."""
+    lib, n, dev = _lib.lib(), tril_a.n, tril_a.device
+    plan = plan or analyse(tril_a, upper=False)
+    l_val = torch.empty(max(tril_a.nnz, 1), dtype=torch.float64, device=dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = _workspace(lib.dp_sptrsv_workspace_bytes(), dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.dp_ic0_f64(n, _lib.ptr(tril_a.rowptr), _lib.ptr(tril_a.col), _lib.ptr(tril_a.val),
+                                  _lib.ptr(l_val), _lib.ptr(plan.plan), plan.nchunks, plan.max_level_chunks,
+                                  _lib.ptr(flag), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "dp_ic0_f64")
+    _lib.raise_on_flag(flag, "dp_ic0_f64 (non-positive pivot)")
+    return CsrMatrix(tril_a.rowptr, tril_a.col, l_val[: tril_a.nnz], n)
+
+
+class _Operator:
+    precond: int = _lib.PRECOND_IDENTITY
+
+    def _apply(self, r: torch.Tensor) -> torch.Tensor:  # device fp64 in, device fp64 out
+        raise NotImplementedError
+
+    def __matmul__(self, r: torch.Tensor) -> torch.Tensor:
+        dev = getattr(self, "device", None) or (r.device if r.is_cuda else torch.device("cuda"))
+        z = self._apply(r.to(device=dev, dtype=torch.float64))
+        return z if r.is_cuda else z.to(r.device)
+
+    def fill(self, system: _lib.PcgSystem) -> None:
+        """Write this operator's arrays into a ``dp_pcg_system_t``."""
+        system.precond = self.precond
+
+    def nnz_explicit(self) -> int | None:
+        return None
+
+
+class Identity(_Operator):
+    precond = _lib.PRECOND_IDENTITY
+
+    def _apply(self, r):
+        return r.clone()
+
+
+class Jacobi(_Operator):
+    precond = _lib.PRECOND_JACOBI
+
+    def __init__(self, matrix) -> None:
+        self.dinv = as_csr(matrix).inv_diagonal()
+        self.device = self.dinv.device
+
+    def _apply(self, r):
+        return self.dinv * r
+
+    def fill(self, system):
+        system.precond = self.precond
+        system.dinv = _lib.ptr(self.dinv)
+
+
+class CsrOperator(_Operator):
+    precond = _lib.PRECOND_CSR
+
+    def __init__(self, matrix, device=None) -> None:
+        self.M = as_csr(matrix, device)
+        self.device = self.M.device
+
+    def _apply(self, r):
+        return self.M.matvec(r)
+
+    def fill(self, system):
+        system.precond = self.precond
+        system.m_rowptr, system.m_col, system.m_val = _lib.ptr(self.M.rowptr), _lib.ptr(self.M.col), _lib.ptr(self.M.val)
+        system.m_nnz = self.M.nnz
+
+
+class FactoredMultiply(_Operator):
+    """``M = L L^T`` applied as two SpMVs, never formed (the reference forms it densely in fp32, ``test.py:104``)."""
+
+    precond = _lib.PRECOND_MULTIPLY
+
+    def __init__(self, L: CsrMatrix, Lt: CsrMatrix | None = None) -> None:
+        self.L, self.Lt = L, Lt if Lt is not None else L.transpose()
+        self.device = L.device
+
+    def _apply(self, r):
+        return self.L.matvec(self.Lt.matvec(r))
+
+    def fill(self, system):
+        system.precond = self.precond
+        system.m_rowptr, system.m_col, system.m_val = _lib.ptr(self.L.rowptr), _lib.ptr(self.L.col), _lib.ptr(self.L.val)
+        system.mt_rowptr, system.mt_col, system.mt_val = (_lib.ptr(self.Lt.rowptr), _lib.ptr(self.Lt.col),
+                                                          _lib.ptr(self.Lt.val))
+        system.m_nnz, system.mt_nnz = self.L.nnz, self.Lt.nnz
+
+
+class FactoredSolve(FactoredMultiply):
+    """``M = (L L^T)^-1`` applied as a forward and a backward sparse triangular solve."""
+
+    precond = _lib.PRECOND_SOLVE
+
+    def __init__(self, L: CsrMatrix, Lt: CsrMatrix | None = None, fwd: TriangularPlan | None = None,
+                 bwd: TriangularPlan | None = None) -> None:
+        super().__init__(L, Lt)
+        self.fwd = fwd or analyse(self.L, upper=False)
+        self.bwd = bwd or analyse(self.Lt, upper=True)
+
+    def _apply(self, r):
+        return triangular_solve(self.Lt, self.bwd, triangular_solve(self.L, self.fwd, r))
+
+    def fill(self, system):
+        super().fill(system)
+        system.precond = self.precond
+        system.fwd_plan, system.bwd_plan = _lib.ptr(self.fwd.plan), _lib.ptr(self.bwd.plan)
+        system.fwd_nchunks, system.bwd_nchunks = self.fwd.nchunks, self.bwd.nchunks
+        system.fwd_max_level_chunks, system.bwd_max_level_chunks = self.fwd.max_level_chunks, self.bwd.max_level_chunks
+
+
+def as_operator(M, device=None) -> _Operator:
+    """Coerce the reference's ``M`` argument: ``None`` -> identity, an operator stays, any matrix -> ``CsrOperator``."""
+    if M is None:
+        return Identity()
+    if isinstance(M, _Operator):
+        return M
+    return CsrOperator(M, device)

@@ -1,0 +1,190 @@
+"""Device-resident CSR operands (fp64 values, int32 indices) built by the K1 kernels of ``libdpcg``.
+
+Replaces the dense round trips of the reference harness:
+
+* ``BenchmarkSuite._reconstruct_system`` (``uibk/deep_preconditioning/test.py:61-68``): ``A = T + tril(T,-1)^T``
+  -> :meth:`CsrMatrix.from_spconv` with ``mode="symmetrise"``;
+* ``BenchmarkSuite._construct_learned`` (``test.py:100-105``): ``dense()[0,0,:n,:n]`` ... ``to_sparse_csr()``
+  -> ``mode="tril"`` (and ``"tril_t"`` / :meth:`CsrMatrix.transpose` for the explicitly stored ``L^T``).
+
+``A @ v`` runs the hand-written CSR SpMV (``dp_spmv_csr_f64``).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_MODES = {"tril": _lib.ASSEMBLE_TRIL, "tril_t": _lib.ASSEMBLE_TRIL_T, "symmetrise": _lib.ASSEMBLE_SYMMETRISE}
+
+
+def _cuda_device(device=None) -> torch.device:
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise _lib.DpcgError("deeppreconditioning_b200 runs on CUDA devices only (no CPU fallback)")
+    return device
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+class CsrMatrix:
+    """Square CSR matrix on a CUDA device: ``rowptr int32[n+1]``, ``col int32[nnz]`` (sorted per row), ``val float64[nnz]``."""
+
+    def __init__(self, rowptr: torch.Tensor, col: torch.Tensor, val: torch.Tensor, n: int) -> None:
+        assert rowptr.dtype == torch.int32 and col.dtype == torch.int32 and val.dtype == torch.float64
+        assert rowptr.is_cuda and col.is_cuda and val.is_cuda
+        self.rowptr, self.col, self.val, self.n = rowptr.contiguous(), col.contiguous(), val.contiguous(), int(n)
+        self._t: CsrMatrix | None = None
+        self._dinv: torch.Tensor | None = None
+
+    # ---- construction ----------------------------------------------------------------------------------------
+    @classmethod
+    def from_spconv(cls, tensor, original_size: int, mode: str = "tril", batch: int = 0) -> "CsrMatrix":
+        """Assemble from a ``SparseConvTensor``-like object (``features [nnz,C]`` fp32, ``indices [nnz,3]`` int32).
+
+        ``mode``: ``"tril"`` keeps ``row >= col`` and ``value != 0`` (what ``dense().to_sparse_csr()`` of the
+        lower-triangular network output keeps), ``"tril_t"`` the same entries transposed, ``"symmetrise"`` rebuilds
+        the full symmetric system from its stored lower triangle.
+        """
+        n = int(original_size)
+        indices, features = tensor.indices, tensor.features
+        device = _cuda_device(indices.device if indices.is_cuda else None)
+        indices = indices.to(device=device, dtype=torch.int32).contiguous()
+        feats = features.detach().to(device=device, dtype=torch.float32)
+        feats = (feats[:, 0] if feats.dim() == 2 else feats).contiguous()
+        nnz_in = int(indices.shape[0])
+        cap = max(nnz_in * (2 if mode == "symmetrise" else 1), 1)
+        rowptr = torch.empty(n + 1, dtype=torch.int32, device=device)
+        col = torch.empty(cap, dtype=torch.int32, device=device)
+        val = torch.empty(cap, dtype=torch.float64, device=device)
+        nnz_out = torch.zeros(1, dtype=torch.int32, device=device)
+        flag = torch.zeros(1, dtype=torch.int32, device=device)
+        lib = _lib.lib()
+        ws = _workspace(lib.dp_csr_from_coo_workspace_bytes(n, nnz_in), device)
+        with torch.cuda.device(device):
+            _lib.check(lib.dp_csr_from_coo(_lib.ptr(indices), _lib.ptr(feats), nnz_in, int(batch), n, _MODES[mode],
+                                           _lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(val), _lib.ptr(nnz_out),
+                                           _lib.ptr(flag), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(device)),
+                       "dp_csr_from_coo")
+        nnz = int(nnz_out.item())  # one sync per assembled matrix
+        _lib.raise_on_flag(flag, "dp_csr_from_coo (duplicate (row, col) in the COO input)")
+        return cls(rowptr, col[:nnz], val[:nnz], n)
+
+    @classmethod
+    def from_arrays(cls, rowptr, col, val, device=None) -> "CsrMatrix":
+        """From host or device CSR arrays (columns must already be sorted per row)."""
+        device = _cuda_device(device)
+        as_t = lambda a, dt: torch.as_tensor(np.asarray(a) if not torch.is_tensor(a) else a).to(device=device, dtype=dt)
+        rowptr = as_t(rowptr, torch.int32)
+        return cls(rowptr, as_t(col, torch.int32), as_t(val, torch.float64), rowptr.shape[0] - 1)
+
+    @classmethod
+    def from_torch(cls, matrix: torch.Tensor, device=None) -> "CsrMatrix":
+        """From what the reference hands to ``cg.py``: a dense fp64 matrix (``test.py:68``) or a sparse CSR/COO tensor
+        (``test.py:72,79,88,105``), on any device. Exact zeros of a dense input are dropped (``to_sparse_csr``)."""
+        if device is None and matrix.is_cuda:
+            device = matrix.device
+        if matrix.layout == torch.strided:
+            matrix = matrix.to_sparse_csr()
+        elif matrix.layout != torch.sparse_csr:
+            matrix = matrix.coalesce().to_sparse_csr() if matrix.layout == torch.sparse_coo else matrix.to_sparse_csr()
+        return cls.from_arrays(matrix.crow_indices(), matrix.col_indices(), matrix.values(), device)
+
+    @classmethod
+    def from_scipy(cls, matrix, device=None) -> "CsrMatrix":
+        m = matrix.tocsr()
+        m.sort_indices()
+        return cls.from_arrays(m.indptr, m.indices, m.data, device)
+
+    # ---- properties --------------------------------------------------------------------------------------------
+    @property
+    def shape(self):
+        return (self.n, self.n)
+
+    @property
+    def nnz(self) -> int:
+        return int(self.col.shape[0])
+
+    @property
+    def device(self):
+        return self.val.device
+
+    def values(self) -> torch.Tensor:
+        """Stored values, like ``Tensor.values()`` of a sparse CSR tensor (``test.py:109`` reads ``len(matrix.values())``)."""
+        return self.val
+
+    # ---- operations ----------------------------------------------------------------------------------------------
+    def transpose(self) -> "CsrMatrix":
+        """Explicit CSR of the transpose (``dp_csr_transpose``), cached."""
+        if self._t is None:
+            n, nnz, dev = self.n, self.nnz, self.device
+            rowptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+            col = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+            val = torch.empty(max(nnz, 1), dtype=torch.float64, device=dev)
+            lib = _lib.lib()
+            ws = _workspace(lib.dp_csr_transpose_workspace_bytes(n, nnz), dev)
+            with torch.cuda.device(dev):
+                _lib.check(lib.dp_csr_transpose(n, nnz, _lib.ptr(self.rowptr), _lib.ptr(self.col), _lib.ptr(self.val),
+                                                _lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(val), _lib.ptr(ws),
+                                                ws.numel(), _lib.stream_ptr(dev)), "dp_csr_transpose")
+            self._t = CsrMatrix(rowptr, col[:nnz], val[:nnz], n)
+            self._t._t = self
+        return self._t
+
+    @property
+    def T(self) -> "CsrMatrix":
+        return self.transpose()
+
+    def matvec(self, x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """``y = A x`` on the device (``dp_spmv_csr_f64``)."""
+        assert x.is_cuda and x.dtype == torch.float64 and x.shape == (self.n,)
+        x = x.contiguous()
+        y = out if out is not None else torch.empty(self.n, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().dp_spmv_csr_f64(self.n, self.nnz, _lib.ptr(self.rowptr), _lib.ptr(self.col),
+                                                  _lib.ptr(self.val), _lib.ptr(x), _lib.ptr(y),
+                                                  _lib.stream_ptr(self.device)), "dp_spmv_csr_f64")
+        return y
+
+    def __matmul__(self, x: torch.Tensor) -> torch.Tensor:
+        """Duck-typed ``A @ v`` (``cg.py:60,75``): accepts a CPU or CUDA fp64 vector, answers on the same device."""
+        y = self.matvec(x.to(device=self.device, dtype=torch.float64))
+        return y if x.is_cuda else y.to(x.device)
+
+    def inv_diagonal(self) -> torch.Tensor:
+        """``1 / diag(A)`` (``test.py:76``), cached."""
+        if self._dinv is None:
+            dinv = torch.empty(self.n, dtype=torch.float64, device=self.device)
+            flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().dp_csr_inv_diagonal(self.n, _lib.ptr(self.rowptr), _lib.ptr(self.col),
+                                                          _lib.ptr(self.val), _lib.ptr(dinv), _lib.ptr(flag),
+                                                          _lib.stream_ptr(self.device)), "dp_csr_inv_diagonal")
+            _lib.raise_on_flag(flag, "dp_csr_inv_diagonal (row without a stored diagonal)")
+            self._dinv = dinv
+        return self._dinv
+
+    # ---- export ----------------------------------------------------------------------------------------------------
+    def to_host(self):
+        return self.rowptr.cpu().numpy(), self.col.cpu().numpy(), self.val.cpu().numpy()
+
+    def to_torch_csr(self, device="cpu") -> torch.Tensor:
+        return torch.sparse_csr_tensor(self.rowptr.to(device).long(), self.col.to(device).long(), self.val.to(device),
+                                       size=self.shape)
+
+
+def as_csr(matrix, device=None) -> CsrMatrix:
+    """Coerce anything the reference passes as ``A``/``M`` into a device CSR matrix."""
+    if isinstance(matrix, CsrMatrix):
+        return matrix
+    if torch.is_tensor(matrix):
+        return CsrMatrix.from_torch(matrix, device)
+    if hasattr(matrix, "tocsr"):
+        return CsrMatrix.from_scipy(matrix, device)
+    raise TypeError(f"cannot interpret {type(matrix).__name__} as a sparse matrix")

@@ -1,0 +1,179 @@
+/*
+ * dpcg.h — C ABI of libdpcg.so: the B200-native PCG hot path of DeepPreconditioning.
+ *
+ * The reference (jsappl/DeepPreconditioning) has no FFI: its boundary is a set of duck-typed Python call
+ * signatures. Each entry point below names the reference code it replaces (file:line relative
+ * to the reference root). The Python shim in deeppreconditioning_b200/ keeps the reference signatures and
+ * calls these through ctypes; INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; every pointer is a DEVICE pointer unless named *_host.
+ *   - values fp64, indices int32, 16-byte aligned arrays (checked: DP_ERR_ALIGNMENT).
+ *   - returns int status, 0 = DP_OK; never throws; no hidden allocation: scratch comes from the caller,
+ *     sized by the matching *_workspace_bytes() query; work is enqueued on `stream` (a cudaStream_t passed as
+ *     void*) and is asynchronous unless stated.
+ *   - one host thread per GPU; re-entrant per stream as long as workspaces are distinct.
+ */
+#ifndef DPCG_H
+#define DPCG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DP_VERSION 100
+
+enum dp_status {
+    DP_OK = 0,
+    DP_ERR_INVALID = 1,    /* bad argument (null pointer, negative size, unknown mode) */
+    DP_ERR_ALIGNMENT = 2,  /* an array is not 16-byte aligned */
+    DP_ERR_WORKSPACE = 3,  /* workspace too small */
+    DP_ERR_CUDA = 4,       /* a CUDA runtime call failed; see dp_last_cuda_error() */
+    DP_ERR_STRUCTURE = 5,  /* matrix structure violates the contract (reported through a device flag, see below) */
+    DP_ERR_TIMEOUT = 6     /* a dependency spin exceeded its budget (device flag) */
+};
+
+/* Preconditioner application z = M r inside the loop (reference: `zk = M @ rk`, cg.py:61,81). */
+enum dp_precond {
+    DP_PRECOND_IDENTITY = 0, /* _construct_vanilla, test.py:70-72 */
+    DP_PRECOND_JACOBI = 1,   /* _construct_jacobi, test.py:74-79: z = dinv .* r */
+    DP_PRECOND_MULTIPLY = 2, /* _construct_learned, test.py:100-105 in factored form: z = L (L^T r) */
+    DP_PRECOND_SOLVE = 3,    /* north_star apply mode for IC(0): z = L^-T (L^-1 r) */
+    DP_PRECOND_CSR = 4       /* any explicit CSR M (what test.py:88,105 hand to cg.py): z = M r */
+};
+
+enum dp_engine {
+    DP_ENGINE_FUSED = 0,   /* one persistent cooperative kernel for the whole solve (device-side loop control) */
+    DP_ENGINE_STEPPED = 1  /* one launch per phase; host polls the done counter every `check_every` iterations */
+};
+
+enum dp_assemble_mode {
+    DP_ASSEMBLE_TRIL = 0,       /* keep row >= col && value != 0  -> L        (test.py:103-105 minus the product) */
+    DP_ASSEMBLE_TRIL_T = 1,     /* same entries, transposed          -> L^T as CSR                                  */
+    DP_ASSEMBLE_SYMMETRISE = 2  /* T + tril(T,-1)^T                  -> A        (test.py:65-68)                    */
+};
+
+int dp_version(void);
+const char* dp_status_string(int status);
+const char* dp_last_cuda_error(void);
+/* sm_count, resident CTAs the fused PCG kernel gets per SM, bytes of L2. Synchronous. */
+int dp_device_info(int* sm_count_host, int* pcg_ctas_per_sm_host, int* l2_bytes_host);
+
+/* ---- K1: CSR assembly (bit-exact integer/value output) ------------------------------------------------
+ * Replaces the dense round trip of BenchmarkSuite._construct_learned (test.py:100-105) and
+ * _reconstruct_system (test.py:61-68). Input is the spconv COO layout of data_set.py:121-125:
+ * indices int32[nnz_in,3] = (batch,row,col), unordered; features fp32[nnz_in] (channel 0).
+ * Only entries of `batch` with row < n && col < n take part (the `[0, 0, :n, :n]` slice).
+ * Output rows sorted by column, values widened fp32 -> fp64 exactly. col/val need capacity for
+ * nnz_in entries (2*nnz_in for SYMMETRISE); the stored count is rowptr[n], also written to *nnz_out.
+ * *flag_out (device int32) is set to DP_ERR_STRUCTURE when a (row,col) pair occurs twice. */
+size_t dp_csr_from_coo_workspace_bytes(int32_t n, int64_t nnz_in);
+int dp_csr_from_coo(const int32_t* indices, const float* features, int64_t nnz_in, int32_t batch, int32_t n,
+                    int32_t mode, int32_t* rowptr, int32_t* col, double* val, int32_t* nnz_out, int32_t* flag_out,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Explicit transpose CSR -> CSR (the north_star stores L^T explicitly). Same sorting contract. */
+size_t dp_csr_transpose_workspace_bytes(int32_t n, int32_t nnz);
+int dp_csr_transpose(int32_t n, int32_t nnz, const int32_t* rowptr, const int32_t* col, const double* val,
+                     int32_t* rowptr_t, int32_t* col_t, double* val_t, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* dinv[i] = 1 / A_ii (test.py:76); rows without a stored diagonal get 0 and raise *flag_out. */
+int dp_csr_inv_diagonal(int32_t n, const int32_t* rowptr, const int32_t* col, const double* val, double* dinv,
+                        int32_t* flag_out, void* stream);
+
+/* ---- K2: CSR SpMV fp64 ---------------------------------------------------------------------------------
+ * y = A x. Replaces `A @ p` / `M @ r` (cg.py:60,61,75,81). Row sums are sequential in column order with
+ * separately rounded products and sums, i.e. bit-identical to scipy's csr_matvec. */
+int dp_spmv_csr_f64(int32_t n, int32_t nnz, const int32_t* rowptr, const int32_t* col, const double* val,
+                    const double* x, double* y, void* stream);
+
+/* Batched COO SpMV of utils.py:15-43 (sparse_matvec_mul), fp32: out[b,row] += feat * vec[b,col]
+ * (row/col swapped when transpose != 0). out is [nbatch, n] and is zeroed first. */
+int dp_coo_spmv_batch_f32(const int32_t* indices, const float* features, int64_t nnz, int32_t nbatch, int32_t n,
+                          const float* vec, int32_t transpose, float* out, void* stream);
+
+/* ---- K3: level analysis of a triangular CSR pattern (bit-exact integer output) ---------------------------
+ * lower (upper == 0): level[i] = 1 + max(level[j] : j < i stored in row i), 0 if none; the diagonal must be
+ * the LAST entry of each row. upper: j > i, diagonal FIRST (L^T as produced by dp_csr_transpose).
+ * Outputs: level int32[n]; perm int32[n] = rows stably sorted by level; level_ptr int32[n+1] (first
+ * *nlevels_out+1 entries valid); *nlevels_out, *flag_out device int32. No reference counterpart. */
+size_t dp_sptrsv_analyse_workspace_bytes(int32_t n);
+int dp_sptrsv_analyse(int32_t n, const int32_t* rowptr, const int32_t* col, int32_t upper, int32_t* level,
+                      int32_t* perm, int32_t* level_ptr, int32_t* nlevels_out, int32_t* flag_out, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* Execution plan derived from (perm, level_ptr): rows of a level padded to whole warps (-1 = idle lane).
+ * nchunks = sum over levels of ceil(size/32) <= n/32 + nlevels; plan needs 32*nchunks int32.
+ * The caller reads level_ptr[0..nlevels] back once per matrix (HOST copy), sizes the plan with
+ * dp_sptrsv_plan_chunks, and uploads chunk_ptr[l] = sum_{l'<l} ceil(size(l')/32) (nlevels+1 int32, DEVICE). */
+int64_t dp_sptrsv_plan_chunks(int32_t nlevels, const int32_t* level_ptr_host);
+int dp_sptrsv_plan_build(int32_t n, int32_t nlevels, const int32_t* perm, const int32_t* level_ptr,
+                         const int32_t* chunk_ptr, int32_t* plan, int64_t nchunks, void* stream);
+
+/* ---- K4: sparse triangular solves ------------------------------------------------------------------------
+ * lower: L y = b;  upper: U z = b with U = L^T in CSR. x_i = (b_i - sum_j T_ij x_j) * (1 / T_ii), the sum
+ * sequential in column order: bit-identical to plain forward/backward substitution (oracle/kernels.c).
+ * Sync-free: one cooperative launch, dependencies resolved by spinning on the solution vector itself.
+ * *flag_out receives DP_ERR_TIMEOUT if a dependency never arrives (malformed plan). */
+size_t dp_sptrsv_workspace_bytes(void);
+int dp_sptrsv_solve_f64(int32_t n, const int32_t* rowptr, const int32_t* col, const double* val, int32_t upper,
+                        const int32_t* plan, int64_t nchunks, int32_t max_level_chunks, const double* b, double* x,
+                        int32_t* flag_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- IC(0) on the pattern of tril(A) (stands in for ilupp.ichol0, test.py:84) -------------------------------
+ * Level-scheduled, sync-free numeric factorisation; uses the lower plan of the same pattern.
+ * *flag_out: DP_ERR_STRUCTURE on a non-positive pivot. */
+int dp_ic0_f64(int32_t n, const int32_t* rowptr, const int32_t* col, const double* a_val, double* l_val,
+               const int32_t* plan, int64_t nchunks, int32_t max_level_chunks, int32_t* flag_out, void* workspace,
+               size_t workspace_bytes, void* stream);
+
+/* ---- K5: the whole PCG loop ----------------------------------------------------------------------------------
+ * Replaces preconditioned_conjugate_gradient (cg.py:50-90) with its exact semantics: iteration-0 check on
+ * <z0,z0>/<b,b> (cg.py:66), later checks on <r,r>/<b,b> < rtol (cg.py:15-17,71,86), at most max_iter bodies,
+ * iterations = number of loop bodies executed (cg.py:90). One descriptor per independent system (the
+ * data-parallel axis of BenchmarkSuite.run, test.py:121); all systems of a call advance in lock step inside one
+ * launch and drop out individually when converged. */
+typedef struct dp_pcg_system {
+    int32_t n;
+    int32_t precond; /* enum dp_precond */
+    int32_t a_nnz, m_nnz, mt_nnz;
+    int32_t fwd_nchunks, bwd_nchunks;       /* SOLVE: plan sizes */
+    int32_t fwd_max_level_chunks, bwd_max_level_chunks;
+    int32_t reserved;
+    const int32_t* a_rowptr; const int32_t* a_col; const double* a_val;     /* A (full symmetric CSR) */
+    const int32_t* m_rowptr; const int32_t* m_col; const double* m_val;     /* L (MULTIPLY/SOLVE) or M (CSR) */
+    const int32_t* mt_rowptr; const int32_t* mt_col; const double* mt_val;  /* L^T (MULTIPLY/SOLVE) */
+    const double* dinv;                                                     /* JACOBI */
+    const int32_t* fwd_plan; const int32_t* bwd_plan;                       /* SOLVE */
+    const double* b;   /* right-hand side, n */
+    double* x;         /* in: x0, out: x_hat, n */
+    double* work;      /* dp_pcg_work_doubles(n) doubles of scratch, contents ignored on entry */
+    int32_t* iters_out;   /* 1 */
+    double* res_out;      /* 1: last value of the stopping criterion (squared relative residual) */
+    double* history;      /* optional, max_iter+1 doubles: criterion before every body (cg.py:67,87) */
+} dp_pcg_system_t;
+
+typedef struct dp_pcg_params {
+    double rtol;          /* cg.py:51 default 1e-8, compared with the SQUARED relative residual */
+    int32_t max_iter;     /* cg.py:51 default 1024 */
+    int32_t engine;       /* enum dp_engine */
+    int32_t check_every;  /* STEPPED: iterations between host polls of the done counter (>= 1) */
+    int32_t reserved;
+} dp_pcg_params_t;
+
+int64_t dp_pcg_work_doubles(int32_t n);
+size_t dp_pcg_workspace_bytes(int32_t nsys);
+/* systems_host: HOST array of nsys descriptors (device pointers inside). Enqueues the solve on `stream`;
+ * FUSED is fully asynchronous, STEPPED synchronises the stream every check_every iterations.
+ * *flag_out (device int32): DP_ERR_TIMEOUT / DP_ERR_STRUCTURE raised on the device. */
+int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp_pcg_params_t* params_host,
+                     int32_t* flag_out, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPCG_H */
