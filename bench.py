@@ -1,0 +1,465 @@
+#!/usr/bin/env python
+"""Benchmark of the PCG hot path (BASELINE.json metric: PCG solves/sec + ms-to-tol per system; HBM roofline).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (config.workload): every GPU holds a batch of independent 316x316 5-point variable-coefficient pressure
+systems (N = 99 856 unknowns each, BASELINE config 2 shape) with the factor L of a random-init PreconditionerNet
+(multiply mode, the reference's `learned` technique). 128 systems per GPU: at 8 GPUs that is exactly BASELINE config 3
+(1024 systems sharded over 8 B200). A step = one fused-PCG solve of the rank's whole batch to rtol=1e-8
+(squared criterion, cg.py:17), max_iter 20000 (the default 1024 saturates).
+
+value   : solves/s with operands resident in HBM (CUDA events, max over ranks).
+e2e     : the same through the reference-facing call with HOST operands (pinned CSR of A and L, b): H2D copies, L^T
+          assembly, workspace setup, solve, D2H of x/iterations inside the timed region.
+roofline: fused PCG kernel, algorithmic bytes per launch (12 nnzA + 24 nnzL + 132 N + 12 per iteration and system,
+          SURVEY §8d) / CUDA-event duration, against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
+cpu_baseline / --impl reference: the CPU restatement of the reference loop (oracle/pcg.py, torch CPU CSR operands,
+          all host threads) on a bounded sample of the same workload. The reference itself is Python and cannot
+          travel to the GPU box; tests pin the restatement to it.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "pcg_solves_per_sec"
+UNIT = "solves/s"
+RTOL = 1e-8
+MAX_ITER = 20000
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--systems-per-gpu", type=int, default=128)
+    ap.add_argument("--side", type=int, default=316)
+    ap.add_argument("--net", default="net", choices=["net", "tril"])
+    ap.add_argument("--no-extras", action="store_true", help="skip single-system latency and 128^3 kernel numbers")
+    return ap.parse_args()
+
+
+def workload_name(args):
+    return (f"{args.systems_per_gpu} x poisson2d {args.side}x{args.side} (N={args.side ** 2}) per GPU, "
+            f"random-init Preconditioner{'Net' if args.net == 'net' else 'TrilNet'} L, multiply mode, "
+            f"rtol=1e-8 (squared), max_iter={MAX_ITER}")
+
+
+def iter_bytes(n, nnz_a, nnz_l):
+    """Algorithmic bytes of one PCG iteration: SpMV(A) + SpMV(L^T) + SpMV(L) + 72 N."""
+    spmv = lambda nnz: 12 * nnz + 4 * (n + 1) + 16 * n
+    return spmv(nnz_a) + 2 * spmv(nnz_l) + 72 * n
+
+
+# ---- clocks ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])), smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---- workload -----------------------------------------------------------------------------------------------------------
+def build_host_systems(args, rank, world, device):
+    """Synthetic systems of this rank (interleaved shard of the global list) as pinned HOST CSR operands.
+
+    Assembly of A and L runs on the GPU (K1 kernels) once, then the operands are read back to pinned host memory so
+    that the e2e leg can start from host buffers like the reference's harness does (everything `.cpu()`, test.py:68,105).
+    """
+    from deeppreconditioning_b200 import model as models
+    from deeppreconditioning_b200 import synthetic
+    from deeppreconditioning_b200.distributed import shard_indices
+    from deeppreconditioning_b200.sparse import CsrMatrix
+
+    n_global = args.systems_per_gpu * world
+    mine = shard_indices(n_global, rank, world)
+    torch.manual_seed(69)  # test.py:205
+    cls = models.PreconditionerNet if args.net == "net" else models.PreconditionerTrilNet
+    net = cls(models.DEFAULT_CHANNELS).to(device)
+    host = []
+    for index in mine:
+        st, _, rhs, sizes = synthetic.make_batch("poisson2d", args.side, [index], device=device)
+        n = sizes[0]
+        with torch.no_grad():
+            learned = net(st)
+        A = CsrMatrix.from_spconv(st, n, "symmetrise")
+        L = CsrMatrix.from_spconv(learned, n, "tril")
+        pin = lambda t: t.cpu().pin_memory()
+        host.append(dict(index=index, n=n, a=tuple(pin(t) for t in (A.rowptr, A.col, A.val)),
+                         l=tuple(pin(t) for t in (L.rowptr, L.col, L.val)),
+                         b=pin(rhs[0, :n].to(torch.float64))))
+        del st, learned, A, L
+    torch.cuda.empty_cache()
+    return mine, host
+
+
+def device_batch(host, device):
+    import deeppreconditioning_b200 as dp
+    from deeppreconditioning_b200.sparse import CsrMatrix
+
+    systems = []
+    for h in host:
+        A = CsrMatrix.from_arrays(*h["a"], device=device)
+        L = CsrMatrix.from_arrays(*h["l"], device=device)
+        systems.append((A, h["b"].to(device, non_blocking=True), dp.FactoredMultiply(L)))
+    return dp.PcgBatch(systems, RTOL, MAX_ITER, engine="fused", device=device)
+
+
+def dist_setup(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29531")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+        local = 0
+    return rank, world, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(value, world, device):
+    if world == 1:
+        return value
+    import torch.distributed as dist
+
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value, world, device):
+    if world == 1:
+        return value
+    import torch.distributed as dist
+
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def cpu_solve_sample(host_system, threads):
+    """One system through the CPU restatement of the reference loop (oracle/pcg.py), reference operand types."""
+    from oracle import operators, pcg
+    from oracle import sparse as osp
+
+    torch.set_num_threads(threads)
+    a = osp.to_torch_csr(*(t.numpy() for t in host_system["a"]))
+    m = operators.FactoredMultiply(*(t.numpy() for t in host_system["l"]))
+    result = pcg.preconditioned_conjugate_gradient(a, host_system["b"].clone(), m, rtol=RTOL, max_iter=MAX_ITER)
+    return result
+
+
+def peaks():
+    path = ROOT / "MEASURED_PEAKS.json"
+    if path.exists():
+        return float(json.loads(path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---- reference arm ---------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    device = torch.device("cuda", 0) if torch.cuda.is_available() else None
+    threads = os.cpu_count() or 1
+    one = argparse.Namespace(**{**vars(args), "systems_per_gpu": max(args.steps + args.warmup, 1)})
+    if device is not None:
+        _, host = build_host_systems(one, 0, 1, device)
+    else:
+        raise SystemExit("the reference arm builds its operands with the same GPU assembly path; no GPU found")
+    times, iters = [], []
+    for step in range(args.warmup + args.steps):
+        h = host[step % len(host)]
+        t0 = time.perf_counter()
+        r = cpu_solve_sample(h, threads)
+        dt = time.perf_counter() - t0
+        if step >= args.warmup:
+            times.append(dt), iters.append(r.iterations)
+    total = float(np.sum(times))
+    value = len(times) / total
+    sample = (f"1 system per step ({len(times)} timed, distinct seeds) of the {args.systems_per_gpu}-system per-GPU batch; "
+              f"mean {np.mean(iters):.0f} iterations")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": workload_name(args)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ---- our arm ------------------------------------------------------------------------------------------------------------
+def extras(device, host0):
+    """Single-system latency (BASELINE config 2) and HBM-bound kernel numbers on 128^3 (config 4)."""
+    import deeppreconditioning_b200 as dp
+    from deeppreconditioning_b200 import precond, synthetic
+    from deeppreconditioning_b200.sparse import CsrMatrix
+
+    out = {}
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        best = float("inf")
+        for _ in range(reps):
+            a, b = ev(), ev()
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b))
+        return best
+
+    # config 2: one 316^2 system, CNN L (multiply) vs IC(0) (solve) vs Jacobi
+    A = CsrMatrix.from_arrays(*host0["a"], device=device)
+    L = CsrMatrix.from_arrays(*host0["l"], device=device)
+    b = host0["b"].to(device)
+    n = A.n
+    single = {}
+    st, _, _, _ = synthetic.make_batch("poisson2d", int(round(n ** 0.5)), [host0["index"]], device=device)
+    T = CsrMatrix.from_spconv(st, n, "tril")
+    t0 = time.perf_counter()
+    fwd = precond.analyse(T, False)
+    factor = precond.incomplete_cholesky0(T, fwd)
+    ic = dp.FactoredSolve(factor, None, fwd)
+    torch.cuda.synchronize()
+    ic_setup_ms = 1e3 * (time.perf_counter() - t0)
+    for name, M in [("cnn_multiply", dp.FactoredMultiply(L)), ("ic0_solve", ic), ("jacobi", dp.Jacobi(A)),
+                    ("identity", dp.Identity())]:
+        batch = dp.PcgBatch([(A, b, M)], RTOL, MAX_ITER)
+
+        def go():
+            batch.reset()
+            batch.solve()
+
+        ms = timed(go)
+        r = batch.results()[0]
+        nnz_l = L.nnz if name == "cnn_multiply" else (T.nnz if name == "ic0_solve" else 0)
+        single[name] = {"ms_to_tol": ms, "iterations": r.iterations, "us_per_iteration": 1e3 * ms / max(r.iterations, 1),
+                        "res": r.res, "algorithmic_gbs": iter_bytes(n, A.nnz, nnz_l) * r.iterations / ms / 1e6}
+    single["ic0_solve"]["setup_ms_analysis_plus_factorisation"] = ic_setup_ms
+    single["ic0_solve"]["levels"] = fwd.nlevels
+    out["single_system_316x316"] = single
+
+    # config 4: 128^3, HBM-bound SpMV and SpTRSV
+    st, _, rhs, sizes = synthetic.make_batch("poisson3d", 128, [0], device=device)
+    n3 = sizes[0]
+    A3, T3 = CsrMatrix.from_spconv(st, n3, "symmetrise"), CsrMatrix.from_spconv(st, n3, "tril")
+    x = rhs[0, :n3].to(torch.float64)
+    y = torch.empty_like(x)
+    peak, _ = peaks()
+    ms = timed(lambda: A3.matvec(x, y), reps=10)
+    spmv_bytes = 12 * A3.nnz + 4 * (n3 + 1) + 16 * n3
+    out["spmv_128^3"] = {"ms": ms, "algorithmic_gbs": spmv_bytes / ms / 1e6, "frac_of_hbm_peak": spmv_bytes / ms / 1e6 / peak}
+    fwd3 = precond.analyse(T3, False)
+    ms = timed(lambda: precond.triangular_solve(T3, fwd3, x, y), reps=5)
+    trsv_bytes = 12 * T3.nnz + 4 * (n3 + 1) + 16 * n3
+    out["sptrsv_128^3"] = {"ms": ms, "levels": fwd3.nlevels, "algorithmic_gbs": trsv_bytes / ms / 1e6,
+                           "frac_of_hbm_peak": trsv_bytes / ms / 1e6 / peak, "us_per_level": 1e3 * ms / fwd3.nlevels}
+    return out
+
+
+def run_ours(args):
+    from deeppreconditioning_b200 import build as dp_build
+    from deeppreconditioning_b200.distributed import gather_records, make_records
+
+    rank, world, local = dist_setup(args)
+    if rank == 0:
+        dp_build.build()
+    barrier(world)
+    device = torch.device("cuda", local)
+    mine, host = build_host_systems(args, rank, world, device)
+    batch = device_batch(host, device)
+    n_sys_global = args.systems_per_gpu * world
+
+    # ---- resident-operand measurement -----------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        batch.reset()
+        batch.solve()
+    barrier(world)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    barrier(world)
+    start.record()
+    for _ in range(args.steps):
+        batch.reset()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        batch.solve()  # ONE kernel launch: pcg_fused_kernel
+        k1.record()
+        kernel_ms.append((k0, k1))
+    stop.record()
+    barrier(world)
+    elapsed_ms = max_over_ranks(start.elapsed_time(stop), world, device)
+    clocks = sampler.stop() if rank == 0 else None
+    results = batch.results()
+    kernel_ms = [a.elapsed_time(b) for a, b in kernel_ms]
+    value = n_sys_global * args.steps / (elapsed_ms / 1e3)
+
+    # per-system records: the only collective of the path
+    records = gather_records(make_records(mine, results, [np.mean(kernel_ms)] * len(mine)), n_sys_global)
+    iterations = records[:, 1].numpy()
+
+    # roofline of the dominant (only) kernel, rank-local bytes / rank-local kernel time, summed over ranks
+    local_bytes = sum(iter_bytes(h["n"], h["a"][1].numel(), h["l"][1].numel()) * r.iterations for h, r in zip(host, results))
+    local_gbs = local_bytes / (np.mean(kernel_ms) / 1e3) / 1e9
+    peak, peak_source = peaks()
+    mean_gbs = sum_over_ranks(local_gbs, world, device) / world
+
+    # ---- e2e: host operands through the public call ------------------------------------------------------------------
+    import deeppreconditioning_b200 as dp
+    from deeppreconditioning_b200.sparse import CsrMatrix
+
+    h2d = sum(sum(t.numel() * t.element_size() for t in h["a"] + h["l"]) + h["b"].numel() * 8 for h in host)
+    d2h = sum(h["n"] * 8 + 12 for h in host)
+    del batch
+    torch.cuda.empty_cache()
+
+    def e2e_step():
+        systems = []
+        for h in host:
+            A = CsrMatrix.from_arrays(*h["a"], device=device)
+            L = CsrMatrix.from_arrays(*h["l"], device=device)
+            systems.append((A, h["b"], dp.FactoredMultiply(L)))  # b stays a (pinned) host tensor: x_hat returns to host
+        out = dp.pcg_solve_batch(systems, RTOL, MAX_ITER, device=device)
+        return out
+
+    e2e_steps = max(1, min(args.steps, 2))
+    e2e_step()
+    barrier(world)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        out = e2e_step()
+    barrier(world)
+    e2e_s = max_over_ranks(time.perf_counter() - t0, world, device)
+    assert [r.iterations for r in out] == [r.iterations for r in results], "e2e and resident runs disagree"
+    e2e_value = n_sys_global * e2e_steps / e2e_s
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1 only) -----------------------------------------------------------
+    cpu = None
+    extra = None
+    if rank == 0 and world == 1:
+        threads = os.cpu_count() or 1
+        t0 = time.perf_counter()
+        r = cpu_solve_sample(host[0], threads)
+        dt = time.perf_counter() - t0
+        cpu = {"value": 1.0 / dt, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"system {host[0]['index']} of the batch: {r.iterations} iterations in {dt:.2f} s "
+                         f"(GPU: {results[0].iterations} iterations)", "ms_per_iteration": 1e3 * dt / max(r.iterations, 1)}
+        if not args.no_extras:
+            extra = extras(device, host[0])
+
+    if rank == 0:
+        traffic = None
+        tpath = ROOT / "profiles" / "traffic.json"
+        if tpath.exists():
+            traffic = json.loads(tpath.read_text()).get("pcg_fused_kernel_bytes_per_launch")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "systems_total": n_sys_global, "l2": "per-GPU working set "
+                       f"{sum(sum(t.numel() * t.element_size() for t in h['a'] + h['l']) for h in host) * 1.5 / 1e9:.1f} GB >> 126 MB L2 (no flush needed)",
+                       "iterations_mean": float(iterations.mean()), "iterations_min": int(iterations.min()),
+                       "iterations_max": int(iterations.max()), "engine": "fused persistent cooperative kernel"},
+            "ms_to_tol_per_system": elapsed_ms / args.steps / args.systems_per_gpu,
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(sum_over_ranks(h2d, world, device)) if world > 1 else h2d,
+                    "d2h_bytes_per_step": int(sum_over_ranks(d2h, world, device)) if world > 1 else d2h, "steps": e2e_steps},
+            "gpu_launches": args.steps * world,
+            "roofline": {"bound": "hbm", "kernel": "pcg_fused_kernel", "achieved": mean_gbs, "peak": peak, "unit": "GB/s",
+                         "frac": mean_gbs / peak, "traffic": traffic, "peak_source": peak_source,
+                         "bytes_per_launch": local_bytes, "ms_per_launch": float(np.mean(kernel_ms))},
+            "cpu_baseline": cpu,
+        }
+        if extra:
+            line["extras"] = extra
+        print(json.dumps(line))
+    else:
+        # keep collectives matched on the other ranks
+        if world > 1:
+            sum_over_ranks(h2d, world, device)
+            sum_over_ranks(d2h, world, device)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,323 @@
+"""GPU parity tests (run with `-m gpu` on the B200 box): every kernel of libdpcg, called through the C ABI, against
+the oracle on the same seeded inputs; bit-exact for integer/index work and for the sequential-sum kernels, toleranced
+only where the reduction order legitimately differs (dot products)."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+import deeppreconditioning_b200 as dp
+from deeppreconditioning_b200 import precond, utils
+from deeppreconditioning_b200.sparse import CsrMatrix
+from deeppreconditioning_b200.test import BenchmarkSuite
+from deeppreconditioning_b200 import model as models, synthetic
+from oracle import ckernels, operators, pcg
+from oracle import sparse as osp
+from test_oracle import GOLDEN, build_operator, iteration_tolerance
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("poisson2d", 16, "net"), ("poisson2d", 64, "net"), ("poisson3d", 12, "tril"), ("poisson2d", 100, "tril"),
+         ("poisson2d", 37, "net"), ("poisson3d", 5, "net")]
+
+
+def gpu_operands(p, cuda):
+    st = helpers.to_device(p.systems_tril, cuda)
+    out = {"A": CsrMatrix.from_spconv(st, p.n, "symmetrise"), "T": CsrMatrix.from_spconv(st, p.n, "tril")}
+    if p.learned is not None:
+        ln = helpers.to_device(p.learned, cuda)
+        out["L"] = CsrMatrix.from_spconv(ln, p.n, "tril")
+        out["Lt"] = CsrMatrix.from_spconv(ln, p.n, "tril_t")
+    return out
+
+
+def gpu_operator(name, ops, p, cuda):
+    if name == "identity":
+        return dp.Identity()
+    if name == "jacobi":
+        return dp.Jacobi(ops["A"])
+    if name == "multiply":
+        return dp.FactoredMultiply(ops["L"], ops["Lt"])
+    if name == "explicit":
+        return dp.CsrOperator(osp.explicit_product(*p.L), cuda)
+    if name == "ic0_solve":
+        return dp.FactoredSolve(precond.incomplete_cholesky0(ops["T"]))
+    raise KeyError(name)
+
+
+# ---- K1 -------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,side,net", CASES)
+def test_assembly_bit_exact(cuda, kind, side, net):
+    p = helpers.problem(kind, side, 0, 0.5, net)
+    ops = gpu_operands(p, cuda)
+    helpers.assert_csr_equal(ops["A"], p.A)
+    helpers.assert_csr_equal(ops["T"], p.T)
+    helpers.assert_csr_equal(ops["L"], p.L)
+    helpers.assert_csr_equal(ops["Lt"], osp.transpose_csr(*p.L))
+    helpers.assert_csr_equal(ops["L"].transpose(), osp.transpose_csr(*p.L))
+    helpers.assert_csr_equal(ops["A"].transpose(), p.A)  # symmetric
+    dinv = ops["A"].inv_diagonal().cpu().numpy()
+    assert np.array_equal(dinv, 1 / osp.to_scipy(*p.A).diagonal())
+
+
+def test_assembly_batches_padding_and_zeros(cuda):
+    """Ragged batch padded with trivial equations (data_set.py:95-118): only `[b, 0, :n, :n]` of the right batch
+    element is assembled; exact zeros (and -0.0) are dropped like to_sparse_csr() does; duplicates are an error."""
+    st, _, _, sizes = synthetic.make_batch("poisson2d", 9, [4, 5, 6], pad_to=100)
+    dev = helpers.to_device(st, cuda)
+    for b, n in enumerate(sizes):
+        want = osp.symmetrise_tril(st.indices.numpy(), st.features.numpy(), b, n)
+        helpers.assert_csr_equal(CsrMatrix.from_spconv(dev, n, "symmetrise", batch=b), want)
+        full = osp.tril_coo_to_csr(st.indices.numpy(), st.features.numpy(), b, 100)
+        helpers.assert_csr_equal(CsrMatrix.from_spconv(dev, 100, "tril", batch=b), full)
+    feats = st.features.clone()
+    feats[::7] = 0.0
+    feats[3::11] = -0.0
+    zeroed = models.SparseConvTensor(feats, st.indices, st.spatial_shape, st.batch_size)
+    want = osp.tril_coo_to_csr(st.indices.numpy(), feats.numpy(), 1, sizes[1])
+    helpers.assert_csr_equal(CsrMatrix.from_spconv(helpers.to_device(zeroed, cuda), sizes[1], "tril", batch=1), want)
+    dup = models.SparseConvTensor(torch.cat([st.features, st.features[:1]]), torch.cat([st.indices, st.indices[:1]]),
+                                  st.spatial_shape, st.batch_size)
+    with pytest.raises(dp._lib.DpcgError, match="duplicate"):
+        CsrMatrix.from_spconv(helpers.to_device(dup, cuda), sizes[0], "tril", batch=0)
+    empty = models.SparseConvTensor(torch.zeros(0, 1), torch.zeros(0, 3, dtype=torch.int32), [4, 4], 1)
+    e = CsrMatrix.from_spconv(helpers.to_device(empty, cuda), 4, "tril")
+    assert e.nnz == 0 and e.rowptr.cpu().tolist() == [0] * 5
+
+
+# ---- K2 -------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,side,net", CASES)
+def test_spmv_bit_exact(cuda, kind, side, net):
+    p = helpers.problem(kind, side, 0, 0.5, net)
+    ops = gpu_operands(p, cuda)
+    x = np.random.default_rng(7).standard_normal(p.n)
+    xd = torch.from_numpy(x).to(cuda)
+    for key, want in [("A", p.A), ("L", p.L), ("Lt", osp.transpose_csr(*p.L))]:
+        y = ops[key].matvec(xd).cpu().numpy()
+        assert np.array_equal(y, ckernels.spmv_csr(*want, x)), key
+        assert np.array_equal(y, osp.to_scipy(*want) @ x), key  # scipy's csr_matvec: same sequential sums
+
+
+def test_spmv_long_and_empty_rows(cuda):
+    """Rows longer than one shared-memory stage (256 products), empty rows, n not a multiple of 32."""
+    rng = np.random.default_rng(11)
+    import scipy.sparse as sp
+
+    n = 1000 + 7
+    m = sp.random(n, n, density=0.01, random_state=5, format="lil")
+    m[3, :] = rng.standard_normal(n)      # dense row: 1007 entries -> 4 stages
+    m[500, :700] = 1.0
+    m[10, :] = 0
+    m[n - 1, :] = 0
+    m = m.tocsr()
+    m.sort_indices()
+    x = rng.standard_normal(n)
+    y = CsrMatrix.from_scipy(m, cuda).matvec(torch.from_numpy(x).to(cuda)).cpu().numpy()
+    assert np.array_equal(y, ckernels.spmv_csr(m.indptr, m.indices, m.data, x))
+    one = CsrMatrix.from_arrays([0, 1], [0], [2.5], cuda)
+    assert one.matvec(torch.tensor([2.0], dtype=torch.float64, device=cuda)).item() == 5.0
+
+
+def test_sparse_matvec_mul_known_answer(cuda):
+    """tests/test_utils.py:11-41 through the CUDA kernel."""
+    indices = torch.tensor([[0, 0, 0], [0, 0, 1], [0, 1, 0], [0, 1, 1], [0, 2, 2],
+                            [1, 0, 1], [1, 0, 2], [1, 1, 0], [1, 1, 1], [1, 2, 1]]).int()
+    features = torch.tensor([[1, 2, 3, 4, 5, 2, 3, 1, 4, 5]]).T.float()
+    batch = models.SparseConvTensor(features.to(cuda), indices.to(cuda), [3, 3], 2)
+    vectors = torch.tensor([[1, 2, 3], [1, -1, 1]]).float().to(cuda)
+    out = utils.sparse_matvec_mul(batch, vectors, transpose=False)
+    assert torch.allclose(out.cpu(), torch.tensor([[5, 11, 15], [1, -3, -5]]).float())
+    out_t = utils.sparse_matvec_mul(batch, vectors, transpose=True)
+    want_t = osp.sparse_matvec_mul(indices.numpy(), features.numpy(), vectors.cpu().numpy(), True)
+    assert np.array_equal(out_t.cpu().numpy(), want_t)
+
+
+# ---- K3 / K4 / IC(0) --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,side,net", CASES)
+def test_levels_and_triangular_solves_bit_exact(cuda, kind, side, net):
+    p = helpers.problem(kind, side, 0, 0.5, net)
+    ops = gpu_operands(p, cuda)
+    b = p.b.to(cuda)
+    for name, lower, want in [("tril(A)", ops["T"], p.T), ("L", ops["L"], p.L)]:
+        upper_m, want_t = lower.transpose(), osp.transpose_csr(*want)
+        fwd, bwd = precond.analyse(lower, False), precond.analyse(upper_m, True)
+        for plan, o, up in [(fwd, want, False), (bwd, want_t, True)]:
+            level, perm, level_ptr = ckernels.levels(o[0], o[1], up)
+            assert plan.nlevels == len(level_ptr) - 1
+            assert np.array_equal(plan.level.cpu().numpy(), level), name
+            assert np.array_equal(plan.perm.cpu().numpy(), perm), name
+            assert np.array_equal(plan.level_ptr.cpu().numpy(), level_ptr), name
+            rows = plan.plan.cpu().numpy()[: plan.nchunks * 32]
+            assert np.array_equal(rows[rows >= 0], perm) and plan.nchunks == int(((np.diff(level_ptr) + 31) // 32).sum())
+        y = precond.triangular_solve(lower, fwd, b)
+        y_want = ckernels.sptrsv_lower(*want, p.b.numpy())
+        assert np.array_equal(y.cpu().numpy(), y_want), name
+        z = precond.triangular_solve(upper_m, bwd, y)
+        assert np.array_equal(z.cpu().numpy(), ckernels.sptrsv_upper(*want_t, y_want)), name
+
+
+@pytest.mark.parametrize("kind,side", [("poisson2d", 16), ("poisson2d", 64), ("poisson3d", 12), ("poisson2d", 100)])
+def test_ic0_bit_exact(cuda, kind, side):
+    p = helpers.problem(kind, side, 0, 0.5, None)
+    lower = CsrMatrix.from_spconv(helpers.to_device(p.systems_tril, cuda), p.n, "tril")
+    factor = precond.incomplete_cholesky0(lower)
+    assert np.array_equal(factor.val.cpu().numpy(), ckernels.ic0(*p.T))
+
+
+def test_triangular_contract_violations_are_reported(cuda):
+    full = CsrMatrix.from_arrays(*helpers.problem("poisson2d", 8, 0, 0.5, None).A, device=cuda)
+    with pytest.raises(dp._lib.DpcgError, match="triangular"):
+        precond.analyse(full, upper=False)
+
+
+# ---- K5: the loop -----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("engine", ["fused", "stepped"])
+@pytest.mark.parametrize("case", GOLDEN["cases"], ids=lambda c: f"{c['kind']}{c['side']}-{c['net']}-{c['precond']}-{c['max_iter']}")
+def test_pcg_against_oracle_and_reference_golden(cuda, case, engine):
+    """Iteration counts vs the unmodified reference (golden) and vs the oracle run here; x and the criterion vs the
+    oracle. Tolerances: iterations +-1 (+-0.5 % on long solves, see iteration_tolerance); x and res 1e-8 relative
+    where the iterate counts agree (the north_star tolerance), else consistency of the true residual."""
+    p = helpers.problem(case["kind"], case["side"], 0, 0.5, case["net"])
+    ops = gpu_operands(p, cuda)
+    oracle = pcg.preconditioned_conjugate_gradient(osp.to_torch_csr(*p.A), p.b, build_operator(p, case["precond"]),
+                                                   max_iter=case["max_iter"])
+    result = dp.pcg_solve(ops["A"], p.b.to(cuda), gpu_operator(case["precond"], ops, p, cuda),
+                          max_iter=case["max_iter"], engine=engine, history=True)
+    tol = iteration_tolerance(case["iterations"])
+    assert result.info == 0
+    assert abs(result.iterations - case["iterations"]) <= tol
+    assert abs(result.iterations - oracle.iterations) <= tol
+    x, xo = result.x_hat.cpu(), oracle.x_hat
+    head = min(result.iterations, oracle.iterations, 20) + 1
+    np.testing.assert_allclose(result.history[:head], oracle.history[:head], rtol=1e-8)  # same recurrence
+    if result.iterations == oracle.iterations and oracle.iterations <= 100:
+        assert torch.linalg.vector_norm(x - xo) <= 1e-8 * torch.linalg.vector_norm(xo)
+        assert abs(result.res - oracle.res) <= 1e-8 * max(oracle.res, 1e-300) or abs(result.res - oracle.res) < 1e-6 * oracle.res
+    if case["iterations"] < case["max_iter"]:
+        assert result.res < 1e-8
+        a = osp.to_scipy(*p.A)
+        true_rel = np.linalg.norm(a @ x.numpy() - p.b.numpy()) / np.linalg.norm(p.b.numpy())
+        assert true_rel < 2e-4
+        assert torch.linalg.vector_norm(x - xo) <= 1e-3 * torch.linalg.vector_norm(xo)  # both within sqrt(rtol) of A^-1 b
+    else:
+        assert result.iterations == case["max_iter"]
+
+
+def test_pcg_reference_signature_and_host_operands(cuda):
+    """The drop-in call of test.py:138 / train.py:102: CPU fp64 operands in, (seconds, iterations, 0) out, inputs
+    untouched; dense A (test.py:68), sparse-CSR M (test.py:105), x0, zero-iteration and saturated cases."""
+    p = helpers.problem("poisson2d", 16, 0, 0.5, "net")
+    A_dense = osp.to_torch_csr(*p.A).to_dense()
+    M = osp.explicit_product(*p.L)
+    b = p.b.clone()
+    seconds, iterations, info = dp.preconditioned_conjugate_gradient(A_dense, b, M)
+    oracle = pcg.preconditioned_conjugate_gradient(osp.to_torch_csr(*p.A), p.b, M)
+    assert isinstance(seconds, float) and seconds > 0 and info == 0 and abs(iterations - oracle.iterations) <= 1
+    assert torch.equal(b, p.b)
+    _, it_kw, _ = dp.preconditioned_conjugate_gradient(A_dense.to(cuda), b.to(cuda), M=M.to(cuda))  # train.py:102-106
+    assert it_kw == iterations
+    assert dp.preconditioned_conjugate_gradient(A_dense, b, None, rtol=1e30)[1] == 0   # res_0 < rtol: no body runs
+    assert dp.preconditioned_conjugate_gradient(A_dense, b, None, max_iter=5)[1] == 5  # cg.py:70 bound, info stays 0
+    x0 = torch.from_numpy(np.random.default_rng(2).standard_normal(p.n))
+    r = dp.pcg_solve(A_dense, b, dp.Jacobi(osp.to_torch_csr(*p.A)), x0=x0)
+    o = pcg.preconditioned_conjugate_gradient(osp.to_torch_csr(*p.A), p.b, operators.Jacobi(osp.to_scipy(*p.A).diagonal()), x0=x0)
+    assert abs(r.iterations - o.iterations) <= 1 and not r.x_hat.is_cuda
+    assert torch.linalg.vector_norm(r.x_hat - o.x_hat) <= 1e-6 * torch.linalg.vector_norm(o.x_hat)
+    errors, x_hat = dp.conjugate_gradient(A_dense, b)
+    errors_o, x_o = pcg.conjugate_gradient(osp.to_torch_csr(*p.A), p.b)
+    assert abs(len(errors) - len(errors_o)) <= 1 and torch.linalg.vector_norm(x_hat - x_o) <= 1e-6 * torch.linalg.vector_norm(x_o)
+
+
+def test_pcg_batch_is_bitwise_the_single_solves(cuda):
+    """Independent systems of different sizes and preconditioners in ONE launch give exactly the bits each system
+    gives alone (fixed-order reductions per tile, no cross-system coupling), and drop out individually."""
+    systems, singles = [], []
+    specs = [("poisson2d", 16, "net", "multiply"), ("poisson3d", 12, "tril", "ic0_solve"), ("poisson2d", 64, "net", "jacobi"),
+             ("poisson2d", 37, "net", "multiply"), ("poisson2d", 100, "tril", "identity"), ("poisson2d", 16, "net", "explicit")]
+    for kind, side, net, name in specs:
+        p = helpers.problem(kind, side, 0, 0.5, net)
+        ops = gpu_operands(p, cuda)
+        systems.append((ops["A"], p.b.to(cuda), gpu_operator(name, ops, p, cuda)))
+    for engine in ("fused", "stepped"):
+        batch = dp.pcg_solve_batch(systems, max_iter=3000, engine=engine)
+        singles = [dp.pcg_solve(*s, max_iter=3000, engine=engine) for s in systems]
+        for got, want in zip(batch, singles):
+            assert got.iterations == want.iterations and got.res == want.res
+            assert torch.equal(got.x_hat, want.x_hat)
+    assert len({r.iterations for r in batch}) > 3
+
+
+def test_pcg_is_bitwise_reproducible_and_engines_agree(cuda):
+    p = helpers.problem("poisson2d", 64, 0, 0.5, "net")
+    ops = gpu_operands(p, cuda)
+    M = dp.FactoredMultiply(ops["L"], ops["Lt"])
+    runs = [dp.pcg_solve(ops["A"], p.b.to(cuda), M, max_iter=3000, engine=e) for e in ("fused", "fused", "stepped")]
+    for r in runs[1:]:
+        assert r.iterations == runs[0].iterations and r.res == runs[0].res and torch.equal(r.x_hat, runs[0].x_hat)
+
+
+def test_benchmark_suite_end_to_end(cuda, tmp_path):
+    """BenchmarkSuite.run()/dump_csv() (test.py:119-198) on a synthetic test set, all four techniques."""
+    torch.manual_seed(69)
+    net = models.PreconditionerNet(models.DEFAULT_CHANNELS).to(cuda)
+    data = synthetic.SyntheticPressureDataSet("poisson2d", 24, number_samples=2, batch_size=1, device=cuda)
+    suite = BenchmarkSuite(data, net, max_iter=5000)
+    suite.run()
+    suite.dump_csv(tmp_path)
+    for name in suite.techniques:
+        assert len(suite.iterations[name]) == 2 and all(0 < i < 5000 for i in suite.iterations[name])
+        assert all(s == 100 for s in suite.successes[name]) and all(r < 1e-8 for r in suite.residuals[name])
+    assert max(suite.iterations["incomplete_cholesky"]) < min(suite.iterations["vanilla"])
+    table = (tmp_path / "table.csv").read_text().splitlines()
+    assert table[0] == "technique,kappas,densities,iterations,setups,durations,totals,successes" and len(table) == 5
+    assert (tmp_path / "totals.csv").read_text().splitlines()[0] == "vanilla,jacobi,incomplete_cholesky,learned"
+    # density column: explicit nnz(M)/n^2 like test.py:107-109
+    n = 24 * 24
+    assert suite.densities["vanilla"][0] == pytest.approx(100 / n) and suite.densities["learned"][0] > suite.densities["incomplete_cholesky"][0]
+
+
+# ---- full-size properties (BASELINE configs 2 and 4): too large for the dense/CPU oracle in seconds ------------------
+def test_config2_size_properties(cuda):
+    """316^2 (N = 99 856): assembly sizes, SpMV linearity and symmetry, SpTRSV round trip, PCG true residual."""
+    st, _, rhs, sizes = synthetic.make_batch("poisson2d", 316, [0])
+    n = sizes[0]
+    dev = helpers.to_device(st, cuda)
+    A, T = CsrMatrix.from_spconv(dev, n, "symmetrise"), CsrMatrix.from_spconv(dev, n, "tril")
+    assert (n, A.nnz, T.nnz) == (99856, 498016, 298936)  # SURVEY §8d shapes
+    rng = np.random.default_rng(0)
+    x, y = (torch.from_numpy(rng.standard_normal(n)).to(cuda) for _ in range(2))
+    ax, ay = A.matvec(x), A.matvec(y)
+    assert torch.allclose(A.matvec(x + 2 * y), ax + 2 * ay, rtol=1e-12, atol=1e-12)
+    assert abs(torch.dot(y, ax) - torch.dot(x, ay)) <= 1e-10 * abs(torch.dot(y, ax))  # A symmetric
+    helpers.assert_csr_equal(A.transpose(), tuple(a for a in A.to_host()))
+    fwd = precond.analyse(T, False)
+    assert fwd.nlevels == 2 * 316 - 1
+    factor = precond.incomplete_cholesky0(T, fwd)
+    b = rhs[0, :n].to(device=cuda, dtype=torch.float64)
+    yv = precond.triangular_solve(factor, fwd, b)
+    assert torch.allclose(factor.matvec(yv), b, rtol=1e-10, atol=1e-12)  # L (L^-1 b) = b
+    for M in (dp.Jacobi(A), dp.FactoredSolve(factor, None, fwd)):
+        r = dp.pcg_solve(A, b, M, max_iter=20000)
+        assert 0 < r.iterations < 20000 and r.res < 1e-8
+        true_rel = torch.linalg.vector_norm(A.matvec(r.x_hat) - b) / torch.linalg.vector_norm(b)
+        assert true_rel < 2e-4
+
+
+def test_config4_size_spmv_and_levels(cuda):
+    """128^3 (N = 2 097 152, nnz 14 581 760, 382 levels): SpMV against row sums, level count, SpTRSV round trip."""
+    st, _, rhs, sizes = synthetic.make_batch("poisson3d", 128, [0])
+    n = sizes[0]
+    dev = helpers.to_device(st, cuda)
+    A, T = CsrMatrix.from_spconv(dev, n, "symmetrise"), CsrMatrix.from_spconv(dev, n, "tril")
+    assert (n, A.nnz) == (2097152, 14581760)
+    ones = torch.ones(n, dtype=torch.float64, device=cuda)
+    rowsum = A.matvec(ones)
+    assert rowsum.min() > -1e-5 and rowsum.max() < 30  # weakly diagonally dominant up to fp32 rounding
+    fwd = precond.analyse(T, False)
+    assert fwd.nlevels == 3 * 128 - 2
+    b = rhs[0, :n].to(device=cuda, dtype=torch.float64)
+    yv = precond.triangular_solve(T, fwd, b)
+    assert torch.allclose(T.matvec(yv), b, rtol=1e-9, atol=1e-11)

@@ -1,0 +1,125 @@
+"""CPU tests of the host side: the C-ABI library loads and exports what include/dpcg.h declares, descriptor layout,
+no-CPU-fallback behaviour, sharding and the result gather (gloo, world_size 2). No kernel is launched here."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from deeppreconditioning_b200 import _lib, build, distributed
+from deeppreconditioning_b200.cg import PcgResult
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()
+    return _lib.lib()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    header = (ROOT / "include" / "dpcg.h").read_text()
+    declared = set(re.findall(r"\b(dp_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.dp_version() == 100
+    assert lib.dp_status_string(0) == b"ok" and b"aligned" in lib.dp_status_string(2)
+
+
+def test_descriptor_layout_and_size_queries(lib):
+    assert ctypes.sizeof(_lib.PcgSystem) == 10 * 4 + 18 * 8
+    assert ctypes.sizeof(_lib.PcgParams) == 24
+    assert _lib.PcgSystem.a_rowptr.offset == 40 and _lib.PcgSystem.history.offset == 40 + 17 * 8
+    for n in (1, 31, 32, 33, 511, 512, 513, 99856):
+        pad = (n + 31) // 32 * 32
+        tiles = (n + 511) // 512
+        assert lib.dp_pcg_work_doubles(n) == 8 * pad + 5 * ((tiles + 31) // 32 * 32) + 32
+    assert lib.dp_pcg_workspace_bytes(1) >= 512 and lib.dp_pcg_workspace_bytes(1024) > lib.dp_pcg_workspace_bytes(1)
+    level_ptr = np.array([0, 1, 33, 97, 100], np.int32)
+    assert lib.dp_sptrsv_plan_chunks(4, level_ptr.ctypes.data) == 1 + 1 + 2 + 1
+    assert lib.dp_sptrsv_workspace_bytes() >= 8
+
+
+def test_argument_validation_without_a_gpu(lib):
+    """Entry points reject bad arguments before touching CUDA."""
+    assert lib.dp_spmv_csr_f64(-1, 0, None, None, None, None, None, None) == 1
+    assert lib.dp_spmv_csr_f64(4, 4, 16, 20, 32, 48, 64, None) == 2  # col pointer 20 is not 16-byte aligned
+    assert lib.dp_csr_from_coo(None, None, 5, 0, 4, 0, None, None, None, None, None, None, 0, None) == 1
+    params = _lib.PcgParams(1e-8, 10, 0, 1, 0)
+    assert lib.dp_pcg_solve_f64(None, 1, ctypes.byref(params), None, None, 0, None) == 1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the behaviour on a box WITHOUT a GPU")
+def test_no_cpu_fallback():
+    """The product path raises instead of computing on the CPU."""
+    import deeppreconditioning_b200 as dp
+
+    p = helpers.problem("poisson2d", 8, 0, 0.5, None)
+    from oracle import sparse as osp
+
+    with pytest.raises((_lib.DpcgError, RuntimeError, AssertionError)):
+        dp.preconditioned_conjugate_gradient(osp.to_torch_csr(*p.A), p.b, None)
+    with pytest.raises((_lib.DpcgError, RuntimeError, AssertionError)):
+        dp.CsrMatrix.from_spconv(p.systems_tril, p.n, "tril")
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", tmp_path / "libdpcg.so")
+    with pytest.raises(_lib.DpcgError, match="no CPU fallback"):
+        _lib.lib()
+
+
+def test_shard_indices_partition():
+    for n, world in [(1024, 8), (10, 4), (3, 8), (0, 2)]:
+        shards = [distributed.shard_indices(n, r, world) for r in range(world)]
+        assert sorted(i for s in shards for i in s) == list(range(n))
+        assert max(map(len, shards)) - min(map(len, shards)) <= 1
+
+
+def test_gather_records_single_process():
+    results = [PcgResult(0.0, 10 + i, 0, torch.zeros(1), 1e-9 * (i + 1)) for i in range(3)]
+    rec = distributed.make_records([2, 0, 1], results, [1.0, 2.0, 3.0])
+    out = distributed.gather_records(rec, 3)
+    assert out[:, 0].tolist() == [0.0, 1.0, 2.0] and out[:, 1].tolist() == [11.0, 12.0, 10.0]
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+from deeppreconditioning_b200 import distributed
+from deeppreconditioning_b200.cg import PcgResult
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rank, n = dist.get_rank(), 7
+mine = distributed.shard_indices(n, rank, 2)
+res = [PcgResult(0.0, 100 + i, 0, torch.zeros(1), 1e-9 * i) for i in mine]
+out = distributed.gather_records(distributed.make_records(mine, res, [float(i) for i in mine]), n)
+assert out.shape == (n, 4), out.shape
+assert out[:, 0].tolist() == [float(i) for i in range(n)]
+assert out[:, 1].tolist() == [100.0 + i for i in range(n)]
+assert out[:, 3].tolist() == [float(i) for i in range(n)]
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_gather_records_gloo_world_size_2(tmp_path):
+    """The N>1 path of SURVEY §8e on CPU: interleaved shards, one all_gather of fixed-size records (ragged: 4 + 3)."""
+    port = 29500 + os.getpid() % 2000
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=str(ROOT), port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    for r, proc in enumerate(procs):
+        out, _ = proc.communicate(timeout=180)
+        assert proc.returncode == 0, out.decode()
+        assert f"rank {r} ok" in out.decode()
