@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--systems-per-gpu", type=int, default=128)
+    ap.add_argument("--systems-per-gpu", type=int, default=64)
     ap.add_argument("--side", type=int, default=316)
     ap.add_argument("--net", default="net", choices=["net", "tril"])
     ap.add_argument("--no-extras", action="store_true", help="skip single-system latency and 128^3 kernel numbers")

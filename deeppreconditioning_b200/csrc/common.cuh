@@ -89,6 +89,51 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
     return half_warp_sum(w);
 }
 
+// Same reduction for kN values at once (one pair of CTA barriers instead of kN): per value bit-identical to block_sum.
+// `scratch` holds kN * kWarpsPerBlock doubles.
+template <int kN>
+__device__ __forceinline__ void block_sum_n(double (&v)[kN], double* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < kN; ++i) v[i] = warp_sum(v[i]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < kN; ++i) scratch[i * kWarpsPerBlock + warp] = v[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kN; ++i) v[i] = half_warp_sum(scratch[i * kWarpsPerBlock + (lane & (kWarpsPerBlock - 1))]);
+}
+
+// Exclusive prefix sum of one int per thread over the CTA; *total = CTA sum. `sh` holds kWarpsPerBlock + 1 ints.
+__device__ __forceinline__ int block_exclusive_scan_int(int v, int* total, int* sh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += t;
+    }
+    __syncthreads();
+    if (lane == 31) sh[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const int w = lane < kWarpsPerBlock ? sh[lane] : 0;
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(kFull, winc, o);
+            if (lane >= o) winc += t;
+        }
+        if (lane < kWarpsPerBlock) sh[lane] = winc - w;
+        if (lane == 31) sh[kWarpsPerBlock] = winc;
+    }
+    __syncthreads();
+    *total = sh[kWarpsPerBlock];
+    return sh[warp] + inc - v;
+}
+
 // Sum of `count` doubles stored at `p` (global, produced before the last grid-wide barrier): thread t adds
 // p[t], p[t+kBlock], ... in that order, then block_sum. Same bits in every CTA.
 __device__ __forceinline__ double block_reduce_array(const double* p, int count, double* scratch) {
@@ -110,6 +155,8 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
     return v;
 }
 
+constexpr unsigned long long kDoneUnit = 1ull << 32;  // bits 32..62: number of finished systems (PCG bookkeeping)
+
 struct GridBarrier {
     unsigned long long* word;
     int* flag;  // device status word (DP_ERR_TIMEOUT)
@@ -120,23 +167,26 @@ struct GridBarrier {
         atomicCAS(flag, 0, status);
     }
     __device__ __forceinline__ bool aborted() const { return (ld_volatile_u64(word) & kAbortBit) != 0; }
-    __device__ __forceinline__ bool sync() {
+    // Returns -1 once ABORT is up, else the finished-systems count carried in the upper half of the word (the same
+    // value in every CTA: increments happen strictly between two barriers).
+    __device__ __forceinline__ int sync() {
         __syncthreads();
         epoch += nblocks;
-        int bad = 0;
+        int info = 0;
         if (threadIdx.x == 0) {
             __threadfence();
             atomicAdd(word, 1ull);
             unsigned spins = 0;
             for (;;) {
-                unsigned long long v = ld_volatile_u64(word);
-                if (v & kAbortBit) { bad = 1; break; }
-                if ((int)((unsigned)v - epoch) >= 0) break;
-                if (++spins > kSpinBudget) { raise_abort(DP_ERR_TIMEOUT); bad = 1; break; }
+                const unsigned long long v = ld_volatile_u64(word);
+                if (v & kAbortBit) { info = -1; break; }
+                if ((int)((unsigned)v - epoch) >= 0) { info = (int)((v >> 32) & 0x7fffffffu); break; }
+                if (++spins > kSpinBudget) { raise_abort(DP_ERR_TIMEOUT); info = -1; break; }
             }
             __threadfence();
         }
-        return __syncthreads_or(bad) == 0;
+        // broadcast thread 0's word: OR-reduce (everyone else contributes 0)
+        return __syncthreads_or(info);
     }
 };
 

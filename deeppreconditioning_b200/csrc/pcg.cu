@@ -9,7 +9,7 @@
 //   90     iterations = bodies executed
 // Element-wise updates round like torch (product, then sum); SpMV/SpTRSV rows are sequential sums; dot products
 // are fixed-order trees (lane butterfly -> 16 warp sums -> per-tile partial -> strided sum + tree over the tiles),
-// so a solve is bitwise reproducible and independent of which CTA processed which tile.
+// so a solve is bitwise reproducible and independent of which CTA processed which tile or of the batch it ran in.
 //
 // Phase structure (one grid-wide barrier after each phase; k = body index, "old/new" = double buffers):
 //   A       p_new = z + beta p_old fused into the gather of Ap = A p_new; partial <Ap,p>; convergence check
@@ -18,6 +18,16 @@
 //   APPLY2  MULTIPLY: z = L t; partial <r,z>
 //   FWD/BWD SOLVE: y = L^-1 r_new, z = L^-T y (sync-free, sptrsv.cuh), then DOTRZ: partial <r,z>
 // The initial z0 = M r0 runs the same APPLY phases with kInit (no update, <z,z> into the <r,r> slot).
+//
+// Scheduling. A tile is 512 consecutive rows of one system, processed by one CTA (16 warps x 32 rows).
+//   fused engine  : one persistent cooperative launch. Unfinished systems live in a compacted ACTIVE list; its
+//                   tiles are split into gridDim contiguous ranges, so a CTA streams through consecutive tiles of
+//                   (mostly) one system and evaluates that system's scalars once per phase. When systems finish,
+//                   CTA 0 rebuilds the list (double buffered) during the next APPLY1 phase.
+//   stepped engine: one launch per phase over the static list of all systems (round robin); the host polls the
+//                   finished counter every check_every iterations. Same phase code, same bits.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "spmv.cuh"
@@ -45,7 +55,6 @@ struct SysDev {
     double* part_bb;
     double* part_rz[2];
     double* scal;  // [0],[1]: published <r,z> by body parity; [2]: <b,b>
-    int* state;    // [0]: finished
     int* iters_out;
     double* res_out;
     double* history;
@@ -53,27 +62,48 @@ struct SysDev {
 
 struct Ctx {
     const SysDev* sys;
-    const int* tile_ofs;  // nsys+1
-    const int* fwd_ofs;   // nsys+1, plan chunks
+    int* state;           // [nsys] 1 = finished (written in phase A only, read in the other phases)
+    const int* tile_ofs;  // [nsys+1] static tile prefix (stepped engine)
+    const int* fwd_ofs;   // [nsys+1] plan chunk prefixes (SOLVE)
     const int* bwd_ofs;
+    int* act_sys[2];      // active list, double buffered: system ids ...
+    int* act_ofs[2];      // ... and tile prefix (count+1 entries)
+    int* act_meta;        // [2][2]: {count, total tiles}
     int nsys, total_tiles, total_fwd, total_bwd;
     int pw_fwd, pw_bwd;
     int has_multiply, has_solve;
     double rtol;
     int max_iter;
-    unsigned long long* word;
-    int* n_done;
+    unsigned long long* word;  // grid barrier (+ finished count in the upper half)
+    int* n_done;               // finished count for the host (stepped engine)
     int* flag;
+    long long* trace;          // optional timeline of CTA 0 (DPCG_TRACE=1): (label, clock64) pairs
+    int trace_cap;
 };
 
 struct Smem {
     double stage[kWarpsPerBlock][kStageCap];
-    double scratch[kWarpsPerBlock];
-    SysDev sys;   // descriptor of the system this CTA is working on (survives across phases)
+    double scratch[3 * kWarpsPerBlock];
+    SysDev sys;  // descriptor of the system this CTA is working on (survives across phases)
     int sys_id;
+    int scan[kWarpsPerBlock + 1];
+    int trace_pos;
 };
 
 static_assert(sizeof(SysDev) % 8 == 0, "SysDev is copied as 8-byte words");
+
+enum Phase { PH_INIT = 0, PH_A = 1, PH_APPLY1 = 2, PH_APPLY2 = 3, PH_FWD = 4, PH_BWD = 5, PH_DOTRZ = 6 };
+
+__device__ __forceinline__ void trace(const Ctx& ctx, Smem& sm, int label) {
+    if (ctx.trace_cap > 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int i = sm.trace_pos;
+        if (i < ctx.trace_cap) {
+            ctx.trace[2 * i] = label;
+            ctx.trace[2 * i + 1] = clock64();
+            sm.trace_pos = i + 1;
+        }
+    }
+}
 
 // CTA-uniform: make sm.sys hold system s (one L2 round trip only when the system changes).
 __device__ __forceinline__ const SysDev& load_sys(const Ctx& ctx, int s, Smem& sm) {
@@ -88,13 +118,11 @@ __device__ __forceinline__ const SysDev& load_sys(const Ctx& ctx, int s, Smem& s
     return sm.sys;
 }
 
-enum Phase { PH_INIT = 0, PH_A = 1, PH_APPLY1 = 2, PH_APPLY2 = 3, PH_FWD = 4, PH_BWD = 5, PH_DOTRZ = 6 };
-
-__device__ __forceinline__ int find_sys(const int* __restrict__ ofs, int nsys, int g) {
-    int lo = 0, hi = nsys;  // largest s with ofs[s] <= g
+__device__ __forceinline__ int find_segment(const int* ofs, int count, int g) {
+    int lo = 0, hi = count;  // largest i with ofs[i] <= g
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
-        if (__ldg(ofs + mid) <= g) lo = mid; else hi = mid;
+        if (__ldcg(ofs + mid) <= g) lo = mid; else hi = mid;
     }
     return lo;
 }
@@ -107,7 +135,7 @@ struct Scal {
 };
 
 // ---- PH_INIT: r0 = b - A x0 (cg.py:60), <b,b>, p = 0, arm the sync-free buffers -------------------------------
-__device__ __forceinline__ void phase_init(const SysDev& S, int tile, Smem& sm) {
+__device__ __forceinline__ void phase_init(const Ctx& ctx, const SysDev& S, int s, int tile, Smem& sm) {
     const int warp = threadIdx.x >> 5;
     const int row = tile * kTileRows + threadIdx.x;
     const double ax = spmv_chunk(S.A, tile * kTileRows + warp * kWarp, GatherPlain{S.x}, sm.stage[warp]);
@@ -125,47 +153,66 @@ __device__ __forceinline__ void phase_init(const SysDev& S, int tile, Smem& sm) 
     bb = block_sum(bb, sm.scratch);
     if (threadIdx.x == 0) {
         S.part_bb[tile] = bb;
-        if (tile == 0) S.state[0] = 0;
+        if (tile == 0) ctx.state[s] = 0;
     }
 }
 
 // ---- PH_A ---------------------------------------------------------------------------------------------------
+// kCheckState: the static schedule (stepped engine) still visits finished systems and must skip them; the flag is
+// written by another CTA in this very phase, so it is read once per CTA and broadcast (a per-thread read could
+// split the CTA around a barrier). The fused engine's active list never contains a finished system.
+template <bool kCheckState>
 __device__ __forceinline__ void phase_a(const Ctx& ctx, const SysDev& S, int s, int tile, int k, Smem& sm, Scal& sc) {
+    const int warp = threadIdx.x >> 5;
+    const int row = tile * kTileRows + threadIdx.x;
+    const bool valid = row < S.n;
+    const double* z = S.z[k & 1];
+    const double* po = S.p[k & 1];
+    // loads that do not depend on this phase's scalars go first
+    double zr = 0.0, pr = 0.0;
+    if (valid) zr = z[row], pr = po[row];
+    const ChunkHead head = spmv_head(S.A, tile * kTileRows + warp * kWarp);
     if (sc.sys != s) {
         sc.sys = s;
         sc.active = false;
-        const bool done = __ldcg(S.state) != 0;
+        bool done = false;
+        if (kCheckState) done = __syncthreads_or(threadIdx.x == 0 ? ld_relaxed_s32(ctx.state + s) : 0) != 0;
         if (!done) {
-            const double rr = block_reduce_array(S.part_rr, S.ntiles, sm.scratch);
-            const double rz = block_reduce_array(S.part_rz[k & 1], S.ntiles, sm.scratch);
-            const double res = rr / __ldcg(S.scal + 2);  // cg.py:17
+            double v[2] = {0.0, 0.0};
+            const double* prr = S.part_rr;
+            const double* prz = S.part_rz[k & 1];
+            for (int i = threadIdx.x; i < S.ntiles; i += kBlock) {
+                v[0] = __dadd_rn(v[0], __ldcg(prr + i));
+                v[1] = __dadd_rn(v[1], __ldcg(prz + i));
+            }
+            const double bb = __ldcg(S.scal + 2);
+            const double rz_prev = k > 0 ? __ldcg(S.scal + ((k - 1) & 1)) : 1.0;
+            block_sum_n<2>(v, sm.scratch);
+            const double res = v[0] / bb;  // cg.py:17
             const bool finished = (res < ctx.rtol) || (k >= ctx.max_iter);  // cg.py:70-72
             sc.active = !finished;
-            sc.v = k > 0 ? rz / __ldcg(S.scal + ((k - 1) & 1)) : 0.0;  // beta, cg.py:82 (p_0 = z_0, cg.py:62)
+            sc.v = k > 0 ? v[1] / rz_prev : 0.0;  // beta, cg.py:82 (p_0 = z_0, cg.py:62)
             if (tile == 0 && threadIdx.x == 0) {  // tile 0 of a system is visited by exactly one CTA per phase
                 if (S.history) S.history[k] = res;
                 if (finished) {
                     *S.iters_out = k;
                     *S.res_out = res;
-                    S.state[0] = 1;
+                    ctx.state[s] = 1;
                     atomicAdd(ctx.n_done, 1);
+                    atomicAdd(ctx.word, kDoneUnit);
                 } else {
-                    S.scal[k & 1] = rz;
+                    S.scal[k & 1] = v[1];
                 }
             }
         }
     }
     if (!sc.active) return;
-    const int warp = threadIdx.x >> 5;
-    const int row = tile * kTileRows + threadIdx.x;
-    const double* z = S.z[k & 1];
-    const double* po = S.p[k & 1];
     double* pn = S.p[(k + 1) & 1];
     const GatherZBetaP g{z, po, sc.v};
-    const double ap = spmv_chunk(S.A, tile * kTileRows + warp * kWarp, g, sm.stage[warp]);  // cg.py:75
+    const double ap = spmv_body(S.A, head, g, sm.stage[warp]);  // cg.py:75
     double pap = 0.0;
-    if (row < S.n) {
-        const double pi = g(row);  // cg.py:83
+    if (valid) {
+        const double pi = __dadd_rn(zr, __dmul_rn(sc.v, pr));  // cg.py:83
         pn[row] = pi;
         S.ap[row] = ap;
         pap = __dmul_rn(ap, pi);
@@ -178,46 +225,57 @@ __device__ __forceinline__ void phase_a(const Ctx& ctx, const SysDev& S, int s, 
 // ---- PH_APPLY1 ----------------------------------------------------------------------------------------------
 template <bool kInit>
 __device__ __forceinline__ void phase_apply1(const Ctx& ctx, const SysDev& S, int s, int tile, int k, Smem& sm, Scal& sc) {
+    const int warp = threadIdx.x >> 5;
+    const int base = tile * kTileRows + warp * kWarp;
+    const int row = tile * kTileRows + threadIdx.x;
+    const bool valid = row < S.n;
+    const double* ro = S.r[k & 1];
+    double* rnw = S.r[(k + 1) & 1];
+    const double* pn = S.p[(k + 1) & 1];
+    double* zn = S.z[(k + 1) & 1];
+    const int precond = S.precond;
+    // scalar-independent loads first
+    double r_old = 0.0, ap_i = 0.0, x_i = 0.0, p_i = 0.0, dinv_i = 0.0;
+    if (valid) {
+        r_old = ro[row];
+        if (!kInit) ap_i = S.ap[row], x_i = S.x[row], p_i = pn[row];
+        if (precond == DP_PRECOND_JACOBI) dinv_i = __ldg(S.dinv + row);
+    }
+    ChunkHead head{0, 0, 0, 0};
+    if (precond == DP_PRECOND_CSR) head = spmv_head(S.M, base);
+    if (precond == DP_PRECOND_MULTIPLY) head = spmv_head(S.Mt, base);
     if (sc.sys != s) {
         sc.sys = s;
-        sc.active = kInit || __ldcg(S.state) == 0;
+        sc.active = kInit || ld_relaxed_s32(ctx.state + s) == 0;  // written before the previous barrier: uniform
         sc.v = 0.0;
         if (!kInit && sc.active)
             sc.v = __ldcg(S.scal + (k & 1)) / block_reduce_array(S.part_pap, S.ntiles, sm.scratch);  // a, cg.py:78
     }
     if (!sc.active) return;
-    const int warp = threadIdx.x >> 5;
-    const int base = tile * kTileRows + warp * kWarp;
-    const int row = tile * kTileRows + threadIdx.x;
-    const bool valid = row < S.n;
     const double a = sc.v;
-    const double* ro = S.r[k & 1];
-    double* rnw = S.r[(k + 1) & 1];
-    const double* pn = S.p[(k + 1) & 1];
-    double* zn = S.z[(k + 1) & 1];
 
     double rn = 0.0;
     if (valid) {
-        rn = kInit ? ro[row] : __dsub_rn(ro[row], __dmul_rn(a, S.ap[row]));          // cg.py:80
+        rn = kInit ? r_old : __dsub_rn(r_old, __dmul_rn(a, ap_i));      // cg.py:80
         rnw[row] = rn;
-        if (!kInit) S.x[row] = __dadd_rn(S.x[row], __dmul_rn(a, pn[row]));            // cg.py:79
+        if (!kInit) S.x[row] = __dadd_rn(x_i, __dmul_rn(a, p_i));       // cg.py:79
     }
     double zi = 0.0;
     bool have_z = true;
-    switch (S.precond) {
+    switch (precond) {
         case DP_PRECOND_IDENTITY:
             zi = rn;
             break;
         case DP_PRECOND_JACOBI:
-            zi = valid ? __dmul_rn(S.dinv[row], rn) : 0.0;
+            zi = __dmul_rn(dinv_i, rn);
             break;
         case DP_PRECOND_CSR:
-            zi = kInit ? spmv_chunk(S.M, base, GatherPlain{ro}, sm.stage[warp])
-                       : spmv_chunk(S.M, base, GatherRMinusAAp{ro, S.ap, a}, sm.stage[warp]);
+            zi = kInit ? spmv_body(S.M, head, GatherPlain{ro}, sm.stage[warp])
+                       : spmv_body(S.M, head, GatherRMinusAAp{ro, S.ap, a}, sm.stage[warp]);
             break;
         case DP_PRECOND_MULTIPLY: {
-            const double ti = kInit ? spmv_chunk(S.Mt, base, GatherPlain{ro}, sm.stage[warp])
-                                    : spmv_chunk(S.Mt, base, GatherRMinusAAp{ro, S.ap, a}, sm.stage[warp]);
+            const double ti = kInit ? spmv_body(S.Mt, head, GatherPlain{ro}, sm.stage[warp])
+                                    : spmv_body(S.Mt, head, GatherRMinusAAp{ro, S.ap, a}, sm.stage[warp]);
             if (valid) S.t[row] = ti;
             have_z = false;
             break;
@@ -227,16 +285,14 @@ __device__ __forceinline__ void phase_apply1(const Ctx& ctx, const SysDev& S, in
             break;
     }
     if (have_z && valid) zn[row] = zi;
-    if (!kInit) {
-        const double rr = block_sum(__dmul_rn(rn, rn), sm.scratch);  // cg.py:86
-        if (threadIdx.x == 0) S.part_rr[tile] = rr;
-    }
-    if (have_z) {
-        const double rz = block_sum(__dmul_rn(rn, zi), sm.scratch);  // cg.py:82 numerator / cg.py:76
-        if (threadIdx.x == 0) S.part_rz[(k + 1) & 1][tile] = rz;
-        if (kInit) {
-            const double zz = block_sum(__dmul_rn(zi, zi), sm.scratch);  // cg.py:66
-            if (threadIdx.x == 0) S.part_rr[tile] = zz;
+    // partial dot products of this tile: <r,r> (cg.py:86), <r,z> (cg.py:76,82), and <z,z> for iteration 0 (cg.py:66)
+    double v[3] = {__dmul_rn(rn, rn), __dmul_rn(rn, zi), __dmul_rn(zi, zi)};
+    block_sum_n<3>(v, sm.scratch);
+    if (threadIdx.x == 0) {
+        if (!kInit) S.part_rr[tile] = v[0];
+        if (have_z) {
+            S.part_rz[(k + 1) & 1][tile] = v[1];
+            if (kInit) S.part_rr[tile] = v[2];
         }
     }
     if (kInit && tile == 0) {  // publish <b,b> once (all part_bb were written before the previous barrier)
@@ -247,34 +303,32 @@ __device__ __forceinline__ void phase_apply1(const Ctx& ctx, const SysDev& S, in
 
 // ---- PH_APPLY2 (MULTIPLY): z = L t ---------------------------------------------------------------------------
 template <bool kInit>
-__device__ __forceinline__ void phase_apply2(const SysDev& S, int s, int tile, int k, Smem& sm, Scal& sc) {
+__device__ __forceinline__ void phase_apply2(const Ctx& ctx, const SysDev& S, int s, int tile, int k, Smem& sm, Scal& sc) {
     if (sc.sys != s) {
         sc.sys = s;
-        sc.active = S.precond == DP_PRECOND_MULTIPLY && (kInit || __ldcg(S.state) == 0);
+        sc.active = S.precond == DP_PRECOND_MULTIPLY && (kInit || ld_relaxed_s32(ctx.state + s) == 0);
     }
     if (!sc.active) return;
     const int warp = threadIdx.x >> 5;
     const int row = tile * kTileRows + threadIdx.x;
-    const double zi = spmv_chunk(S.M, tile * kTileRows + warp * kWarp, GatherPlain{S.t}, sm.stage[warp]);
     double rn = 0.0;
-    if (row < S.n) {
-        S.z[(k + 1) & 1][row] = zi;
-        rn = S.r[(k + 1) & 1][row];
-    }
-    const double rz = block_sum(__dmul_rn(rn, zi), sm.scratch);
-    if (threadIdx.x == 0) S.part_rz[(k + 1) & 1][tile] = rz;
-    if (kInit) {
-        const double zz = block_sum(__dmul_rn(zi, zi), sm.scratch);
-        if (threadIdx.x == 0) S.part_rr[tile] = zz;
+    if (row < S.n) rn = S.r[(k + 1) & 1][row];
+    const double zi = spmv_chunk(S.M, tile * kTileRows + warp * kWarp, GatherPlain{S.t}, sm.stage[warp]);
+    if (row < S.n) S.z[(k + 1) & 1][row] = zi;
+    double v[2] = {__dmul_rn(rn, zi), __dmul_rn(zi, zi)};
+    block_sum_n<2>(v, sm.scratch);
+    if (threadIdx.x == 0) {
+        S.part_rz[(k + 1) & 1][tile] = v[0];
+        if (kInit) S.part_rr[tile] = v[1];
     }
 }
 
 // ---- PH_DOTRZ (SOLVE): <r,z> after the backward solve -----------------------------------------------------------
 template <bool kInit>
-__device__ __forceinline__ void phase_dotrz(const SysDev& S, int s, int tile, int k, Smem& sm, Scal& sc) {
+__device__ __forceinline__ void phase_dotrz(const Ctx& ctx, const SysDev& S, int s, int tile, int k, Smem& sm, Scal& sc) {
     if (sc.sys != s) {
         sc.sys = s;
-        sc.active = S.precond == DP_PRECOND_SOLVE && (kInit || __ldcg(S.state) == 0);
+        sc.active = S.precond == DP_PRECOND_SOLVE && (kInit || ld_relaxed_s32(ctx.state + s) == 0);
     }
     if (!sc.active) return;
     const int row = tile * kTileRows + threadIdx.x;
@@ -283,11 +337,11 @@ __device__ __forceinline__ void phase_dotrz(const SysDev& S, int s, int tile, in
         rn = S.r[(k + 1) & 1][row];
         zi = S.z[(k + 1) & 1][row];
     }
-    const double rz = block_sum(__dmul_rn(rn, zi), sm.scratch);
-    if (threadIdx.x == 0) S.part_rz[(k + 1) & 1][tile] = rz;
-    if (kInit) {
-        const double zz = block_sum(__dmul_rn(zi, zi), sm.scratch);
-        if (threadIdx.x == 0) S.part_rr[tile] = zz;
+    double v[2] = {__dmul_rn(rn, zi), __dmul_rn(zi, zi)};
+    block_sum_n<2>(v, sm.scratch);
+    if (threadIdx.x == 0) {
+        S.part_rz[(k + 1) & 1][tile] = v[0];
+        if (kInit) S.part_rr[tile] = v[1];
     }
 }
 
@@ -300,58 +354,125 @@ __device__ __forceinline__ bool phase_trsv(const Ctx& ctx, int k, const Smem& sm
     const int total = kUpper ? ctx.total_bwd : ctx.total_fwd;
     const int* ofs = kUpper ? ctx.bwd_ofs : ctx.fwd_ofs;
     const AbortCtl ctl{ctx.word, ctx.flag};
+    const bool light = pw <= 128;  // few pollers: skip the single-word waiting stage
     int cur = -1;
     bool active = false;
     for (int g = gw; g < total; g += pw) {
-        const int s = ctx.nsys == 1 ? 0 : find_sys(ofs, ctx.nsys, g);
+        const int s = ctx.nsys == 1 ? 0 : find_segment(ofs, ctx.nsys, g);
         const SysDev& S = (sm.sys_id == s) ? sm.sys : ctx.sys[s];
         if (s != cur) {
             cur = s;
-            active = kInit || __ldcg(S.state) == 0;
+            active = kInit || ld_relaxed_s32(ctx.state + s) == 0;
         }
         if (!active) continue;
         const int c = ctx.nsys == 1 ? g : g - __ldg(ofs + s);
         bool ok;
         if (kUpper)
-            ok = sptrsv_chunk<true>(S.Mt, S.bwd_plan + (size_t)c * 32, RhsConsume{S.t}, S.z[(k + 1) & 1], ctl);
+            ok = sptrsv_chunk<true>(S.Mt, S.bwd_plan + (size_t)c * 32, RhsConsume{S.t}, S.z[(k + 1) & 1], ctl, light);
         else
-            ok = sptrsv_chunk<false>(S.M, S.fwd_plan + (size_t)c * 32, RhsPlain{S.r[(k + 1) & 1]}, S.t, ctl);
+            ok = sptrsv_chunk<false>(S.M, S.fwd_plan + (size_t)c * 32, RhsPlain{S.r[(k + 1) & 1]}, S.t, ctl, light);
         if (!ok) return false;
     }
     return true;
 }
 
-// ---- tile driver ---------------------------------------------------------------------------------------------
+// ---- tile schedules --------------------------------------------------------------------------------------------
+template <int kPhase, bool kInit, bool kCheckState>
+__device__ __forceinline__ void run_tile(const Ctx& ctx, const SysDev& S, int s, int tile, int k, Smem& sm, Scal& sc) {
+    if (kPhase == PH_INIT) phase_init(ctx, S, s, tile, sm);
+    if (kPhase == PH_A) phase_a<kCheckState>(ctx, S, s, tile, k, sm, sc);
+    if (kPhase == PH_APPLY1) phase_apply1<kInit>(ctx, S, s, tile, k, sm, sc);
+    if (kPhase == PH_APPLY2) phase_apply2<kInit>(ctx, S, s, tile, k, sm, sc);
+    if (kPhase == PH_DOTRZ) phase_dotrz<kInit>(ctx, S, s, tile, k, sm, sc);
+}
+
+// Static schedule: every system, tiles dealt round robin (stepped engine).
 template <int kPhase, bool kInit>
-__device__ __forceinline__ void run_tiles(const Ctx& ctx, int k, Smem& sm) {
+__device__ __forceinline__ void run_tiles_static(const Ctx& ctx, int k, Smem& sm) {
     Scal sc;
     for (int g = blockIdx.x; g < ctx.total_tiles; g += gridDim.x) {
-        const int s = ctx.nsys == 1 ? 0 : find_sys(ctx.tile_ofs, ctx.nsys, g);
+        const int s = ctx.nsys == 1 ? 0 : find_segment(ctx.tile_ofs, ctx.nsys, g);
         const SysDev& S = load_sys(ctx, s, sm);
-        const int tile = ctx.nsys == 1 ? g : g - __ldg(ctx.tile_ofs + s);
-        if (kPhase == PH_INIT) phase_init(S, tile, sm);
-        if (kPhase == PH_A) phase_a(ctx, S, s, tile, k, sm, sc);
-        if (kPhase == PH_APPLY1) phase_apply1<kInit>(ctx, S, s, tile, k, sm, sc);
-        if (kPhase == PH_APPLY2) phase_apply2<kInit>(S, s, tile, k, sm, sc);
-        if (kPhase == PH_DOTRZ) phase_dotrz<kInit>(S, s, tile, k, sm, sc);
+        run_tile<kPhase, kInit, true>(ctx, S, s, ctx.nsys == 1 ? g : g - __ldg(ctx.tile_ofs + s), k, sm, sc);
     }
 }
 
+// Active schedule: the tiles of the unfinished systems, one contiguous range per CTA (fused engine).
+template <int kPhase, bool kInit>
+__device__ __forceinline__ void run_tiles_active(const Ctx& ctx, int k, int cur, Smem& sm) {
+    const int count = __ldcg(ctx.act_meta + 2 * cur), total = __ldcg(ctx.act_meta + 2 * cur + 1);
+    const int per = (total + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int g0 = blockIdx.x * per, g1 = min(total, g0 + per);
+    const int* asys = ctx.act_sys[cur];
+    const int* aofs = ctx.act_ofs[cur];
+    Scal sc;
+    int s = 0, seg_begin = 0, seg_end = -1;
+    const SysDev* S = nullptr;
+    for (int g = g0; g < g1; ++g) {
+        if (g >= seg_end) {
+            const int i = count == 1 ? 0 : find_segment(aofs, count, g);
+            s = __ldcg(asys + i);
+            seg_begin = __ldcg(aofs + i);
+            seg_end = __ldcg(aofs + i + 1);
+            S = &load_sys(ctx, s, sm);
+        }
+        run_tile<kPhase, kInit, false>(ctx, *S, s, g - seg_begin, k, sm, sc);
+    }
+}
+
+// CTA 0: compact the active list `cur` into `cur ^ 1`, dropping the systems whose state flag is up.
+__device__ __forceinline__ void rebuild_active(const Ctx& ctx, int cur, Smem& sm) {
+    const int count = __ldcg(ctx.act_meta + 2 * cur);
+    const int* asys = ctx.act_sys[cur];
+    const int* aofs = ctx.act_ofs[cur];
+    int* nsys_out = ctx.act_sys[cur ^ 1];
+    int* nofs_out = ctx.act_ofs[cur ^ 1];
+    int carry_n = 0, carry_t = 0;
+    for (int i0 = 0; i0 < count; i0 += kBlock) {
+        const int i = i0 + threadIdx.x;
+        int s = -1, alive = 0, nt = 0;
+        if (i < count) {
+            s = __ldcg(asys + i);
+            alive = ld_relaxed_s32(ctx.state + s) == 0;
+            nt = alive ? __ldcg(aofs + i + 1) - __ldcg(aofs + i) : 0;
+        }
+        int tot_n, tot_t;
+        const int pos = block_exclusive_scan_int(alive, &tot_n, sm.scan);
+        const int tofs = block_exclusive_scan_int(nt, &tot_t, sm.scan);
+        if (alive) {
+            nsys_out[carry_n + pos] = s;
+            nofs_out[carry_n + pos] = carry_t + tofs;
+        }
+        carry_n += tot_n;
+        carry_t += tot_t;
+    }
+    if (threadIdx.x == 0) {
+        nofs_out[carry_n] = carry_t;
+        ctx.act_meta[2 * (cur ^ 1)] = carry_n;
+        ctx.act_meta[2 * (cur ^ 1) + 1] = carry_t;
+    }
+}
+
+// Returns false on abort. `done` = finished count of the last barrier.
 template <bool kInit>
-__device__ __forceinline__ bool apply_preconditioner(const Ctx& ctx, int k, GridBarrier& bar, Smem& sm) {
-    run_tiles<PH_APPLY1, kInit>(ctx, k, sm);
-    if (!bar.sync()) return false;
+__device__ __forceinline__ bool apply_preconditioner(const Ctx& ctx, int k, int cur, GridBarrier& bar, Smem& sm) {
+    run_tiles_active<PH_APPLY1, kInit>(ctx, k, cur, sm);
+    trace(ctx, sm, 8 * PH_APPLY1 + 1);
+    if (bar.sync() < 0) return false;
+    trace(ctx, sm, 8 * PH_APPLY1 + 2);
     if (ctx.has_multiply) {
-        run_tiles<PH_APPLY2, kInit>(ctx, k, sm);
-        if (!bar.sync()) return false;
+        run_tiles_active<PH_APPLY2, kInit>(ctx, k, cur, sm);
+        trace(ctx, sm, 8 * PH_APPLY2 + 1);
+        if (bar.sync() < 0) return false;
+        trace(ctx, sm, 8 * PH_APPLY2 + 2);
     }
     if (ctx.has_solve) {
         const bool f = phase_trsv<false, kInit>(ctx, k, sm);
-        if (!bar.sync() || !f) return false;
+        if (bar.sync() < 0 || !f) return false;
         const bool b = phase_trsv<true, kInit>(ctx, k, sm);
-        if (!bar.sync() || !b) return false;
-        run_tiles<PH_DOTRZ, kInit>(ctx, k, sm);
-        if (!bar.sync()) return false;
+        if (bar.sync() < 0 || !b) return false;
+        run_tiles_active<PH_DOTRZ, kInit>(ctx, k, cur, sm);
+        if (bar.sync() < 0) return false;
     }
     return true;
 }
@@ -359,17 +480,26 @@ __device__ __forceinline__ bool apply_preconditioner(const Ctx& ctx, int k, Grid
 // The whole solve in one persistent cooperative launch: device-side loop control, no host round trips.
 __global__ void __launch_bounds__(kBlock, 2) pcg_fused_kernel(Ctx ctx) {
     __shared__ __align__(16) Smem sm;
-    if (threadIdx.x == 0) sm.sys_id = -1;
+    if (threadIdx.x == 0) sm.sys_id = -1, sm.trace_pos = 0;
     __syncthreads();
     GridBarrier bar{ctx.word, ctx.flag, 0u, gridDim.x};
-    run_tiles<PH_INIT, false>(ctx, -1, sm);
-    if (!bar.sync()) return;
-    if (!apply_preconditioner<true>(ctx, -1, bar, sm)) return;
+    int cur = 0;          // active-list buffer in use
+    int done_built = 0;   // finished count the list `cur` reflects
+    run_tiles_active<PH_INIT, false>(ctx, -1, cur, sm);
+    if (bar.sync() < 0) return;
+    if (!apply_preconditioner<true>(ctx, -1, cur, bar, sm)) return;
     for (int k = 0; k <= ctx.max_iter; ++k) {
-        run_tiles<PH_A, false>(ctx, k, sm);
-        if (!bar.sync()) return;
-        if (*reinterpret_cast<volatile int*>(ctx.n_done) >= ctx.nsys) break;
-        if (!apply_preconditioner<false>(ctx, k, bar, sm)) return;
+        trace(ctx, sm, 8 * PH_A + 0);
+        run_tiles_active<PH_A, false>(ctx, k, cur, sm);
+        trace(ctx, sm, 8 * PH_A + 1);
+        const int done = bar.sync();
+        trace(ctx, sm, 8 * PH_A + 2);
+        if (done < 0) return;
+        if (done >= ctx.nsys) break;
+        const bool rebuild = done != done_built;  // same decision in every CTA
+        if (rebuild && blockIdx.x == 0) rebuild_active(ctx, cur, sm);
+        if (!apply_preconditioner<false>(ctx, k, cur, bar, sm)) return;  // >= 1 barrier: the new list is visible
+        if (rebuild) cur ^= 1, done_built = done;
     }
 }
 
@@ -377,33 +507,40 @@ __global__ void __launch_bounds__(kBlock, 2) pcg_fused_kernel(Ctx ctx) {
 template <int kPhase, bool kInit>
 __global__ void __launch_bounds__(kBlock, 2) pcg_phase_kernel(Ctx ctx, int k) {
     __shared__ __align__(16) Smem sm;
-    if (threadIdx.x == 0) sm.sys_id = -1;
+    if (threadIdx.x == 0) sm.sys_id = -1, sm.trace_pos = 0;
     __syncthreads();
     if (kPhase == PH_FWD) {
         phase_trsv<false, kInit>(ctx, k, sm);
     } else if (kPhase == PH_BWD) {
         phase_trsv<true, kInit>(ctx, k, sm);
     } else {
-        run_tiles<kPhase, kInit>(ctx, k, sm);
+        run_tiles_static<kPhase, kInit>(ctx, k, sm);
     }
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------
 static inline int64_t pad32(int64_t v) { return (v + 31) / 32 * 32; }
 static inline int ntiles_of(int n) { return (n + kTileRows - 1) / kTileRows; }
+constexpr int kTraceCap = 4096;
 
 struct WsLayout {
-    size_t word, n_done, sys, tile_ofs, fwd_ofs, bwd_ofs, total;
+    size_t word, n_done, meta, sys, state, tile_ofs, fwd_ofs, bwd_ofs, act_sys[2], act_ofs[2], trace, total;
 };
 static WsLayout ws_layout(int nsys) {
     WsLayout w{};
     size_t off = 0;
-    w.word = off; off += 256;
-    w.n_done = off; off += 256;
-    w.sys = off; off += align_up(sizeof(SysDev) * (size_t)nsys, 256);
-    w.tile_ofs = off; off += align_up(sizeof(int) * ((size_t)nsys + 1), 256);
-    w.fwd_ofs = off; off += align_up(sizeof(int) * ((size_t)nsys + 1), 256);
-    w.bwd_ofs = off; off += align_up(sizeof(int) * ((size_t)nsys + 1), 256);
+    auto take = [&](size_t bytes) { size_t at = off; off += align_up(bytes, 256); return at; };
+    const size_t ints = sizeof(int) * ((size_t)nsys + 1);
+    w.word = take(8);
+    w.n_done = take(4);
+    w.meta = take(16);
+    w.sys = take(sizeof(SysDev) * (size_t)nsys);
+    w.state = take(ints);
+    w.tile_ofs = take(ints);
+    w.fwd_ofs = take(ints);
+    w.bwd_ofs = take(ints);
+    for (int i = 0; i < 2; ++i) w.act_sys[i] = take(ints), w.act_ofs[i] = take(ints);
+    w.trace = take(sizeof(long long) * 2 * kTraceCap);
     w.total = off;
     return w;
 }
@@ -458,6 +595,15 @@ int dp_device_info(int* sm_count_host, int* pcg_ctas_per_sm_host, int* l2_bytes_
     return DP_OK;
 }
 
+int dp_debug_pcg_trace(const void* workspace, int32_t nsys, int64_t* out_host, int32_t capacity) {
+    if (!workspace || !out_host || capacity <= 0 || nsys <= 0) return DP_ERR_INVALID;
+    const WsLayout lay = ws_layout(nsys);
+    const int cap = capacity < kTraceCap ? capacity : kTraceCap;
+    DP_CUDA(cudaMemcpy(out_host, static_cast<const char*>(workspace) + lay.trace, sizeof(long long) * 2 * (size_t)cap,
+                       cudaMemcpyDeviceToHost));
+    return DP_OK;
+}
+
 int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp_pcg_params_t* params_host,
                      int32_t* flag_out, void* workspace, size_t workspace_bytes, void* stream) {
     if (!systems_host || nsys <= 0 || !params_host || !flag_out || !workspace) return DP_ERR_INVALID;
@@ -470,6 +616,7 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
 
     std::vector<SysDev> sys((size_t)nsys);
     std::vector<int> tile_ofs((size_t)nsys + 1, 0), fwd_ofs((size_t)nsys + 1, 0), bwd_ofs((size_t)nsys + 1, 0);
+    std::vector<int> ident((size_t)nsys + 1, 0);
     int has_multiply = 0, has_solve = 0;
     long long sum_fwd_lvl = 0, sum_bwd_lvl = 0;
     for (int i = 0; i < nsys; ++i) {
@@ -504,7 +651,7 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
                 sum_fwd_lvl += u.fwd_max_level_chunks > 0 ? u.fwd_max_level_chunks : (1 << 20);
                 sum_bwd_lvl += u.bwd_max_level_chunks > 0 ? u.bwd_max_level_chunks : (1 << 20);
                 has_solve = 1;
-                // fallthrough: needs L and L^T as well
+                [[fallthrough]];  // needs L and L^T as well
             case DP_PRECOND_MULTIPLY:
                 if (!u.m_rowptr || !u.m_col || !u.m_val || !u.mt_rowptr || !u.mt_col || !u.mt_val) return DP_ERR_INVALID;
                 if (!aligned16(u.m_col) || !aligned16(u.m_val) || !aligned16(u.mt_col) || !aligned16(u.mt_val))
@@ -524,11 +671,11 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
         double* q = w + 8 * np;
         d.part_rr = q; d.part_pap = q + tp; d.part_bb = q + 2 * tp; d.part_rz[0] = q + 3 * tp; d.part_rz[1] = q + 4 * tp;
         d.scal = q + 5 * tp;
-        d.state = reinterpret_cast<int*>(d.scal + 8);
         d.iters_out = u.iters_out;
         d.res_out = u.res_out;
         d.history = u.history;
         sys[(size_t)i] = d;
+        ident[(size_t)i] = i;
         tile_ofs[(size_t)i + 1] = tile_ofs[(size_t)i] + d.ntiles;
         fwd_ofs[(size_t)i + 1] = fwd_ofs[(size_t)i] + fwd_chunks;
         bwd_ofs[(size_t)i + 1] = bwd_ofs[(size_t)i] + bwd_chunks;
@@ -545,9 +692,15 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
 
     Ctx ctx{};
     ctx.sys = reinterpret_cast<const SysDev*>(ws + lay.sys);
+    ctx.state = reinterpret_cast<int*>(ws + lay.state);
     ctx.tile_ofs = reinterpret_cast<const int*>(ws + lay.tile_ofs);
     ctx.fwd_ofs = reinterpret_cast<const int*>(ws + lay.fwd_ofs);
     ctx.bwd_ofs = reinterpret_cast<const int*>(ws + lay.bwd_ofs);
+    for (int i = 0; i < 2; ++i) {
+        ctx.act_sys[i] = reinterpret_cast<int*>(ws + lay.act_sys[i]);
+        ctx.act_ofs[i] = reinterpret_cast<int*>(ws + lay.act_ofs[i]);
+    }
+    ctx.act_meta = reinterpret_cast<int*>(ws + lay.meta);
     ctx.nsys = nsys;
     ctx.total_tiles = tile_ofs[(size_t)nsys];
     ctx.total_fwd = fwd_ofs[(size_t)nsys];
@@ -559,18 +712,37 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
     ctx.word = reinterpret_cast<unsigned long long*>(ws + lay.word);
     ctx.n_done = reinterpret_cast<int*>(ws + lay.n_done);
     ctx.flag = flag_out;
+    ctx.trace = reinterpret_cast<long long*>(ws + lay.trace);
+    const char* tr = getenv("DPCG_TRACE");
+    ctx.trace_cap = (tr && tr[0] == '1') ? kTraceCap : 0;
 
-    DP_CUDA(cudaMemsetAsync(ws, 0, 512, s));  // barrier word + done counter
+    const int meta[4] = {nsys, ctx.total_tiles, 0, 0};
+    DP_CUDA(cudaMemsetAsync(ws + lay.word, 0, 8, s));
+    DP_CUDA(cudaMemsetAsync(ws + lay.n_done, 0, 4, s));
+    if (ctx.trace_cap) DP_CUDA(cudaMemsetAsync(ws + lay.trace, 0, sizeof(long long) * 2 * kTraceCap, s));
+    DP_CUDA(cudaMemcpyAsync(ws + lay.meta, meta, sizeof(meta), cudaMemcpyHostToDevice, s));
     DP_CUDA(cudaMemcpyAsync(ws + lay.sys, sys.data(), sizeof(SysDev) * (size_t)nsys, cudaMemcpyHostToDevice, s));
-    DP_CUDA(cudaMemcpyAsync(ws + lay.tile_ofs, tile_ofs.data(), sizeof(int) * ((size_t)nsys + 1), cudaMemcpyHostToDevice, s));
-    DP_CUDA(cudaMemcpyAsync(ws + lay.fwd_ofs, fwd_ofs.data(), sizeof(int) * ((size_t)nsys + 1), cudaMemcpyHostToDevice, s));
-    DP_CUDA(cudaMemcpyAsync(ws + lay.bwd_ofs, bwd_ofs.data(), sizeof(int) * ((size_t)nsys + 1), cudaMemcpyHostToDevice, s));
+    const size_t ints = sizeof(int) * ((size_t)nsys + 1);
+    DP_CUDA(cudaMemcpyAsync(ws + lay.tile_ofs, tile_ofs.data(), ints, cudaMemcpyHostToDevice, s));
+    DP_CUDA(cudaMemcpyAsync(ws + lay.fwd_ofs, fwd_ofs.data(), ints, cudaMemcpyHostToDevice, s));
+    DP_CUDA(cudaMemcpyAsync(ws + lay.bwd_ofs, bwd_ofs.data(), ints, cudaMemcpyHostToDevice, s));
+    DP_CUDA(cudaMemcpyAsync(ws + lay.act_sys[0], ident.data(), ints, cudaMemcpyHostToDevice, s));
+    DP_CUDA(cudaMemcpyAsync(ws + lay.act_ofs[0], tile_ofs.data(), ints, cudaMemcpyHostToDevice, s));
 
     if (params_host->engine == DP_ENGINE_FUSED) {
-        ctx.pw_fwd = clamp_pw(sum_fwd_lvl, coop);
-        ctx.pw_bwd = clamp_pw(sum_bwd_lvl, coop);
+        // right-size the grid: a CTA per tile is enough for the tile phases; the SpTRSV phases spread their
+        // participating warps one per CTA first. Fewer CTAs = cheaper grid barrier for small systems.
+        int grid = ctx.total_tiles;
+        if (has_solve) {
+            const long long want = 4 * (sum_fwd_lvl > sum_bwd_lvl ? sum_fwd_lvl : sum_bwd_lvl);
+            if (want > grid) grid = want > coop ? coop : (int)want;
+        }
+        if (grid > coop) grid = coop;
+        if (grid < 1) grid = 1;
+        ctx.pw_fwd = clamp_pw(sum_fwd_lvl, grid);
+        ctx.pw_bwd = clamp_pw(sum_bwd_lvl, grid);
         void* args[] = {&ctx};
-        DP_CUDA(cudaLaunchCooperativeKernel((const void*)pcg_fused_kernel, dim3(coop), dim3(kBlock), args, 0, s));
+        DP_CUDA(cudaLaunchCooperativeKernel((const void*)pcg_fused_kernel, dim3(grid), dim3(kBlock), args, 0, s));
         return DP_OK;
     }
     if (params_host->engine != DP_ENGINE_STEPPED) return DP_ERR_INVALID;

@@ -45,19 +45,30 @@ struct GatherRMinusAAp {
     __device__ __forceinline__ double operator()(int c) const { return __dsub_rn(r[c], __dmul_rn(a, ap[c])); }
 };
 
-// Row sum of row (base + lane) of A, 0 for rows >= n. `stage` = this warp's kStageCap doubles of shared memory.
-// Must be called by all 32 lanes.
+// Row extent of this lane's row and of the whole 32-row chunk. Independent of any vector: can be issued early
+// (before the scalars of a phase are known) to overlap its latency.
+struct ChunkHead {
+    int rs, re;  // entries of row (base + lane); empty for rows >= n
+    int cs, ce;  // entries of the chunk
+};
+
+__device__ __forceinline__ ChunkHead spmv_head(const CsrView& A, int base) {
+    const int row = base + (threadIdx.x & 31);
+    ChunkHead h;
+    h.rs = __ldg(A.rowptr + min(row, A.n));
+    h.re = __ldg(A.rowptr + min(row + 1, A.n));
+    h.cs = __shfl_sync(kFull, h.rs, 0);
+    h.ce = __shfl_sync(kFull, h.re, 31);
+    return h;
+}
+
+// Row sum of this lane's row. `stage` = this warp's kStageCap doubles of shared memory. All 32 lanes must call.
 template <class Gather>
-__device__ __forceinline__ double spmv_chunk(const CsrView& A, int base, const Gather& x, double* stage) {
+__device__ __forceinline__ double spmv_body(const CsrView& A, const ChunkHead& h, const Gather& x, double* stage) {
     const int lane = threadIdx.x & 31;
-    const int row = base + lane;
-    const int rs = __ldg(A.rowptr + min(row, A.n));
-    const int re = __ldg(A.rowptr + min(row + 1, A.n));
-    const int cs = __shfl_sync(kFull, rs, 0);
-    const int ce = __shfl_sync(kFull, re, 31);
     double sum = 0.0;
-    for (int bs = cs & ~3; bs < ce; bs += kStageCap) {
-        const int be = min(bs + kStageCap, ce);
+    for (int bs = h.cs & ~3; bs < h.ce; bs += kStageCap) {
+        const int be = min(bs + kStageCap, h.ce);
 #pragma unroll 2
         for (int e = bs + 4 * lane; e < be; e += 4 * kWarp) {
             int c0, c1, c2, c3;
@@ -84,11 +95,16 @@ __device__ __forceinline__ double spmv_chunk(const CsrView& A, int base, const G
             dst[1] = make_double2(__dmul_rn(v2, x2), __dmul_rn(v3, x3));
         }
         __syncwarp();
-        const int lo = max(rs, bs), hi = min(re, be);
+        const int lo = max(h.rs, bs), hi = min(h.re, be);
         for (int q = lo; q < hi; ++q) sum = __dadd_rn(sum, stage[q - bs]);
         __syncwarp();
     }
     return sum;
+}
+
+template <class Gather>
+__device__ __forceinline__ double spmv_chunk(const CsrView& A, int base, const Gather& x, double* stage) {
+    return spmv_body(A, spmv_head(A, base), x, stage);
 }
 
 }  // namespace dp

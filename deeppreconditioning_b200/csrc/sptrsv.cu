@@ -17,9 +17,10 @@ sptrsv_kernel(CsrView T, int upper, const int* __restrict__ plan, long long nchu
     if (gw >= pw) return;
     const AbortCtl ctl{word, flag};
     const RhsPlain rhs{b};
+    const bool light = pw <= 128;
     for (long long c = gw; c < nchunks; c += pw) {
-        const bool ok = upper ? sptrsv_chunk<true>(T, plan + c * 32, rhs, x, ctl)
-                              : sptrsv_chunk<false>(T, plan + c * 32, rhs, x, ctl);
+        const bool ok = upper ? sptrsv_chunk<true>(T, plan + c * 32, rhs, x, ctl, light)
+                              : sptrsv_chunk<false>(T, plan + c * 32, rhs, x, ctl, light);
         if (!ok) return;
     }
 }

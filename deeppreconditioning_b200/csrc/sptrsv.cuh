@@ -40,34 +40,45 @@ struct RhsConsume {
 };
 
 // Returns false if the solve was aborted (spin budget exhausted somewhere). All 32 lanes must call.
+// `light`: few warps take part in this solve (small levels), so every lane may poll all its dependencies right
+// away; otherwise the warp first watches ONE word (one sector request per poll) until its chunk is about to be
+// ready, which keeps the L2 request rate of thousands of waiting warps negligible.
 template <bool kUpper, class Rhs>
 __device__ __forceinline__ bool sptrsv_chunk(const CsrView& T, const int* __restrict__ plan32, const Rhs& rhs,
-                                             double* x, const AbortCtl& ctl) {
+                                             double* x, const AbortCtl& ctl, bool light) {
     const int lane = threadIdx.x & 31;
     const int row = __ldg(plan32 + lane);
     const bool valid = row >= 0;
     int e = 0, end = 0;
     double rcp = 0.0, b = 0.0, sum = 0.0;
+    int c[4] = {0, 0, 0, 0};
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
     int probe = -1;
     if (valid) {
         const int rs = __ldg(T.rowptr + row), re = __ldg(T.rowptr + row + 1);
         e = kUpper ? rs + 1 : rs;        // off-diagonal entries [e, end)
         end = kUpper ? re : re - 1;
+        // everything that does not depend on other rows is fetched before waiting
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (e + k < end) c[k] = __ldg(T.col + e + k), v[k] = __ldg(T.val + e + k);
         rcp = __ddiv_rn(1.0, __ldg(T.val + (kUpper ? rs : re - 1)));
         b = rhs(row);
         // the off-diagonal entry nearest to the diagonal is (heuristically) the last to become available
-        if (lane == 0 && e < end) probe = __ldg(T.col + (kUpper ? e : end - 1));
+        if (!light && lane == 0 && e < end) probe = __ldg(T.col + (kUpper ? e : end - 1));
     }
-    probe = __shfl_sync(kFull, probe, 0);
-    if (probe >= 0) {  // cheap waiting: the whole warp watches ONE word (one sector request per poll)
-        unsigned spins = 0;
-        while (ld_relaxed_u64(x + probe) == kPending) {
-            if (++spins > kSpinBudget) {
-                ctl.raise(DP_ERR_TIMEOUT);
-                return false;
+    if (!light) {
+        probe = __shfl_sync(kFull, probe, 0);
+        if (probe >= 0) {
+            unsigned spins = 0;
+            while (ld_relaxed_u64(x + probe) == kPending) {
+                if (++spins > kSpinBudget) {
+                    ctl.raise(DP_ERR_TIMEOUT);
+                    return false;
+                }
+                if ((spins & 1023u) == 0 && ctl.aborted()) return false;
+                __nanosleep(64);
             }
-            if ((spins & 1023u) == 0 && ctl.aborted()) return false;
-            __nanosleep(64);
         }
     }
     unsigned idle = 0;
@@ -78,22 +89,23 @@ __device__ __forceinline__ bool sptrsv_chunk(const CsrView& T, const int* __rest
         if (pending) {
             // up to 4 entries in flight; consumed strictly in column order
             const int m = min(4, end - e);
-            int c[4];
-            double v[4];
             unsigned long long u[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                c[k] = k < m ? __ldg(T.col + e + k) : 0;
-                v[k] = k < m ? __ldg(T.val + e + k) : 0.0;
-            }
-#pragma unroll
             for (int k = 0; k < 4; ++k) u[k] = k < m ? ld_relaxed_u64(x + c[k]) : kPending;
+            int used = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                if (u[k] == kPending) break;
-                sum = __dadd_rn(sum, __dmul_rn(v[k], as_double(u[k])));
-                ++e;
+                if (used == k && u[k] != kPending) {
+                    sum = __dadd_rn(sum, __dmul_rn(v[k], as_double(u[k])));
+                    ++used;
+                }
+            }
+            if (used) {
+                e += used;
                 progress = true;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (e + k < end) c[k] = __ldg(T.col + e + k), v[k] = __ldg(T.val + e + k);
             }
         }
         if (!__any_sync(kFull, progress)) {

@@ -173,6 +173,10 @@ size_t dp_pcg_workspace_bytes(int32_t nsys);
 int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp_pcg_params_t* params_host,
                      int32_t* flag_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Diagnostics: with DPCG_TRACE=1 in the environment the fused engine records (label, clock64) pairs of CTA 0 into the
+ * workspace; this copies up to `capacity` pairs to out_host[2*capacity] (label = 8*phase + point). Synchronous. */
+int dp_debug_pcg_trace(const void* workspace, int32_t nsys, int64_t* out_host, int32_t capacity);
+
 #ifdef __cplusplus
 }
 #endif
