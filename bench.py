@@ -42,6 +42,7 @@ MAX_ITER = 20000
 
 
 def parse_args():
+    global MAX_ITER
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -50,8 +51,11 @@ def parse_args():
     ap.add_argument("--systems-per-gpu", type=int, default=64)
     ap.add_argument("--side", type=int, default=316)
     ap.add_argument("--net", default="net", choices=["net", "tril"])
+    ap.add_argument("--max-iter", type=int, default=MAX_ITER, help="profiling only: cap the bodies per solve")
     ap.add_argument("--no-extras", action="store_true", help="skip single-system latency and 128^3 kernel numbers")
-    return ap.parse_args()
+    args = ap.parse_args()
+    MAX_ITER = args.max_iter
+    return args
 
 
 def workload_name(args):

@@ -159,7 +159,8 @@ constexpr unsigned long long kDoneUnit = 1ull << 32;  // bits 32..62: number of 
 
 struct GridBarrier {
     unsigned long long* word;
-    int* flag;  // device status word (DP_ERR_TIMEOUT)
+    int* flag;   // device status word (DP_ERR_TIMEOUT)
+    int* bcast;  // one int of shared memory
     unsigned epoch;
     unsigned nblocks;
     __device__ __forceinline__ void raise_abort(int status) {
@@ -185,8 +186,10 @@ struct GridBarrier {
             }
             __threadfence();
         }
-        // broadcast thread 0's word: OR-reduce (everyone else contributes 0)
-        return __syncthreads_or(info);
+        // broadcast thread 0's reading (note: __syncthreads_or reduces a predicate, not the integer)
+        if (threadIdx.x == 0) *bcast = info;
+        __syncthreads();
+        return *bcast;
     }
 };
 

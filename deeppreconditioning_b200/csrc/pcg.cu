@@ -88,6 +88,7 @@ struct Smem {
     int sys_id;
     int scan[kWarpsPerBlock + 1];
     int trace_pos;
+    int bcast;
 };
 
 static_assert(sizeof(SysDev) % 8 == 0, "SysDev is copied as 8-byte words");
@@ -482,7 +483,7 @@ __global__ void __launch_bounds__(kBlock, 2) pcg_fused_kernel(Ctx ctx) {
     __shared__ __align__(16) Smem sm;
     if (threadIdx.x == 0) sm.sys_id = -1, sm.trace_pos = 0;
     __syncthreads();
-    GridBarrier bar{ctx.word, ctx.flag, 0u, gridDim.x};
+    GridBarrier bar{ctx.word, ctx.flag, &sm.bcast, 0u, gridDim.x};
     int cur = 0;          // active-list buffer in use
     int done_built = 0;   // finished count the list `cur` reflects
     run_tiles_active<PH_INIT, false>(ctx, -1, cur, sm);
