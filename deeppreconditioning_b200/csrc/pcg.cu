@@ -33,6 +33,10 @@
 #include "spmv.cuh"
 #include "sptrsv.cuh"
 
+// Inside the fused phases the quad-per-lane streaming variant wins (fewer load instructions, the gather functors
+// already issue two loads per entry); the standalone SpMV uses the stride-32 variant. Same bits either way.
+#define pcg_spmv_body spmv_body_quad
+
 namespace dp {
 
 int coop_grid(const void* kernel, int threads, size_t smem);  // sptrsv.cu
@@ -210,7 +214,7 @@ __device__ __forceinline__ void phase_a(const Ctx& ctx, const SysDev& S, int s, 
     if (!sc.active) return;
     double* pn = S.p[(k + 1) & 1];
     const GatherZBetaP g{z, po, sc.v};
-    const double ap = spmv_body(S.A, head, g, sm.stage[warp]);  // cg.py:75
+    const double ap = pcg_spmv_body(S.A, head, g, sm.stage[warp]);  // cg.py:75
     double pap = 0.0;
     if (valid) {
         const double pi = __dadd_rn(zr, __dmul_rn(sc.v, pr));  // cg.py:83
@@ -271,12 +275,12 @@ __device__ __forceinline__ void phase_apply1(const Ctx& ctx, const SysDev& S, in
             zi = __dmul_rn(dinv_i, rn);
             break;
         case DP_PRECOND_CSR:
-            zi = kInit ? spmv_body(S.M, head, GatherPlain{ro}, sm.stage[warp])
-                       : spmv_body(S.M, head, GatherRMinusAAp{ro, S.ap, a}, sm.stage[warp]);
+            zi = kInit ? pcg_spmv_body(S.M, head, GatherPlain{ro}, sm.stage[warp])
+                       : pcg_spmv_body(S.M, head, GatherRMinusAAp{ro, S.ap, a}, sm.stage[warp]);
             break;
         case DP_PRECOND_MULTIPLY: {
-            const double ti = kInit ? spmv_body(S.Mt, head, GatherPlain{ro}, sm.stage[warp])
-                                    : spmv_body(S.Mt, head, GatherRMinusAAp{ro, S.ap, a}, sm.stage[warp]);
+            const double ti = kInit ? pcg_spmv_body(S.Mt, head, GatherPlain{ro}, sm.stage[warp])
+                                    : pcg_spmv_body(S.Mt, head, GatherRMinusAAp{ro, S.ap, a}, sm.stage[warp]);
             if (valid) S.t[row] = ti;
             have_z = false;
             break;
@@ -314,7 +318,7 @@ __device__ __forceinline__ void phase_apply2(const Ctx& ctx, const SysDev& S, in
     const int row = tile * kTileRows + threadIdx.x;
     double rn = 0.0;
     if (row < S.n) rn = S.r[(k + 1) & 1][row];
-    const double zi = spmv_chunk(S.M, tile * kTileRows + warp * kWarp, GatherPlain{S.t}, sm.stage[warp]);
+    const double zi = pcg_spmv_body(S.M, spmv_head(S.M, tile * kTileRows + warp * kWarp), GatherPlain{S.t}, sm.stage[warp]);
     if (row < S.n) S.z[(k + 1) & 1][row] = zi;
     double v[2] = {__dmul_rn(rn, zi), __dmul_rn(zi, zi)};
     block_sum_n<2>(v, sm.scratch);
@@ -730,6 +734,9 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
     DP_CUDA(cudaMemcpyAsync(ws + lay.act_sys[0], ident.data(), ints, cudaMemcpyHostToDevice, s));
     DP_CUDA(cudaMemcpyAsync(ws + lay.act_ofs[0], tile_ofs.data(), ints, cudaMemcpyHostToDevice, s));
 
+    if (const char* cv = getenv("DPCG_CARVEOUT")) {  // experiment knob: shared-memory carveout in percent
+        DP_CUDA(cudaFuncSetAttribute((const void*)pcg_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
+    }
     if (params_host->engine == DP_ENGINE_FUSED) {
         // right-size the grid: a CTA per tile is enough for the tile phases; the SpTRSV phases spread their
         // participating warps one per CTA first. Fewer CTAs = cheaper grid barrier for small systems.

@@ -1,8 +1,8 @@
 // spmv.cuh — warp-granular CSR "stream" SpMV primitive (K2), shared by the standalone kernel and the PCG phases.
 //
 // A warp owns 32 consecutive rows (a chunk). Its stored entries form ONE contiguous span of col[]/val[], which
-// the warp streams with coalesced 128-bit loads (int4 of column indices, 2x double2 of values per lane and
-// step), multiplies by the gathered x[col] and parks the products in its private 2 KB slice of shared memory.
+// the warp streams with fully coalesced loads, multiplies by the gathered x[col] and parks the products in its
+// private 2 KB slice of shared memory.
 // Each lane then adds up the products of its own row, left to right. Products and sums are rounded separately
 // (__dmul_rn/__dadd_rn, no FMA contraction) so a row sum is bit-identical to the sequential CPU loop
 // `sum += val[p] * x[col[p]]` (scipy csr_matvec / oracle_spmv_csr) — replaces `A @ p`, `M @ r`, cg.py:60,61,75,81.
@@ -63,8 +63,49 @@ __device__ __forceinline__ ChunkHead spmv_head(const CsrView& A, int base) {
 }
 
 // Row sum of this lane's row. `stage` = this warp's kStageCap doubles of shared memory. All 32 lanes must call.
+//
+// The chunk's span is streamed in rounds of 32 consecutive entries per load instruction (lane l takes entry e0+l):
+// col/val loads are perfectly coalesced (128 B / 256 B per instruction) and - what matters more - the 32 GATHER
+// addresses of one instruction belong to ~6 consecutive rows, i.e. to a handful of cache lines (the stencil's
+// diagonals), instead of 32 different rows: 4-5x fewer L1 wavefronts per gather than a quad-per-lane layout, and
+// conflict-free shared-memory stores. kSpmvUnroll rounds are in flight before the first product is needed.
+constexpr int kSpmvUnroll = 8;
+
 template <class Gather>
 __device__ __forceinline__ double spmv_body(const CsrView& A, const ChunkHead& h, const Gather& x, double* stage) {
+    const int lane = threadIdx.x & 31;
+    double sum = 0.0;
+    for (int bs = h.cs; bs < h.ce; bs += kStageCap) {
+        const int be = min(bs + kStageCap, h.ce);
+        for (int e0 = bs + lane; e0 < be; e0 += kWarp * kSpmvUnroll) {
+            int c[kSpmvUnroll];
+            double v[kSpmvUnroll];
+#pragma unroll
+            for (int u = 0; u < kSpmvUnroll; ++u) {
+                const int e = e0 + kWarp * u;
+                c[u] = e < be ? __ldg(A.col + e) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < kSpmvUnroll; ++u) {
+                const int e = e0 + kWarp * u;
+                v[u] = e < be ? __ldg(A.val + e) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < kSpmvUnroll; ++u)
+                if (c[u] >= 0) stage[e0 + kWarp * u - bs] = __dmul_rn(v[u], x(c[u]));
+        }
+        __syncwarp();
+        const int lo = max(h.rs, bs), hi = min(h.re, be);
+        for (int q = lo; q < hi; ++q) sum = __dadd_rn(sum, stage[q - bs]);
+        __syncwarp();
+    }
+    return sum;
+}
+
+// Variant: every lane takes 4 consecutive entries per step (one int4 + two double2 loads). Fewer load
+// instructions, but the 32 gather addresses of an instruction spread over ~25 rows. Same bits as spmv_body.
+template <class Gather>
+__device__ __forceinline__ double spmv_body_quad(const CsrView& A, const ChunkHead& h, const Gather& x, double* stage) {
     const int lane = threadIdx.x & 31;
     double sum = 0.0;
     for (int bs = h.cs & ~3; bs < h.ce; bs += kStageCap) {
