@@ -6,11 +6,13 @@ There is deliberately **no fallback**: if the shared object is missing or a call
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import torch
 
-LIB_PATH = Path(__file__).resolve().parent / "lib" / "libdpcg.so"
+# DPCG_LIB selects another build of the same library (tuning variants made by `build.build_variant`).
+LIB_PATH = Path(os.environ.get("DPCG_LIB") or Path(__file__).resolve().parent / "lib" / "libdpcg.so")
 
 DP_OK = 0
 DP_ERR_STRUCTURE = 5

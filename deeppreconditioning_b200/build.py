@@ -52,5 +52,17 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+def build_variant(tag: str, defines: dict[str, int]) -> Path:
+    """Tuning build: libdpcg_<tag>.so with -D overrides of the pipeline constants (select it with DPCG_LIB)."""
+    LIB_DIR.mkdir(exist_ok=True)
+    out = LIB_DIR / f"libdpcg_{tag}.so"
+    cmd = [nvcc(), *NVCC_FLAGS, *[f"-D{k}={v}" for k, v in defines.items()], "-o", str(out), *[str(CSRC / s) for s in SOURCES]]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode:
+        sys.stderr.write(proc.stdout + proc.stderr)
+        raise RuntimeError(f"nvcc failed building {out.name}")
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -30,12 +30,8 @@
 
 #include <vector>
 
-#include "spmv.cuh"
 #include "sptrsv.cuh"
-
-// Inside the fused phases the quad-per-lane streaming variant wins (fewer load instructions, the gather functors
-// already issue two loads per entry); the standalone SpMV uses the stride-32 variant. Same bits either way.
-#define pcg_spmv_body spmv_body_quad
+#include "tilepipe.cuh"
 
 namespace dp {
 
@@ -85,11 +81,20 @@ struct Ctx {
     int trace_cap;
 };
 
+// Tile tables: the stream descriptors of the tiles of this CTA's range, one table per SpMV-shaped phase. They
+// survive across iterations (the range only changes when the active list is rebuilt), so the producer thread finds
+// the next item's addresses in shared memory instead of chasing rowptr through L2.
+constexpr int kMaxRoundTiles = 64;
+enum Table { TAB_A = 0, TAB_P1 = 1, TAB_P2 = 2 };  // A | L^T (MULTIPLY) or M (CSR) | L (MULTIPLY)
+
 struct Smem {
-    double stage[kWarpsPerBlock][kStageCap];
-    double scratch[3 * kWarpsPerBlock];
+    PipeShared pipe;
+    TileDesc tab[3][kMaxRoundTiles];
+    double scratch[2][3 * kWarpsPerBlock];  // tile_reduce (double buffered)
+    double scratch2[3 * kWarpsPerBlock];    // block_sum* of the per-system scalar evaluation
     SysDev sys;  // descriptor of the system this CTA is working on (survives across phases)
     int sys_id;
+    int tab_ver[3], tab_ga[3], tab_gb[3];  // what each table currently describes (ver 0 = nothing)
     int scan[kWarpsPerBlock + 1];
     int trace_pos;
     int bcast;
@@ -140,25 +145,26 @@ struct Scal {
 };
 
 // ---- PH_INIT: r0 = b - A x0 (cg.py:60), <b,b>, p = 0, arm the sync-free buffers -------------------------------
-__device__ __forceinline__ void phase_init(const Ctx& ctx, const SysDev& S, int s, int tile, Smem& sm) {
-    const int warp = threadIdx.x >> 5;
+__device__ __forceinline__ void phase_init(const Ctx& ctx, const SysDev& S, const TileDesc& d, int rs, int re,
+                                           Smem& sm, Pipe& pipe) {
+    const int tile = d.ltile;
     const int row = tile * kTileRows + threadIdx.x;
-    const double ax = spmv_chunk(S.A, tile * kTileRows + warp * kWarp, GatherPlain{S.x}, sm.stage[warp]);
-    double bb = 0.0;
+    const double ax = pipe.tile_spmv(d, rs, re, GatherPlain{S.x}, true);
+    double bb[1] = {0.0};
     if (row < S.n) {
         const double bi = S.b[row];
         S.r[1][row] = __dsub_rn(bi, ax);
         S.p[0][row] = 0.0;
-        bb = __dmul_rn(bi, bi);
+        bb[0] = __dmul_rn(bi, bi);
         if (S.precond == DP_PRECOND_SOLVE) {
             st_relaxed_u64(S.z[0] + row, kPending);
             st_relaxed_u64(S.t + row, kPending);
         }
     }
-    bb = block_sum(bb, sm.scratch);
+    tile_reduce<1>(bb, sm.scratch, pipe);
     if (threadIdx.x == 0) {
-        S.part_bb[tile] = bb;
-        if (tile == 0) ctx.state[s] = 0;
+        S.part_bb[tile] = bb[0];
+        if (tile == 0) ctx.state[d.sys] = 0;
     }
 }
 
@@ -167,8 +173,9 @@ __device__ __forceinline__ void phase_init(const Ctx& ctx, const SysDev& S, int 
 // written by another CTA in this very phase, so it is read once per CTA and broadcast (a per-thread read could
 // split the CTA around a barrier). The fused engine's active list never contains a finished system.
 template <bool kCheckState>
-__device__ __forceinline__ void phase_a(const Ctx& ctx, const SysDev& S, int s, int tile, int k, Smem& sm, Scal& sc) {
-    const int warp = threadIdx.x >> 5;
+__device__ __forceinline__ void phase_a(const Ctx& ctx, const SysDev& S, const TileDesc& d, int rs, int re, int k,
+                                        Smem& sm, Scal& sc, Pipe& pipe) {
+    const int s = d.sys, tile = d.ltile;
     const int row = tile * kTileRows + threadIdx.x;
     const bool valid = row < S.n;
     const double* z = S.z[k & 1];
@@ -176,7 +183,6 @@ __device__ __forceinline__ void phase_a(const Ctx& ctx, const SysDev& S, int s, 
     // loads that do not depend on this phase's scalars go first
     double zr = 0.0, pr = 0.0;
     if (valid) zr = z[row], pr = po[row];
-    const ChunkHead head = spmv_head(S.A, tile * kTileRows + warp * kWarp);
     if (sc.sys != s) {
         sc.sys = s;
         sc.active = false;
@@ -192,7 +198,7 @@ __device__ __forceinline__ void phase_a(const Ctx& ctx, const SysDev& S, int s, 
             }
             const double bb = __ldcg(S.scal + 2);
             const double rz_prev = k > 0 ? __ldcg(S.scal + ((k - 1) & 1)) : 1.0;
-            block_sum_n<2>(v, sm.scratch);
+            block_sum_n<2>(v, sm.scratch2);
             const double res = v[0] / bb;  // cg.py:17
             const bool finished = (res < ctx.rtol) || (k >= ctx.max_iter);  // cg.py:70-72
             sc.active = !finished;
@@ -211,27 +217,29 @@ __device__ __forceinline__ void phase_a(const Ctx& ctx, const SysDev& S, int s, 
             }
         }
     }
-    if (!sc.active) return;
+    if (!sc.active) {
+        pipe.tile_skip(d);
+        return;
+    }
     double* pn = S.p[(k + 1) & 1];
-    const GatherZBetaP g{z, po, sc.v};
-    const double ap = pcg_spmv_body(S.A, head, g, sm.stage[warp]);  // cg.py:75
-    double pap = 0.0;
+    const double ap = pipe.tile_spmv(d, rs, re, GatherZBetaP{z, po, sc.v}, true);  // cg.py:75
+    double pap[1] = {0.0};
     if (valid) {
         const double pi = __dadd_rn(zr, __dmul_rn(sc.v, pr));  // cg.py:83
         pn[row] = pi;
         S.ap[row] = ap;
-        pap = __dmul_rn(ap, pi);
+        pap[0] = __dmul_rn(ap, pi);
         if (S.precond == DP_PRECOND_SOLVE) st_relaxed_u64(S.z[(k + 1) & 1] + row, kPending);  // re-arm next z
     }
-    pap = block_sum(pap, sm.scratch);
-    if (threadIdx.x == 0) S.part_pap[tile] = pap;
+    tile_reduce<1>(pap, sm.scratch, pipe);
+    if (threadIdx.x == 0) S.part_pap[tile] = pap[0];
 }
 
 // ---- PH_APPLY1 ----------------------------------------------------------------------------------------------
 template <bool kInit>
-__device__ __forceinline__ void phase_apply1(const Ctx& ctx, const SysDev& S, int s, int tile, int k, Smem& sm, Scal& sc) {
-    const int warp = threadIdx.x >> 5;
-    const int base = tile * kTileRows + warp * kWarp;
+__device__ __forceinline__ void phase_apply1(const Ctx& ctx, const SysDev& S, const TileDesc& d, int rs, int re, int k,
+                                             Smem& sm, Scal& sc, Pipe& pipe) {
+    const int s = d.sys, tile = d.ltile;
     const int row = tile * kTileRows + threadIdx.x;
     const bool valid = row < S.n;
     const double* ro = S.r[k & 1];
@@ -246,17 +254,17 @@ __device__ __forceinline__ void phase_apply1(const Ctx& ctx, const SysDev& S, in
         if (!kInit) ap_i = S.ap[row], x_i = S.x[row], p_i = pn[row];
         if (precond == DP_PRECOND_JACOBI) dinv_i = __ldg(S.dinv + row);
     }
-    ChunkHead head{0, 0, 0, 0};
-    if (precond == DP_PRECOND_CSR) head = spmv_head(S.M, base);
-    if (precond == DP_PRECOND_MULTIPLY) head = spmv_head(S.Mt, base);
     if (sc.sys != s) {
         sc.sys = s;
         sc.active = kInit || ld_relaxed_s32(ctx.state + s) == 0;  // written before the previous barrier: uniform
         sc.v = 0.0;
         if (!kInit && sc.active)
-            sc.v = __ldcg(S.scal + (k & 1)) / block_reduce_array(S.part_pap, S.ntiles, sm.scratch);  // a, cg.py:78
+            sc.v = __ldcg(S.scal + (k & 1)) / block_reduce_array(S.part_pap, S.ntiles, sm.scratch2);  // a, cg.py:78
     }
-    if (!sc.active) return;
+    if (!sc.active) {
+        pipe.tile_skip(d);
+        return;
+    }
     const double a = sc.v;
 
     double rn = 0.0;
@@ -274,13 +282,13 @@ __device__ __forceinline__ void phase_apply1(const Ctx& ctx, const SysDev& S, in
         case DP_PRECOND_JACOBI:
             zi = __dmul_rn(dinv_i, rn);
             break;
-        case DP_PRECOND_CSR:
-            zi = kInit ? pcg_spmv_body(S.M, head, GatherPlain{ro}, sm.stage[warp])
-                       : pcg_spmv_body(S.M, head, GatherRMinusAAp{ro, S.ap, a}, sm.stage[warp]);
+        case DP_PRECOND_CSR:  // table P1 streams M
+            zi = kInit ? pipe.tile_spmv(d, rs, re, GatherPlain{ro}, true)
+                       : pipe.tile_spmv(d, rs, re, GatherRMinusAAp{ro, S.ap, a}, true);
             break;
-        case DP_PRECOND_MULTIPLY: {
-            const double ti = kInit ? pcg_spmv_body(S.Mt, head, GatherPlain{ro}, sm.stage[warp])
-                                    : pcg_spmv_body(S.Mt, head, GatherRMinusAAp{ro, S.ap, a}, sm.stage[warp]);
+        case DP_PRECOND_MULTIPLY: {  // table P1 streams L^T
+            const double ti = kInit ? pipe.tile_spmv(d, rs, re, GatherPlain{ro}, true)
+                                    : pipe.tile_spmv(d, rs, re, GatherRMinusAAp{ro, S.ap, a}, true);
             if (valid) S.t[row] = ti;
             have_z = false;
             break;
@@ -292,7 +300,7 @@ __device__ __forceinline__ void phase_apply1(const Ctx& ctx, const SysDev& S, in
     if (have_z && valid) zn[row] = zi;
     // partial dot products of this tile: <r,r> (cg.py:86), <r,z> (cg.py:76,82), and <z,z> for iteration 0 (cg.py:66)
     double v[3] = {__dmul_rn(rn, rn), __dmul_rn(rn, zi), __dmul_rn(zi, zi)};
-    block_sum_n<3>(v, sm.scratch);
+    tile_reduce<3>(v, sm.scratch, pipe);
     if (threadIdx.x == 0) {
         if (!kInit) S.part_rr[tile] = v[0];
         if (have_z) {
@@ -301,27 +309,31 @@ __device__ __forceinline__ void phase_apply1(const Ctx& ctx, const SysDev& S, in
         }
     }
     if (kInit && tile == 0) {  // publish <b,b> once (all part_bb were written before the previous barrier)
-        const double bb = block_reduce_array(S.part_bb, S.ntiles, sm.scratch);
+        const double bb = block_reduce_array(S.part_bb, S.ntiles, sm.scratch2);
         if (threadIdx.x == 0) S.scal[2] = bb;
     }
 }
 
 // ---- PH_APPLY2 (MULTIPLY): z = L t ---------------------------------------------------------------------------
 template <bool kInit>
-__device__ __forceinline__ void phase_apply2(const Ctx& ctx, const SysDev& S, int s, int tile, int k, Smem& sm, Scal& sc) {
+__device__ __forceinline__ void phase_apply2(const Ctx& ctx, const SysDev& S, const TileDesc& d, int rs, int re, int k,
+                                             Smem& sm, Scal& sc, Pipe& pipe) {
+    const int s = d.sys, tile = d.ltile;
     if (sc.sys != s) {
         sc.sys = s;
         sc.active = S.precond == DP_PRECOND_MULTIPLY && (kInit || ld_relaxed_s32(ctx.state + s) == 0);
     }
-    if (!sc.active) return;
-    const int warp = threadIdx.x >> 5;
+    if (!sc.active) {
+        pipe.tile_skip(d);
+        return;
+    }
     const int row = tile * kTileRows + threadIdx.x;
     double rn = 0.0;
     if (row < S.n) rn = S.r[(k + 1) & 1][row];
-    const double zi = pcg_spmv_body(S.M, spmv_head(S.M, tile * kTileRows + warp * kWarp), GatherPlain{S.t}, sm.stage[warp]);
+    const double zi = pipe.tile_spmv(d, rs, re, GatherPlain{S.t}, true);
     if (row < S.n) S.z[(k + 1) & 1][row] = zi;
     double v[2] = {__dmul_rn(rn, zi), __dmul_rn(zi, zi)};
-    block_sum_n<2>(v, sm.scratch);
+    tile_reduce<2>(v, sm.scratch, pipe);
     if (threadIdx.x == 0) {
         S.part_rz[(k + 1) & 1][tile] = v[0];
         if (kInit) S.part_rr[tile] = v[1];
@@ -330,7 +342,9 @@ __device__ __forceinline__ void phase_apply2(const Ctx& ctx, const SysDev& S, in
 
 // ---- PH_DOTRZ (SOLVE): <r,z> after the backward solve -----------------------------------------------------------
 template <bool kInit>
-__device__ __forceinline__ void phase_dotrz(const Ctx& ctx, const SysDev& S, int s, int tile, int k, Smem& sm, Scal& sc) {
+__device__ __forceinline__ void phase_dotrz(const Ctx& ctx, const SysDev& S, const TileDesc& d, int k, Smem& sm, Scal& sc,
+                                            Pipe& pipe) {
+    const int s = d.sys, tile = d.ltile;
     if (sc.sys != s) {
         sc.sys = s;
         sc.active = S.precond == DP_PRECOND_SOLVE && (kInit || ld_relaxed_s32(ctx.state + s) == 0);
@@ -343,7 +357,7 @@ __device__ __forceinline__ void phase_dotrz(const Ctx& ctx, const SysDev& S, int
         zi = S.z[(k + 1) & 1][row];
     }
     double v[2] = {__dmul_rn(rn, zi), __dmul_rn(zi, zi)};
-    block_sum_n<2>(v, sm.scratch);
+    tile_reduce<2>(v, sm.scratch, pipe);
     if (threadIdx.x == 0) {
         S.part_rz[(k + 1) & 1][tile] = v[0];
         if (kInit) S.part_rr[tile] = v[1];
@@ -381,47 +395,77 @@ __device__ __forceinline__ bool phase_trsv(const Ctx& ctx, int k, const Smem& sm
     return true;
 }
 
-// ---- tile schedules --------------------------------------------------------------------------------------------
+// ---- tile schedule ---------------------------------------------------------------------------------------------
 template <int kPhase, bool kInit, bool kCheckState>
-__device__ __forceinline__ void run_tile(const Ctx& ctx, const SysDev& S, int s, int tile, int k, Smem& sm, Scal& sc) {
-    if (kPhase == PH_INIT) phase_init(ctx, S, s, tile, sm);
-    if (kPhase == PH_A) phase_a<kCheckState>(ctx, S, s, tile, k, sm, sc);
-    if (kPhase == PH_APPLY1) phase_apply1<kInit>(ctx, S, s, tile, k, sm, sc);
-    if (kPhase == PH_APPLY2) phase_apply2<kInit>(ctx, S, s, tile, k, sm, sc);
-    if (kPhase == PH_DOTRZ) phase_dotrz<kInit>(ctx, S, s, tile, k, sm, sc);
+__device__ __forceinline__ void run_tile(const Ctx& ctx, const SysDev& S, const TileDesc& d, int rs, int re, int k,
+                                         Smem& sm, Scal& sc, Pipe& pipe) {
+    if (kPhase == PH_INIT) phase_init(ctx, S, d, rs, re, sm, pipe);
+    if (kPhase == PH_A) phase_a<kCheckState>(ctx, S, d, rs, re, k, sm, sc, pipe);
+    if (kPhase == PH_APPLY1) phase_apply1<kInit>(ctx, S, d, rs, re, k, sm, sc, pipe);
+    if (kPhase == PH_APPLY2) phase_apply2<kInit>(ctx, S, d, rs, re, k, sm, sc, pipe);
+    if (kPhase == PH_DOTRZ) phase_dotrz<kInit>(ctx, S, d, k, sm, sc, pipe);
 }
 
-// Static schedule: every system, tiles dealt round robin (stepped engine).
-template <int kPhase, bool kInit>
-__device__ __forceinline__ void run_tiles_static(const Ctx& ctx, int k, Smem& sm) {
-    Scal sc;
-    for (int g = blockIdx.x; g < ctx.total_tiles; g += gridDim.x) {
-        const int s = ctx.nsys == 1 ? 0 : find_segment(ctx.tile_ofs, ctx.nsys, g);
-        const SysDev& S = load_sys(ctx, s, sm);
-        run_tile<kPhase, kInit, true>(ctx, S, s, ctx.nsys == 1 ? g : g - __ldg(ctx.tile_ofs + s), k, sm, sc);
+// Describe tiles [ga, gb) of list `cur` for table kTab: which system / local tile, and what the phase streams.
+template <int kTab>
+__device__ __forceinline__ void build_table(const Ctx& ctx, int cur, int ga, int gb, Smem& sm) {
+    const int count = __ldcg(ctx.act_meta + 2 * cur);
+    const int* asys = ctx.act_sys[cur];
+    const int* aofs = ctx.act_ofs[cur];
+    for (int i = threadIdx.x; i < gb - ga; i += kBlock) {
+        const int g = ga + i;
+        const int seg = count == 1 ? 0 : find_segment(aofs, count, g);
+        const int s = __ldcg(asys + seg);
+        const int lt = g - __ldcg(aofs + seg);
+        const SysDev* S = ctx.sys + s;
+        const int precond = S->precond;
+        CsrView M{nullptr, nullptr, nullptr, 0, 0};
+        if (kTab == TAB_A) M = S->A;
+        if (kTab == TAB_P1 && precond == DP_PRECOND_MULTIPLY) M = S->Mt;
+        if (kTab == TAB_P1 && precond == DP_PRECOND_CSR) M = S->M;
+        if (kTab == TAB_P2 && precond == DP_PRECOND_MULTIPLY) M = S->M;
+        TileDesc d;
+        tile_desc_fill(d, M, lt);
+        d.sys = s;
+        sm.tab[kTab][i] = d;
     }
 }
 
-// Active schedule: the tiles of the unfinished systems, one contiguous range per CTA (fused engine).
-template <int kPhase, bool kInit>
-__device__ __forceinline__ void run_tiles_active(const Ctx& ctx, int k, int cur, Smem& sm) {
-    const int count = __ldcg(ctx.act_meta + 2 * cur), total = __ldcg(ctx.act_meta + 2 * cur + 1);
+template <int kTab>
+__device__ __forceinline__ void ensure_table(const Ctx& ctx, int cur, int ver, int ga, int gb, Smem& sm) {
+    if (sm.tab_ver[kTab] == ver && sm.tab_ga[kTab] == ga && sm.tab_gb[kTab] == gb) return;  // CTA-uniform
+    __syncthreads();  // every thread has compared the keys / left the old table
+    build_table<kTab>(ctx, cur, ga, gb, sm);
+    if (threadIdx.x == 0) sm.tab_ver[kTab] = ver, sm.tab_ga[kTab] = ga, sm.tab_gb[kTab] = gb;
+    __syncthreads();
+}
+
+// The tiles of the systems in list `cur`, one contiguous range per CTA, streamed through the tile pipeline.
+// fused engine: `cur` = the active list (unfinished systems); stepped engine: list 0 = all systems, kCheckState.
+template <int kPhase, bool kInit, bool kCheckState>
+__device__ __forceinline__ void run_tiles(const Ctx& ctx, int k, int cur, int ver, Smem& sm, Pipe& pipe) {
+    constexpr int kTab = kPhase == PH_APPLY1 ? TAB_P1 : kPhase == PH_APPLY2 ? TAB_P2 : TAB_A;
+    constexpr bool kStream = kPhase != PH_DOTRZ;
+    const int total = __ldcg(ctx.act_meta + 2 * cur + 1);
     const int per = (total + (int)gridDim.x - 1) / (int)gridDim.x;
     const int g0 = blockIdx.x * per, g1 = min(total, g0 + per);
-    const int* asys = ctx.act_sys[cur];
-    const int* aofs = ctx.act_ofs[cur];
     Scal sc;
-    int s = 0, seg_begin = 0, seg_end = -1;
-    const SysDev* S = nullptr;
-    for (int g = g0; g < g1; ++g) {
-        if (g >= seg_end) {
-            const int i = count == 1 ? 0 : find_segment(aofs, count, g);
-            s = __ldcg(asys + i);
-            seg_begin = __ldcg(aofs + i);
-            seg_end = __ldcg(aofs + i + 1);
-            S = &load_sys(ctx, s, sm);
+    for (int ga = g0; ga < g1; ga += kMaxRoundTiles) {
+        const int gb = min(g1, ga + kMaxRoundTiles);
+        ensure_table<kTab>(ctx, cur, ver, ga, gb, sm);
+        const TileDesc* tab = sm.tab[kTab];
+        int rs_n = 0, re_n = 0;
+        if (kStream) {
+            pipe.begin(tab, gb - ga);
+            tile_row_extent(tab[0], rs_n, re_n);
         }
-        run_tile<kPhase, kInit, false>(ctx, *S, s, g - seg_begin, k, sm, sc);
+        for (int i = 0; i < gb - ga; ++i) {
+            const TileDesc& d = tab[i];
+            const SysDev& S = load_sys(ctx, d.sys, sm);
+            const int rs = rs_n, re = re_n;
+            if (kStream && i + 1 < gb - ga) tile_row_extent(tab[i + 1], rs_n, re_n);  // one tile ahead
+            run_tile<kPhase, kInit, kCheckState>(ctx, S, d, rs, re, k, sm, sc, pipe);
+        }
     }
 }
 
@@ -460,13 +504,14 @@ __device__ __forceinline__ void rebuild_active(const Ctx& ctx, int cur, Smem& sm
 
 // Returns false on abort. `done` = finished count of the last barrier.
 template <bool kInit>
-__device__ __forceinline__ bool apply_preconditioner(const Ctx& ctx, int k, int cur, GridBarrier& bar, Smem& sm) {
-    run_tiles_active<PH_APPLY1, kInit>(ctx, k, cur, sm);
+__device__ __forceinline__ bool apply_preconditioner(const Ctx& ctx, int k, int cur, int ver, GridBarrier& bar, Smem& sm,
+                                                     Pipe& pipe) {
+    run_tiles<PH_APPLY1, kInit, false>(ctx, k, cur, ver, sm, pipe);
     trace(ctx, sm, 8 * PH_APPLY1 + 1);
     if (bar.sync() < 0) return false;
     trace(ctx, sm, 8 * PH_APPLY1 + 2);
     if (ctx.has_multiply) {
-        run_tiles_active<PH_APPLY2, kInit>(ctx, k, cur, sm);
+        run_tiles<PH_APPLY2, kInit, false>(ctx, k, cur, ver, sm, pipe);
         trace(ctx, sm, 8 * PH_APPLY2 + 1);
         if (bar.sync() < 0) return false;
         trace(ctx, sm, 8 * PH_APPLY2 + 2);
@@ -476,26 +521,37 @@ __device__ __forceinline__ bool apply_preconditioner(const Ctx& ctx, int k, int 
         if (bar.sync() < 0 || !f) return false;
         const bool b = phase_trsv<true, kInit>(ctx, k, sm);
         if (bar.sync() < 0 || !b) return false;
-        run_tiles_active<PH_DOTRZ, kInit>(ctx, k, cur, sm);
+        run_tiles<PH_DOTRZ, kInit, false>(ctx, k, cur, ver, sm, pipe);
         if (bar.sync() < 0) return false;
     }
     return true;
 }
 
+__device__ __forceinline__ Smem& smem_init(unsigned char* raw, Pipe& pipe) {
+    Smem& sm = *reinterpret_cast<Smem*>(raw);
+    if (threadIdx.x == 0) {
+        sm.sys_id = -1, sm.trace_pos = 0;
+        sm.tab_ver[0] = sm.tab_ver[1] = sm.tab_ver[2] = 0;
+    }
+    pipe.init(&sm.pipe);  // ends with a CTA barrier
+    return sm;
+}
+
 // The whole solve in one persistent cooperative launch: device-side loop control, no host round trips.
 __global__ void __launch_bounds__(kBlock, 2) pcg_fused_kernel(Ctx ctx) {
-    __shared__ __align__(16) Smem sm;
-    if (threadIdx.x == 0) sm.sys_id = -1, sm.trace_pos = 0;
-    __syncthreads();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Pipe pipe;
+    Smem& sm = smem_init(smem_raw, pipe);
     GridBarrier bar{ctx.word, ctx.flag, &sm.bcast, 0u, gridDim.x};
     int cur = 0;          // active-list buffer in use
+    int ver = 1;          // bumped whenever the list (hence every CTA's tile range) changes
     int done_built = 0;   // finished count the list `cur` reflects
-    run_tiles_active<PH_INIT, false>(ctx, -1, cur, sm);
+    run_tiles<PH_INIT, false, false>(ctx, -1, cur, ver, sm, pipe);
     if (bar.sync() < 0) return;
-    if (!apply_preconditioner<true>(ctx, -1, cur, bar, sm)) return;
+    if (!apply_preconditioner<true>(ctx, -1, cur, ver, bar, sm, pipe)) return;
     for (int k = 0; k <= ctx.max_iter; ++k) {
         trace(ctx, sm, 8 * PH_A + 0);
-        run_tiles_active<PH_A, false>(ctx, k, cur, sm);
+        run_tiles<PH_A, false, false>(ctx, k, cur, ver, sm, pipe);
         trace(ctx, sm, 8 * PH_A + 1);
         const int done = bar.sync();
         trace(ctx, sm, 8 * PH_A + 2);
@@ -503,23 +559,24 @@ __global__ void __launch_bounds__(kBlock, 2) pcg_fused_kernel(Ctx ctx) {
         if (done >= ctx.nsys) break;
         const bool rebuild = done != done_built;  // same decision in every CTA
         if (rebuild && blockIdx.x == 0) rebuild_active(ctx, cur, sm);
-        if (!apply_preconditioner<false>(ctx, k, cur, bar, sm)) return;  // >= 1 barrier: the new list is visible
-        if (rebuild) cur ^= 1, done_built = done;
+        if (!apply_preconditioner<false>(ctx, k, cur, ver, bar, sm, pipe)) return;  // >= 1 barrier: the new list is visible
+        if (rebuild) cur ^= 1, done_built = done, ++ver;
     }
 }
 
-// Stepped engine: the same phases, one launch each (the launch boundary is the barrier).
+// Stepped engine: the same phases, one launch each (the launch boundary is the barrier), over the static list of
+// all systems (list 0 as uploaded by the host); finished systems are skipped by their state flag.
 template <int kPhase, bool kInit>
 __global__ void __launch_bounds__(kBlock, 2) pcg_phase_kernel(Ctx ctx, int k) {
-    __shared__ __align__(16) Smem sm;
-    if (threadIdx.x == 0) sm.sys_id = -1, sm.trace_pos = 0;
-    __syncthreads();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Pipe pipe;
+    Smem& sm = smem_init(smem_raw, pipe);
     if (kPhase == PH_FWD) {
         phase_trsv<false, kInit>(ctx, k, sm);
     } else if (kPhase == PH_BWD) {
         phase_trsv<true, kInit>(ctx, k, sm);
     } else {
-        run_tiles_static<kPhase, kInit>(ctx, k, sm);
+        run_tiles<kPhase, kInit, true>(ctx, k, 0, 1, sm, pipe);
     }
 }
 
@@ -550,14 +607,29 @@ static WsLayout ws_layout(int nsys) {
     return w;
 }
 
+// Every PCG kernel carries the tile pipeline's stages in dynamic shared memory (> 48 KB: opt in once per kernel).
+template <class Kernel>
+static int allow_smem(Kernel kernel) {
+    static thread_local const void* done[16];
+    static thread_local int ndone = 0;
+    for (int i = 0; i < ndone; ++i)
+        if (done[i] == (const void*)kernel) return DP_OK;
+    DP_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+    if (ndone < 16) done[ndone++] = (const void*)kernel;
+    return DP_OK;
+}
+
 template <int kPhase, bool kInit>
 static int launch_phase(const Ctx& ctx, int k, int grid, bool cooperative, cudaStream_t s) {
+    int st = allow_smem(pcg_phase_kernel<kPhase, kInit>);
+    if (st != DP_OK) return st;
     if (cooperative) {
         Ctx c = ctx;
         void* args[] = {&c, &k};
-        DP_CUDA(cudaLaunchCooperativeKernel((const void*)pcg_phase_kernel<kPhase, kInit>, dim3(grid), dim3(kBlock), args, 0, s));
+        DP_CUDA(cudaLaunchCooperativeKernel((const void*)pcg_phase_kernel<kPhase, kInit>, dim3(grid), dim3(kBlock), args,
+                                            sizeof(Smem), s));
     } else {
-        pcg_phase_kernel<kPhase, kInit><<<grid, kBlock, 0, s>>>(ctx, k);
+        pcg_phase_kernel<kPhase, kInit><<<grid, kBlock, sizeof(Smem), s>>>(ctx, k);
         DP_LAUNCH_CHECK();
     }
     return DP_OK;
@@ -596,7 +668,10 @@ int dp_device_info(int* sm_count_host, int* pcg_ctas_per_sm_host, int* l2_bytes_
     DP_CUDA(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev));
     if (sm_count_host) *sm_count_host = sms;
     if (l2_bytes_host) *l2_bytes_host = l2;
-    if (pcg_ctas_per_sm_host) *pcg_ctas_per_sm_host = coop_grid((const void*)pcg_fused_kernel, kBlock, 0) / (sms > 0 ? sms : 1);
+    if (pcg_ctas_per_sm_host) {
+        if (allow_smem(pcg_fused_kernel) != DP_OK) return DP_ERR_CUDA;
+        *pcg_ctas_per_sm_host = coop_grid((const void*)pcg_fused_kernel, kBlock, sizeof(Smem)) / (sms > 0 ? sms : 1);
+    }
     return DP_OK;
 }
 
@@ -686,8 +761,9 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
         bwd_ofs[(size_t)i + 1] = bwd_ofs[(size_t)i] + bwd_chunks;
     }
 
-    const int coop = coop_grid((const void*)pcg_fused_kernel, kBlock, 0);
-    const int coop_phase = coop_grid((const void*)pcg_phase_kernel<PH_FWD, false>, kBlock, 0);
+    if (allow_smem(pcg_fused_kernel) != DP_OK || allow_smem(pcg_phase_kernel<PH_FWD, false>) != DP_OK) return DP_ERR_CUDA;
+    const int coop = coop_grid((const void*)pcg_fused_kernel, kBlock, sizeof(Smem));
+    const int coop_phase = coop_grid((const void*)pcg_phase_kernel<PH_FWD, false>, kBlock, sizeof(Smem));
     auto clamp_pw = [](long long lvl_chunks, int grid) {
         long long pw = 4 * lvl_chunks;
         if (pw < 32) pw = 32;
@@ -734,9 +810,6 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
     DP_CUDA(cudaMemcpyAsync(ws + lay.act_sys[0], ident.data(), ints, cudaMemcpyHostToDevice, s));
     DP_CUDA(cudaMemcpyAsync(ws + lay.act_ofs[0], tile_ofs.data(), ints, cudaMemcpyHostToDevice, s));
 
-    if (const char* cv = getenv("DPCG_CARVEOUT")) {  // experiment knob: shared-memory carveout in percent
-        DP_CUDA(cudaFuncSetAttribute((const void*)pcg_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
-    }
     if (params_host->engine == DP_ENGINE_FUSED) {
         // right-size the grid: a CTA per tile is enough for the tile phases; the SpTRSV phases spread their
         // participating warps one per CTA first. Fewer CTAs = cheaper grid barrier for small systems.
@@ -750,7 +823,7 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
         ctx.pw_fwd = clamp_pw(sum_fwd_lvl, grid);
         ctx.pw_bwd = clamp_pw(sum_bwd_lvl, grid);
         void* args[] = {&ctx};
-        DP_CUDA(cudaLaunchCooperativeKernel((const void*)pcg_fused_kernel, dim3(grid), dim3(kBlock), args, 0, s));
+        DP_CUDA(cudaLaunchCooperativeKernel((const void*)pcg_fused_kernel, dim3(grid), dim3(kBlock), args, sizeof(Smem), s));
         return DP_OK;
     }
     if (params_host->engine != DP_ENGINE_STEPPED) return DP_ERR_INVALID;

@@ -2,7 +2,7 @@
 #include <stdio.h>
 #include <string.h>
 
-#include "spmv.cuh"
+#include "tilepipe.cuh"
 
 namespace dp {
 
@@ -13,17 +13,45 @@ const char* set_cuda_error(cudaError_t e) {
     return g_cuda_error;
 }
 
-// One warp per 32-row chunk, grid-stride over chunks. 2 CTAs of 512 threads per SM.
+// Persistent CTAs, one contiguous range of 512-row tiles each, streamed through the tile pipeline (tilepipe.cuh).
+constexpr int kSpmvRound = 32;  // tile descriptors per table refill
+
+struct SpmvSmem {
+    PipeShared pipe;
+    TileDesc tab[kSpmvRound];
+};
+
 __global__ void __launch_bounds__(kBlock, 2)
 spmv_csr_kernel(CsrView A, const double* __restrict__ x, double* __restrict__ y) {
-    __shared__ __align__(16) double stage[kWarpsPerBlock][kStageCap];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nchunks = (A.n + kWarp - 1) / kWarp;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SpmvSmem& sm = *reinterpret_cast<SpmvSmem*>(smem_raw);
+    Pipe pipe;
+    pipe.init(&sm.pipe);
+    const int ntiles = (A.n + kTileRows - 1) / kTileRows;
+    const int per = (ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int g0 = blockIdx.x * per, g1 = min(ntiles, g0 + per);
     const GatherReadOnly gx{x};
-    for (int chunk = blockIdx.x * kWarpsPerBlock + warp; chunk < nchunks; chunk += gridDim.x * kWarpsPerBlock) {
-        const int base = chunk * kWarp;
-        const double s = spmv_chunk(A, base, gx, stage[warp]);
-        if (base + lane < A.n) y[base + lane] = s;
+    for (int ga = g0; ga < g1; ga += kSpmvRound) {
+        const int cnt = min(kSpmvRound, g1 - ga);
+        __syncthreads();  // the previous round's table is no longer read
+        for (int i = threadIdx.x; i < cnt; i += kBlock) {
+            TileDesc d;
+            tile_desc_fill(d, A, ga + i);
+            d.sys = 0;
+            sm.tab[i] = d;
+        }
+        __syncthreads();
+        pipe.begin(sm.tab, cnt);
+        int rs_n, re_n;
+        tile_row_extent(sm.tab[0], rs_n, re_n);
+        for (int i = 0; i < cnt; ++i) {
+            const TileDesc& d = sm.tab[i];
+            const int rs = rs_n, re = re_n;
+            if (i + 1 < cnt) tile_row_extent(sm.tab[i + 1], rs_n, re_n);  // one tile ahead
+            const double s = pipe.tile_spmv(d, rs, re, gx, true);
+            const int row = d.ltile * kTileRows + (int)threadIdx.x;
+            if (row < A.n) y[row] = s;
+        }
     }
 }
 
@@ -78,11 +106,17 @@ int dp_spmv_csr_f64(int32_t n, int32_t nnz, const int32_t* rowptr, const int32_t
     if (n < 0 || nnz < 0 || !rowptr || !y || (nnz > 0 && (!col || !val || !x))) return DP_ERR_INVALID;
     if (!aligned16(col) || !aligned16(val)) return DP_ERR_ALIGNMENT;
     if (n == 0) return DP_OK;
-    const int nchunks = (n + kWarp - 1) / kWarp;
-    const int tiles = (nchunks + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    const int grid = tiles < sm_count() * 2 * 8 ? tiles : sm_count() * 2 * 8;
+    static thread_local bool smem_ok = false;
+    if (!smem_ok) {
+        DP_CUDA(cudaFuncSetAttribute((const void*)spmv_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(SpmvSmem)));
+        smem_ok = true;
+    }
+    const int tiles = (n + kTileRows - 1) / kTileRows;
+    const int resident = 2 * sm_count();
+    const int grid = tiles < resident ? tiles : resident;
     CsrView A{rowptr, col, val, n, nnz};
-    spmv_csr_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>(A, x, y);
+    spmv_csr_kernel<<<grid, kBlock, sizeof(SpmvSmem), (cudaStream_t)stream>>>(A, x, y);
     DP_LAUNCH_CHECK();
     return DP_OK;
 }

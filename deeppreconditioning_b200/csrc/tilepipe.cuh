@@ -1,0 +1,278 @@
+// tilepipe.cuh — the CSR tile pipeline (K2 primitive): TMA-staged, lane-per-row SpMV over 512-row tiles.
+//
+// Replaces `A @ p` / `M @ r` (cg.py:60,61,75,81) for the standalone SpMV and for every SpMV-shaped PCG phase.
+//
+// A tile = 512 consecutive rows of one CSR matrix = ONE contiguous span of col[]/val[]. The span is cut into blocks
+// of at most kPipeCap entries; each block is an ITEM of the pipeline: lane 0 of warp 0 arms the stage's `full`
+// mbarrier with the byte count and issues two bulk async copies (cp.async.bulk, SASS UBLKCP: the TMA engine streams
+// col[] and val[] into a shared-memory stage), up to kPipeStages items ahead, so the HBM stream never waits for the
+// arithmetic. Every warp passes through every item on its own: wait on `full`, walk the part of ITS 32 rows that
+// lies in the block, arrive on the stage's `empty` mbarrier (16 arrivals re-arm the stage). Warps are not coupled by
+// CTA barriers while streaming, so different warps work on different blocks of a tile at the same time.
+// Inside a stage every lane walks its own row:
+//     sum = sum + val[q] * x[col[q]]        q ascending, product and sum rounded separately (no FMA)
+// which is bit-identical to the sequential CPU loop (scipy csr_matvec / oracle_spmv_csr). Reading the stage at a
+// stride of one row length is bank-conflict free for odd row lengths (5/7-point stencils, the CNN's 15/row), and -
+// what matters most - the 32 gather addresses of one load instruction are 32 CONSECUTIVE rows' k-th neighbours, i.e.
+// 2-3 cache lines for stencil-like matrices instead of ~10 for an entry-major sweep: the kernel stays HBM-bound
+// instead of L1-wavefront-bound. No product staging, no shared-memory stores at all.
+//
+// Bulk copies need 16-byte aligned addresses and sizes: a block's copy starts at the 16-byte boundary at or below its
+// first entry and ends at the one at or above its last. The few bytes read beyond the matrix's last entry stay inside
+// the 16-byte unit that holds that entry (arrays are 16-byte aligned, dpcg.h), so they can never touch another page.
+#pragma once
+
+#include "common.cuh"
+#include "spmv.cuh"
+
+#ifndef DPCG_PIPE_CAP
+#define DPCG_PIPE_CAP 3840
+#endif
+#ifndef DPCG_PIPE_STAGES
+#define DPCG_PIPE_STAGES 2
+#endif
+#ifndef DPCG_PIPE_UNROLL
+#define DPCG_PIPE_UNROLL 4
+#endif
+
+namespace dp {
+
+constexpr int kPipeCap = DPCG_PIPE_CAP;        // entries per stage (multiple of 4)
+constexpr int kPipeStages = DPCG_PIPE_STAGES;
+constexpr int kPipeSlots = kPipeCap + 8;       // up to 3 lead-in entries (16-byte alignment) + tail rounding
+constexpr int kPipeUnroll = DPCG_PIPE_UNROLL;  // gathers in flight per thread
+static_assert(kPipeCap % 4 == 0 && kPipeCap >= 64, "stage capacity");
+
+// ---- PTX wrappers (sm_90+/sm_100a) ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool mbar_test_wait(unsigned long long* bar, unsigned parity) {  // never suspends
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on `bar`. 16-byte aligned addresses and size.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- descriptors ------------------------------------------------------------------------------------------------
+struct TileDesc {
+    const int* rowptr;  // nullptr: this tile streams nothing in this phase
+    const int* col;
+    const double* val;
+    int n, nnz;  // rows / stored entries of the matrix
+    int cs, ce;  // entries of the tile
+    int ltile;   // tile index inside its matrix
+    int sys;     // system id (PCG), unused by the standalone kernel
+};
+
+struct PipeShared {
+    alignas(16) double val[kPipeStages][kPipeSlots];
+    alignas(16) int col[kPipeStages][kPipeSlots];
+    alignas(8) unsigned long long full[kPipeStages];   // producer -> consumers: bytes have landed
+    alignas(8) unsigned long long empty[kPipeStages];  // consumers -> producer: all 16 warps are done with the stage
+};
+
+__device__ __forceinline__ int tile_blocks(const TileDesc& d) { return (d.ce - d.cs + kPipeCap - 1) / kPipeCap; }
+
+// Fill the stream part of a descriptor for tile `ltile` of matrix M (one dependent load pair; CTA-parallel in the
+// table builders).
+__device__ __forceinline__ void tile_desc_fill(TileDesc& d, const CsrView& M, int ltile) {
+    d.rowptr = M.rowptr;
+    d.col = M.col;
+    d.val = M.val;
+    d.n = M.n;
+    d.nnz = M.nnz;
+    d.ltile = ltile;
+    if (M.rowptr) {
+        d.cs = __ldg(M.rowptr + min(ltile * kTileRows, M.n));
+        d.ce = __ldg(M.rowptr + min((ltile + 1) * kTileRows, M.n));
+    } else {
+        d.cs = d.ce = 0;
+    }
+}
+
+// Register state of the pipeline; lives for the whole kernel. Items are numbered since kernel start: item i lives in
+// stage i % kPipeStages and is the (i / kPipeStages)-th use of that stage, which fixes the mbarrier parities.
+struct Pipe {
+    PipeShared* sh;
+    const TileDesc* tab;
+    int ntiles;
+    unsigned c_count;   // items this warp has consumed
+    unsigned p_count;   // items issued (meaningful in lane 0 of warp 0 only, like the cursor below)
+    int p_tile, p_blk;  // next item of the round to issue
+    int flip;           // tile_reduce scratch buffer in use next
+
+    __device__ __forceinline__ void init(PipeShared* shared) {
+        sh = shared;
+        tab = nullptr;
+        ntiles = 0;
+        c_count = 0u, p_count = 0u, p_tile = 0, p_blk = 0, flip = 0;
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int s = 0; s < kPipeStages; ++s) {
+                mbar_init(&sh->full[s], 1u);
+                mbar_init(&sh->empty[s], (unsigned)kWarpsPerBlock);
+            }
+            mbar_fence_init();
+        }
+        __syncthreads();
+    }
+
+    // Lane 0 of warp 0: issue the next item of the round if its stage is free. `blocking`: wait for the stage
+    // (only legal when this warp has itself consumed the stage's previous item). Returns true if an item went out.
+    __device__ __forceinline__ bool issue_one(bool blocking) {
+        while (p_tile < ntiles) {
+            if (p_blk < tile_blocks(tab[p_tile])) break;
+            ++p_tile, p_blk = 0;
+        }
+        if (p_tile >= ntiles) return false;
+        if (p_count - c_count >= (unsigned)kPipeStages) return false;  // this warp still owns the stage's previous item
+        const unsigned stage = p_count % kPipeStages, use = p_count / kPipeStages;
+        if (use > 0) {
+            const unsigned par = (use - 1u) & 1u;
+            if (blocking) {
+                while (!mbar_try_wait(&sh->empty[stage], par)) {
+                }
+            } else if (!mbar_test_wait(&sh->empty[stage], par)) {
+                return false;
+            }
+        }
+        const TileDesc& d = tab[p_tile];
+        const int bs = d.cs + p_blk * kPipeCap;
+        const int be = min(d.ce, bs + kPipeCap);
+        const int as = bs & ~3;
+        const unsigned ncol = (unsigned)(((be + 3) & ~3) - as), nval = (unsigned)(((be + 1) & ~1) - as);
+        unsigned long long* bar = &sh->full[stage];
+        mbar_arrive_expect_tx(bar, ncol * 4u + nval * 8u);
+        bulk_g2s(sh->val[stage], d.val + as, nval * 8u, bar);
+        bulk_g2s(sh->col[stage], d.col + as, ncol * 4u, bar);
+        ++p_blk, ++p_count;
+        return true;
+    }
+
+    // All threads, after the table `t` (shared memory) is complete and visible. Every warp has consumed every item of
+    // the previous round (the caller's CTA barrier), so all stages are free.
+    __device__ __forceinline__ void begin(const TileDesc* t, int count) {
+        tab = t;
+        ntiles = count;
+        p_tile = 0, p_blk = 0;
+        if (threadIdx.x == 0) {
+            while (issue_one(true)) {
+            }
+        }
+    }
+
+    // Row sum of this thread's row (entries [rs, re) of the matrix, empty for rows >= n) of tile d.
+    // Every warp of the CTA must call it for every tile of the round, in order (`compute == false` only drains).
+    template <class Gather>
+    __device__ __forceinline__ double tile_spmv(const TileDesc& d, int rs, int re, const Gather& x, bool compute) {
+        double sum = 0.0;
+        const int nb = tile_blocks(d);
+        const int lane = threadIdx.x & 31;
+        for (int j = 0; j < nb; ++j) {
+            const int bs = d.cs + j * kPipeCap;
+            const int be = min(d.ce, bs + kPipeCap);
+            const int as = bs & ~3;
+            if (threadIdx.x == 0) {  // producer duty: the item about to be consumed must be out; then top up
+                while (p_count <= c_count) issue_one(true);
+                while (issue_one(false)) {
+                }
+            }
+            const unsigned stage = c_count % kPipeStages;
+            const unsigned par = (c_count / kPipeStages) & 1u;
+            while (!mbar_try_wait(&sh->full[stage], par)) {
+            }
+            if (compute) {
+                const double* __restrict__ sv = sh->val[stage];
+                const int* __restrict__ sc = sh->col[stage];
+                const int qe = min(re, be) - as;
+                for (int q = max(rs, bs) - as; q < qe; q += kPipeUnroll) {
+                    int c[kPipeUnroll];
+                    double v[kPipeUnroll], xv[kPipeUnroll];
+#pragma unroll
+                    for (int u = 0; u < kPipeUnroll; ++u) {
+                        const bool on = q + u < qe;
+                        c[u] = on ? sc[q + u] : 0;
+                        v[u] = on ? sv[q + u] : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < kPipeUnroll; ++u) xv[u] = (q + u < qe) ? x(c[u]) : 0.0;
+#pragma unroll
+                    for (int u = 0; u < kPipeUnroll; ++u)
+                        if (q + u < qe) sum = __dadd_rn(sum, __dmul_rn(v[u], xv[u]));
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh->empty[stage]);
+            ++c_count;
+        }
+        return sum;
+    }
+
+    // Drain the items of a tile whose result is not wanted (its system finished in this very iteration).
+    __device__ __forceinline__ void tile_skip(const TileDesc& d) { tile_spmv(d, 0, 0, GatherPlain{nullptr}, false); }
+};
+
+// Row extent of this thread's row in tile d (coalesced; issue one tile ahead to hide the latency).
+__device__ __forceinline__ void tile_row_extent(const TileDesc& d, int& rs, int& re) {
+    rs = re = 0;
+    if (d.rowptr) {
+        const int row = d.ltile * kTileRows + (int)threadIdx.x;
+        rs = __ldg(d.rowptr + min(row, d.n));
+        re = __ldg(d.rowptr + min(row + 1, d.n));
+    }
+}
+
+// CTA sum of kN <= 3 values per thread with ONE barrier: `scratch` is double buffered (pipe.flip alternates).
+// Per value bit-identical to block_sum (lane butterfly -> 16 warp sums -> 16-wide butterfly).
+constexpr int kReduceSlots = 3 * kWarpsPerBlock;
+
+template <int kN>
+__device__ __forceinline__ void tile_reduce(double (&v)[kN], double (*scratch2x)[kReduceSlots], Pipe& pipe) {
+    static_assert(kN <= 3, "scratch holds 3 values per warp");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* scratch = scratch2x[pipe.flip];
+    pipe.flip ^= 1;
+#pragma unroll
+    for (int i = 0; i < kN; ++i) v[i] = warp_sum(v[i]);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < kN; ++i) scratch[i * kWarpsPerBlock + warp] = v[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kN; ++i) v[i] = half_warp_sum(scratch[i * kWarpsPerBlock + (lane & (kWarpsPerBlock - 1))]);
+}
+
+}  // namespace dp
