@@ -85,12 +85,17 @@ struct Ctx {
 // survive across iterations (the range only changes when the active list is rebuilt), so the producer thread finds
 // the next item's addresses in shared memory instead of chasing rowptr through L2.
 constexpr int kMaxRoundTiles = 64;
+#ifndef DPCG_APPLY2_UNROLL
+#define DPCG_APPLY2_UNROLL kPipeUnroll
+#endif
+constexpr int kApply2Unroll = DPCG_APPLY2_UNROLL;  // single-gather phase: can afford more loads in flight
 enum Table { TAB_A = 0, TAB_P1 = 1, TAB_P2 = 2 };  // A | L^T (MULTIPLY) or M (CSR) | L (MULTIPLY)
 
 struct Smem {
     PipeShared pipe;
     TileDesc tab[3][kMaxRoundTiles];
     double scratch[2][3 * kWarpsPerBlock];  // tile_reduce (double buffered)
+    TileRed red;                            // tile_reduce_async (tiles that went through the pipeline)
     double scratch2[3 * kWarpsPerBlock];    // block_sum* of the per-system scalar evaluation
     SysDev sys;  // descriptor of the system this CTA is working on (survives across phases)
     int sys_id;
@@ -161,10 +166,14 @@ __device__ __forceinline__ void phase_init(const Ctx& ctx, const SysDev& S, cons
             st_relaxed_u64(S.t + row, kPending);
         }
     }
-    tile_reduce<1>(bb, sm.scratch, pipe);
-    if (threadIdx.x == 0) {
-        S.part_bb[tile] = bb[0];
-        if (tile == 0) ctx.state[d.sys] = 0;
+    if (threadIdx.x == 0 && tile == 0) ctx.state[d.sys] = 0;
+    double* part_bb = S.part_bb;
+    auto write = [part_bb, tile](const double (&v)[1]) { part_bb[tile] = v[0]; };
+    if (tile_blocks(d) > 0) {
+        tile_reduce_async<1>(bb, sm.red, pipe, write);
+    } else {
+        tile_reduce<1>(bb, sm.scratch, pipe);
+        if (threadIdx.x == 0) write(bb);
     }
 }
 
@@ -231,8 +240,14 @@ __device__ __forceinline__ void phase_a(const Ctx& ctx, const SysDev& S, const T
         pap[0] = __dmul_rn(ap, pi);
         if (S.precond == DP_PRECOND_SOLVE) st_relaxed_u64(S.z[(k + 1) & 1] + row, kPending);  // re-arm next z
     }
-    tile_reduce<1>(pap, sm.scratch, pipe);
-    if (threadIdx.x == 0) S.part_pap[tile] = pap[0];
+    double* part_pap = S.part_pap;
+    auto write = [part_pap, tile](const double (&v)[1]) { part_pap[tile] = v[0]; };
+    if (tile_blocks(d) > 0) {
+        tile_reduce_async<1>(pap, sm.red, pipe, write);
+    } else {
+        tile_reduce<1>(pap, sm.scratch, pipe);
+        if (threadIdx.x == 0) write(pap);
+    }
 }
 
 // ---- PH_APPLY1 ----------------------------------------------------------------------------------------------
@@ -300,13 +315,20 @@ __device__ __forceinline__ void phase_apply1(const Ctx& ctx, const SysDev& S, co
     if (have_z && valid) zn[row] = zi;
     // partial dot products of this tile: <r,r> (cg.py:86), <r,z> (cg.py:76,82), and <z,z> for iteration 0 (cg.py:66)
     double v[3] = {__dmul_rn(rn, rn), __dmul_rn(rn, zi), __dmul_rn(zi, zi)};
-    tile_reduce<3>(v, sm.scratch, pipe);
-    if (threadIdx.x == 0) {
-        if (!kInit) S.part_rr[tile] = v[0];
+    double* part_rr = S.part_rr;
+    double* part_rz = S.part_rz[(k + 1) & 1];
+    auto write = [part_rr, part_rz, tile, have_z](const double (&w)[3]) {
+        if (!kInit) part_rr[tile] = w[0];
         if (have_z) {
-            S.part_rz[(k + 1) & 1][tile] = v[1];
-            if (kInit) S.part_rr[tile] = v[2];
+            part_rz[tile] = w[1];
+            if (kInit) part_rr[tile] = w[2];
         }
+    };
+    if (tile_blocks(d) > 0) {
+        tile_reduce_async<3>(v, sm.red, pipe, write);
+    } else {
+        tile_reduce<3>(v, sm.scratch, pipe);
+        if (threadIdx.x == 0) write(v);
     }
     if (kInit && tile == 0) {  // publish <b,b> once (all part_bb were written before the previous barrier)
         const double bb = block_reduce_array(S.part_bb, S.ntiles, sm.scratch2);
@@ -330,13 +352,20 @@ __device__ __forceinline__ void phase_apply2(const Ctx& ctx, const SysDev& S, co
     const int row = tile * kTileRows + threadIdx.x;
     double rn = 0.0;
     if (row < S.n) rn = S.r[(k + 1) & 1][row];
-    const double zi = pipe.tile_spmv(d, rs, re, GatherPlain{S.t}, true);
+    const double zi = pipe.tile_spmv<kApply2Unroll>(d, rs, re, GatherPlain{S.t}, true);
     if (row < S.n) S.z[(k + 1) & 1][row] = zi;
     double v[2] = {__dmul_rn(rn, zi), __dmul_rn(zi, zi)};
-    tile_reduce<2>(v, sm.scratch, pipe);
-    if (threadIdx.x == 0) {
-        S.part_rz[(k + 1) & 1][tile] = v[0];
-        if (kInit) S.part_rr[tile] = v[1];
+    double* part_rr = S.part_rr;
+    double* part_rz = S.part_rz[(k + 1) & 1];
+    auto write = [part_rr, part_rz, tile](const double (&w)[2]) {
+        part_rz[tile] = w[0];
+        if (kInit) part_rr[tile] = w[1];
+    };
+    if (tile_blocks(d) > 0) {
+        tile_reduce_async<2>(v, sm.red, pipe, write);
+    } else {
+        tile_reduce<2>(v, sm.scratch, pipe);
+        if (threadIdx.x == 0) write(v);
     }
 }
 
@@ -532,6 +561,7 @@ __device__ __forceinline__ Smem& smem_init(unsigned char* raw, Pipe& pipe) {
     if (threadIdx.x == 0) {
         sm.sys_id = -1, sm.trace_pos = 0;
         sm.tab_ver[0] = sm.tab_ver[1] = sm.tab_ver[2] = 0;
+        for (int i = 0; i < kRedRing; ++i) sm.red.count[i] = 0;
     }
     pipe.init(&sm.pipe);  // ends with a CTA barrier
     return sm;

@@ -15,6 +15,9 @@ const char* set_cuda_error(cudaError_t e) {
 
 // Persistent CTAs, one contiguous range of 512-row tiles each, streamed through the tile pipeline (tilepipe.cuh).
 constexpr int kSpmvRound = 32;  // tile descriptors per table refill
+#ifndef DPCG_SPMV_UNROLL
+#define DPCG_SPMV_UNROLL 8
+#endif
 
 struct SpmvSmem {
     PipeShared pipe;
@@ -48,7 +51,7 @@ spmv_csr_kernel(CsrView A, const double* __restrict__ x, double* __restrict__ y)
             const TileDesc& d = sm.tab[i];
             const int rs = rs_n, re = re_n;
             if (i + 1 < cnt) tile_row_extent(sm.tab[i + 1], rs_n, re_n);  // one tile ahead
-            const double s = pipe.tile_spmv(d, rs, re, gx, true);
+            const double s = pipe.tile_spmv<DPCG_SPMV_UNROLL>(d, rs, re, gx, true);
             const int row = d.ltile * kTileRows + (int)threadIdx.x;
             if (row < A.n) y[row] = s;
         }

@@ -34,6 +34,9 @@
 #ifndef DPCG_PIPE_UNROLL
 #define DPCG_PIPE_UNROLL 4
 #endif
+#ifndef DPCG_PIPE_EVICT_FIRST
+#define DPCG_PIPE_EVICT_FIRST 1
+#endif
 
 namespace dp {
 
@@ -78,13 +81,28 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // 1-D bulk copy global -> shared, completion counted in bytes on `bar`. 16-byte aligned addresses and size.
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+// The matrix stream is read once per SpMV: mark its lines evict-first so that the vectors (gathered with L2
+// latency instead of DRAM latency when they survive) keep the cache.
+__device__ __forceinline__ unsigned long long l2_policy_stream() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar,
+                                         unsigned long long policy) {
+#if DPCG_PIPE_EVICT_FIRST
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+#else
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+#endif
 }
-
 // ---- descriptors ------------------------------------------------------------------------------------------------
 struct TileDesc {
     const int* rowptr;  // nullptr: this tile streams nothing in this phase
@@ -131,13 +149,14 @@ struct Pipe {
     unsigned c_count;   // items this warp has consumed
     unsigned p_count;   // items issued (meaningful in lane 0 of warp 0 only, like the cursor below)
     int p_tile, p_blk;  // next item of the round to issue
+    unsigned t_count;   // streaming tiles this warp has reduced (ring index of tile_reduce_async)
     int flip;           // tile_reduce scratch buffer in use next
 
     __device__ __forceinline__ void init(PipeShared* shared) {
         sh = shared;
         tab = nullptr;
         ntiles = 0;
-        c_count = 0u, p_count = 0u, p_tile = 0, p_blk = 0, flip = 0;
+        c_count = 0u, p_count = 0u, p_tile = 0, p_blk = 0, t_count = 0u, flip = 0;
         if (threadIdx.x == 0) {
 #pragma unroll
             for (int s = 0; s < kPipeStages; ++s) {
@@ -174,9 +193,10 @@ struct Pipe {
         const int as = bs & ~3;
         const unsigned ncol = (unsigned)(((be + 3) & ~3) - as), nval = (unsigned)(((be + 1) & ~1) - as);
         unsigned long long* bar = &sh->full[stage];
+        const unsigned long long pol = l2_policy_stream();
         mbar_arrive_expect_tx(bar, ncol * 4u + nval * 8u);
-        bulk_g2s(sh->val[stage], d.val + as, nval * 8u, bar);
-        bulk_g2s(sh->col[stage], d.col + as, ncol * 4u, bar);
+        bulk_g2s(sh->val[stage], d.val + as, nval * 8u, bar, pol);
+        bulk_g2s(sh->col[stage], d.col + as, ncol * 4u, bar, pol);
         ++p_blk, ++p_count;
         return true;
     }
@@ -195,7 +215,7 @@ struct Pipe {
 
     // Row sum of this thread's row (entries [rs, re) of the matrix, empty for rows >= n) of tile d.
     // Every warp of the CTA must call it for every tile of the round, in order (`compute == false` only drains).
-    template <class Gather>
+    template <int kUnroll = kPipeUnroll, class Gather>
     __device__ __forceinline__ double tile_spmv(const TileDesc& d, int rs, int re, const Gather& x, bool compute) {
         double sum = 0.0;
         const int nb = tile_blocks(d);
@@ -217,19 +237,19 @@ struct Pipe {
                 const double* __restrict__ sv = sh->val[stage];
                 const int* __restrict__ sc = sh->col[stage];
                 const int qe = min(re, be) - as;
-                for (int q = max(rs, bs) - as; q < qe; q += kPipeUnroll) {
-                    int c[kPipeUnroll];
-                    double v[kPipeUnroll], xv[kPipeUnroll];
+                for (int q = max(rs, bs) - as; q < qe; q += kUnroll) {
+                    int c[kUnroll];
+                    double v[kUnroll], xv[kUnroll];
 #pragma unroll
-                    for (int u = 0; u < kPipeUnroll; ++u) {
+                    for (int u = 0; u < kUnroll; ++u) {
                         const bool on = q + u < qe;
                         c[u] = on ? sc[q + u] : 0;
                         v[u] = on ? sv[q + u] : 0.0;
                     }
 #pragma unroll
-                    for (int u = 0; u < kPipeUnroll; ++u) xv[u] = (q + u < qe) ? x(c[u]) : 0.0;
+                    for (int u = 0; u < kUnroll; ++u) xv[u] = (q + u < qe) ? x(c[u]) : 0.0;
 #pragma unroll
-                    for (int u = 0; u < kPipeUnroll; ++u)
+                    for (int u = 0; u < kUnroll; ++u)
                         if (q + u < qe) sum = __dadd_rn(sum, __dmul_rn(v[u], xv[u]));
                 }
             }
@@ -241,7 +261,7 @@ struct Pipe {
     }
 
     // Drain the items of a tile whose result is not wanted (its system finished in this very iteration).
-    __device__ __forceinline__ void tile_skip(const TileDesc& d) { tile_spmv(d, 0, 0, GatherPlain{nullptr}, false); }
+    __device__ __forceinline__ void tile_skip(const TileDesc& d) { tile_spmv<1>(d, 0, 0, GatherPlain{nullptr}, false); }
 };
 
 // Row extent of this thread's row in tile d (coalesced; issue one tile ahead to hide the latency).
@@ -273,6 +293,46 @@ __device__ __forceinline__ void tile_reduce(double (&v)[kN], double (*scratch2x)
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < kN; ++i) v[i] = half_warp_sum(scratch[i * kWarpsPerBlock + (lane & (kWarpsPerBlock - 1))]);
+}
+
+
+// The same sum for a tile that went through the pipeline, WITHOUT a CTA barrier: every warp parks its warp sums in a
+// ring slot and bumps the slot's counter; the warp that arrives last folds the 16 warp sums (same fixed order, same
+// bits as tile_reduce) and hands them to `write` in its lane 0. Warps are at most kPipeStages streaming tiles apart
+// (a stage is re-armed only after all 16 warps passed it), so a ring of kRedRing slots is never overrun.
+constexpr int kRedRing = 4;
+static_assert(kPipeStages < kRedRing, "reduction ring must outlast the warps' maximum distance");
+
+struct TileRed {
+    double slot[kRedRing][3][kWarpsPerBlock];
+    int count[kRedRing];
+};
+
+template <int kN, class Write>
+__device__ __forceinline__ void tile_reduce_async(double (&v)[kN], TileRed& red, Pipe& pipe, const Write& write) {
+    static_assert(kN <= 3, "ring slots hold 3 values per warp");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned r = pipe.t_count % kRedRing;
+    ++pipe.t_count;
+#pragma unroll
+    for (int i = 0; i < kN; ++i) v[i] = warp_sum(v[i]);
+    int old = 0;
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < kN; ++i) red.slot[r][i][warp] = v[i];
+        __threadfence_block();
+        old = atomicAdd(&red.count[r], 1);
+    }
+    old = __shfl_sync(kFull, old, 0);
+    if (old == kWarpsPerBlock - 1) {
+        __threadfence_block();
+#pragma unroll
+        for (int i = 0; i < kN; ++i) v[i] = half_warp_sum(red.slot[r][i][lane & (kWarpsPerBlock - 1)]);
+        if (lane == 0) {
+            red.count[r] = 0;
+            write(v);
+        }
+    }
 }
 
 }  // namespace dp
