@@ -37,6 +37,13 @@ class PcgSystem(C.Structure):
             "dinv", "fwd_plan", "bwd_plan", "b", "x", "work", "iters_out", "res_out", "history")]
 
 
+class TrsvSystem(C.Structure):
+    """``dp_trsv_system_t``."""
+
+    _fields_ = [("n", _i32), ("upper", _i32), ("max_level_chunks", _i32), ("reserved", _i32), ("nchunks", _i64)] + [
+        (name, _p) for name in ("rowptr", "col", "val", "plan", "b", "x")]
+
+
 class PcgParams(C.Structure):
     """``dp_pcg_params_t``."""
 
@@ -65,6 +72,8 @@ _SIGNATURES = {
     "dp_sptrsv_plan_build": (C.c_int, [_i32, _i32, _p, _p, _p, _p, _i64, _p]),
     "dp_sptrsv_workspace_bytes": (C.c_size_t, []),
     "dp_sptrsv_solve_f64": (C.c_int, [_i32, _p, _p, _p, _i32, _p, _i64, _i32, _p, _p, _p, _p, C.c_size_t, _p]),
+    "dp_sptrsv_batch_workspace_bytes": (C.c_size_t, [_i32]),
+    "dp_sptrsv_solve_batch_f64": (C.c_int, [C.POINTER(TrsvSystem), _i32, _p, _p, C.c_size_t, _p]),
     "dp_ic0_f64": (C.c_int, [_i32, _p, _p, _p, _p, _p, _i64, _i32, _p, _p, C.c_size_t, _p]),
     "dp_pcg_work_doubles": (_i64, [_i32]),
     "dp_pcg_workspace_bytes": (C.c_size_t, [_i32]),

@@ -36,9 +36,11 @@
 namespace dp {
 
 int coop_grid(const void* kernel, int threads, size_t smem);  // sptrsv.cu
+int trsv_lookahead();                                          // sptrsv.cu
 
 struct SysDev {
     int n, precond, ntiles, pad;
+    int fwd_look, bwd_look;  // SOLVE: chunks of the widest level (parking distance of the sync-free solves)
     CsrView A, M, Mt;
     const double* dinv;
     const int* fwd_plan;
@@ -394,31 +396,29 @@ __device__ __forceinline__ void phase_dotrz(const Ctx& ctx, const SysDev& S, con
 }
 
 // ---- PH_FWD / PH_BWD (SOLVE): y = L^-1 r_new ; z_new = L^-T y ---------------------------------------------------
+// The participating warps are dealt to the systems (system s gets warps s, s + nsys, ...), so the solves of a batch
+// advance side by side: the critical path (levels x L2 round trip) is paid once per batch, not once per system.
 template <bool kUpper, bool kInit>
 __device__ __forceinline__ bool phase_trsv(const Ctx& ctx, int k, const Smem& sm) {
     const int pw = kUpper ? ctx.pw_bwd : ctx.pw_fwd;
     const int gw = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
     if (gw >= pw) return true;
-    const int total = kUpper ? ctx.total_bwd : ctx.total_fwd;
     const int* ofs = kUpper ? ctx.bwd_ofs : ctx.fwd_ofs;
     const AbortCtl ctl{ctx.word, ctx.flag};
-    const bool light = pw <= 128;  // few pollers: skip the single-word waiting stage
-    int cur = -1;
-    bool active = false;
-    for (int g = gw; g < total; g += pw) {
-        const int s = ctx.nsys == 1 ? 0 : find_segment(ofs, ctx.nsys, g);
+    const int nsys = ctx.nsys;
+    const int wps = pw >= nsys ? pw / nsys : 1;       // warps per system
+    const int local = pw >= nsys ? gw / nsys : 0;     // this warp's index inside its system's team
+    if (local >= wps) return true;
+    for (int s = pw >= nsys ? gw % nsys : gw; s < nsys; s += pw) {
         const SysDev& S = (sm.sys_id == s) ? sm.sys : ctx.sys[s];
-        if (s != cur) {
-            cur = s;
-            active = kInit || ld_relaxed_s32(ctx.state + s) == 0;
-        }
-        if (!active) continue;
-        const int c = ctx.nsys == 1 ? g : g - __ldg(ofs + s);
+        if (S.precond != DP_PRECOND_SOLVE) continue;
+        if (!kInit && ld_relaxed_s32(ctx.state + s) != 0) continue;
+        const long long nchunks = __ldg(ofs + s + 1) - __ldg(ofs + s);
         bool ok;
         if (kUpper)
-            ok = sptrsv_chunk<true>(S.Mt, S.bwd_plan + (size_t)c * 32, RhsConsume{S.t}, S.z[(k + 1) & 1], ctl, light);
+            ok = sptrsv_stream<true>(S.Mt, S.bwd_plan, local, wps, nchunks, S.bwd_look, RhsConsume{S.t}, S.z[(k + 1) & 1], ctl);
         else
-            ok = sptrsv_chunk<false>(S.M, S.fwd_plan + (size_t)c * 32, RhsPlain{S.r[(k + 1) & 1]}, S.t, ctl, light);
+            ok = sptrsv_stream<false>(S.M, S.fwd_plan, local, wps, nchunks, S.fwd_look, RhsPlain{S.r[(k + 1) & 1]}, S.t, ctl);
         if (!ok) return false;
     }
     return true;
@@ -744,6 +744,8 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
         d.dinv = u.dinv;
         d.fwd_plan = u.fwd_plan;
         d.bwd_plan = u.bwd_plan;
+        d.fwd_look = u.fwd_max_level_chunks > 0 ? u.fwd_max_level_chunks : 1;
+        d.bwd_look = u.bwd_max_level_chunks > 0 ? u.bwd_max_level_chunks : 1;
         int fwd_chunks = 0, bwd_chunks = 0;
         switch (u.precond) {
             case DP_PRECOND_IDENTITY: break;
@@ -795,7 +797,7 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
     const int coop = coop_grid((const void*)pcg_fused_kernel, kBlock, sizeof(Smem));
     const int coop_phase = coop_grid((const void*)pcg_phase_kernel<PH_FWD, false>, kBlock, sizeof(Smem));
     auto clamp_pw = [](long long lvl_chunks, int grid) {
-        long long pw = 4 * lvl_chunks;
+        long long pw = (long long)trsv_lookahead() * lvl_chunks;
         if (pw < 32) pw = 32;
         const long long w = (long long)grid * kWarpsPerBlock;
         return (int)(pw > w ? w : pw);
@@ -845,7 +847,7 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
         // participating warps one per CTA first. Fewer CTAs = cheaper grid barrier for small systems.
         int grid = ctx.total_tiles;
         if (has_solve) {
-            const long long want = 4 * (sum_fwd_lvl > sum_bwd_lvl ? sum_fwd_lvl : sum_bwd_lvl);
+            const long long want = (long long)trsv_lookahead() * (sum_fwd_lvl > sum_bwd_lvl ? sum_fwd_lvl : sum_bwd_lvl);
             if (want > grid) grid = want > coop ? coop : (int)want;
         }
         if (grid > coop) grid = coop;

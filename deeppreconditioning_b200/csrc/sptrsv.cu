@@ -1,4 +1,8 @@
 // sptrsv.cu — standalone K4 entry point (dp_sptrsv_solve_f64) and the sync-free IC(0) factorisation (dp_ic0_f64).
+#include <stdlib.h>
+
+#include <vector>
+
 #include "sptrsv.cuh"
 
 namespace dp {
@@ -11,16 +15,55 @@ __global__ void fill_u64_kernel(unsigned long long* __restrict__ p, long long co
 
 // Participating warps: `pw` of them, spread one per CTA first (gw = warp * gridDim + block), chunk c -> warp c % pw.
 __global__ void __launch_bounds__(kBlock, 2)
-sptrsv_kernel(CsrView T, int upper, const int* __restrict__ plan, long long nchunks, int pw,
+sptrsv_kernel(CsrView T, int upper, const int* __restrict__ plan, long long nchunks, int pw, int lookback,
               const double* __restrict__ b, double* x, unsigned long long* word, int* flag) {
     const int gw = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
     if (gw >= pw) return;
     const AbortCtl ctl{word, flag};
     const RhsPlain rhs{b};
-    const bool light = pw <= 128;
-    for (long long c = gw; c < nchunks; c += pw) {
-        const bool ok = upper ? sptrsv_chunk<true>(T, plan + c * 32, rhs, x, ctl, light)
-                              : sptrsv_chunk<false>(T, plan + c * 32, rhs, x, ctl, light);
+    if (upper)
+        sptrsv_stream<true>(T, plan, gw, pw, nchunks, lookback, rhs, x, ctl);
+    else
+        sptrsv_stream<false>(T, plan, gw, pw, nchunks, lookback, rhs, x, ctl);
+}
+
+// Batch of independent solves in one launch: the resident warps are dealt to the systems (system s gets warps
+// s, s + nsys, ...), so the solves advance side by side and the HBM stream of the batch hides each system's
+// level-by-level critical path (BASELINE configs 3 and 5: many systems per GPU).
+struct TrsvSysDev {
+    CsrView T;
+    const int* plan;
+    const double* b;
+    double* x;
+    long long nchunks;
+    int upper, lookback;
+};
+
+__global__ void fill_pending_batch_kernel(const TrsvSysDev* __restrict__ sys, int nsys) {
+    for (int s = blockIdx.y; s < nsys; s += gridDim.y) {
+        unsigned long long* x = reinterpret_cast<unsigned long long*>(sys[s].x);
+        const int n = sys[s].T.n;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) x[i] = kPending;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock, 2)
+sptrsv_batch_kernel(const TrsvSysDev* __restrict__ sys, int nsys, int wps, unsigned long long* word, int* flag) {
+    const int gw = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+    const int total = gridDim.x * kWarpsPerBlock;
+    const AbortCtl ctl{word, flag};
+    const int local = total >= nsys ? gw / nsys : 0;
+    if (local >= wps) return;
+    for (int s = total >= nsys ? gw % nsys : gw; s < nsys; s += total) {
+        const TrsvSysDev S = sys[s];
+        const int team = min((long long)wps, S.nchunks) > 0 ? (int)min((long long)wps, S.nchunks) : 1;
+        if (local >= team) continue;
+        const RhsPlain rhs{S.b};
+        bool ok;
+        if (S.upper)
+            ok = sptrsv_stream<true>(S.T, S.plan, local, team, S.nchunks, S.lookback, rhs, S.x, ctl);
+        else
+            ok = sptrsv_stream<false>(S.T, S.plan, local, team, S.nchunks, S.lookback, rhs, S.x, ctl);
         if (!ok) return;
     }
 }
@@ -96,10 +139,19 @@ int coop_grid(const void* kernel, int threads, size_t smem) {
     return per_sm * sm_count();
 }
 
+int trsv_lookahead() {  // levels' worth of warps that take part in a solve (DPCG_TRSV_LOOKAHEAD: experiments)
+    static int cached = 0;
+    if (!cached) {
+        const char* e = getenv("DPCG_TRSV_LOOKAHEAD");
+        cached = e && atoi(e) > 0 ? atoi(e) : 4;
+    }
+    return cached;
+}
+
 static int participating_warps(int max_level_chunks, int grid) {
     const int w = grid * kWarpsPerBlock;
     if (max_level_chunks <= 0) return w;
-    long long pw = 4ll * max_level_chunks;
+    long long pw = (long long)trsv_lookahead() * max_level_chunks;
     if (pw < 32) pw = 32;
     return pw > w ? w : (int)pw;
 }
@@ -130,8 +182,58 @@ int dp_sptrsv_solve_f64(int32_t n, const int32_t* rowptr, const int32_t* col, co
     CsrView T{rowptr, col, val, n, 0};
     int upper_i = upper ? 1 : 0;
     long long nch = nchunks;
-    void* args[] = {&T, &upper_i, (void*)&plan, &nch, &pw, (void*)&b, &x, &word, &flag_out};
+    int lookback = max_level_chunks > 0 ? max_level_chunks : 1;
+    void* args[] = {&T, &upper_i, (void*)&plan, &nch, &pw, &lookback, (void*)&b, &x, &word, &flag_out};
     DP_CUDA(cudaLaunchCooperativeKernel((const void*)sptrsv_kernel, dim3(grid), dim3(kBlock), args, 0, s));
+    return DP_OK;
+}
+
+size_t dp_sptrsv_batch_workspace_bytes(int32_t nsys) {
+    return 256 + sizeof(TrsvSysDev) * (size_t)(nsys > 0 ? nsys : 0);
+}
+
+int dp_sptrsv_solve_batch_f64(const dp_trsv_system_t* systems_host, int32_t nsys, int32_t* flag_out, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+    if (!systems_host || nsys <= 0 || !flag_out || !workspace) return DP_ERR_INVALID;
+    if (workspace_bytes < dp_sptrsv_batch_workspace_bytes(nsys)) return DP_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    std::vector<TrsvSysDev> dev((size_t)nsys);
+    long long want = 0;
+    int nmax = 0;
+    for (int i = 0; i < nsys; ++i) {
+        const dp_trsv_system_t& u = systems_host[i];
+        if (u.n <= 0 || u.nchunks <= 0 || !u.rowptr || !u.col || !u.val || !u.plan || !u.b || !u.x) return DP_ERR_INVALID;
+        TrsvSysDev d{};
+        d.T = CsrView{u.rowptr, u.col, u.val, u.n, 0};
+        d.plan = u.plan, d.b = u.b, d.x = u.x, d.nchunks = u.nchunks, d.upper = u.upper ? 1 : 0;
+        d.lookback = u.max_level_chunks > 0 ? u.max_level_chunks : 1;
+        dev[(size_t)i] = d;
+        const long long w = (long long)trsv_lookahead() * d.lookback;
+        if (w > want) want = w;
+        if (u.n > nmax) nmax = u.n;
+    }
+    char* ws = static_cast<char*>(workspace);
+    unsigned long long* word = reinterpret_cast<unsigned long long*>(ws);
+    TrsvSysDev* sys = reinterpret_cast<TrsvSysDev*>(ws + 256);
+    DP_CUDA(cudaMemsetAsync(word, 0, sizeof(unsigned long long), s));
+    DP_CUDA(cudaMemcpyAsync(sys, dev.data(), sizeof(TrsvSysDev) * (size_t)nsys, cudaMemcpyHostToDevice, s));
+    DP_CUDA(cudaStreamSynchronize(s));  // `dev` is a stack-lifetime staging buffer
+    const int fill_x = (nmax + 255) / 256 < sm_count() * 4 ? (nmax + 255) / 256 : sm_count() * 4;
+    fill_pending_batch_kernel<<<dim3(fill_x, nsys < 1024 ? nsys : 1024), 256, 0, s>>>(sys, nsys);
+    DP_LAUNCH_CHECK();
+    int grid = coop_grid((const void*)sptrsv_batch_kernel, kBlock, 0);
+    const long long total = (long long)grid * kWarpsPerBlock;
+    long long wps = total >= nsys ? total / nsys : 1;  // warps per system
+    if (want < 32) want = 32;
+    if (wps > want) wps = want;
+    const long long need_warps = wps * nsys;
+    if (need_warps < total) {  // one participating warp per CTA first: do not launch idle CTAs
+        const long long g = need_warps < grid ? need_warps : grid;
+        grid = (int)(g > 0 ? g : 1);
+    }
+    int wps_i = (int)wps, nsys_i = nsys;
+    void* args[] = {&sys, &nsys_i, &wps_i, &word, &flag_out};
+    DP_CUDA(cudaLaunchCooperativeKernel((const void*)sptrsv_batch_kernel, dim3(grid), dim3(kBlock), args, 0, s));
     return DP_OK;
 }
 

@@ -1,5 +1,5 @@
-// sptrsv.cuh — K4 primitive: one warp resolves one plan chunk (<= 32 rows of ONE level) of a sparse triangular
-// solve, sync-free. No reference counterpart; the arithmetic is plain substitution
+// sptrsv.cuh — K4 primitive: a warp resolves a SEQUENCE of plan chunks (<= 32 rows of ONE level each) of a sparse
+// triangular solve, sync-free. No reference counterpart; the arithmetic is plain substitution
 //   x_i = (b_i - sum_j T_ij x_j) * (1 / T_ii),   sum sequential in column order, products/sums rounded separately
 // so the result is bit-identical to oracle_sptrsv_lower/upper.
 //
@@ -7,6 +7,13 @@
 // consumer spins (ld.relaxed.gpu, L1-bypassing) until the 8-byte word changes — data is its own flag, one store
 // per row, no fences. Rows of a chunk share a level, so they never depend on each other. Forward progress:
 // chunks are handed to resident warps in plan order (round robin), every dependency lives in an earlier chunk.
+//
+// The critical path of a solve is (levels) x (store -> L2 -> poll hit). Everything else is taken off that path:
+//   * chunk metadata is software-pipelined (plan row two chunks ahead, row extent one chunk ahead, entries / diagonal /
+//     rhs requested on arrival, before any waiting), so the dependent loads of a chunk never queue up behind its wait;
+//   * a warp whose chunk is still levels away parks on ONE word (lane 0, x of a row `lookback` chunks earlier in the
+//     plan, i.e. about one level back) with a short sleep; once that is solved every lane polls its own dependencies
+//     back to back, so the last store is seen one L2 round trip later and the L2 never sees thousands of idle pollers.
 #pragma once
 
 #include "common.cuh"
@@ -39,85 +46,130 @@ struct RhsConsume {
     }
 };
 
-// Returns false if the solve was aborted (spin budget exhausted somewhere). All 32 lanes must call.
-// `light`: few warps take part in this solve (small levels), so every lane may poll all its dependencies right
-// away; otherwise the warp first watches ONE word (one sector request per poll) until its chunk is about to be
-// ready, which keeps the L2 request rate of thousands of waiting warps negligible.
-template <bool kUpper, class Rhs>
-__device__ __forceinline__ bool sptrsv_chunk(const CsrView& T, const int* __restrict__ plan32, const Rhs& rhs,
-                                             double* x, const AbortCtl& ctl, bool light) {
-    const int lane = threadIdx.x & 31;
-    const int row = __ldg(plan32 + lane);
-    const bool valid = row >= 0;
-    int e = 0, end = 0;
-    double rcp = 0.0, b = 0.0, sum = 0.0;
-    int c[4] = {0, 0, 0, 0};
-    double v[4] = {0.0, 0.0, 0.0, 0.0};
-    int probe = -1;
-    if (valid) {
+constexpr int kTrsvInflight = 4;  // dependencies polled per lane and round
+#ifndef DPCG_TRSV_SLEEP
+#define DPCG_TRSV_SLEEP 0
+#endif
+#ifndef DPCG_TRSV_PARK_MULT
+#define DPCG_TRSV_PARK_MULT 1
+#endif
+
+// Everything a lane needs to solve its row except the dependencies' values.
+struct TrsvRow {
+    int row;       // -1: idle lane
+    int e, end;    // off-diagonal entries [e, end)
+    double rcp, b;
+    int c[kTrsvInflight];
+    double v[kTrsvInflight];
+};
+
+template <bool kUpper>
+__device__ __forceinline__ void trsv_row_extent(const CsrView& T, int row, int& e, int& end, int& dpos) {
+    e = end = dpos = 0;
+    if (row >= 0) {
         const int rs = __ldg(T.rowptr + row), re = __ldg(T.rowptr + row + 1);
-        e = kUpper ? rs + 1 : rs;        // off-diagonal entries [e, end)
+        e = kUpper ? rs + 1 : rs;
         end = kUpper ? re : re - 1;
-        // everything that does not depend on other rows is fetched before waiting
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (e + k < end) c[k] = __ldg(T.col + e + k), v[k] = __ldg(T.val + e + k);
-        rcp = __ddiv_rn(1.0, __ldg(T.val + (kUpper ? rs : re - 1)));
-        b = rhs(row);
-        // the off-diagonal entry nearest to the diagonal is (heuristically) the last to become available
-        if (!light && lane == 0 && e < end) probe = __ldg(T.col + (kUpper ? e : end - 1));
+        dpos = kUpper ? rs : re - 1;
     }
-    if (!light) {
-        probe = __shfl_sync(kFull, probe, 0);
-        if (probe >= 0) {
+}
+
+template <class Rhs>
+__device__ __forceinline__ void trsv_row_entries(const CsrView& T, int row, int e, int end, int dpos, const Rhs& rhs,
+                                                 TrsvRow& r) {
+    r.row = row, r.e = e, r.end = end;
+    r.rcp = 0.0, r.b = 0.0;
+#pragma unroll
+    for (int k = 0; k < kTrsvInflight; ++k) r.c[k] = 0, r.v[k] = 0.0;
+    if (row >= 0) {
+#pragma unroll
+        for (int k = 0; k < kTrsvInflight; ++k)
+            if (e + k < end) r.c[k] = __ldg(T.col + e + k), r.v[k] = __ldg(T.val + e + k);
+        r.rcp = __ddiv_rn(1.0, __ldg(T.val + dpos));
+        r.b = rhs(row);
+    }
+}
+
+// Solve chunks c0, c0 + stride, ... < cend of the plan. `lookback` = chunks per (largest) level: the parking word of
+// chunk c is the first row of chunk c - lookback. Returns false if the solve was aborted. All 32 lanes must call.
+template <bool kUpper, class Rhs>
+__device__ __forceinline__ bool sptrsv_stream(const CsrView& T, const int* __restrict__ plan, long long c0, long long stride,
+                                              long long cend, int lookback, const Rhs& rhs, double* x, const AbortCtl& ctl) {
+    const int lane = threadIdx.x & 31;
+    auto plan_row = [&](long long c) { return c < cend ? __ldg(plan + c * 32 + lane) : -1; };
+    lookback *= DPCG_TRSV_PARK_MULT;
+    auto park_row = [&](long long c) { return (c < cend && c >= lookback) ? __ldg(plan + (c - lookback) * 32) : -1; };
+
+    // pipeline fill: chunk c0 up to its row extent, c0 + stride up to its row index
+    int row0, e0, end0, dpos0, park0;
+    int row1, park1;
+    row0 = plan_row(c0), park0 = park_row(c0);
+    row1 = plan_row(c0 + stride), park1 = park_row(c0 + stride);
+    trsv_row_extent<kUpper>(T, row0, e0, end0, dpos0);
+    for (long long c = c0; c < cend; c += stride) {
+        // everything that does not depend on other rows is requested before waiting on anything: this chunk's
+        // entries, the next chunk's row extent, the one after's row index
+        TrsvRow cur;
+        trsv_row_entries(T, row0, e0, end0, dpos0, rhs, cur);
+        const int row2 = plan_row(c + 2 * stride), park2 = park_row(c + 2 * stride);
+        int e1, end1, dpos1;
+        trsv_row_extent<kUpper>(T, row1, e1, end1, dpos1);
+
+        // park until the plan is about one level away from this chunk
+        if (park0 >= 0) {
             unsigned spins = 0;
-            while (ld_relaxed_u64(x + probe) == kPending) {
+            while (ld_relaxed_u64(x + park0) == kPending) {
                 if (++spins > kSpinBudget) {
                     ctl.raise(DP_ERR_TIMEOUT);
                     return false;
                 }
                 if ((spins & 1023u) == 0 && ctl.aborted()) return false;
-                __nanosleep(64);
+                if (DPCG_TRSV_SLEEP > 0) __nanosleep(DPCG_TRSV_SLEEP);
             }
         }
-    }
-    unsigned idle = 0;
-    for (;;) {
-        const bool pending = valid && e < end;
-        if (!__any_sync(kFull, pending)) break;
-        bool progress = false;
-        if (pending) {
-            // up to 4 entries in flight; consumed strictly in column order
-            const int m = min(4, end - e);
-            unsigned long long u[4];
+        // resolve: every lane polls its own dependencies, consumed strictly in column order
+        double sum = 0.0;
+        unsigned idle = 0;
+        for (;;) {
+            const bool pending = cur.row >= 0 && cur.e < cur.end;
+            if (!__any_sync(kFull, pending)) break;
+            bool progress = false;
+            if (pending) {
+                const int m = min(kTrsvInflight, cur.end - cur.e);
+                unsigned long long u[kTrsvInflight];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) u[k] = k < m ? ld_relaxed_u64(x + c[k]) : kPending;
-            int used = 0;
+                for (int k = 0; k < kTrsvInflight; ++k) u[k] = k < m ? ld_relaxed_u64(x + cur.c[k]) : kPending;
+                int used = 0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (used == k && u[k] != kPending) {
-                    sum = __dadd_rn(sum, __dmul_rn(v[k], as_double(u[k])));
-                    ++used;
+                for (int k = 0; k < kTrsvInflight; ++k) {
+                    if (used == k && u[k] != kPending) {
+                        sum = __dadd_rn(sum, __dmul_rn(cur.v[k], as_double(u[k])));
+                        ++used;
+                    }
+                }
+                if (used) {
+                    cur.e += used;
+                    progress = true;
+                    if (cur.e < cur.end) {  // rows with more than kTrsvInflight dependencies: fetch the next ones
+#pragma unroll
+                        for (int k = 0; k < kTrsvInflight; ++k)
+                            if (cur.e + k < cur.end) cur.c[k] = __ldg(T.col + cur.e + k), cur.v[k] = __ldg(T.val + cur.e + k);
+                    }
                 }
             }
-            if (used) {
-                e += used;
-                progress = true;
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (e + k < end) c[k] = __ldg(T.col + e + k), v[k] = __ldg(T.val + e + k);
+            if (!__any_sync(kFull, progress)) {
+                if (++idle > kSpinBudget) {
+                    ctl.raise(DP_ERR_TIMEOUT);
+                    return false;
+                }
+                if ((idle & 1023u) == 0 && ctl.aborted()) return false;
             }
         }
-        if (!__any_sync(kFull, progress)) {
-            if (++idle > kSpinBudget) {
-                ctl.raise(DP_ERR_TIMEOUT);
-                return false;
-            }
-            if ((idle & 1023u) == 0 && ctl.aborted()) return false;
-            __nanosleep(32);
-        }
+        if (cur.row >= 0) st_relaxed_u64(x + cur.row, as_bits(__dmul_rn(__dsub_rn(cur.b, sum), cur.rcp)));
+        // rotate the pipeline
+        row0 = row1, e0 = e1, end0 = end1, dpos0 = dpos1, park0 = park1;
+        row1 = row2, park1 = park2;
     }
-    if (valid) st_relaxed_u64(x + row, as_bits(__dmul_rn(__dsub_rn(b, sum), rcp)));
     return true;
 }
 

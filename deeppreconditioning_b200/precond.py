@@ -85,6 +85,36 @@ def triangular_solve(matrix: CsrMatrix, plan: TriangularPlan, b: torch.Tensor, o
     return x
 
 
+def triangular_solve_batch(systems, outs=None):
+    """Independent solves ``T_s x_s = b_s`` in ONE launch (``dp_sptrsv_solve_batch_f64``).
+
+    ``systems``: list of ``(matrix, plan, b)``; returns the list of solutions. The resident warps are dealt to the
+    systems so that they advance side by side (the data-parallel axis of ``BenchmarkSuite.run``, ``test.py:121``).
+    """
+    lib = _lib.lib()
+    dev = systems[0][0].device
+    nsys = len(systems)
+    descs = (_lib.TrsvSystem * nsys)()
+    xs, keep = [], []
+    for i, (matrix, plan, b) in enumerate(systems):
+        n = matrix.n
+        assert b.is_cuda and b.dtype == torch.float64 and b.shape == (n,)
+        b = b.contiguous()
+        x = outs[i] if outs is not None else torch.empty(n, dtype=torch.float64, device=dev)
+        d = descs[i]
+        d.n, d.upper, d.max_level_chunks, d.nchunks = n, int(plan.upper), plan.max_level_chunks, plan.nchunks
+        d.rowptr, d.col, d.val = _lib.ptr(matrix.rowptr), _lib.ptr(matrix.col), _lib.ptr(matrix.val)
+        d.plan, d.b, d.x = _lib.ptr(plan.plan), _lib.ptr(b), _lib.ptr(x)
+        xs.append(x), keep.append(b)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = _workspace(lib.dp_sptrsv_batch_workspace_bytes(nsys), dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.dp_sptrsv_solve_batch_f64(descs, nsys, _lib.ptr(flag), _lib.ptr(ws), ws.numel(),
+                                                 _lib.stream_ptr(dev)), "dp_sptrsv_solve_batch_f64")
+    _lib.raise_on_flag(flag, "dp_sptrsv_solve_batch_f64")
+    return xs
+
+
 def incomplete_cholesky0(tril_a: CsrMatrix, plan: TriangularPlan | None = None) -> CsrMatrix:
     """IC(0) factor on the pattern of ``tril(A)`` (``dp_ic0_f64``) — stands in for ``ilupp.ichol0`` (``test.py:84``)."""
     lib, n, dev = _lib.lib(), tril_a.n, tril_a.device

@@ -124,6 +124,24 @@ int dp_sptrsv_solve_f64(int32_t n, const int32_t* rowptr, const int32_t* col, co
                         const int32_t* plan, int64_t nchunks, int32_t max_level_chunks, const double* b, double* x,
                         int32_t* flag_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Batch of independent triangular solves in ONE launch (BenchmarkSuite.run's data-parallel axis, test.py:121): the
+ * resident warps are dealt to the systems, so the solves advance side by side and the batch's HBM stream hides each
+ * system's level-by-level critical path. Same arithmetic (bit-identical) as dp_sptrsv_solve_f64 per system. */
+typedef struct dp_trsv_system {
+    int32_t n;
+    int32_t upper;            /* 0: lower (diagonal last in each row), 1: upper (diagonal first) */
+    int32_t max_level_chunks; /* chunks of the widest level (from the analysis) */
+    int32_t reserved;
+    int64_t nchunks;
+    const int32_t* rowptr; const int32_t* col; const double* val;
+    const int32_t* plan;
+    const double* b;
+    double* x;
+} dp_trsv_system_t;
+size_t dp_sptrsv_batch_workspace_bytes(int32_t nsys);
+int dp_sptrsv_solve_batch_f64(const dp_trsv_system_t* systems_host, int32_t nsys, int32_t* flag_out, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
 /* ---- IC(0) on the pattern of tril(A) (stands in for ilupp.ichol0, test.py:84) -------------------------------
  * Level-scheduled, sync-free numeric factorisation; uses the lower plan of the same pattern.
  * *flag_out: DP_ERR_STRUCTURE on a non-positive pivot. */

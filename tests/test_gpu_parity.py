@@ -102,13 +102,13 @@ def test_spmv_bit_exact(cuda, kind, side, net):
 
 
 def test_spmv_long_and_empty_rows(cuda):
-    """Rows longer than one shared-memory stage (256 products), empty rows, n not a multiple of 32."""
+    """Rows spanning several pipeline blocks / tiles' worth of entries, empty rows, n not a multiple of 32 or 512."""
     rng = np.random.default_rng(11)
     import scipy.sparse as sp
 
     n = 1000 + 7
     m = sp.random(n, n, density=0.01, random_state=5, format="lil")
-    m[3, :] = rng.standard_normal(n)      # dense row: 1007 entries -> 4 stages
+    m[3, :] = rng.standard_normal(n)      # dense row: 1007 entries
     m[500, :700] = 1.0
     m[10, :] = 0
     m[n - 1, :] = 0
@@ -157,6 +157,41 @@ def test_levels_and_triangular_solves_bit_exact(cuda, kind, side, net):
         assert np.array_equal(y.cpu().numpy(), y_want), name
         z = precond.triangular_solve(upper_m, bwd, y)
         assert np.array_equal(z.cpu().numpy(), ckernels.sptrsv_upper(*want_t, y_want)), name
+
+
+def test_triangular_solve_batch_is_bitwise_the_single_solves(cuda):
+    """Ragged batch (different sizes, lower and upper factors mixed) in one launch == one launch per system."""
+    systems, singles = [], []
+    for kind, side, seed in [("poisson2d", 37, 0), ("poisson3d", 9, 1), ("poisson2d", 64, 2), ("poisson2d", 5, 3), ("poisson3d", 12, 4)]:
+        p = helpers.problem(kind, side, seed, 0.5, None)
+        lower = CsrMatrix.from_spconv(helpers.to_device(p.systems_tril, cuda), p.n, "tril")
+        upper_m = lower.transpose()
+        b = p.b.to(cuda)
+        for m, up in [(lower, False), (upper_m, True)]:
+            plan = precond.analyse(m, up)
+            systems.append((m, plan, b))
+            singles.append(precond.triangular_solve(m, plan, b))
+        want = ckernels.sptrsv_lower(*p.T, p.b.numpy())
+        assert np.array_equal(singles[-2].cpu().numpy(), want)
+    for got, want in zip(precond.triangular_solve_batch(systems), singles):
+        assert torch.equal(got, want)
+
+
+def test_spmv_pipeline_block_boundaries(cuda):
+    """Tiles whose entry count straddles the pipeline's stage capacity, rows cut by a block boundary, a matrix whose nnz
+    is not a multiple of 4 (bulk copies are 16-byte granular) and rows of even length (bank-conflicting strides)."""
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(3)
+    for n, per_row in [(512, 7), (513, 8), (1500, 9), (2048, 16), (700, 23), (5000, 4)]:
+        rows = np.repeat(np.arange(n), per_row)
+        cols = rng.integers(0, n, size=n * per_row)
+        m = sp.csr_matrix((rng.standard_normal(n * per_row), (rows, cols)), shape=(n, n))
+        m.sum_duplicates()
+        m.sort_indices()
+        x = rng.standard_normal(n)
+        y = CsrMatrix.from_scipy(m, cuda).matvec(torch.from_numpy(x).to(cuda)).cpu().numpy()
+        assert np.array_equal(y, ckernels.spmv_csr(m.indptr, m.indices, m.data, x)), (n, per_row, m.nnz)
 
 
 @pytest.mark.parametrize("kind,side", [("poisson2d", 16), ("poisson2d", 64), ("poisson3d", 12), ("poisson2d", 100)])

@@ -68,6 +68,11 @@ if not {"spmv", "trsv"} <= skip:
         best, med = timed(lambda: precond.triangular_solve(T3, fwd3, x, y), 5)
         byt = 12 * T3.nnz + 4 * (n3 + 1) + 16 * n3
         print(f"sptrsv {a.side3}^3: best {best*1e3:.1f} us ({byt/best/1e6:.0f} GB/s), {best*1e3/fwd3.nlevels:.2f} us/level", flush=True)
+        for nb in (4, 8, 16):
+            sys_ = [(T3, fwd3, x)] * nb
+            outs = [torch.empty_like(x) for _ in range(nb)]
+            best, med = timed(lambda: precond.triangular_solve_batch(sys_, outs), 3)
+            print(f"sptrsv batch {nb} x {a.side3}^3 (same operands, distinct outputs): best {best*1e3:.1f} us ({nb*byt/best/1e6:.0f} GB/s)", flush=True)
     del st, A3, T3, x, y
 
 args = argparse.Namespace(systems_per_gpu=a.systems, side=316, net="net")
@@ -90,7 +95,11 @@ if "single" not in skip:
     bench.MAX_ITER = 20000
     h = host[0]
     A = CsrMatrix.from_arrays(*h["a"], device=dev); L = CsrMatrix.from_arrays(*h["l"], device=dev); b = h["b"].to(dev)
-    for name, M in [("cnn_multiply", dp.FactoredMultiply(L)), ("jacobi", dp.Jacobi(A))]:
+    st, _, _, _ = synthetic.make_batch("poisson2d", 316, [h["index"]], device=dev)
+    T = CsrMatrix.from_spconv(st, A.n, "tril")
+    fwd = precond.analyse(T, False)
+    ic = dp.FactoredSolve(precond.incomplete_cholesky0(T, fwd), None, fwd)
+    for name, M in [("cnn_multiply", dp.FactoredMultiply(L)), ("jacobi", dp.Jacobi(A)), ("ic0_solve", ic)]:
         batch = dp.PcgBatch([(A, b, M)], 1e-8, 20000)
 
         def go1():
