@@ -323,7 +323,15 @@ def extras(device, host0):
     ms = timed(lambda: precond.triangular_solve(T3, fwd3, x, y), reps=5)
     trsv_bytes = 12 * T3.nnz + 4 * (n3 + 1) + 16 * n3
     out["sptrsv_128^3"] = {"ms": ms, "levels": fwd3.nlevels, "algorithmic_gbs": trsv_bytes / ms / 1e6,
-                           "frac_of_hbm_peak": trsv_bytes / ms / 1e6 / peak, "us_per_level": 1e3 * ms / fwd3.nlevels}
+                           "frac_of_hbm_peak": trsv_bytes / ms / 1e6 / peak, "us_per_level": 1e3 * ms / fwd3.nlevels,
+                           "bound": "levels x (store -> L2 -> poll) latency, not HBM: see profiles/README.md"}
+    # several independent solves in flight (the batch axis of configs 3/5): bytes grow, the critical path does not
+    nb = 16
+    outs = [torch.empty_like(x) for _ in range(nb)]
+    ms = timed(lambda: precond.triangular_solve_batch([(T3, fwd3, x)] * nb, outs), reps=3)
+    out["sptrsv_batch16_128^3"] = {"ms": ms, "systems": nb, "algorithmic_gbs": nb * trsv_bytes / ms / 1e6,
+                                   "frac_of_hbm_peak": nb * trsv_bytes / ms / 1e6 / peak,
+                                   "note": "one factor shared by the 16 solves (distinct right-hand sides/outputs)"}
     return out
 
 
@@ -421,10 +429,14 @@ def run_ours(args):
             extra = extras(device, host[0])
 
     if rank == 0:
+        # DRAM traffic of the fused kernel: ncu (--set full) measured dram__bytes_read+write on a short launch of the same
+        # kernel and workload shape; profiles/traffic.json keeps it per system-iteration, scaled here to this launch.
         traffic = None
         tpath = ROOT / "profiles" / "traffic.json"
         if tpath.exists():
-            traffic = json.loads(tpath.read_text()).get("pcg_fused_kernel_bytes_per_launch")
+            per_iter = json.loads(tpath.read_text()).get("pcg_fused_kernel_dram_bytes_per_system_iteration")
+            if per_iter:
+                traffic = float(per_iter) * float(sum(r.iterations for r in results))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -12,7 +12,6 @@ constexpr int kWarp = 32;
 constexpr int kBlock = 512;                  // threads per CTA of every row-parallel kernel
 constexpr int kWarpsPerBlock = kBlock / kWarp;
 constexpr int kTileRows = kBlock;            // one CTA pass covers 512 consecutive rows (16 chunks of 32)
-constexpr int kStageCap = 256;               // products staged per warp in shared memory (2 KB)
 constexpr unsigned kFull = 0xffffffffu;
 
 // "Not yet produced" marker for sync-free dependency resolution: a quiet NaN with a payload that IEEE

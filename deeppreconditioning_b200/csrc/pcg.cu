@@ -19,13 +19,15 @@
 //   FWD/BWD SOLVE: y = L^-1 r_new, z = L^-T y (sync-free, sptrsv.cuh), then DOTRZ: partial <r,z>
 // The initial z0 = M r0 runs the same APPLY phases with kInit (no update, <z,z> into the <r,r> slot).
 //
-// Scheduling. A tile is 512 consecutive rows of one system, processed by one CTA (16 warps x 32 rows).
+// Scheduling. A tile is 512 consecutive rows of one system, processed by one CTA (one row per thread); its matrix
+// entries arrive through the TMA tile pipeline (tilepipe.cuh), warps of a CTA are not coupled by barriers while they
+// stream, and the per-tile dot partials are folded by whichever warp finishes last.
 //   fused engine  : one persistent cooperative launch. Unfinished systems live in a compacted ACTIVE list; its
 //                   tiles are split into gridDim contiguous ranges, so a CTA streams through consecutive tiles of
 //                   (mostly) one system and evaluates that system's scalars once per phase. When systems finish,
 //                   CTA 0 rebuilds the list (double buffered) during the next APPLY1 phase.
-//   stepped engine: one launch per phase over the static list of all systems (round robin); the host polls the
-//                   finished counter every check_every iterations. Same phase code, same bits.
+//   stepped engine: one launch per phase over the static list of all systems (same contiguous ranges); the host polls
+//                   the finished counter every check_every iterations. Same phase code, same bits.
 #include <stdlib.h>
 
 #include <vector>
