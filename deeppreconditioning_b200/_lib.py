@@ -34,7 +34,10 @@ class PcgSystem(C.Structure):
         "n", "precond", "a_nnz", "m_nnz", "mt_nnz", "fwd_nchunks", "bwd_nchunks",
         "fwd_max_level_chunks", "bwd_max_level_chunks", "reserved")] + [(name, _p) for name in (
             "a_rowptr", "a_col", "a_val", "m_rowptr", "m_col", "m_val", "mt_rowptr", "mt_col", "mt_val",
-            "dinv", "fwd_plan", "bwd_plan", "b", "x", "work", "iters_out", "res_out", "history")]
+            "dinv", "fwd_plan", "bwd_plan",
+            "fwd_ls_rowptr", "fwd_ls_col", "fwd_ls_val", "fwd_ls_perm", "fwd_ls_level",
+            "bwd_ls_rowptr", "bwd_ls_col", "bwd_ls_val", "bwd_ls_perm", "bwd_ls_level",
+            "b", "x", "work", "iters_out", "res_out", "history")]
 
 
 class TrsvSystem(C.Structure):
@@ -42,6 +45,13 @@ class TrsvSystem(C.Structure):
 
     _fields_ = [("n", _i32), ("upper", _i32), ("max_level_chunks", _i32), ("reserved", _i32), ("nchunks", _i64)] + [
         (name, _p) for name in ("rowptr", "col", "val", "plan", "b", "x")]
+
+
+class TrsvLsSystem(C.Structure):
+    """``dp_trsv_ls_system_t``."""
+
+    _fields_ = [("n", _i32), ("nnz", _i32), ("upper", _i32), ("reserved", _i32)] + [
+        (name, _p) for name in ("rowptr_p", "col_p", "val_p", "perm", "level_sorted", "b", "x")]
 
 
 class PcgParams(C.Structure):
@@ -74,6 +84,11 @@ _SIGNATURES = {
     "dp_sptrsv_solve_f64": (C.c_int, [_i32, _p, _p, _p, _i32, _p, _i64, _i32, _p, _p, _p, _p, C.c_size_t, _p]),
     "dp_sptrsv_batch_workspace_bytes": (C.c_size_t, [_i32]),
     "dp_sptrsv_solve_batch_f64": (C.c_int, [C.POINTER(TrsvSystem), _i32, _p, _p, C.c_size_t, _p]),
+    "dp_sptrsv_permute_workspace_bytes": (C.c_size_t, [_i32]),
+    "dp_sptrsv_permute": (C.c_int, [_i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
+    "dp_sptrsv_ls_limits": (None, [_p]),
+    "dp_sptrsv_ls_workspace_bytes": (C.c_size_t, [_i32]),
+    "dp_sptrsv_ls_solve_batch_f64": (C.c_int, [C.POINTER(TrsvLsSystem), _i32, _p, C.c_size_t, _p]),
     "dp_ic0_f64": (C.c_int, [_i32, _p, _p, _p, _p, _p, _i64, _i32, _p, _p, C.c_size_t, _p]),
     "dp_pcg_work_doubles": (_i64, [_i32]),
     "dp_pcg_workspace_bytes": (C.c_size_t, [_i32]),

@@ -173,6 +173,60 @@ __global__ void plan_build_kernel(int nlevels, const int* __restrict__ perm, con
     }
 }
 
+// ---- level-ordered copy of a triangular factor (input of the level-stream solve, trsv_ls.cuh) -------------------
+__global__ void inv_perm_kernel(int n, const int* __restrict__ perm, int* __restrict__ inv) {
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) inv[perm[r]] = r;
+}
+
+__global__ void perm_rowlen_kernel(int n, const int* __restrict__ rowptr, const int* __restrict__ perm,
+                                   const int* __restrict__ level, int* __restrict__ len, int* __restrict__ level_sorted) {
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r <= n; r += gridDim.x * blockDim.x) {
+        if (r < n) {
+            const int row = perm[r];
+            len[r] = rowptr[row + 1] - rowptr[row];
+            level_sorted[r] = level[row];
+        } else {
+            len[r] = 0;
+        }
+    }
+}
+
+// One warp per row of the copy: entries keep their order inside the row, columns become positions.
+__global__ void perm_fill_kernel(int n, const int* __restrict__ rowptr, const int* __restrict__ col,
+                                 const double* __restrict__ val, const int* __restrict__ perm, const int* __restrict__ inv,
+                                 const int* __restrict__ rowptr_p, int* __restrict__ col_p, double* __restrict__ val_p) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+        const int row = perm[r];
+        const int src = rowptr[row], cnt = rowptr[row + 1] - src, dst = rowptr_p[r];
+        for (int k = lane; k < cnt; k += 32) {
+            col_p[dst + k] = inv[col[src + k]];
+            val_p[dst + k] = val[src + k];
+        }
+    }
+}
+
+// What the level-stream solve needs to know about the copy: stats[0] = most entries in a 512-row tile, stats[1] = most
+// entries in a row, stats[2] = largest distance (in positions) between a row and one of its dependencies.
+__global__ void perm_stats_kernel(int n, const int* __restrict__ rowptr_p, const int* __restrict__ col_p, int* __restrict__ stats) {
+    int tile_max = 0, row_max = 0, dist_max = 0;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        const int rs = rowptr_p[r], re = rowptr_p[r + 1];
+        row_max = max(row_max, re - rs);
+        for (int q = rs; q < re; ++q) dist_max = max(dist_max, r - col_p[q]);
+        if (r % kTileRows == 0) tile_max = max(tile_max, rowptr_p[min(n, r + kTileRows)] - rs);
+    }
+    tile_max = __reduce_max_sync(kFull, tile_max);
+    row_max = __reduce_max_sync(kFull, row_max);
+    dist_max = __reduce_max_sync(kFull, dist_max);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(stats + 0, tile_max);
+        atomicMax(stats + 1, row_max);
+        atomicMax(stats + 2, dist_max);
+    }
+}
+
 static int grid_for(long long items, int threads) {
     long long b = (items + threads - 1) / threads;
     long long cap = (long long)sm_count() * 16;
@@ -263,6 +317,37 @@ int dp_sptrsv_analyse(int32_t n, const int32_t* rowptr, const int32_t* col, int3
         kin = kout;
         vin = vout;
     }
+    return DP_OK;
+}
+
+size_t dp_sptrsv_permute_workspace_bytes(int32_t n) {
+    const size_t m = (size_t)(n < 0 ? 0 : n);
+    return align_up(sizeof(int) * m, 256) + align_up(scan_workspace_bytes((long long)m + 1), 256);
+}
+
+int dp_sptrsv_permute(int32_t n, const int32_t* rowptr, const int32_t* col, const double* val, const int32_t* perm,
+                      const int32_t* level, int32_t* rowptr_p, int32_t* col_p, double* val_p, int32_t* level_sorted,
+                      int32_t* stats_out, void* workspace, size_t workspace_bytes, void* stream) {
+    if (n < 0 || !rowptr_p || !stats_out || !workspace) return DP_ERR_INVALID;
+    if (workspace_bytes < dp_sptrsv_permute_workspace_bytes(n)) return DP_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    DP_CUDA(cudaMemsetAsync(stats_out, 0, 3 * sizeof(int), s));
+    DP_CUDA(cudaMemsetAsync(rowptr_p, 0, sizeof(int), s));
+    if (n == 0) return DP_OK;
+    if (!rowptr || !col || !val || !perm || !level || !col_p || !val_p || !level_sorted) return DP_ERR_INVALID;
+    if (!aligned16(col_p) || !aligned16(val_p) || !aligned16(workspace)) return DP_ERR_ALIGNMENT;
+    int* inv = static_cast<int*>(workspace);
+    void* scan_ws = static_cast<char*>(workspace) + align_up(sizeof(int) * (size_t)n, 256);
+    inv_perm_kernel<<<grid_for(n, 256), 256, 0, s>>>(n, perm, inv);
+    DP_LAUNCH_CHECK();
+    perm_rowlen_kernel<<<grid_for((long long)n + 1, 256), 256, 0, s>>>(n, rowptr, perm, level, rowptr_p, level_sorted);
+    DP_LAUNCH_CHECK();
+    const int st = exclusive_scan_i32(rowptr_p, rowptr_p, (long long)n + 1, scan_ws, s);
+    if (st != DP_OK) return st;
+    perm_fill_kernel<<<grid_for(32ll * n, 256), 256, 0, s>>>(n, rowptr, col, val, perm, inv, rowptr_p, col_p, val_p);
+    DP_LAUNCH_CHECK();
+    perm_stats_kernel<<<grid_for(n, 256), 256, 0, s>>>(n, rowptr_p, col_p, stats_out);
+    DP_LAUNCH_CHECK();
     return DP_OK;
 }
 

@@ -34,6 +34,7 @@
 
 #include "sptrsv.cuh"
 #include "tilepipe.cuh"
+#include "trsv_ls.cuh"
 
 namespace dp {
 
@@ -47,6 +48,7 @@ struct SysDev {
     const double* dinv;
     const int* fwd_plan;
     const int* bwd_plan;
+    LsFactor fwd_ls, bwd_ls;  // SOLVE, optional: level-ordered copies (rowptr == nullptr: sync-free solve)
     const double* b;
     double* x;
     double* r[2];
@@ -75,7 +77,7 @@ struct Ctx {
     int* act_meta;        // [2][2]: {count, total tiles}
     int nsys, total_tiles, total_fwd, total_bwd;
     int pw_fwd, pw_bwd;
-    int has_multiply, has_solve;
+    int has_multiply, has_solve, has_ls;
     double rtol;
     int max_iter;
     unsigned long long* word;  // grid barrier (+ finished count in the upper half)
@@ -100,6 +102,7 @@ struct Smem {
     TileDesc tab[3][kMaxRoundTiles];
     double scratch[2][3 * kWarpsPerBlock];  // tile_reduce (double buffered)
     TileRed red;                            // tile_reduce_async (tiles that went through the pipeline)
+    LsShared ls;                            // level-stream solves: barriers of their pipeline geometry, window
     double scratch2[3 * kWarpsPerBlock];    // block_sum* of the per-system scalar evaluation
     SysDev sys;  // descriptor of the system this CTA is working on (survives across phases)
     int sys_id;
@@ -110,6 +113,7 @@ struct Smem {
 };
 
 static_assert(sizeof(SysDev) % 8 == 0, "SysDev is copied as 8-byte words");
+static_assert(sizeof(Smem) <= (233472 / 2) - 1024, "two CTAs per SM: 228 KB of shared memory, 1 KB reserved per CTA");
 
 enum Phase { PH_INIT = 0, PH_A = 1, PH_APPLY1 = 2, PH_APPLY2 = 3, PH_FWD = 4, PH_BWD = 5, PH_DOTRZ = 6 };
 
@@ -173,7 +177,7 @@ __device__ __forceinline__ void phase_init(const Ctx& ctx, const SysDev& S, cons
     if (threadIdx.x == 0 && tile == 0) ctx.state[d.sys] = 0;
     double* part_bb = S.part_bb;
     auto write = [part_bb, tile](const double (&v)[1]) { part_bb[tile] = v[0]; };
-    if (tile_blocks(d) > 0) {
+    if (d.ce > d.cs) {
         tile_reduce_async<1>(bb, sm.red, pipe, write);
     } else {
         tile_reduce<1>(bb, sm.scratch, pipe);
@@ -246,7 +250,7 @@ __device__ __forceinline__ void phase_a(const Ctx& ctx, const SysDev& S, const T
     }
     double* part_pap = S.part_pap;
     auto write = [part_pap, tile](const double (&v)[1]) { part_pap[tile] = v[0]; };
-    if (tile_blocks(d) > 0) {
+    if (d.ce > d.cs) {
         tile_reduce_async<1>(pap, sm.red, pipe, write);
     } else {
         tile_reduce<1>(pap, sm.scratch, pipe);
@@ -328,7 +332,7 @@ __device__ __forceinline__ void phase_apply1(const Ctx& ctx, const SysDev& S, co
             if (kInit) part_rr[tile] = w[2];
         }
     };
-    if (tile_blocks(d) > 0) {
+    if (d.ce > d.cs) {
         tile_reduce_async<3>(v, sm.red, pipe, write);
     } else {
         tile_reduce<3>(v, sm.scratch, pipe);
@@ -365,7 +369,7 @@ __device__ __forceinline__ void phase_apply2(const Ctx& ctx, const SysDev& S, co
         part_rz[tile] = w[0];
         if (kInit) part_rr[tile] = w[1];
     };
-    if (tile_blocks(d) > 0) {
+    if (d.ce > d.cs) {
         tile_reduce_async<2>(v, sm.red, pipe, write);
     } else {
         tile_reduce<2>(v, sm.scratch, pipe);
@@ -400,6 +404,37 @@ __device__ __forceinline__ void phase_dotrz(const Ctx& ctx, const SysDev& S, con
 // ---- PH_FWD / PH_BWD (SOLVE): y = L^-1 r_new ; z_new = L^-T y ---------------------------------------------------
 // The participating warps are dealt to the systems (system s gets warps s, s + nsys, ...), so the solves of a batch
 // advance side by side: the critical path (levels x L2 round trip) is paid once per batch, not once per system.
+// Out of line on purpose: the level-stream solve keeps two tiles of row metadata in registers; inlined into the
+// persistent kernel it would push the SpMV phases into register spills.
+template <bool kUpper>
+__device__ __noinline__ void trsv_level_stream_outlined(const LsFactor* F, const double* rhs, double* x,
+                                                        unsigned char* stage_bytes, LsShared* ls, TileDesc* tab) {
+    trsv_level_stream<kUpper>(*F, rhs, x, stage_bytes, *ls, tab, kMaxRoundTiles);
+}
+
+// Systems that come with a level-ordered copy of the factor are solved by ONE CTA each (trsv_ls.cuh); they borrow table
+// P2 for their tile descriptors (a SOLVE system never streams in APPLY2).
+template <bool kUpper, bool kInit>
+__device__ __forceinline__ void phase_trsv_ls(const Ctx& ctx, int k, Smem& sm) {
+    bool used = false;
+    for (int s = blockIdx.x; s < ctx.nsys; s += gridDim.x) {
+        const SysDev* S = ctx.sys + s;
+        if (S->precond != DP_PRECOND_SOLVE) continue;
+        const LsFactor F = kUpper ? S->bwd_ls : S->fwd_ls;
+        if (!F.rowptr) continue;
+        if (!kInit && ld_relaxed_s32(ctx.state + s) != 0) continue;
+        const double* rhs = kUpper ? S->t : S->r[(k + 1) & 1];
+        double* x = kUpper ? S->z[(k + 1) & 1] : S->t;
+        trsv_level_stream_outlined<kUpper>(&F, rhs, x, sm.pipe.bytes, &sm.ls, sm.tab[TAB_P2]);
+        used = true;
+    }
+    if (used) {
+        __syncthreads();
+        if (threadIdx.x == 0) sm.tab_ver[TAB_P2] = 0;
+        __syncthreads();
+    }
+}
+
 template <bool kUpper, bool kInit>
 __device__ __forceinline__ bool phase_trsv(const Ctx& ctx, int k, const Smem& sm) {
     const int pw = kUpper ? ctx.pw_bwd : ctx.pw_fwd;
@@ -414,6 +449,7 @@ __device__ __forceinline__ bool phase_trsv(const Ctx& ctx, int k, const Smem& sm
     for (int s = pw >= nsys ? gw % nsys : gw; s < nsys; s += pw) {
         const SysDev& S = (sm.sys_id == s) ? sm.sys : ctx.sys[s];
         if (S.precond != DP_PRECOND_SOLVE) continue;
+        if ((kUpper ? S.bwd_ls.rowptr : S.fwd_ls.rowptr) != nullptr) continue;  // solved by phase_trsv_ls
         if (!kInit && ld_relaxed_s32(ctx.state + s) != 0) continue;
         const long long nchunks = __ldg(ofs + s + 1) - __ldg(ofs + s);
         bool ok;
@@ -548,8 +584,10 @@ __device__ __forceinline__ bool apply_preconditioner(const Ctx& ctx, int k, int 
         trace(ctx, sm, 8 * PH_APPLY2 + 2);
     }
     if (ctx.has_solve) {
+        if (ctx.has_ls) phase_trsv_ls<false, kInit>(ctx, k, sm);
         const bool f = phase_trsv<false, kInit>(ctx, k, sm);
         if (bar.sync() < 0 || !f) return false;
+        if (ctx.has_ls) phase_trsv_ls<true, kInit>(ctx, k, sm);
         const bool b = phase_trsv<true, kInit>(ctx, k, sm);
         if (bar.sync() < 0 || !b) return false;
         run_tiles<PH_DOTRZ, kInit, false>(ctx, k, cur, ver, sm, pipe);
@@ -564,8 +602,9 @@ __device__ __forceinline__ Smem& smem_init(unsigned char* raw, Pipe& pipe) {
         sm.sys_id = -1, sm.trace_pos = 0;
         sm.tab_ver[0] = sm.tab_ver[1] = sm.tab_ver[2] = 0;
         for (int i = 0; i < kRedRing; ++i) sm.red.count[i] = 0;
+        sm.ls.init();
     }
-    pipe.init(&sm.pipe);  // ends with a CTA barrier
+    pipe.init(sm.pipe.bytes, &sm.pipe.bar);  // ends with a CTA barrier
     return sm;
 }
 
@@ -604,8 +643,10 @@ __global__ void __launch_bounds__(kBlock, 2) pcg_phase_kernel(Ctx ctx, int k) {
     Pipe pipe;
     Smem& sm = smem_init(smem_raw, pipe);
     if (kPhase == PH_FWD) {
+        if (ctx.has_ls) phase_trsv_ls<false, kInit>(ctx, k, sm);
         phase_trsv<false, kInit>(ctx, k, sm);
     } else if (kPhase == PH_BWD) {
+        if (ctx.has_ls) phase_trsv_ls<true, kInit>(ctx, k, sm);
         phase_trsv<true, kInit>(ctx, k, sm);
     } else {
         run_tiles<kPhase, kInit, true>(ctx, k, 0, 1, sm, pipe);
@@ -729,7 +770,7 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
     std::vector<SysDev> sys((size_t)nsys);
     std::vector<int> tile_ofs((size_t)nsys + 1, 0), fwd_ofs((size_t)nsys + 1, 0), bwd_ofs((size_t)nsys + 1, 0);
     std::vector<int> ident((size_t)nsys + 1, 0);
-    int has_multiply = 0, has_solve = 0;
+    int has_multiply = 0, has_solve = 0, has_ls = 0;
     long long sum_fwd_lvl = 0, sum_bwd_lvl = 0;
     for (int i = 0; i < nsys; ++i) {
         const dp_pcg_system_t& u = systems_host[i];
@@ -746,6 +787,20 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
         d.dinv = u.dinv;
         d.fwd_plan = u.fwd_plan;
         d.bwd_plan = u.bwd_plan;
+        d.fwd_ls = LsFactor{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
+        d.bwd_ls = d.fwd_ls;
+        if (u.precond == DP_PRECOND_SOLVE) {
+            if (u.fwd_ls_rowptr && u.fwd_ls_col && u.fwd_ls_val && u.fwd_ls_perm && u.fwd_ls_level) {
+                if (!aligned16(u.fwd_ls_col) || !aligned16(u.fwd_ls_val)) return DP_ERR_ALIGNMENT;
+                d.fwd_ls = LsFactor{u.fwd_ls_rowptr, u.fwd_ls_col, u.fwd_ls_val, u.fwd_ls_perm, u.fwd_ls_level, u.n, u.m_nnz};
+                has_ls = 1;
+            }
+            if (u.bwd_ls_rowptr && u.bwd_ls_col && u.bwd_ls_val && u.bwd_ls_perm && u.bwd_ls_level) {
+                if (!aligned16(u.bwd_ls_col) || !aligned16(u.bwd_ls_val)) return DP_ERR_ALIGNMENT;
+                d.bwd_ls = LsFactor{u.bwd_ls_rowptr, u.bwd_ls_col, u.bwd_ls_val, u.bwd_ls_perm, u.bwd_ls_level, u.n, u.mt_nnz};
+                has_ls = 1;
+            }
+        }
         d.fwd_look = u.fwd_max_level_chunks > 0 ? u.fwd_max_level_chunks : 1;
         d.bwd_look = u.bwd_max_level_chunks > 0 ? u.bwd_max_level_chunks : 1;
         int fwd_chunks = 0, bwd_chunks = 0;
@@ -822,6 +877,7 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
     ctx.total_bwd = bwd_ofs[(size_t)nsys];
     ctx.has_multiply = has_multiply;
     ctx.has_solve = has_solve;
+    ctx.has_ls = has_ls;
     ctx.rtol = params_host->rtol;
     ctx.max_iter = params_host->max_iter;
     ctx.word = reinterpret_cast<unsigned long long*>(ws + lay.word);

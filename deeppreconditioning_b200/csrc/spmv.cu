@@ -29,7 +29,7 @@ spmv_csr_kernel(CsrView A, const double* __restrict__ x, double* __restrict__ y)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SpmvSmem& sm = *reinterpret_cast<SpmvSmem*>(smem_raw);
     Pipe pipe;
-    pipe.init(&sm.pipe);
+    pipe.init(sm.pipe.bytes, &sm.pipe.bar);
     const int ntiles = (A.n + kTileRows - 1) / kTileRows;
     const int per = (ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
     const int g0 = blockIdx.x * per, g1 = min(ntiles, g0 + per);

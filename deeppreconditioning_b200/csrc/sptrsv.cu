@@ -4,6 +4,7 @@
 #include <vector>
 
 #include "sptrsv.cuh"
+#include "trsv_ls.cuh"
 
 namespace dp {
 
@@ -65,6 +66,37 @@ sptrsv_batch_kernel(const TrsvSysDev* __restrict__ sys, int nsys, int wps, unsig
         else
             ok = sptrsv_stream<false>(S.T, S.plan, local, team, S.nchunks, S.lookback, rhs, S.x, ctl);
         if (!ok) return;
+    }
+}
+
+// ---- level-stream solve (trsv_ls.cuh): one CTA per system, systems dealt round robin -----------------------------
+constexpr int kLsRound = 16;  // tile descriptors per table refill
+
+struct LsSysDev {
+    LsFactor F;
+    const double* b;
+    double* x;
+    int upper, pad;
+};
+
+struct LsSmem {
+    alignas(16) unsigned char bytes[PipeGeom<kLsCap, kLsStages>::kBytes];
+    LsShared ls;
+    TileDesc tab[kLsRound];
+};
+
+// One CTA per SM is enough (a solve is latency bound, not occupancy bound) and leaves the registers to avoid spills.
+__global__ void __launch_bounds__(kBlock, 1) sptrsv_ls_batch_kernel(const LsSysDev* __restrict__ sys, int nsys) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    LsSmem& sm = *reinterpret_cast<LsSmem*>(smem_raw);
+    if (threadIdx.x == 0) sm.ls.init();
+    __syncthreads();
+    for (int s = blockIdx.x; s < nsys; s += gridDim.x) {
+        const LsSysDev S = sys[s];
+        if (S.upper)
+            trsv_level_stream<true>(S.F, S.b, S.x, sm.bytes, sm.ls, sm.tab, kLsRound);
+        else
+            trsv_level_stream<false>(S.F, S.b, S.x, sm.bytes, sm.ls, sm.tab, kLsRound);
     }
 }
 
@@ -234,6 +266,51 @@ int dp_sptrsv_solve_batch_f64(const dp_trsv_system_t* systems_host, int32_t nsys
     int wps_i = (int)wps, nsys_i = nsys;
     void* args[] = {&sys, &nsys_i, &wps_i, &word, &flag_out};
     DP_CUDA(cudaLaunchCooperativeKernel((const void*)sptrsv_batch_kernel, dim3(grid), dim3(kBlock), args, 0, s));
+    return DP_OK;
+}
+
+#ifdef DPCG_LS_TRACE
+int dp_debug_ls_trace(long long* out_host) {
+    DP_CUDA(cudaMemcpyFromSymbol(out_host, g_ls_trace, sizeof(long long) * 8 * 256));
+    return DP_OK;
+}
+#endif
+
+void dp_sptrsv_ls_limits(int32_t* limits_host) {
+    limits_host[0] = kLsCap;                  // one pipeline item per 512-row tile
+    limits_host[1] = kLsRowEntries;           // a row's entries live in registers
+    limits_host[2] = kLsWindow - kTileRows;   // every dependency is still in the shared-memory window
+}
+
+size_t dp_sptrsv_ls_workspace_bytes(int32_t nsys) { return align_up(sizeof(LsSysDev) * (size_t)(nsys > 0 ? nsys : 0), 256); }
+
+int dp_sptrsv_ls_solve_batch_f64(const dp_trsv_ls_system_t* systems_host, int32_t nsys, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+    if (!systems_host || nsys <= 0 || !workspace) return DP_ERR_INVALID;
+    if (workspace_bytes < dp_sptrsv_ls_workspace_bytes(nsys)) return DP_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    std::vector<LsSysDev> dev((size_t)nsys);
+    for (int i = 0; i < nsys; ++i) {
+        const dp_trsv_ls_system_t& u = systems_host[i];
+        if (u.n <= 0 || !u.rowptr_p || !u.col_p || !u.val_p || !u.perm || !u.level_sorted || !u.b || !u.x) return DP_ERR_INVALID;
+        if (!aligned16(u.col_p) || !aligned16(u.val_p)) return DP_ERR_ALIGNMENT;
+        LsSysDev d{};
+        d.F = LsFactor{u.rowptr_p, u.col_p, u.val_p, u.perm, u.level_sorted, u.n, u.nnz};
+        d.b = u.b, d.x = u.x, d.upper = u.upper ? 1 : 0;
+        dev[(size_t)i] = d;
+    }
+    LsSysDev* sys = static_cast<LsSysDev*>(workspace);
+    DP_CUDA(cudaMemcpyAsync(sys, dev.data(), sizeof(LsSysDev) * (size_t)nsys, cudaMemcpyHostToDevice, s));
+    DP_CUDA(cudaStreamSynchronize(s));  // `dev` is a stack-lifetime staging buffer
+    static thread_local bool smem_ok = false;
+    if (!smem_ok) {
+        DP_CUDA(cudaFuncSetAttribute((const void*)sptrsv_ls_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(LsSmem)));
+        smem_ok = true;
+    }
+    const int resident = sm_count();
+    sptrsv_ls_batch_kernel<<<nsys < resident ? nsys : resident, kBlock, sizeof(LsSmem), s>>>(sys, nsys);
+    DP_LAUNCH_CHECK();
     return DP_OK;
 }
 

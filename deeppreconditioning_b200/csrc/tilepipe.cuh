@@ -42,9 +42,7 @@ namespace dp {
 
 constexpr int kPipeCap = DPCG_PIPE_CAP;        // entries per stage (multiple of 4)
 constexpr int kPipeStages = DPCG_PIPE_STAGES;
-constexpr int kPipeSlots = kPipeCap + 8;       // up to 3 lead-in entries (16-byte alignment) + tail rounding
 constexpr int kPipeUnroll = DPCG_PIPE_UNROLL;  // gathers in flight per thread
-static_assert(kPipeCap % 4 == 0 && kPipeCap >= 64, "stage capacity");
 
 // ---- PTX wrappers (sm_90+/sm_100a) ---------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -114,14 +112,31 @@ struct TileDesc {
     int sys;     // system id (PCG), unused by the standalone kernel
 };
 
-struct PipeShared {
-    alignas(16) double val[kPipeStages][kPipeSlots];
-    alignas(16) int col[kPipeStages][kPipeSlots];
-    alignas(8) unsigned long long full[kPipeStages];   // producer -> consumers: bytes have landed
-    alignas(8) unsigned long long empty[kPipeStages];  // consumers -> producer: all 16 warps are done with the stage
+// Shared memory of a pipeline of geometry (kCap entries per stage, kStages stages): the stages' bytes (values first,
+// then column indices) and one full/empty mbarrier pair per stage. Several geometries may be laid over the same bytes
+// (each with its own barriers) as long as only one of them has items in flight at a time.
+template <int kCap, int kStages>
+struct PipeGeom {
+    static constexpr int kSlots = kCap + 8;  // up to 3 lead-in entries (16-byte alignment) + tail rounding
+    static constexpr size_t kBytes = (size_t)kStages * kSlots * 12;
+    static_assert(kCap % 4 == 0 && kCap >= 64, "stage capacity");
 };
-
-__device__ __forceinline__ int tile_blocks(const TileDesc& d) { return (d.ce - d.cs + kPipeCap - 1) / kPipeCap; }
+template <int kStages>
+struct PipeBarriers {
+    alignas(8) unsigned long long full[kStages];   // producer -> consumers: bytes have landed
+    alignas(8) unsigned long long empty[kStages];  // consumers -> producer: all 16 warps are done with the stage
+};
+// The level-stream triangular solve (trsv_ls.cuh) lays a finer, deeper geometry over the same bytes: its tiles are
+// small (a stencil factor has 3 entries per row) and its stream is latency bound, so it wants many items in flight.
+constexpr int kLsCap = 1536;
+constexpr int kLsStages = 5;
+constexpr size_t kPipeRawBytes = PipeGeom<kPipeCap, kPipeStages>::kBytes > PipeGeom<kLsCap, kLsStages>::kBytes
+                                     ? PipeGeom<kPipeCap, kPipeStages>::kBytes
+                                     : PipeGeom<kLsCap, kLsStages>::kBytes;
+struct PipeShared {
+    alignas(16) unsigned char bytes[kPipeRawBytes];
+    PipeBarriers<kPipeStages> bar;
+};
 
 // Fill the stream part of a descriptor for tile `ltile` of matrix M (one dependent load pair; CTA-parallel in the
 // table builders).
@@ -140,10 +155,16 @@ __device__ __forceinline__ void tile_desc_fill(TileDesc& d, const CsrView& M, in
     }
 }
 
-// Register state of the pipeline; lives for the whole kernel. Items are numbered since kernel start: item i lives in
-// stage i % kPipeStages and is the (i / kPipeStages)-th use of that stage, which fixes the mbarrier parities.
-struct Pipe {
-    PipeShared* sh;
+// Register state of a pipeline; lives for the whole kernel (or is saved/restored through `counts()`/`resume()`).
+// Items are numbered since kernel start: item i lives in stage i % kStages and is the (i / kStages)-th use of that
+// stage, which fixes the mbarrier parities.
+template <int kCap, int kStages>
+struct PipeT {
+    static constexpr int kSlots = PipeGeom<kCap, kStages>::kSlots;
+    double* val0;  // stage s: val0 + s * kSlots, col0 + s * kSlots
+    int* col0;
+    unsigned long long* full;
+    unsigned long long* empty;
     const TileDesc* tab;
     int ntiles;
     unsigned c_count;   // items this warp has consumed
@@ -152,51 +173,63 @@ struct Pipe {
     unsigned t_count;   // streaming tiles this warp has reduced (ring index of tile_reduce_async)
     int flip;           // tile_reduce scratch buffer in use next
 
-    __device__ __forceinline__ void init(PipeShared* shared) {
-        sh = shared;
+    static __device__ __forceinline__ int blocks(const TileDesc& d) { return (d.ce - d.cs + kCap - 1) / kCap; }
+    __device__ __forceinline__ const double* stage_val(unsigned s) const { return val0 + (size_t)s * kSlots; }
+    __device__ __forceinline__ const int* stage_col(unsigned s) const { return col0 + (size_t)s * kSlots; }
+
+    // Bind to shared memory. `fresh`: initialise the barriers (once per kernel and geometry); ends with a CTA barrier.
+    __device__ __forceinline__ void init(unsigned char* bytes, PipeBarriers<kStages>* bar, bool fresh = true) {
+        val0 = reinterpret_cast<double*>(bytes);
+        col0 = reinterpret_cast<int*>(bytes + (size_t)kStages * kSlots * 8);
+        full = bar->full, empty = bar->empty;
         tab = nullptr;
         ntiles = 0;
         c_count = 0u, p_count = 0u, p_tile = 0, p_blk = 0, t_count = 0u, flip = 0;
-        if (threadIdx.x == 0) {
+        if (fresh) {
+            if (threadIdx.x == 0) {
 #pragma unroll
-            for (int s = 0; s < kPipeStages; ++s) {
-                mbar_init(&sh->full[s], 1u);
-                mbar_init(&sh->empty[s], (unsigned)kWarpsPerBlock);
+                for (int s = 0; s < kStages; ++s) {
+                    mbar_init(&full[s], 1u);
+                    mbar_init(&empty[s], (unsigned)kWarpsPerBlock);
+                }
+                mbar_fence_init();
             }
-            mbar_fence_init();
+            __syncthreads();
         }
-        __syncthreads();
     }
+    // A pipeline that is only used now and then inside a long kernel keeps nothing but its item count between uses
+    // (all items consumed, producer and consumers agree): resume(count) after init(..., false).
+    __device__ __forceinline__ void resume(unsigned items) { c_count = p_count = items; }
 
     // Lane 0 of warp 0: issue the next item of the round if its stage is free. `blocking`: wait for the stage
     // (only legal when this warp has itself consumed the stage's previous item). Returns true if an item went out.
     __device__ __forceinline__ bool issue_one(bool blocking) {
         while (p_tile < ntiles) {
-            if (p_blk < tile_blocks(tab[p_tile])) break;
+            if (p_blk < blocks(tab[p_tile])) break;
             ++p_tile, p_blk = 0;
         }
         if (p_tile >= ntiles) return false;
-        if (p_count - c_count >= (unsigned)kPipeStages) return false;  // this warp still owns the stage's previous item
-        const unsigned stage = p_count % kPipeStages, use = p_count / kPipeStages;
+        if (p_count - c_count >= (unsigned)kStages) return false;  // this warp still owns the stage's previous item
+        const unsigned stage = p_count % kStages, use = p_count / kStages;
         if (use > 0) {
             const unsigned par = (use - 1u) & 1u;
             if (blocking) {
-                while (!mbar_try_wait(&sh->empty[stage], par)) {
+                while (!mbar_try_wait(&empty[stage], par)) {
                 }
-            } else if (!mbar_test_wait(&sh->empty[stage], par)) {
+            } else if (!mbar_test_wait(&empty[stage], par)) {
                 return false;
             }
         }
         const TileDesc& d = tab[p_tile];
-        const int bs = d.cs + p_blk * kPipeCap;
-        const int be = min(d.ce, bs + kPipeCap);
+        const int bs = d.cs + p_blk * kCap;
+        const int be = min(d.ce, bs + kCap);
         const int as = bs & ~3;
         const unsigned ncol = (unsigned)(((be + 3) & ~3) - as), nval = (unsigned)(((be + 1) & ~1) - as);
-        unsigned long long* bar = &sh->full[stage];
+        unsigned long long* bar = &full[stage];
         const unsigned long long pol = l2_policy_stream();
         mbar_arrive_expect_tx(bar, ncol * 4u + nval * 8u);
-        bulk_g2s(sh->val[stage], d.val + as, nval * 8u, bar, pol);
-        bulk_g2s(sh->col[stage], d.col + as, ncol * 4u, bar, pol);
+        bulk_g2s(val0 + (size_t)stage * kSlots, d.val + as, nval * 8u, bar, pol);
+        bulk_g2s(col0 + (size_t)stage * kSlots, d.col + as, ncol * 4u, bar, pol);
         ++p_blk, ++p_count;
         return true;
     }
@@ -213,29 +246,67 @@ struct Pipe {
         }
     }
 
+    // Lean producer for streams whose tiles are exactly one item each (the level-stream solve): thread 0 issues tile t
+    // of the round into the next stage, waiting for the stage if it has been used before. No table walk.
+    __device__ __forceinline__ void issue_tile(int t) {
+        const unsigned stage = p_count % kStages, use = p_count / kStages;
+        if (use > 0) {  // spin without suspending: the caller issues into a stage that was released a tile ago
+            while (!mbar_test_wait(&empty[stage], (use - 1u) & 1u)) {
+            }
+        }
+        const TileDesc& d = tab[t];
+        const int as = d.cs & ~3;
+        const unsigned ncol = (unsigned)(((d.ce + 3) & ~3) - as), nval = (unsigned)(((d.ce + 1) & ~1) - as);
+        unsigned long long* bar = &full[stage];
+        const unsigned long long pol = l2_policy_stream();
+        mbar_arrive_expect_tx(bar, ncol * 4u + nval * 8u);
+        bulk_g2s(val0 + (size_t)stage * kSlots, d.val + as, nval * 8u, bar, pol);
+        bulk_g2s(col0 + (size_t)stage * kSlots, d.col + as, ncol * 4u, bar, pol);
+        ++p_count;
+    }
+    // ... and its consumer side: wait for the next item without any producer duty.
+    __device__ __forceinline__ unsigned wait_item() {
+        const unsigned stage = c_count % kStages;
+        while (!mbar_try_wait(&full[stage], (c_count / kStages) & 1u)) {
+        }
+        return stage;
+    }
+
+    // Consumer side of one item: acquire() waits until the item's bytes have landed and returns its stage; release()
+    // hands the stage back once this warp has read what it needs. Every warp acquires and releases every item of the
+    // round, in order. Thread 0 doubles as the producer: the item about to be consumed must be out, then it tops up.
+    __device__ __forceinline__ unsigned acquire() {
+        if (threadIdx.x == 0) {
+            while (p_count <= c_count) issue_one(true);
+            while (issue_one(false)) {
+            }
+        }
+        const unsigned stage = c_count % kStages;
+        const unsigned par = (c_count / kStages) & 1u;
+        while (!mbar_try_wait(&full[stage], par)) {
+        }
+        return stage;
+    }
+    __device__ __forceinline__ void release() {
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[c_count % kStages]);
+        ++c_count;
+    }
+
     // Row sum of this thread's row (entries [rs, re) of the matrix, empty for rows >= n) of tile d.
     // Every warp of the CTA must call it for every tile of the round, in order (`compute == false` only drains).
     template <int kUnroll = kPipeUnroll, class Gather>
     __device__ __forceinline__ double tile_spmv(const TileDesc& d, int rs, int re, const Gather& x, bool compute) {
         double sum = 0.0;
-        const int nb = tile_blocks(d);
-        const int lane = threadIdx.x & 31;
+        const int nb = blocks(d);
         for (int j = 0; j < nb; ++j) {
-            const int bs = d.cs + j * kPipeCap;
-            const int be = min(d.ce, bs + kPipeCap);
+            const int bs = d.cs + j * kCap;
+            const int be = min(d.ce, bs + kCap);
             const int as = bs & ~3;
-            if (threadIdx.x == 0) {  // producer duty: the item about to be consumed must be out; then top up
-                while (p_count <= c_count) issue_one(true);
-                while (issue_one(false)) {
-                }
-            }
-            const unsigned stage = c_count % kPipeStages;
-            const unsigned par = (c_count / kPipeStages) & 1u;
-            while (!mbar_try_wait(&sh->full[stage], par)) {
-            }
+            const unsigned stage = acquire();
             if (compute) {
-                const double* __restrict__ sv = sh->val[stage];
-                const int* __restrict__ sc = sh->col[stage];
+                const double* __restrict__ sv = stage_val(stage);
+                const int* __restrict__ sc = stage_col(stage);
                 const int qe = min(re, be) - as;
                 for (int q = max(rs, bs) - as; q < qe; q += kUnroll) {
                     int c[kUnroll];
@@ -253,9 +324,7 @@ struct Pipe {
                         if (q + u < qe) sum = __dadd_rn(sum, __dmul_rn(v[u], xv[u]));
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sh->empty[stage]);
-            ++c_count;
+            release();
         }
         return sum;
     }
@@ -263,6 +332,8 @@ struct Pipe {
     // Drain the items of a tile whose result is not wanted (its system finished in this very iteration).
     __device__ __forceinline__ void tile_skip(const TileDesc& d) { tile_spmv<1>(d, 0, 0, GatherPlain{nullptr}, false); }
 };
+
+using Pipe = PipeT<kPipeCap, kPipeStages>;  // the SpMV geometry: whole tiles per stage
 
 // Row extent of this thread's row in tile d (coalesced; issue one tile ahead to hide the latency).
 __device__ __forceinline__ void tile_row_extent(const TileDesc& d, int& rs, int& re) {

@@ -37,11 +37,55 @@ class TriangularPlan:
     nchunks: int
     max_level_chunks: int
     upper: bool
+    ls: "LevelOrdered | None" = None  # level-ordered copy of the factor (narrow levels): level-stream solve
 
 
-def analyse(matrix: CsrMatrix, upper: bool) -> TriangularPlan:
+@dataclass
+class LevelOrdered:
+    """Level-ordered copy of a triangular factor (``dp_sptrsv_permute``), input of the level-stream solve."""
+
+    rowptr: torch.Tensor        # int32[n+1]
+    col: torch.Tensor           # int32[nnz], positions in level order
+    val: torch.Tensor           # fp64[nnz], entries in the factor's order inside each row
+    level_sorted: torch.Tensor  # int32[n]
+    nnz: int
+    source: int                 # data_ptr of the values it was copied from (a plan may serve several factors)
+
+    def matches(self, matrix: CsrMatrix) -> bool:
+        return self.source == matrix.val.data_ptr()
+
+
+LS_MAX_MEAN_LEVEL_ROWS = 1024  # level-stream solve when n / nlevels is at most this (one CTA must keep up)
+
+
+def level_ordered(matrix: CsrMatrix, plan: TriangularPlan) -> LevelOrdered | None:
+    """Build the level-ordered copy if the factor qualifies for the level-stream solve, else ``None``."""
+    lib, n, dev = _lib.lib(), matrix.n, matrix.device
+    if n == 0 or plan.nlevels == 0 or n / plan.nlevels > LS_MAX_MEAN_LEVEL_ROWS:
+        return None
+    i32 = dict(dtype=torch.int32, device=dev)
+    rowptr_p, level_sorted = torch.empty(n + 1, **i32), torch.empty(n, **i32)
+    col_p = torch.empty(max(matrix.nnz, 1), **i32)
+    val_p = torch.empty(max(matrix.nnz, 1), dtype=torch.float64, device=dev)
+    stats = torch.zeros(3, **i32)
+    ws = _workspace(lib.dp_sptrsv_permute_workspace_bytes(n), dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.dp_sptrsv_permute(n, _lib.ptr(matrix.rowptr), _lib.ptr(matrix.col), _lib.ptr(matrix.val),
+                                         _lib.ptr(plan.perm), _lib.ptr(plan.level), _lib.ptr(rowptr_p), _lib.ptr(col_p),
+                                         _lib.ptr(val_p), _lib.ptr(level_sorted), _lib.ptr(stats), _lib.ptr(ws), ws.numel(),
+                                         _lib.stream_ptr(dev)), "dp_sptrsv_permute")
+    limits = np.zeros(3, np.int32)
+    lib.dp_sptrsv_ls_limits(limits.ctypes.data)
+    if np.any(stats.cpu().numpy() > limits):  # once per matrix: tile entries, row entries, dependency distance
+        return None
+    return LevelOrdered(rowptr_p, col_p[: matrix.nnz], val_p[: matrix.nnz], level_sorted, matrix.nnz, matrix.val.data_ptr())
+
+
+def analyse(matrix: CsrMatrix, upper: bool, level_stream: bool = True) -> TriangularPlan:
     """``dp_sptrsv_analyse`` + ``dp_sptrsv_plan_build``. ``upper=False``: lower triangular, diagonal last in each row;
-    ``upper=True``: upper triangular (``L^T``), diagonal first."""
+    ``upper=True``: upper triangular (``L^T``), diagonal first. With ``level_stream`` a factor with narrow levels also
+    gets its level-ordered copy (``dp_sptrsv_permute``) and is then solved by the level-stream kernel. The copy holds
+    the VALUES of ``matrix`` at analysis time: analyse the numeric factor, not just its pattern."""
     lib, n, dev = _lib.lib(), matrix.n, matrix.device
     i32 = dict(dtype=torch.int32, device=dev)
     level, perm = torch.empty(n, **i32), torch.empty(n, **i32)
@@ -64,16 +108,26 @@ def analyse(matrix: CsrMatrix, upper: bool) -> TriangularPlan:
     with torch.cuda.device(dev):
         _lib.check(lib.dp_sptrsv_plan_build(n, nlevels, _lib.ptr(perm), _lib.ptr(level_ptr), _lib.ptr(chunk_ptr),
                                             _lib.ptr(plan), nchunks, _lib.stream_ptr(dev)), "dp_sptrsv_plan_build")
-    return TriangularPlan(level, perm, level_ptr[: nlevels + 1], nlevels, plan, nchunks,
-                          int(chunks.max()) if nlevels else 0, bool(upper))
+    out = TriangularPlan(level, perm, level_ptr[: nlevels + 1], nlevels, plan, nchunks,
+                         int(chunks.max()) if nlevels else 0, bool(upper))
+    if level_stream:
+        out.ls = level_ordered(matrix, out)
+    return out
 
 
-def triangular_solve(matrix: CsrMatrix, plan: TriangularPlan, b: torch.Tensor, out: torch.Tensor | None = None):
-    """Solve ``T x = b`` with the sync-free kernel (``dp_sptrsv_solve_f64``)."""
+def triangular_solve(matrix: CsrMatrix, plan: TriangularPlan, b: torch.Tensor, out: torch.Tensor | None = None,
+                     algorithm: str = "auto"):
+    """Solve ``T x = b``: level-stream kernel when the plan carries a level-ordered copy (``algorithm`` "auto"/"ls"),
+    else the sync-free kernel (``dp_sptrsv_solve_f64``, forced with "syncfree"). Same bits either way."""
     lib, n, dev = _lib.lib(), matrix.n, matrix.device
     assert b.is_cuda and b.dtype == torch.float64 and b.shape == (n,)
     b = b.contiguous()
     x = out if out is not None else torch.empty(n, dtype=torch.float64, device=dev)
+    has_ls = plan.ls is not None and plan.ls.matches(matrix)
+    if algorithm == "ls" and not has_ls:
+        raise _lib.DpcgError("this plan has no level-ordered copy of this matrix (levels too wide or rows too long)")
+    if algorithm != "syncfree" and has_ls:
+        return _level_stream_batch([(matrix, plan, b)], [x])[0]
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
     ws = _workspace(lib.dp_sptrsv_workspace_bytes(), dev)
     with torch.cuda.device(dev):
@@ -85,7 +139,30 @@ def triangular_solve(matrix: CsrMatrix, plan: TriangularPlan, b: torch.Tensor, o
     return x
 
 
-def triangular_solve_batch(systems, outs=None):
+def _level_stream_batch(systems, outs=None, copies=None):
+    lib = _lib.lib()
+    dev = systems[0][0].device
+    nsys = len(systems)
+    descs = (_lib.TrsvLsSystem * nsys)()
+    xs, keep = [], []
+    for i, (matrix, plan, b) in enumerate(systems):
+        n, ls = matrix.n, (copies[i] if copies is not None else plan.ls)
+        assert b.is_cuda and b.dtype == torch.float64 and b.shape == (n,)
+        b = b.contiguous()
+        x = outs[i] if outs is not None else torch.empty(n, dtype=torch.float64, device=dev)
+        d = descs[i]
+        d.n, d.nnz, d.upper = n, ls.nnz, int(plan.upper)
+        d.rowptr_p, d.col_p, d.val_p = _lib.ptr(ls.rowptr), _lib.ptr(ls.col), _lib.ptr(ls.val)
+        d.perm, d.level_sorted, d.b, d.x = _lib.ptr(plan.perm), _lib.ptr(ls.level_sorted), _lib.ptr(b), _lib.ptr(x)
+        xs.append(x), keep.append(b)
+    ws = _workspace(lib.dp_sptrsv_ls_workspace_bytes(nsys), dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.dp_sptrsv_ls_solve_batch_f64(descs, nsys, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)),
+                   "dp_sptrsv_ls_solve_batch_f64")
+    return xs
+
+
+def triangular_solve_batch(systems, outs=None, algorithm: str = "auto"):
     """Independent solves ``T_s x_s = b_s`` in ONE launch (``dp_sptrsv_solve_batch_f64``).
 
     ``systems``: list of ``(matrix, plan, b)``; returns the list of solutions. The resident warps are dealt to the
@@ -94,6 +171,10 @@ def triangular_solve_batch(systems, outs=None):
     lib = _lib.lib()
     dev = systems[0][0].device
     nsys = len(systems)
+    if algorithm != "syncfree" and all(plan.ls is not None and plan.ls.matches(m) for m, plan, _ in systems):
+        return _level_stream_batch(systems, outs)
+    if algorithm == "ls":
+        raise _lib.DpcgError("a plan of this batch has no level-ordered copy")
     descs = (_lib.TrsvSystem * nsys)()
     xs, keep = [], []
     for i, (matrix, plan, b) in enumerate(systems):
@@ -213,13 +294,22 @@ class FactoredSolve(FactoredMultiply):
     precond = _lib.PRECOND_SOLVE
 
     def __init__(self, L: CsrMatrix, Lt: CsrMatrix | None = None, fwd: TriangularPlan | None = None,
-                 bwd: TriangularPlan | None = None) -> None:
+                 bwd: TriangularPlan | None = None, level_stream: bool = True) -> None:
         super().__init__(L, Lt)
-        self.fwd = fwd or analyse(self.L, upper=False)
-        self.bwd = bwd or analyse(self.Lt, upper=True)
+        self.fwd = fwd or analyse(self.L, upper=False, level_stream=False)
+        self.bwd = bwd or analyse(self.Lt, upper=True, level_stream=False)
+        # level-ordered copies of THIS factor's values (a plan may have been made on another matrix of the same pattern)
+        own = lambda plan, m: plan.ls if (plan.ls is not None and plan.ls.matches(m)) else level_ordered(m, plan)
+        self.fwd_ls = own(self.fwd, self.L) if level_stream else None
+        self.bwd_ls = own(self.bwd, self.Lt) if level_stream else None
 
     def _apply(self, r):
-        return triangular_solve(self.Lt, self.bwd, triangular_solve(self.L, self.fwd, r))
+        def one(m, plan, copy, b):
+            if copy is not None:
+                return _level_stream_batch([(m, plan, b)], None, [copy])[0]
+            return triangular_solve(m, plan, b, algorithm="syncfree")
+
+        return one(self.Lt, self.bwd, self.bwd_ls, one(self.L, self.fwd, self.fwd_ls, r))
 
     def fill(self, system):
         super().fill(system)
@@ -227,6 +317,11 @@ class FactoredSolve(FactoredMultiply):
         system.fwd_plan, system.bwd_plan = _lib.ptr(self.fwd.plan), _lib.ptr(self.bwd.plan)
         system.fwd_nchunks, system.bwd_nchunks = self.fwd.nchunks, self.bwd.nchunks
         system.fwd_max_level_chunks, system.bwd_max_level_chunks = self.fwd.max_level_chunks, self.bwd.max_level_chunks
+        for tag, plan, ls in (("fwd", self.fwd, self.fwd_ls), ("bwd", self.bwd, self.bwd_ls)):
+            if ls is not None:
+                for name, t in (("rowptr", ls.rowptr), ("col", ls.col), ("val", ls.val), ("perm", plan.perm),
+                                ("level", ls.level_sorted)):
+                    setattr(system, f"{tag}_ls_{name}", _lib.ptr(t))
 
 
 def as_operator(M, device=None) -> _Operator:

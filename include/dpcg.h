@@ -114,6 +114,17 @@ int64_t dp_sptrsv_plan_chunks(int32_t nlevels, const int32_t* level_ptr_host);
 int dp_sptrsv_plan_build(int32_t n, int32_t nlevels, const int32_t* perm, const int32_t* level_ptr,
                          const int32_t* chunk_ptr, int32_t* plan, int64_t nchunks, void* stream);
 
+/* Level-ordered copy of a triangular factor, the input of the level-stream solve (below): row r of the copy is row
+ * perm[r] of T, column indices are renumbered to positions in that order, entries keep T's order inside a row (sums
+ * stay bit-identical), level_sorted[r] = level[perm[r]]. rowptr_p int32[n+1], col_p/val_p as large as col/val.
+ * stats_out (device int32[3]): most entries in any 512 consecutive rows of the copy, most entries in a row, largest
+ * distance in positions between a row and a dependency. The level-stream solve accepts the copy when each is within
+ * the matching limit of dp_sptrsv_ls_limits(). */
+size_t dp_sptrsv_permute_workspace_bytes(int32_t n);
+int dp_sptrsv_permute(int32_t n, const int32_t* rowptr, const int32_t* col, const double* val, const int32_t* perm,
+                      const int32_t* level, int32_t* rowptr_p, int32_t* col_p, double* val_p, int32_t* level_sorted,
+                      int32_t* stats_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- K4: sparse triangular solves ------------------------------------------------------------------------
  * lower: L y = b;  upper: U z = b with U = L^T in CSR. x_i = (b_i - sum_j T_ij x_j) * (1 / T_ii), the sum
  * sequential in column order: bit-identical to plain forward/backward substitution (oracle/kernels.c).
@@ -142,6 +153,27 @@ size_t dp_sptrsv_batch_workspace_bytes(int32_t nsys);
 int dp_sptrsv_solve_batch_f64(const dp_trsv_system_t* systems_host, int32_t nsys, int32_t* flag_out, void* workspace,
                               size_t workspace_bytes, void* stream);
 
+/* Level-stream solve: ONE CTA per system walks the level-ordered copy through the TMA tile pipeline and releases the
+ * rows level by level with a CTA barrier; dependencies are picked up from a shared-memory window instead of polling
+ * L2. For factors with narrow levels (2-D stencils: 2n-1 levels of <= n rows) this replaces an L2 hop per level by a
+ * barrier (~10x faster per solve); a batch keeps one SM busy per system. Bit-identical to dp_sptrsv_solve_f64.
+ * b and x are in the ORIGINAL numbering. No cooperative launch, no device flag: nothing spins. */
+typedef struct dp_trsv_ls_system {
+    int32_t n;
+    int32_t nnz;
+    int32_t upper;   /* 0: lower (diagonal last in each row), 1: upper (diagonal first) */
+    int32_t reserved;
+    const int32_t* rowptr_p; const int32_t* col_p; const double* val_p; /* dp_sptrsv_permute outputs */
+    const int32_t* perm;
+    const int32_t* level_sorted;
+    const double* b;
+    double* x;
+} dp_trsv_ls_system_t;
+void dp_sptrsv_ls_limits(int32_t* limits_host /* [3]: tile entries, row entries, dependency distance */);
+size_t dp_sptrsv_ls_workspace_bytes(int32_t nsys);
+int dp_sptrsv_ls_solve_batch_f64(const dp_trsv_ls_system_t* systems_host, int32_t nsys, void* workspace,
+                                 size_t workspace_bytes, void* stream);
+
 /* ---- IC(0) on the pattern of tril(A) (stands in for ilupp.ichol0, test.py:84) -------------------------------
  * Level-scheduled, sync-free numeric factorisation; uses the lower plan of the same pattern.
  * *flag_out: DP_ERR_STRUCTURE on a non-positive pivot. */
@@ -167,6 +199,12 @@ typedef struct dp_pcg_system {
     const int32_t* mt_rowptr; const int32_t* mt_col; const double* mt_val;  /* L^T (MULTIPLY/SOLVE) */
     const double* dinv;                                                     /* JACOBI */
     const int32_t* fwd_plan; const int32_t* bwd_plan;                       /* SOLVE */
+    /* SOLVE, optional: level-ordered copies of L and L^T (dp_sptrsv_permute). When all five pointers of a direction
+     * are set that solve runs as a level-stream solve (one CTA per system) instead of the sync-free one. */
+    const int32_t* fwd_ls_rowptr; const int32_t* fwd_ls_col; const double* fwd_ls_val;
+    const int32_t* fwd_ls_perm; const int32_t* fwd_ls_level;
+    const int32_t* bwd_ls_rowptr; const int32_t* bwd_ls_col; const double* bwd_ls_val;
+    const int32_t* bwd_ls_perm; const int32_t* bwd_ls_level;
     const double* b;   /* right-hand side, n */
     double* x;         /* in: x0, out: x_hat, n */
     double* work;      /* dp_pcg_work_doubles(n) doubles of scratch, contents ignored on entry */

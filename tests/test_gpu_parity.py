@@ -152,29 +152,78 @@ def test_levels_and_triangular_solves_bit_exact(cuda, kind, side, net):
             assert np.array_equal(plan.level_ptr.cpu().numpy(), level_ptr), name
             rows = plan.plan.cpu().numpy()[: plan.nchunks * 32]
             assert np.array_equal(rows[rows >= 0], perm) and plan.nchunks == int(((np.diff(level_ptr) + 31) // 32).sum())
-        y = precond.triangular_solve(lower, fwd, b)
         y_want = ckernels.sptrsv_lower(*want, p.b.numpy())
-        assert np.array_equal(y.cpu().numpy(), y_want), name
-        z = precond.triangular_solve(upper_m, bwd, y)
-        assert np.array_equal(z.cpu().numpy(), ckernels.sptrsv_upper(*want_t, y_want)), name
+        z_want = ckernels.sptrsv_upper(*want_t, y_want)
+        algorithms = ["syncfree"] + (["ls"] if fwd.ls is not None and bwd.ls is not None else [])
+        if name == "tril(A)" and kind == "poisson2d":
+            assert "ls" in algorithms, "2-D stencil factors (3 entries per row) qualify for the level-stream solve"
+        if name == "L" and net == "net":
+            assert "ls" not in algorithms, "the CNN factor's rows are too long for the level-stream solve"
+        for algorithm in algorithms:  # both solvers: bit-identical to plain substitution
+            y = precond.triangular_solve(lower, fwd, b, algorithm=algorithm)
+            assert np.array_equal(y.cpu().numpy(), y_want), (name, algorithm)
+            z = precond.triangular_solve(upper_m, bwd, y, algorithm=algorithm)
+            assert np.array_equal(z.cpu().numpy(), z_want), (name, algorithm)
 
 
 def test_triangular_solve_batch_is_bitwise_the_single_solves(cuda):
     """Ragged batch (different sizes, lower and upper factors mixed) in one launch == one launch per system."""
     systems, singles = [], []
-    for kind, side, seed in [("poisson2d", 37, 0), ("poisson3d", 9, 1), ("poisson2d", 64, 2), ("poisson2d", 5, 3), ("poisson3d", 12, 4)]:
+    for kind, side, seed in [("poisson2d", 37, 0), ("poisson2d", 9, 1), ("poisson2d", 64, 2), ("poisson2d", 5, 3), ("poisson2d", 100, 4)]:
         p = helpers.problem(kind, side, seed, 0.5, None)
         lower = CsrMatrix.from_spconv(helpers.to_device(p.systems_tril, cuda), p.n, "tril")
         upper_m = lower.transpose()
         b = p.b.to(cuda)
         for m, up in [(lower, False), (upper_m, True)]:
             plan = precond.analyse(m, up)
+            assert plan.ls is not None
             systems.append((m, plan, b))
-            singles.append(precond.triangular_solve(m, plan, b))
+            singles.append(precond.triangular_solve(m, plan, b, algorithm="syncfree"))
         want = ckernels.sptrsv_lower(*p.T, p.b.numpy())
         assert np.array_equal(singles[-2].cpu().numpy(), want)
-    for got, want in zip(precond.triangular_solve_batch(systems), singles):
+    for algorithm in ("syncfree", "ls"):
+        for got, want in zip(precond.triangular_solve_batch(systems, algorithm=algorithm), singles):
+            assert torch.equal(got, want), algorithm
+    many = systems * 80  # more systems than resident CTAs: the level-stream kernel loops
+    for got, want in zip(precond.triangular_solve_batch(many, algorithm="ls"), singles * 80):
         assert torch.equal(got, want)
+
+
+def test_level_stream_eligibility(cuda):
+    """Factors the level-stream solve cannot take (a dependency further back than its shared-memory window, rows too
+    long for registers, tiles larger than a pipeline stage) are refused at analysis and solved sync-free; a chain of
+    6000 one-row levels inside the window is taken."""
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(5)
+    n = 6000
+
+    def lower_matrix(back):
+        rows = np.concatenate([np.arange(n), np.arange(1, n), np.arange(back, n)])
+        cols = np.concatenate([np.arange(n), np.arange(n - 1), np.arange(0, n - back)])
+        vals = np.concatenate([2.0 + rng.random(n), -rng.random(n - 1), -rng.random(n - back)])
+        m = sp.csr_matrix((vals, (rows, cols)), shape=(n, n))
+        m.sort_indices()
+        return m
+
+    b = rng.standard_normal(n)
+    for back, eligible in [(300, True), (3000, False)]:
+        m = lower_matrix(back)
+        lower = CsrMatrix.from_scipy(m, cuda)
+        plan = precond.analyse(lower, False)
+        assert plan.nlevels == n and (plan.ls is not None) == eligible
+        want = ckernels.sptrsv_lower(m.indptr, m.indices, m.data, b)
+        for algorithm in (["ls"] if eligible else []) + ["syncfree", "auto"]:
+            got = precond.triangular_solve(lower, plan, torch.from_numpy(b).to(cuda), algorithm=algorithm)
+            assert np.array_equal(got.cpu().numpy(), want), (back, algorithm)
+    dense_rows = sp.tril(sp.random(4096, 4096, density=0.02, random_state=3) + sp.eye(4096) * 4.0).tocsr()
+    dense_rows.sort_indices()
+    wide = CsrMatrix.from_scipy(dense_rows, cuda)
+    wplan = precond.analyse(wide, False)
+    assert wplan.ls is None
+    bw = rng.standard_normal(4096)
+    got = precond.triangular_solve(wide, wplan, torch.from_numpy(bw).to(cuda))
+    assert np.array_equal(got.cpu().numpy(), ckernels.sptrsv_lower(dense_rows.indptr, dense_rows.indices, dense_rows.data, bw))
 
 
 def test_spmv_pipeline_block_boundaries(cuda):
@@ -245,6 +294,33 @@ def test_pcg_against_oracle_and_reference_golden(cuda, case, engine):
         assert torch.linalg.vector_norm(x - xo) <= 1e-3 * torch.linalg.vector_norm(xo)  # both within sqrt(rtol) of A^-1 b
     else:
         assert result.iterations == case["max_iter"]
+
+
+@pytest.mark.parametrize("engine", ["fused", "stepped"])
+def test_pcg_solve_mode_level_stream_equals_sync_free(cuda, engine):
+    """IC(0) in solve mode: the level-stream solves (one CTA per system) and the sync-free solves give the same bits,
+    for a single system and inside a mixed batch."""
+    systems_ls, systems_sf = [], []
+    for side, seed in [(64, 0), (37, 1), (100, 2)]:
+        p = helpers.problem("poisson2d", side, seed, 0.5, None)
+        st = helpers.to_device(p.systems_tril, cuda)
+        A, T = CsrMatrix.from_spconv(st, p.n, "symmetrise"), CsrMatrix.from_spconv(st, p.n, "tril")
+        factor = precond.incomplete_cholesky0(T)
+        ls, sf = dp.FactoredSolve(factor), dp.FactoredSolve(factor, level_stream=False)
+        assert ls.fwd_ls is not None and ls.bwd_ls is not None and sf.fwd_ls is None
+        b = p.b.to(cuda)
+        systems_ls.append((A, b, ls)), systems_sf.append((A, b, sf))
+        one_ls = dp.pcg_solve(A, b, ls, max_iter=2000, engine=engine)
+        one_sf = dp.pcg_solve(A, b, sf, max_iter=2000, engine=engine)
+        assert one_ls.iterations == one_sf.iterations and torch.equal(one_ls.x_hat, one_sf.x_hat)
+        assert torch.equal(ls @ b, sf @ b)
+    p = helpers.problem("poisson2d", 64, 0, 0.5, "net")
+    ops = gpu_operands(p, cuda)
+    extra = (ops["A"], p.b.to(cuda), dp.FactoredMultiply(ops["L"], ops["Lt"]))
+    got = dp.pcg_solve_batch(systems_ls + [extra], 1e-8, 2000, engine=engine)
+    want = dp.pcg_solve_batch(systems_sf + [extra], 1e-8, 2000, engine=engine)
+    for g, w in zip(got, want):
+        assert g.iterations == w.iterations and torch.equal(g.x_hat, w.x_hat)
 
 
 def test_pcg_reference_signature_and_host_operands(cuda):

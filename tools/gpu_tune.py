@@ -98,8 +98,21 @@ if "single" not in skip:
     st, _, _, _ = synthetic.make_batch("poisson2d", 316, [h["index"]], device=dev)
     T = CsrMatrix.from_spconv(st, A.n, "tril")
     fwd = precond.analyse(T, False)
-    ic = dp.FactoredSolve(precond.incomplete_cholesky0(T, fwd), None, fwd)
-    for name, M in [("cnn_multiply", dp.FactoredMultiply(L)), ("jacobi", dp.Jacobi(A)), ("ic0_solve", ic)]:
+    factor = precond.incomplete_cholesky0(T, fwd)
+    ic = dp.FactoredSolve(factor, None, fwd)
+    ic_sf = dp.FactoredSolve(factor, None, fwd, level_stream=False)
+    r0 = b.clone(); out = torch.empty_like(r0)
+    fplan = precond.analyse(factor, False)
+    for nm, alg in (("level-stream", "ls"), ("sync-free", "syncfree")):
+        best, med = timed(lambda: precond.triangular_solve(factor, fplan, r0, out, algorithm=alg), 5)
+        print(f"sptrsv 316^2 IC(0) factor, {nm}: {best*1e3:.1f} us ({best*1e3/fplan.nlevels:.3f} us/level)", flush=True)
+    for nb in (16, 64, 128):
+        sys_ = [(factor, fplan, r0)] * nb
+        outs = [torch.empty_like(r0) for _ in range(nb)]
+        byt1 = 12 * factor.nnz + 4 * (A.n + 1) + 16 * A.n
+        best, med = timed(lambda: precond.triangular_solve_batch(sys_, outs, algorithm="ls"), 3)
+        print(f"sptrsv level-stream batch {nb} x 316^2: {best*1e3:.1f} us ({nb*byt1/best/1e6:.0f} GB/s algorithmic)", flush=True)
+    for name, M in [("cnn_multiply", dp.FactoredMultiply(L)), ("jacobi", dp.Jacobi(A)), ("ic0_solve", ic), ("ic0_solve_syncfree", ic_sf)]:
         batch = dp.PcgBatch([(A, b, M)], 1e-8, 20000)
 
         def go1():
