@@ -287,13 +287,14 @@ def extras(device, host0):
     st, _, _, _ = synthetic.make_batch("poisson2d", int(round(n ** 0.5)), [host0["index"]], device=device)
     T = CsrMatrix.from_spconv(st, n, "tril")
     t0 = time.perf_counter()
-    fwd = precond.analyse(T, False)
+    fwd = precond.analyse(T, False, level_stream=False)
     factor = precond.incomplete_cholesky0(T, fwd)
     ic = dp.FactoredSolve(factor, None, fwd)
     torch.cuda.synchronize()
     ic_setup_ms = 1e3 * (time.perf_counter() - t0)
-    for name, M in [("cnn_multiply", dp.FactoredMultiply(L)), ("ic0_solve", ic), ("jacobi", dp.Jacobi(A)),
-                    ("identity", dp.Identity())]:
+    ic_sync_free = dp.FactoredSolve(factor, None, fwd, level_stream=False)
+    for name, M in [("cnn_multiply", dp.FactoredMultiply(L)), ("ic0_solve", ic), ("ic0_solve_sync_free", ic_sync_free),
+                    ("jacobi", dp.Jacobi(A)), ("identity", dp.Identity())]:
         batch = dp.PcgBatch([(A, b, M)], RTOL, MAX_ITER)
 
         def go():
@@ -302,12 +303,29 @@ def extras(device, host0):
 
         ms = timed(go)
         r = batch.results()[0]
-        nnz_l = L.nnz if name == "cnn_multiply" else (T.nnz if name == "ic0_solve" else 0)
+        nnz_l = L.nnz if name == "cnn_multiply" else (T.nnz if name.startswith("ic0_solve") else 0)
         single[name] = {"ms_to_tol": ms, "iterations": r.iterations, "us_per_iteration": 1e3 * ms / max(r.iterations, 1),
                         "res": r.res, "algorithmic_gbs": iter_bytes(n, A.nnz, nnz_l) * r.iterations / ms / 1e6}
     single["ic0_solve"]["setup_ms_analysis_plus_factorisation"] = ic_setup_ms
     single["ic0_solve"]["levels"] = fwd.nlevels
+    single["ic0_solve"]["triangular_solves"] = "level-stream (one CTA, shared-memory dependencies)"
+    single["ic0_solve_sync_free"]["triangular_solves"] = "sync-free (dependencies polled through L2)"
     out["single_system_316x316"] = single
+
+    # the two triangular-solve kernels on the IC(0) factor of that system, alone and as a batch of independent solves
+    fplan = precond.analyse(factor, False)
+    r0, y0 = b.clone(), torch.empty_like(b)
+    trsv_bytes2 = 12 * factor.nnz + 4 * (n + 1) + 16 * n
+    trsv2 = {"levels": fplan.nlevels}
+    for key, alg in (("level_stream", "ls"), ("sync_free", "syncfree")):
+        ms = timed(lambda: precond.triangular_solve(factor, fplan, r0, y0, algorithm=alg), reps=5)
+        trsv2[key] = {"ms": ms, "us_per_level": 1e3 * ms / fplan.nlevels, "algorithmic_gbs": trsv_bytes2 / ms / 1e6}
+    nb2 = 128
+    outs2 = [torch.empty_like(b) for _ in range(nb2)]
+    ms = timed(lambda: precond.triangular_solve_batch([(factor, fplan, r0)] * nb2, outs2, algorithm="ls"), reps=3)
+    trsv2["level_stream_batch128"] = {"ms": ms, "algorithmic_gbs": nb2 * trsv_bytes2 / ms / 1e6,
+                                      "frac_of_hbm_peak": nb2 * trsv_bytes2 / ms / 1e6 / peaks()[0]}
+    out["sptrsv_316x316_ic0"] = trsv2
 
     # config 4: 128^3, HBM-bound SpMV and SpTRSV
     st, _, rhs, sizes = synthetic.make_batch("poisson3d", 128, [0], device=device)
