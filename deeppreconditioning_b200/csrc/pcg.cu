@@ -509,8 +509,10 @@ __device__ __forceinline__ void ensure_table(const Ctx& ctx, int cur, int ver, i
 
 // The tiles of the systems in list `cur`, one contiguous range per CTA, streamed through the tile pipeline.
 // fused engine: `cur` = the active list (unfinished systems); stepped engine: list 0 = all systems, kCheckState.
+// `next_tab` (fused engine only, -1 = none): the table the NEXT phase will stream; when it is still valid for this
+// CTA's range its first items are issued before the grid barrier (Pipe::begin_early).
 template <int kPhase, bool kInit, bool kCheckState>
-__device__ __forceinline__ void run_tiles(const Ctx& ctx, int k, int cur, int ver, Smem& sm, Pipe& pipe) {
+__device__ __forceinline__ void run_tiles(const Ctx& ctx, int k, int cur, int ver, Smem& sm, Pipe& pipe, int next_tab = -1) {
     constexpr int kTab = kPhase == PH_APPLY1 ? TAB_P1 : kPhase == PH_APPLY2 ? TAB_P2 : TAB_A;
     constexpr bool kStream = kPhase != PH_DOTRZ;
     const int total = __ldcg(ctx.act_meta + 2 * cur + 1);
@@ -523,7 +525,10 @@ __device__ __forceinline__ void run_tiles(const Ctx& ctx, int k, int cur, int ve
         const TileDesc* tab = sm.tab[kTab];
         int rs_n = 0, re_n = 0;
         if (kStream) {
-            pipe.begin(tab, gb - ga);
+            if (!pipe.begin_resume(tab, gb - ga, kTab)) {
+                pipe.drain_early();  // (never taken: the prediction below is exact; kept as the safe way out)
+                pipe.begin(tab, gb - ga);
+            }
             tile_row_extent(tab[0], rs_n, re_n);
         }
         for (int i = 0; i < gb - ga; ++i) {
@@ -534,6 +539,9 @@ __device__ __forceinline__ void run_tiles(const Ctx& ctx, int k, int cur, int ve
             run_tile<kPhase, kInit, kCheckState>(ctx, S, d, rs, re, k, sm, sc, pipe);
         }
     }
+    if (next_tab >= 0 && g1 > g0 && g1 - g0 <= kMaxRoundTiles && sm.tab_ver[next_tab] == ver &&
+        sm.tab_ga[next_tab] == g0 && sm.tab_gb[next_tab] == g1)
+        pipe.begin_early(sm.tab[next_tab], g1 - g0, next_tab);
 }
 
 // CTA 0: compact the active list `cur` into `cur ^ 1`, dropping the systems whose state flag is up.
@@ -570,15 +578,18 @@ __device__ __forceinline__ void rebuild_active(const Ctx& ctx, int cur, Smem& sm
 }
 
 // Returns false on abort. `done` = finished count of the last barrier.
+// `list_stays`: the active list (hence every table) survives this iteration, so the last phase may start table A early.
 template <bool kInit>
 __device__ __forceinline__ bool apply_preconditioner(const Ctx& ctx, int k, int cur, int ver, GridBarrier& bar, Smem& sm,
-                                                     Pipe& pipe) {
-    run_tiles<PH_APPLY1, kInit, false>(ctx, k, cur, ver, sm, pipe);
+                                                     Pipe& pipe, bool list_stays) {
+    const int tab_a = list_stays ? (int)TAB_A : -1;
+    run_tiles<PH_APPLY1, kInit, false>(ctx, k, cur, ver, sm, pipe,
+                                       ctx.has_multiply ? (int)TAB_P2 : (ctx.has_solve ? -1 : tab_a));
     trace(ctx, sm, 8 * PH_APPLY1 + 1);
     if (bar.sync() < 0) return false;
     trace(ctx, sm, 8 * PH_APPLY1 + 2);
     if (ctx.has_multiply) {
-        run_tiles<PH_APPLY2, kInit, false>(ctx, k, cur, ver, sm, pipe);
+        run_tiles<PH_APPLY2, kInit, false>(ctx, k, cur, ver, sm, pipe, ctx.has_solve ? -1 : tab_a);
         trace(ctx, sm, 8 * PH_APPLY2 + 1);
         if (bar.sync() < 0) return false;
         trace(ctx, sm, 8 * PH_APPLY2 + 2);
@@ -590,7 +601,7 @@ __device__ __forceinline__ bool apply_preconditioner(const Ctx& ctx, int k, int 
         if (ctx.has_ls) phase_trsv_ls<true, kInit>(ctx, k, sm);
         const bool b = phase_trsv<true, kInit>(ctx, k, sm);
         if (bar.sync() < 0 || !b) return false;
-        run_tiles<PH_DOTRZ, kInit, false>(ctx, k, cur, ver, sm, pipe);
+        run_tiles<PH_DOTRZ, kInit, false>(ctx, k, cur, ver, sm, pipe, tab_a);
         if (bar.sync() < 0) return false;
     }
     return true;
@@ -617,20 +628,23 @@ __global__ void __launch_bounds__(kBlock, 2) pcg_fused_kernel(Ctx ctx) {
     int cur = 0;          // active-list buffer in use
     int ver = 1;          // bumped whenever the list (hence every CTA's tile range) changes
     int done_built = 0;   // finished count the list `cur` reflects
-    run_tiles<PH_INIT, false, false>(ctx, -1, cur, ver, sm, pipe);
+    run_tiles<PH_INIT, false, false>(ctx, -1, cur, ver, sm, pipe, TAB_P1);
     if (bar.sync() < 0) return;
-    if (!apply_preconditioner<true>(ctx, -1, cur, ver, bar, sm, pipe)) return;
+    if (!apply_preconditioner<true>(ctx, -1, cur, ver, bar, sm, pipe, true)) return;
     for (int k = 0; k <= ctx.max_iter; ++k) {
         trace(ctx, sm, 8 * PH_A + 0);
-        run_tiles<PH_A, false, false>(ctx, k, cur, ver, sm, pipe);
+        run_tiles<PH_A, false, false>(ctx, k, cur, ver, sm, pipe, TAB_P1);
         trace(ctx, sm, 8 * PH_A + 1);
         const int done = bar.sync();
         trace(ctx, sm, 8 * PH_A + 2);
         if (done < 0) return;
-        if (done >= ctx.nsys) break;
+        if (done >= ctx.nsys) {
+            pipe.drain_early();  // do not exit with bulk copies in flight
+            break;
+        }
         const bool rebuild = done != done_built;  // same decision in every CTA
         if (rebuild && blockIdx.x == 0) rebuild_active(ctx, cur, sm);
-        if (!apply_preconditioner<false>(ctx, k, cur, ver, bar, sm, pipe)) return;  // >= 1 barrier: the new list is visible
+        if (!apply_preconditioner<false>(ctx, k, cur, ver, bar, sm, pipe, !rebuild)) return;  // >= 1 barrier: the new list is visible
         if (rebuild) cur ^= 1, done_built = done, ++ver;
     }
 }

@@ -172,6 +172,7 @@ struct PipeT {
     int p_tile, p_blk;  // next item of the round to issue
     unsigned t_count;   // streaming tiles this warp has reduced (ring index of tile_reduce_async)
     int flip;           // tile_reduce scratch buffer in use next
+    int early;          // 1 + id of the table whose first items are already in flight (begin_early), else 0
 
     static __device__ __forceinline__ int blocks(const TileDesc& d) { return (d.ce - d.cs + kCap - 1) / kCap; }
     __device__ __forceinline__ const double* stage_val(unsigned s) const { return val0 + (size_t)s * kSlots; }
@@ -184,7 +185,7 @@ struct PipeT {
         full = bar->full, empty = bar->empty;
         tab = nullptr;
         ntiles = 0;
-        c_count = 0u, p_count = 0u, p_tile = 0, p_blk = 0, t_count = 0u, flip = 0;
+        c_count = 0u, p_count = 0u, p_tile = 0, p_blk = 0, t_count = 0u, flip = 0, early = 0;
         if (fresh) {
             if (threadIdx.x == 0) {
 #pragma unroll
@@ -270,6 +271,37 @@ struct PipeT {
         while (!mbar_try_wait(&full[stage], (c_count / kStages) & 1u)) {
         }
         return stage;
+    }
+
+    // Start the NEXT round before the current phase's grid barrier: the matrices are immutable, so the first items of
+    // the next phase's table can be on their way while the CTAs wait for each other. Every thread calls it after its
+    // own last tile; thread 0 waits for the stages (the other warps release them as they finish). The next round must
+    // open with begin_resume(id) instead of begin(), or be drained with drain_early().
+    __device__ __forceinline__ void begin_early(const TileDesc* t, int count, int id) {
+        begin(t, count);
+        early = id + 1;
+    }
+    __device__ __forceinline__ bool begin_resume(const TileDesc* t, int count, int id) {
+        if (early != id + 1) return false;
+        early = 0;
+        tab = t, ntiles = count;  // (already set by begin_early; kept for symmetry)
+        return true;
+    }
+    // Consume what begin_early put in flight without using it (the kernel is about to exit, or the prediction of the
+    // next table failed). begin() issues min(kStages, items of the table) items.
+    __device__ __forceinline__ void drain_early() {
+        if (!early) return;
+        early = 0;
+        int issued = 0;
+        for (int t = 0; t < ntiles && issued < kStages; ++t) issued += blocks(tab[t]);
+        issued = min(issued, kStages);
+        for (int j = 0; j < issued; ++j) {
+            const unsigned stage = c_count % kStages;
+            while (!mbar_try_wait(&full[stage], (c_count / kStages) & 1u)) {
+            }
+            release();
+        }
+        if (threadIdx.x == 0) p_tile = ntiles;  // nothing more to issue from that table
     }
 
     // Consumer side of one item: acquire() waits until the item's bytes have landed and returns its stage; release()
