@@ -343,6 +343,34 @@ def extras(device, host0):
     out["sptrsv_128^3"] = {"ms": ms, "levels": fwd3.nlevels, "algorithmic_gbs": trsv_bytes / ms / 1e6,
                            "frac_of_hbm_peak": trsv_bytes / ms / 1e6 / peak, "us_per_level": 1e3 * ms / fwd3.nlevels,
                            "bound": "levels x (store -> L2 -> poll) latency, not HBM: see profiles/README.md"}
+    # config 4 proper: single-system PCG on 128^3 (654 MB per iteration with a tril-pattern factor: HBM bound)
+    from deeppreconditioning_b200 import model as models
+
+    torch.manual_seed(69)
+    with torch.no_grad():
+        learned3 = models.PreconditionerTrilNet(models.DEFAULT_CHANNELS).to(device)(st)
+    L3 = CsrMatrix.from_spconv(learned3, n3, "tril")
+    del learned3
+    b3 = rhs[0, :n3].to(torch.float64)
+    ic3 = dp.FactoredSolve(precond.incomplete_cholesky0(T3, fwd3), None, fwd3)
+    pcg3 = {}
+    for name, M, nnz_l in [("jacobi", dp.Jacobi(A3), 0), ("cnn_tril_multiply", dp.FactoredMultiply(L3), L3.nnz),
+                           ("ic0_solve", ic3, T3.nnz)]:
+        batch3 = dp.PcgBatch([(A3, b3, M)], RTOL, MAX_ITER)
+
+        def go3():
+            batch3.reset()
+            batch3.solve()
+
+        ms = timed(go3, reps=2)
+        r = batch3.results()[0]
+        gbs = iter_bytes(n3, A3.nnz, nnz_l) * r.iterations / ms / 1e6
+        pcg3[name] = {"ms_to_tol": ms, "iterations": r.iterations, "us_per_iteration": 1e3 * ms / max(r.iterations, 1),
+                      "res": r.res, "algorithmic_gbs": gbs, "frac_of_hbm_peak": gbs / peak}
+        del batch3
+    pcg3["ic0_solve"]["triangular_solves"] = "sync-free (levels of up to 12 k rows: not level-stream material)"
+    out["pcg_single_system_128^3"] = pcg3
+    del L3, ic3
     # several independent solves in flight (the batch axis of configs 3/5): bytes grow, the critical path does not
     nb = 16
     outs = [torch.empty_like(x) for _ in range(nb)]
