@@ -95,6 +95,14 @@ constexpr int kMaxRoundTiles = 64;
 #define DPCG_APPLY2_UNROLL kPipeUnroll
 #endif
 constexpr int kApply2Unroll = DPCG_APPLY2_UNROLL;  // single-gather phase: can afford more loads in flight
+#ifndef DPCG_PHASEA_UNROLL
+#define DPCG_PHASEA_UNROLL 3
+#endif
+#ifndef DPCG_APPLY1_UNROLL
+#define DPCG_APPLY1_UNROLL 3
+#endif
+constexpr int kPhaseAUnroll = DPCG_PHASEA_UNROLL;  // double-gather phases: two loads per entry
+constexpr int kApply1Unroll = DPCG_APPLY1_UNROLL;
 enum Table { TAB_A = 0, TAB_P1 = 1, TAB_P2 = 2 };  // A | L^T (MULTIPLY) or M (CSR) | L (MULTIPLY)
 
 struct Smem {
@@ -239,7 +247,7 @@ __device__ __forceinline__ void phase_a(const Ctx& ctx, const SysDev& S, const T
         return;
     }
     double* pn = S.p[(k + 1) & 1];
-    const double ap = pipe.tile_spmv(d, rs, re, GatherZBetaP{z, po, sc.v}, true);  // cg.py:75
+    const double ap = pipe.tile_spmv<kPhaseAUnroll>(d, rs, re, GatherZBetaP{z, po, sc.v}, true);  // cg.py:75
     double pap[1] = {0.0};
     if (valid) {
         const double pi = __dadd_rn(zr, __dmul_rn(sc.v, pr));  // cg.py:83
@@ -307,11 +315,11 @@ __device__ __forceinline__ void phase_apply1(const Ctx& ctx, const SysDev& S, co
             break;
         case DP_PRECOND_CSR:  // table P1 streams M
             zi = kInit ? pipe.tile_spmv(d, rs, re, GatherPlain{ro}, true)
-                       : pipe.tile_spmv(d, rs, re, GatherRMinusAAp{ro, S.ap, a}, true);
+                       : pipe.tile_spmv<kApply1Unroll>(d, rs, re, GatherRMinusAAp{ro, S.ap, a}, true);
             break;
         case DP_PRECOND_MULTIPLY: {  // table P1 streams L^T
             const double ti = kInit ? pipe.tile_spmv(d, rs, re, GatherPlain{ro}, true)
-                                    : pipe.tile_spmv(d, rs, re, GatherRMinusAAp{ro, S.ap, a}, true);
+                                    : pipe.tile_spmv<kApply1Unroll>(d, rs, re, GatherRMinusAAp{ro, S.ap, a}, true);
             if (valid) S.t[row] = ti;
             have_z = false;
             break;
@@ -523,19 +531,19 @@ __device__ __forceinline__ void run_tiles(const Ctx& ctx, int k, int cur, int ve
         const int gb = min(g1, ga + kMaxRoundTiles);
         ensure_table<kTab>(ctx, cur, ver, ga, gb, sm);
         const TileDesc* tab = sm.tab[kTab];
-        int rs_n = 0, re_n = 0;
         if (kStream) {
             if (!pipe.begin_resume(tab, gb - ga, kTab)) {
                 pipe.drain_early();  // (never taken: the prediction below is exact; kept as the safe way out)
                 pipe.begin(tab, gb - ga);
             }
-            tile_row_extent(tab[0], rs_n, re_n);
         }
         for (int i = 0; i < gb - ga; ++i) {
             const TileDesc& d = tab[i];
             const SysDev& S = load_sys(ctx, d.sys, sm);
-            const int rs = rs_n, re = re_n;
-            if (kStream && i + 1 < gb - ga) tile_row_extent(tab[i + 1], rs_n, re_n);  // one tile ahead
+            // row extents: requested here, they land while the scalars are evaluated and the stage arrives (holding them
+            // in registers a tile ahead only produced spills whose stores waited for the loads)
+            int rs = 0, re = 0;
+            if (kStream) tile_row_extent(d, rs, re);
             run_tile<kPhase, kInit, kCheckState>(ctx, S, d, rs, re, k, sm, sc, pipe);
         }
     }
