@@ -85,7 +85,7 @@ _SIGNATURES = {
     "dp_sptrsv_batch_workspace_bytes": (C.c_size_t, [_i32]),
     "dp_sptrsv_solve_batch_f64": (C.c_int, [C.POINTER(TrsvSystem), _i32, _p, _p, C.c_size_t, _p]),
     "dp_sptrsv_permute_workspace_bytes": (C.c_size_t, [_i32]),
-    "dp_sptrsv_permute": (C.c_int, [_i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
+    "dp_sptrsv_permute": (C.c_int, [_i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
     "dp_sptrsv_ls_limits": (None, [_p]),
     "dp_sptrsv_ls_workspace_bytes": (C.c_size_t, [_i32]),
     "dp_sptrsv_ls_solve_batch_f64": (C.c_int, [C.POINTER(TrsvLsSystem), _i32, _p, C.c_size_t, _p]),

@@ -60,6 +60,19 @@ __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
     asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// Read-only loads the compiler must issue WHERE THEY ARE WRITTEN: a plain __ldg is a pure expression to nvcc, which
+// happily sinks a software-prefetch load down to its first use a whole tile later (measured: 700 cycles of exposed
+// latency per tile in the level-stream solve). volatile asm keeps its place among the other volatile statements.
+__device__ __forceinline__ int ldg_here_s32(const int* p) {
+    int v;
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ldcg_here_f64(const double* p) {
+    double v;
+    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ double as_double(unsigned long long u) { return __longlong_as_double((long long)u); }
 __device__ __forceinline__ unsigned long long as_bits(double d) { return (unsigned long long)__double_as_longlong(d); }
 

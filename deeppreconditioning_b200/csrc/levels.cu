@@ -191,8 +191,10 @@ __global__ void perm_rowlen_kernel(int n, const int* __restrict__ rowptr, const 
     }
 }
 
-// One warp per row of the copy: entries keep their order inside the row, columns become positions.
-__global__ void perm_fill_kernel(int n, const int* __restrict__ rowptr, const int* __restrict__ col,
+// One warp per row of the copy: entries keep their order inside the row, columns become positions, and the diagonal
+// entry (last in a lower row, first in an upper one) is replaced by its reciprocal, rounded exactly like the solve
+// kernels round it (__ddiv_rn(1, d)): the level-stream solve multiplies by it.
+__global__ void perm_fill_kernel(int n, int upper, const int* __restrict__ rowptr, const int* __restrict__ col,
                                  const double* __restrict__ val, const int* __restrict__ perm, const int* __restrict__ inv,
                                  const int* __restrict__ rowptr_p, int* __restrict__ col_p, double* __restrict__ val_p) {
     const int lane = threadIdx.x & 31;
@@ -200,9 +202,10 @@ __global__ void perm_fill_kernel(int n, const int* __restrict__ rowptr, const in
     for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
         const int row = perm[r];
         const int src = rowptr[row], cnt = rowptr[row + 1] - src, dst = rowptr_p[r];
+        const int dk = upper ? 0 : cnt - 1;
         for (int k = lane; k < cnt; k += 32) {
             col_p[dst + k] = inv[col[src + k]];
-            val_p[dst + k] = val[src + k];
+            val_p[dst + k] = k == dk ? __ddiv_rn(1.0, val[src + k]) : val[src + k];
         }
     }
 }
@@ -325,7 +328,7 @@ size_t dp_sptrsv_permute_workspace_bytes(int32_t n) {
     return align_up(sizeof(int) * m, 256) + align_up(scan_workspace_bytes((long long)m + 1), 256);
 }
 
-int dp_sptrsv_permute(int32_t n, const int32_t* rowptr, const int32_t* col, const double* val, const int32_t* perm,
+int dp_sptrsv_permute(int32_t n, int32_t upper, const int32_t* rowptr, const int32_t* col, const double* val, const int32_t* perm,
                       const int32_t* level, int32_t* rowptr_p, int32_t* col_p, double* val_p, int32_t* level_sorted,
                       int32_t* stats_out, void* workspace, size_t workspace_bytes, void* stream) {
     if (n < 0 || !rowptr_p || !stats_out || !workspace) return DP_ERR_INVALID;
@@ -344,7 +347,7 @@ int dp_sptrsv_permute(int32_t n, const int32_t* rowptr, const int32_t* col, cons
     DP_LAUNCH_CHECK();
     const int st = exclusive_scan_i32(rowptr_p, rowptr_p, (long long)n + 1, scan_ws, s);
     if (st != DP_OK) return st;
-    perm_fill_kernel<<<grid_for(32ll * n, 256), 256, 0, s>>>(n, rowptr, col, val, perm, inv, rowptr_p, col_p, val_p);
+    perm_fill_kernel<<<grid_for(32ll * n, 256), 256, 0, s>>>(n, upper ? 1 : 0, rowptr, col, val, perm, inv, rowptr_p, col_p, val_p);
     DP_LAUNCH_CHECK();
     perm_stats_kernel<<<grid_for(n, 256), 256, 0, s>>>(n, rowptr_p, col_p, stats_out);
     DP_LAUNCH_CHECK();

@@ -280,6 +280,8 @@ void dp_sptrsv_ls_limits(int32_t* limits_host) {
     limits_host[0] = kLsCap;                  // one pipeline item per 512-row tile
     limits_host[1] = kLsRowEntries;           // a row's entries live in registers
     limits_host[2] = kLsWindow - kTileRows;   // every dependency is still in the shared-memory window
+    limits_host[3] = kTileRows;               // rows of the widest level: a window slot is never rewritten by a row of
+                                              // the level that still reads it
 }
 
 size_t dp_sptrsv_ls_workspace_bytes(int32_t nsys) { return align_up(sizeof(LsSysDev) * (size_t)(nsys > 0 ? nsys : 0), 256); }

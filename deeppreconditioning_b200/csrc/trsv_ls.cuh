@@ -8,13 +8,16 @@
 //     columns renumbered to positions in that order, entries of a row in T's order (so the sum stays bit-identical
 //     to plain substitution). The copy is still triangular, and a level is a contiguous run of rows AND of entries;
 //   * the CTA streams the copy through the TMA tile pipeline (tilepipe.cuh) - 512 rows per tile, one thread per row;
-//   * rows of a tile are released level by level with a CTA barrier; a solved value goes to global memory in the
-//     original numbering and into a shared-memory window indexed by position (the last kLsWindow positions), where
-//     the next levels pick it up with shared-memory latency.
+//   * levels are ordered by a ring of mbarriers, one phase per level step: a warp arrives at a step as soon as its own
+//     rows of that level are solved (at once if it has none) and waits on the previous step only right before it
+//     solves rows itself. Warps with nothing to do in the remaining levels of a tile are already fetching the next
+//     tile's rows into registers, so the hand-over between tiles is off the critical path;
+//   * a solved value goes to global memory in the original numbering and into a shared-memory window indexed by
+//     position (the last kLsWindow positions), where the next levels pick it up with shared-memory latency.
 // A factor qualifies (dp_sptrsv_ls_limits) when a 512-row tile of the copy fits one pipeline stage, a row has at most
 // kLsRowEntries entries (they live in registers) and no dependency is further back than the window reaches; stencil
 // IC(0) factors do. Everything else is solved by the sync-free kernel.
-// Per level the cost is a CTA barrier plus a few shared-memory reads instead of an L2 hop; a batch runs one system per
+// Per level the cost is an mbarrier hand-off plus a few shared-memory reads instead of an L2 hop; a batch runs one system per
 // CTA, so 64+ systems keep the whole HBM busy. Wide levels (3-D factors) stay with the sync-free multi-SM solve.
 #pragma once
 
@@ -41,6 +44,8 @@ __device__ __forceinline__ void g_ls_trace_levels(int tile, int nl) {
 __device__ __forceinline__ void g_ls_trace_levels(int, int) {}
 #endif
 
+constexpr int kLsRing = 16;  // level steps a warp may be ahead of the slowest one (enforced every kLsRing / 2 steps)
+
 using LsPipe = PipeT<kLsCap, kLsStages>;  // 5 stages of 1536 entries over the SpMV pipeline's bytes
 
 // Shared memory of the solve besides the stage bytes and the tile table. `items` carries the pipeline's item count
@@ -48,22 +53,24 @@ using LsPipe = PipeT<kLsCap, kLsStages>;  // 5 stages of 1536 entries over the S
 struct LsShared {
     PipeBarriers<kLsStages> bar;
     unsigned items;
-    int pad;
+    unsigned steps;  // level steps taken so far (carried like `items`: fixes the parities of the ring below)
+    alignas(8) unsigned long long level_done[kLsRing];  // step s completes phase s / kLsRing of slot s % kLsRing
     double win[kLsWindow];
     __device__ __forceinline__ void init() {  // thread 0, once per kernel, before a CTA barrier
         for (int s = 0; s < kLsStages; ++s) {
             mbar_init(&bar.full[s], 1u);
             mbar_init(&bar.empty[s], (unsigned)kWarpsPerBlock);
         }
+        for (int s = 0; s < kLsRing; ++s) mbar_init(&level_done[s], (unsigned)kWarpsPerBlock);
         mbar_fence_init();
-        items = 0u;
+        items = 0u, steps = 0u;
     }
 };
 
 struct LsFactor {
     const int* rowptr;  // nullptr: no level-ordered copy, use the sync-free solve
     const int* col;     // positions (level order)
-    const double* val;
+    const double* val;  // the diagonal entry of each row holds 1 / T_ii
     const int* perm;    // position -> row of T
     const int* lvl;     // level of the row at each position (non-decreasing)
     int n, nnz;
@@ -84,7 +91,14 @@ __device__ __forceinline__ void trsv_level_stream(const LsFactor& F, const doubl
     const int ntiles = (n + kTileRows - 1) / kTileRows;
     const int tid = threadIdx.x;
     constexpr int kDeps = kLsRowEntries - 1;
-    constexpr int kAhead = kLsStages - 2;  // tiles in flight; the stage issued into was released a whole tile ago
+    constexpr int kAhead = kLsStages - 2;      // tiles in flight; the stage issued into was released a whole tile ago
+    constexpr int kProducer = kBlock - kWarp;  // lane 0 of the LAST warp: its rows come last in every tile
+    const int lane = tid & 31;
+    unsigned step0 = ls.steps;  // step of the first level of the current tile
+    auto step_wait = [&](unsigned s) {  // all 16 warps have arrived at step s
+        while (!mbar_try_wait(&ls.level_done[s % kLsRing], (s / kLsRing) & 1u)) {
+        }
+    };
     for (int ga = 0; ga < ntiles; ga += tabcap) {
         const int cnt = min(tabcap, ntiles - ga);
         __syncthreads();  // the previous round's table (and the previous system's window) are no longer read
@@ -98,9 +112,10 @@ __device__ __forceinline__ void trsv_level_stream(const LsFactor& F, const doubl
             tab[i] = d;
         }
         __syncthreads();
-        // every tile is one item: thread 0 keeps kAhead tiles in flight with the lean producer
+        // every tile is one item: the producer lane keeps kAhead tiles in flight
         pipe.tab = tab, pipe.ntiles = cnt;
-        if (tid == 0)
+        pipe.p_count = pipe.c_count;  // every thread tracks the count; only the producer's copy is used to issue
+        if (tid == kProducer)
             for (int t = 0; t < min(cnt, kAhead); ++t) pipe.issue_tile(t);
         // per-row metadata one tile ahead: original row, level, row extent
         int orig_n = -1, lvl_n = -1, rs_n = 0, re_n = 0;
@@ -108,19 +123,26 @@ __device__ __forceinline__ void trsv_level_stream(const LsFactor& F, const doubl
             const int r = tile * kTileRows + tid;
             orig_n = -1, lvl_n = -1, rs_n = 0, re_n = 0;
             if (r < n) {
-                orig_n = __ldg(F.perm + r), lvl_n = __ldg(F.lvl + r);
-                rs_n = __ldg(F.rowptr + r), re_n = __ldg(F.rowptr + r + 1);
+                orig_n = ldg_here_s32(F.perm + r), lvl_n = ldg_here_s32(F.lvl + r);
+                rs_n = ldg_here_s32(F.rowptr + r), re_n = ldg_here_s32(F.rowptr + r + 1);
             }
         };
         load_meta(ga);
+        int pre = 0;  // level steps of the upcoming tile this warp has already arrived at
+        auto step_arrive = [&](unsigned s) {
+            // a slot of the ring is reused every kLsRing steps: stay less than a ring ahead of the slowest warp
+            if (s % (kLsRing / 2) == 0u && s >= (unsigned)(kLsRing / 2)) step_wait(s - kLsRing / 2);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ls.level_done[s % kLsRing]);
+        };
         for (int i = 0; i < cnt; ++i) {
             const TileDesc& d = tab[i];
             LS_TRACE(ga + i, 0);
             const int orig = orig_n, lvl = lvl_n, rs = rs_n, re = re_n;
-            const double bi = orig >= 0 ? __ldcg(rhs + orig) : 0.0;
+            const double bi = orig >= 0 ? ldcg_here_f64(rhs + orig) : 0.0;
             if (i + 1 < cnt) load_meta(ga + i + 1);
             LS_TRACE(ga + i, 1);
-            if (tid == 0 && i + kAhead < cnt) pipe.issue_tile(i + kAhead);
+            if (tid == kProducer && i + kAhead < cnt) pipe.issue_tile(i + kAhead);
             LS_TRACE(ga + i, 2);
             const unsigned stage = pipe.wait_item();
             LS_TRACE(ga + i, 3);
@@ -133,28 +155,45 @@ __device__ __forceinline__ void trsv_level_stream(const LsFactor& F, const doubl
             int w[kDeps];
 #pragma unroll
             for (int u = 0; u < kDeps; ++u) {
-                w[u] = 0, v[u] = 0.0;  // an absent dependency reads slot 0 with coefficient 0 ... and is skipped below
+                w[u] = 0, v[u] = 0.0;
                 if (u < ndep) w[u] = sc[e + u] & (kLsWindow - 1), v[u] = sv[e + u];
             }
-            if (orig >= 0) rcp = __ddiv_rn(1.0, sv[(kUpper ? rs : re - 1) - as]);
+            if (orig >= 0) rcp = sv[(kUpper ? rs : re - 1) - as];  // the copy stores 1 / diagonal (dp_sptrsv_permute)
             const int slot = (d.ltile * kTileRows + tid) & (kLsWindow - 1);
-            const int lv1 = d.nnz;
+            // levels of this warp's rows: [wl0, wl1] (levels ascend with the position; -1 = the warp has no rows)
+            const int wl0 = __shfl_sync(kFull, lvl, 0);
+            const int wl1 = __reduce_max_sync(kFull, lvl);
+            const int lv0 = d.n, lv1 = d.nnz;
             double xsol = 0.0;
             LS_TRACE(ga + i, 4);
-            g_ls_trace_levels(ga + i, lv1 - d.n + 1);
+            g_ls_trace_levels(ga + i, lv1 - lv0 + 1);
 #pragma unroll 1
-            for (int l = d.n; l <= lv1; ++l) {
-                if (lvl == l) {
-                    double sum = 0.0;
+            for (int l = lv0 + pre; l <= lv1; ++l) {
+                const unsigned s = step0 + (unsigned)(l - lv0);
+                if (wl0 >= 0 && l >= wl0 && l <= wl1) {
+                    if (s > 0u) step_wait(s - 1u);  // every row of the earlier levels is solved
+                    if (lvl == l) {
+                        double sum = 0.0;
 #pragma unroll
-                    for (int u = 0; u < kDeps; ++u)
-                        if (u < ndep) sum = __dadd_rn(sum, __dmul_rn(v[u], win[w[u]]));
-                    xsol = __dmul_rn(__dsub_rn(bi, sum), rcp);
-                    win[slot] = xsol;
+                        for (int u = 0; u < kDeps; ++u)
+                            if (u < ndep) sum = __dadd_rn(sum, __dmul_rn(v[u], win[w[u]]));
+                        xsol = __dmul_rn(__dsub_rn(bi, sum), rcp);
+                        win[slot] = xsol;
+                    }
                 }
-                __syncthreads();
+                step_arrive(s);
             }
-            // the global copy (original numbering) leaves after the level loop
+            step0 += (unsigned)(lv1 - lv0 + 1);
+            // Before the hand-over (store, stage release, next rows into registers) the warp already arrives at the
+            // steps of the next tile that come before its own first level there: nobody waits for its hand-over.
+            pre = 0;
+            if (i + 1 < cnt) {
+                const int lv0n = tab[i + 1].n, lv1n = tab[i + 1].nnz;
+                const int wl0n = __shfl_sync(kFull, lvl_n, 0);  // lvl_n: this thread's level in the next tile
+                pre = wl0n < 0 ? lv1n - lv0n + 1 : max(0, wl0n - lv0n);
+                for (int k = 0; k < pre; ++k) step_arrive(step0 + (unsigned)k);
+            }
+            // the global copy (original numbering)
             LS_TRACE(ga + i, 5);
             if (orig >= 0) x[orig] = xsol;
             pipe.release();
@@ -162,7 +201,7 @@ __device__ __forceinline__ void trsv_level_stream(const LsFactor& F, const doubl
         }
     }
     __syncthreads();
-    if (tid == 0) ls.items = pipe.c_count;
+    if (tid == 0) ls.items = pipe.c_count, ls.steps = step0;
     __syncthreads();
 }
 

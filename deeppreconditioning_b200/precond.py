@@ -70,13 +70,14 @@ def level_ordered(matrix: CsrMatrix, plan: TriangularPlan) -> LevelOrdered | Non
     stats = torch.zeros(3, **i32)
     ws = _workspace(lib.dp_sptrsv_permute_workspace_bytes(n), dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.dp_sptrsv_permute(n, _lib.ptr(matrix.rowptr), _lib.ptr(matrix.col), _lib.ptr(matrix.val),
+        _lib.check(lib.dp_sptrsv_permute(n, int(plan.upper), _lib.ptr(matrix.rowptr), _lib.ptr(matrix.col), _lib.ptr(matrix.val),
                                          _lib.ptr(plan.perm), _lib.ptr(plan.level), _lib.ptr(rowptr_p), _lib.ptr(col_p),
                                          _lib.ptr(val_p), _lib.ptr(level_sorted), _lib.ptr(stats), _lib.ptr(ws), ws.numel(),
                                          _lib.stream_ptr(dev)), "dp_sptrsv_permute")
-    limits = np.zeros(3, np.int32)
+    limits = np.zeros(4, np.int32)
     lib.dp_sptrsv_ls_limits(limits.ctypes.data)
-    if np.any(stats.cpu().numpy() > limits):  # once per matrix: tile entries, row entries, dependency distance
+    widest = int(torch.diff(plan.level_ptr).max().item())
+    if widest > limits[3] or np.any(stats.cpu().numpy() > limits[:3]):  # once per matrix: tile entries, row entries, dependency distance
         return None
     return LevelOrdered(rowptr_p, col_p[: matrix.nnz], val_p[: matrix.nnz], level_sorted, matrix.nnz, matrix.val.data_ptr())
 

@@ -116,12 +116,14 @@ int dp_sptrsv_plan_build(int32_t n, int32_t nlevels, const int32_t* perm, const 
 
 /* Level-ordered copy of a triangular factor, the input of the level-stream solve (below): row r of the copy is row
  * perm[r] of T, column indices are renumbered to positions in that order, entries keep T's order inside a row (sums
- * stay bit-identical), level_sorted[r] = level[perm[r]]. rowptr_p int32[n+1], col_p/val_p as large as col/val.
+ * stay bit-identical), the diagonal entry (last of a lower row, first of an upper one) holds 1 / T_ii;
+ * level_sorted[r] = level[perm[r]]. rowptr_p int32[n+1], col_p/val_p as large as col/val.
  * stats_out (device int32[3]): most entries in any 512 consecutive rows of the copy, most entries in a row, largest
  * distance in positions between a row and a dependency. The level-stream solve accepts the copy when each is within
- * the matching limit of dp_sptrsv_ls_limits(). */
+ * the matching limit of dp_sptrsv_ls_limits() and no level has more rows than its fourth limit (the caller knows the
+ * level sizes from level_ptr). */
 size_t dp_sptrsv_permute_workspace_bytes(int32_t n);
-int dp_sptrsv_permute(int32_t n, const int32_t* rowptr, const int32_t* col, const double* val, const int32_t* perm,
+int dp_sptrsv_permute(int32_t n, int32_t upper, const int32_t* rowptr, const int32_t* col, const double* val, const int32_t* perm,
                       const int32_t* level, int32_t* rowptr_p, int32_t* col_p, double* val_p, int32_t* level_sorted,
                       int32_t* stats_out, void* workspace, size_t workspace_bytes, void* stream);
 
@@ -154,9 +156,9 @@ int dp_sptrsv_solve_batch_f64(const dp_trsv_system_t* systems_host, int32_t nsys
                               size_t workspace_bytes, void* stream);
 
 /* Level-stream solve: ONE CTA per system walks the level-ordered copy through the TMA tile pipeline and releases the
- * rows level by level with a CTA barrier; dependencies are picked up from a shared-memory window instead of polling
- * L2. For factors with narrow levels (2-D stencils: 2n-1 levels of <= n rows) this replaces an L2 hop per level by a
- * barrier (~10x faster per solve); a batch keeps one SM busy per system. Bit-identical to dp_sptrsv_solve_f64.
+ * rows level by level through a ring of shared-memory mbarriers; dependencies are picked up from a shared-memory
+ * window instead of polling L2. For factors with narrow levels (2-D stencils: 2n-1 levels of <= n rows) this replaces
+ * an L2 hop per level by an mbarrier hand-off; a batch keeps one SM busy per system. Bit-identical to dp_sptrsv_solve_f64.
  * b and x are in the ORIGINAL numbering. No cooperative launch, no device flag: nothing spins. */
 typedef struct dp_trsv_ls_system {
     int32_t n;
@@ -169,7 +171,7 @@ typedef struct dp_trsv_ls_system {
     const double* b;
     double* x;
 } dp_trsv_ls_system_t;
-void dp_sptrsv_ls_limits(int32_t* limits_host /* [3]: tile entries, row entries, dependency distance */);
+void dp_sptrsv_ls_limits(int32_t* limits_host /* [4]: tile entries, row entries, dependency distance, rows per level */);
 size_t dp_sptrsv_ls_workspace_bytes(int32_t nsys);
 int dp_sptrsv_ls_solve_batch_f64(const dp_trsv_ls_system_t* systems_host, int32_t nsys, void* workspace,
                                  size_t workspace_bytes, void* stream);
