@@ -48,6 +48,63 @@ __global__ void barchain(int n, int active_warps, long long* out, double* sink) 
     if (threadIdx.x == 0) out[0] = t1 - t0;
     sink[threadIdx.x] = x;
 }
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool try_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool test_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// The same level step ordered by a ring of mbarriers (16 arrivals per step, one per warp): owners of step i are the
+// warps [first, first + active) rotating with i; they wait for step i-1, compute, arrive; the others just arrive.
+template <bool kTest>
+__global__ void ringchain(int n, int active_warps, long long* out, double* sink) {
+    __shared__ double win[1024];
+    __shared__ __align__(8) unsigned long long ring[16];
+    win[threadIdx.x] = threadIdx.x;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 16; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 16;" ::"r"(smem_u32(&ring[i])));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    __syncthreads();
+    double x = 1.0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    long long t0 = clock64();
+    for (int i = 0; i < n; ++i) {
+        const int first = (i * 5) & 15;
+        const bool owner = ((warp - first) & 15) < active_warps;
+        if (owner) {
+            if (i > 0) {
+                unsigned long long* b = &ring[(i - 1) & 15];
+                const unsigned par = ((i - 1) >> 4) & 1;
+                while (!(kTest ? test_wait(b, par) : try_wait(b, par))) {
+                }
+            }
+            double s = 0.0;
+            s = __dadd_rn(s, __dmul_rn(1.0000001, win[(threadIdx.x + i) & 1023]));
+            s = __dadd_rn(s, __dmul_rn(0.9999999, win[(threadIdx.x + i + 317) & 1023]));
+            s = __dadd_rn(s, __dmul_rn(1.0000002, win[(threadIdx.x + i + 5) & 1023]));
+            x = __dmul_rn(__dsub_rn(x, s), 0.5);
+            win[(threadIdx.x + i + 158) & 1023] = x;
+        }
+        if ((i & 7) == 0 && i >= 8) {
+            unsigned long long* b = &ring[(i - 8) & 15];
+            while (!try_wait(b, ((i - 8) >> 4) & 1)) {
+            }
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&ring[i & 15])) : "memory");
+    }
+    long long t1 = clock64();
+    if (threadIdx.x == 0) out[0] = t1 - t0;
+    sink[threadIdx.x] = x;
+}
 int main() {
     long long* out; double* sink; int* isink;
     cudaMalloc(&out, 64); cudaMalloc(&sink, 8192); cudaMalloc(&isink, 8192);
@@ -63,6 +120,14 @@ int main() {
         barchain<<<1, 512>>>(n, aw, out, sink); barchain<<<1, 512>>>(n, aw, out, sink);
         cudaMemcpy(h, out, 8, cudaMemcpyDeviceToHost);
         printf("level step (16 warps, %2d active) %.1f cycles per step\n", aw, (double)h[0] / n);
+    }
+    for (int aw : {1, 5, 16}) {
+        ringchain<false><<<1, 512>>>(n, aw, out, sink); ringchain<false><<<1, 512>>>(n, aw, out, sink);
+        cudaMemcpy(h, out, 8, cudaMemcpyDeviceToHost);
+        printf("level step, mbarrier ring + try_wait (16 warps, %2d owners) %.1f cycles per step\n", aw, (double)h[0] / n);
+        ringchain<true><<<1, 512>>>(n, aw, out, sink); ringchain<true><<<1, 512>>>(n, aw, out, sink);
+        cudaMemcpy(h, out, 8, cudaMemcpyDeviceToHost);
+        printf("level step, mbarrier ring + test_wait spin (16 warps, %2d owners) %.1f cycles per step\n", aw, (double)h[0] / n);
     }
     printf("status: %s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
