@@ -85,7 +85,8 @@ struct LsSmem {
     TileDesc tab[kLsRound];
 };
 
-// One CTA per SM is enough (a solve is latency bound, not occupancy bound) and leaves the registers to avoid spills.
+// One CTA per SM: a solve is latency bound and wants its registers; two systems per SM were measured slower per
+// solve AND in aggregate (profiles/r1/tune26.log, tune27.log), so bigger batches loop.
 __global__ void __launch_bounds__(kBlock, 1) sptrsv_ls_batch_kernel(const LsSysDev* __restrict__ sys, int nsys) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LsSmem& sm = *reinterpret_cast<LsSmem*>(smem_raw);

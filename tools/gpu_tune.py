@@ -106,8 +106,21 @@ if "single" not in skip:
     for nm, alg in (("level-stream", "ls"), ("sync-free", "syncfree")):
         best, med = timed(lambda: precond.triangular_solve(factor, fplan, r0, out, algorithm=alg), 5)
         print(f"sptrsv 316^2 IC(0) factor, {nm}: {best*1e3:.1f} us ({best*1e3/fplan.nlevels:.3f} us/level)", flush=True)
-    for nb in (16, 64, 128):
-        sys_ = [(factor, fplan, r0)] * nb
+    import copy
+
+    def clone_system():  # distinct memory for every system of the batch (a shared factor makes all CTAs hit the same L2 lines)
+        f = CsrMatrix(factor.rowptr.clone(), factor.col.clone(), factor.val.clone(), factor.n)
+        p = copy.copy(fplan)
+        p.perm = fplan.perm.clone()
+        p.ls = copy.copy(fplan.ls)
+        for name in ("rowptr", "col", "val", "level_sorted"):
+            setattr(p.ls, name, getattr(fplan.ls, name).clone())
+        p.ls.source = f.val.data_ptr()
+        return (f, p, r0.clone())
+
+    pool = [clone_system() for _ in range(592)]
+    for nb in (64, 128, 296, 592):
+        sys_ = pool[:nb]
         outs = [torch.empty_like(r0) for _ in range(nb)]
         byt1 = 12 * factor.nnz + 4 * (A.n + 1) + 16 * A.n
         best, med = timed(lambda: precond.triangular_solve_batch(sys_, outs, algorithm="ls"), 3)
