@@ -358,6 +358,24 @@ def extras(device, host0):
     out["sptrsv_128^3"] = {"ms": ms, "levels": fwd3.nlevels, "algorithmic_gbs": trsv_bytes / ms / 1e6,
                            "frac_of_hbm_peak": trsv_bytes / ms / 1e6 / peak, "us_per_level": 1e3 * ms / fwd3.nlevels,
                            "bound": "levels x (store -> L2 -> poll) latency, not HBM: see profiles/README.md"}
+    # config 5 operator size: SpMV on one 256^3 system (1.9 GB per product, far beyond the 126 MB L2)
+    del y
+    try:
+        st5, _, rhs5, sizes5 = synthetic.make_batch("poisson3d", 256, [0], device=device)
+        n5 = sizes5[0]
+        A5 = CsrMatrix.from_spconv(st5, n5, "symmetrise")
+        del st5
+        x5 = rhs5[0, :n5].to(torch.float64)
+        y5 = torch.empty_like(x5)
+        ms = timed(lambda: A5.matvec(x5, y5), reps=5)
+        bytes5 = 12 * A5.nnz + 4 * (n5 + 1) + 16 * n5
+        out["spmv_256^3"] = {"ms": ms, "n": n5, "nnz": A5.nnz, "algorithmic_gbs": bytes5 / ms / 1e6,
+                             "frac_of_hbm_peak": bytes5 / ms / 1e6 / peak}
+        del A5, x5, y5, rhs5
+        torch.cuda.empty_cache()
+    except Exception as exc:  # an extra must never take the bench line down (host memory on small boxes)
+        out["spmv_256^3"] = {"skipped": repr(exc)[:200]}
+
     # config 4 proper: single-system PCG on 128^3 (654 MB per iteration with a tril-pattern factor: HBM bound)
     from deeppreconditioning_b200 import model as models
 
