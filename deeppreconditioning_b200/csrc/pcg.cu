@@ -524,8 +524,9 @@ __device__ __forceinline__ void run_tiles(const Ctx& ctx, int k, int cur, int ve
     constexpr int kTab = kPhase == PH_APPLY1 ? TAB_P1 : kPhase == PH_APPLY2 ? TAB_P2 : TAB_A;
     constexpr bool kStream = kPhase != PH_DOTRZ;
     const int total = __ldcg(ctx.act_meta + 2 * cur + 1);
-    const int per = (total + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int g0 = blockIdx.x * per, g1 = min(total, g0 + per);
+    // contiguous ranges that differ by at most one tile: the first `rem` CTAs take one more
+    const int quot = total / (int)gridDim.x, rem = total % (int)gridDim.x;
+    const int g0 = (int)blockIdx.x * quot + min((int)blockIdx.x, rem), g1 = g0 + quot + ((int)blockIdx.x < rem ? 1 : 0);
     Scal sc;
     for (int ga = g0; ga < g1; ga += kMaxRoundTiles) {
         const int gb = min(g1, ga + kMaxRoundTiles);

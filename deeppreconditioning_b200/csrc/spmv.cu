@@ -31,8 +31,8 @@ spmv_csr_kernel(CsrView A, const double* __restrict__ x, double* __restrict__ y)
     Pipe pipe;
     pipe.init(sm.pipe.bytes, &sm.pipe.bar);
     const int ntiles = (A.n + kTileRows - 1) / kTileRows;
-    const int per = (ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int g0 = blockIdx.x * per, g1 = min(ntiles, g0 + per);
+    const int quot = ntiles / (int)gridDim.x, rem = ntiles % (int)gridDim.x;  // ranges differ by at most one tile
+    const int g0 = (int)blockIdx.x * quot + min((int)blockIdx.x, rem), g1 = g0 + quot + ((int)blockIdx.x < rem ? 1 : 0);
     const GatherReadOnly gx{x};
     for (int ga = g0; ga < g1; ga += kSpmvRound) {
         const int cnt = min(kSpmvRound, g1 - ga);

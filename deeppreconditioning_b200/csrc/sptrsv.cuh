@@ -12,7 +12,7 @@
 //   * chunk metadata is software-pipelined (plan row two chunks ahead, row extent one chunk ahead, entries / diagonal /
 //     rhs requested on arrival, before any waiting), so the dependent loads of a chunk never queue up behind its wait;
 //   * a warp whose chunk is still levels away parks on ONE word (lane 0, x of a row `lookback` chunks earlier in the
-//     plan, i.e. about one level back) with a short sleep; once that is solved every lane polls its own dependencies
+//     plan, i.e. about one level back: one sector request per poll); once that is solved every lane polls its own dependencies
 //     back to back, so the last store is seen one L2 round trip later and the L2 never sees thousands of idle pollers.
 #pragma once
 
@@ -47,12 +47,6 @@ struct RhsConsume {
 };
 
 constexpr int kTrsvInflight = 4;  // dependencies polled per lane and round
-#ifndef DPCG_TRSV_SLEEP
-#define DPCG_TRSV_SLEEP 0
-#endif
-#ifndef DPCG_TRSV_PARK_MULT
-#define DPCG_TRSV_PARK_MULT 1
-#endif
 
 // Everything a lane needs to solve its row except the dependencies' values.
 struct TrsvRow {
@@ -97,7 +91,6 @@ __device__ __forceinline__ bool sptrsv_stream(const CsrView& T, const int* __res
                                               long long cend, int lookback, const Rhs& rhs, double* x, const AbortCtl& ctl) {
     const int lane = threadIdx.x & 31;
     auto plan_row = [&](long long c) { return c < cend ? __ldg(plan + c * 32 + lane) : -1; };
-    lookback *= DPCG_TRSV_PARK_MULT;
     auto park_row = [&](long long c) { return (c < cend && c >= lookback) ? __ldg(plan + (c - lookback) * 32) : -1; };
 
     // pipeline fill: chunk c0 up to its row extent, c0 + stride up to its row index
@@ -124,7 +117,6 @@ __device__ __forceinline__ bool sptrsv_stream(const CsrView& T, const int* __res
                     return false;
                 }
                 if ((spins & 1023u) == 0 && ctl.aborted()) return false;
-                if (DPCG_TRSV_SLEEP > 0) __nanosleep(DPCG_TRSV_SLEEP);
             }
         }
         // resolve: every lane polls its own dependencies, consumed strictly in column order
