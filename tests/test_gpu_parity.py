@@ -367,6 +367,49 @@ def test_pcg_batch_is_bitwise_the_single_solves(cuda):
     assert len({r.iterations for r in batch}) > 3
 
 
+@pytest.mark.parametrize("engine", ["fused", "stepped"])
+def test_pcg_degenerate_inputs_follow_the_reference(cuda, engine):
+    """Edge cases of cg.py:58-90 against the oracle: 1x1 system, max_iter = 0, x0 already exact (iteration-0 check),
+    zero right-hand side (criterion 0/0 = NaN never passes `res < rtol`: the loop runs to max_iter like the reference),
+    and a ragged batch of many tiny systems beside a large one."""
+    one = CsrMatrix.from_arrays([0, 1], [0], [4.0], cuda)
+    b1 = torch.tensor([2.0], dtype=torch.float64)
+    r = dp.pcg_solve(one, b1.to(cuda), None, engine=engine)
+    o = pcg.preconditioned_conjugate_gradient(osp.to_torch_csr(np.array([0, 1]), np.array([0]), np.array([4.0])), b1,
+                                              operators.Identity())
+    assert r.iterations == o.iterations == 1 and r.x_hat.item() == o.x_hat.item() == 0.5
+
+    p = helpers.problem("poisson2d", 16, 0, 0.5, "net")
+    ops = gpu_operands(p, cuda)
+    At, b = osp.to_torch_csr(*p.A), p.b.to(cuda)
+    jac_o = operators.Jacobi(osp.to_scipy(*p.A).diagonal())
+    assert dp.pcg_solve(ops["A"], b, dp.Jacobi(ops["A"]), max_iter=0, engine=engine).iterations == 0
+    exact = dp.pcg_solve(ops["A"], b, dp.Jacobi(ops["A"]), max_iter=3000, rtol=1e-28, engine=engine).x_hat
+    again = dp.pcg_solve(ops["A"], b, dp.Jacobi(ops["A"]), x0=exact, max_iter=3000, engine=engine)
+    want = pcg.preconditioned_conjugate_gradient(At, p.b, jac_o, x0=exact.cpu(), max_iter=3000)
+    assert again.iterations == want.iterations == 0
+    zero = dp.pcg_solve(ops["A"], torch.zeros_like(b), dp.Jacobi(ops["A"]), max_iter=7, engine=engine)
+    zero_o = pcg.preconditioned_conjugate_gradient(At, torch.zeros_like(p.b), jac_o, max_iter=7)
+    assert zero.iterations == zero_o.iterations == 7 and zero.info == 0
+
+    systems, sizes = [], [1, 2, 3, 5, 31, 33, 64, 511, 513]
+    rng = np.random.default_rng(9)
+    import scipy.sparse as sp
+    for n in sizes * 3:  # 27 tridiagonal SPD systems: most are smaller than one 512-row tile
+        m = sp.diags([-np.ones(n - 1), 2.5 + rng.random(n), -np.ones(n - 1)], [-1, 0, 1], format="csr") if n > 1 else sp.csr_matrix([[3.0]])
+        m.sort_indices()
+        systems.append((CsrMatrix.from_scipy(m, cuda), torch.from_numpy(rng.standard_normal(n)).to(cuda), None, m))
+    systems.insert(5, (ops["A"], b, dp.FactoredMultiply(ops["L"], ops["Lt"]), None))
+    got = dp.pcg_solve_batch([s[:3] for s in systems], 1e-8, 3000, engine=engine)
+    for s, g in zip(systems, got):
+        if s[3] is None:
+            continue
+        m, rhs = s[3], s[1].cpu()
+        o = pcg.preconditioned_conjugate_gradient(osp.to_torch_csr(m.indptr, m.indices, m.data), rhs, operators.Identity(), max_iter=3000)
+        assert abs(g.iterations - o.iterations) <= 1, (m.shape, g.iterations, o.iterations)
+        assert np.linalg.norm(m @ g.x_hat.cpu().numpy() - rhs.numpy()) <= 2e-4 * np.linalg.norm(rhs.numpy()) + 1e-300
+
+
 def test_pcg_is_bitwise_reproducible_and_engines_agree(cuda):
     p = helpers.problem("poisson2d", 64, 0, 0.5, "net")
     ops = gpu_operands(p, cuda)
