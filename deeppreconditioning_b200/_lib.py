@@ -37,7 +37,7 @@ class PcgSystem(C.Structure):
             "dinv", "fwd_plan", "bwd_plan",
             "fwd_ls_rowptr", "fwd_ls_col", "fwd_ls_val", "fwd_ls_perm", "fwd_ls_level",
             "bwd_ls_rowptr", "bwd_ls_col", "bwd_ls_val", "bwd_ls_perm", "bwd_ls_level",
-            "b", "x", "work", "iters_out", "res_out", "history")]
+            "b", "x", "work", "iters_out", "res_out", "history", "coef")]
 
 
 class TrsvSystem(C.Structure):

@@ -38,6 +38,15 @@ class PcgResult:
     x_hat: torch.Tensor
     res: float
     history: list = field(default_factory=list)
+    alphas: list = field(default_factory=list)  # a of every body (cg.py:78), with history=True
+    betas: list = field(default_factory=list)   # beta behind every body's p (cg.py:82; betas[0] = 0)
+
+    @property
+    def kappa(self) -> float:
+        """Condition-number estimate of ``M A`` from the CG coefficients (see :mod:`.spectrum`); needs history=True."""
+        from .spectrum import kappa_estimate
+
+        return kappa_estimate(self.alphas, self.betas) if self.alphas else float("nan")
 
 
 def stopping_criterion(_, rk, b):
@@ -79,7 +88,8 @@ class PcgBatch:
             x = (x0.detach().to(**f64).clone() if x0 is not None else torch.zeros(n, **f64)).contiguous()
             work = torch.empty(lib.dp_pcg_work_doubles(n), **f64)
             hist = torch.full((self.max_iter + 1,), float("nan"), **f64) if history else None
-            self.entries.append(dict(A=A, M=M, b=b_dev, x=x, work=work, hist=hist, out_device=b.device))
+            coef = torch.full((2 * (self.max_iter + 1),), float("nan"), **f64) if history else None
+            self.entries.append(dict(A=A, M=M, b=b_dev, x=x, work=work, hist=hist, coef=coef, out_device=b.device))
         nsys = len(self.entries)
         self.iters = torch.full((nsys,), -1, dtype=torch.int32, device=self.device)
         self.res = torch.full((nsys,), float("nan"), dtype=torch.float64, device=self.device)
@@ -95,6 +105,7 @@ class PcgBatch:
             d.iters_out = self.iters.data_ptr() + 4 * i
             d.res_out = self.res.data_ptr() + 8 * i
             d.history = _lib.ptr(e["hist"])
+            d.coef = _lib.ptr(e["coef"])
 
     def __len__(self) -> int:
         return len(self.entries)
@@ -123,7 +134,12 @@ class PcgBatch:
         out = []
         for i, e in enumerate(self.entries):
             hist = e["hist"][: iters[i] + 1].cpu().tolist() if e["hist"] is not None and iters[i] >= 0 else []
-            out.append(PcgResult(seconds, int(iters[i]), 0, e["x"].to(e["out_device"]), float(res[i]), hist))
+            alphas, betas = [], []
+            if e["coef"] is not None and iters[i] > 0:
+                c = e["coef"][: 2 * iters[i]].cpu().view(-1, 2)
+                alphas, betas = c[:, 0].tolist(), c[:, 1].tolist()
+                betas[0] = 0.0
+            out.append(PcgResult(seconds, int(iters[i]), 0, e["x"].to(e["out_device"]), float(res[i]), hist, alphas, betas))
         return out
 
 

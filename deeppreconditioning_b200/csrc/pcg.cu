@@ -64,6 +64,7 @@ struct SysDev {
     int* iters_out;
     double* res_out;
     double* history;
+    double* coef;
 };
 
 struct Ctx {
@@ -238,6 +239,7 @@ __device__ __forceinline__ void phase_a(const Ctx& ctx, const SysDev& S, const T
                     atomicAdd(ctx.word, kDoneUnit);
                 } else {
                     S.scal[k & 1] = v[1];
+                    if (S.coef) S.coef[2 * k + 1] = sc.v;  // beta behind this body's p (cg.py:82,83)
                 }
             }
         }
@@ -289,8 +291,10 @@ __device__ __forceinline__ void phase_apply1(const Ctx& ctx, const SysDev& S, co
         sc.sys = s;
         sc.active = kInit || ld_relaxed_s32(ctx.state + s) == 0;  // written before the previous barrier: uniform
         sc.v = 0.0;
-        if (!kInit && sc.active)
+        if (!kInit && sc.active) {
             sc.v = __ldcg(S.scal + (k & 1)) / block_reduce_array(S.part_pap, S.ntiles, sm.scratch2);  // a, cg.py:78
+            if (tile == 0 && threadIdx.x == 0 && S.coef) S.coef[2 * k] = sc.v;  // tile 0: one CTA per system and phase
+        }
     }
     if (!sc.active) {
         pipe.tile_skip(d);
@@ -866,6 +870,7 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
         d.iters_out = u.iters_out;
         d.res_out = u.res_out;
         d.history = u.history;
+        d.coef = u.coef;
         sys[(size_t)i] = d;
         ident[(size_t)i] = i;
         tile_ofs[(size_t)i + 1] = tile_ofs[(size_t)i] + d.ntiles;

@@ -9,8 +9,11 @@ Same class name, constructor fields, private helper names and ``run()`` / ``dump
   multiplies by ``L L^T``, which approximates ``A`` instead of ``A^-1``, and tags the technique "unstable");
 * ``preconditioned_conjugate_gradient`` (test.py:138) -> the fused B200 solve.
 
-Out of scope: dense condition numbers / singular values (``_compute_kappa``, ``_compute_eigenvalues``,
-O(n^3) diagnostics, reported as NaN), histogram plots, the ``main()`` pipeline glue (dvc, checkpoint loading).
+* ``_compute_kappa`` (test.py:111-113, a dense ``cond(M @ A)``) -> the Lanczos estimate ``lambda_max / lambda_min`` of the
+  preconditioned operator from the solve's own CG coefficients (:mod:`.spectrum`).
+
+Out of scope: dense singular values (``_compute_eigenvalues``, O(n^3)), histogram plots, the ``main()``
+pipeline glue (dvc, checkpoint loading).
 """
 
 from __future__ import annotations
@@ -130,7 +133,7 @@ class BenchmarkSuite:
                 setup = time.perf_counter() - start_time if name != "vanilla" else 0.0  # test.py:135
 
                 density = self._compute_sparsity(preconditioner)
-                batch = PcgBatch([(matrix, rhs, preconditioner)], self.rtol, self.max_iter)
+                batch = PcgBatch([(matrix, rhs, preconditioner)], self.rtol, self.max_iter, history=True)
                 torch.cuda.synchronize()
                 start_time = time.perf_counter()
                 batch.solve()
@@ -138,7 +141,9 @@ class BenchmarkSuite:
                 duration = time.perf_counter() - start_time
                 result = batch.results(duration)[0]
 
-                self.kappas[name].append(float("nan"))  # dense cond(): out of scope
+                # test.py:111-113 takes a dense cond(M @ A); here the solve's own CG coefficients give the Lanczos
+                # estimate lambda_max / lambda_min of the preconditioned operator (spectrum.py)
+                self.kappas[name].append(result.kappa)
                 self.densities[name].append(density)
                 self.iterations[name].append(result.iterations)
                 self.setups[name].append(setup)

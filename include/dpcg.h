@@ -213,6 +213,10 @@ typedef struct dp_pcg_system {
     int32_t* iters_out;   /* 1 */
     double* res_out;      /* 1: last value of the stopping criterion (squared relative residual) */
     double* history;      /* optional, max_iter+1 doubles: criterion before every body (cg.py:67,87) */
+    double* coef;         /* optional, 2*(max_iter+1) doubles: coef[2k] = a of body k (cg.py:78), coef[2k+1] = beta that
+                           * built p for body k (cg.py:82 of body k-1; 0 for k = 0). The CG coefficients are the Lanczos
+                           * tridiagonal of M*A: the host turns them into the condition-number estimate that replaces
+                           * the dense torch.linalg.cond of test.py:111-113. */
 } dp_pcg_system_t;
 
 typedef struct dp_pcg_params {

@@ -2,8 +2,8 @@
 
 Follows the reference line by line and with the same torch CPU operators (``@``, ``torch.inner``) so the
 floating-point history is the reference's; the only addition is that it hands back what the reference
-computes but drops (``x_hat``, the last ``res``, the residual history) — ``cg.py:90`` returns only
-``(seconds, iterations, 0)``.
+computes but drops (``x_hat``, the last ``res``, the residual history, the coefficients ``a``/``beta``) —
+``cg.py:90`` returns only ``(seconds, iterations, 0)``.
 """
 
 from __future__ import annotations
@@ -27,6 +27,8 @@ class PcgResult:
     x_hat: torch.Tensor
     res: float
     history: list = field(default_factory=list)
+    alphas: list = field(default_factory=list)  # a of every body (cg.py:78)
+    betas: list = field(default_factory=list)   # beta behind every body's p (cg.py:82 of the previous body; 0 first)
 
 
 def preconditioned_conjugate_gradient(A, b, M, x0=None, x_true=None, rtol=1e-8, max_iter=1024) -> PcgResult:
@@ -39,6 +41,7 @@ def preconditioned_conjugate_gradient(A, b, M, x0=None, x_true=None, rtol=1e-8, 
 
     res = stopping_criterion(A, zk, b)  # cg.py:66 — iteration 0 checks the PRECONDITIONED residual
     history = [res.item()]
+    alphas, betas, beta = [], [], torch.zeros((), dtype=torch.float64)
 
     start_time = time.perf_counter()  # cg.py:69
     for _ in range(max_iter):  # cg.py:70
@@ -47,6 +50,7 @@ def preconditioned_conjugate_gradient(A, b, M, x0=None, x_true=None, rtol=1e-8, 
         Ap = A @ pk  # cg.py:75
         rz = torch.inner(rk, zk)  # cg.py:76
         a = rz / torch.inner(Ap, pk)  # cg.py:78
+        alphas.append(a.item()), betas.append(beta.item())
         x_hat = x_hat + a * pk  # cg.py:79
         rk = rk - a * Ap  # cg.py:80
         zk = M @ rk  # cg.py:81
@@ -56,7 +60,7 @@ def preconditioned_conjugate_gradient(A, b, M, x0=None, x_true=None, rtol=1e-8, 
         history.append(res.item())  # cg.py:87 (the A-norm error term is dropped: x_true is None on the path)
     end_time = time.perf_counter()  # cg.py:88
 
-    return PcgResult(end_time - start_time, len(history) - 1, 0, x_hat, float(history[-1]), history)  # cg.py:90
+    return PcgResult(end_time - start_time, len(history) - 1, 0, x_hat, float(history[-1]), history, alphas, betas)  # cg.py:90
 
 
 def conjugate_gradient(A, b, x0=None, x_true=None, rtol=1e-8, max_iter=1024):

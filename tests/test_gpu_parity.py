@@ -410,6 +410,29 @@ def test_pcg_degenerate_inputs_follow_the_reference(cuda, engine):
         assert np.linalg.norm(m @ g.x_hat.cpu().numpy() - rhs.numpy()) <= 2e-4 * np.linalg.norm(rhs.numpy()) + 1e-300
 
 
+@pytest.mark.parametrize("engine", ["fused", "stepped"])
+def test_cg_coefficients_and_kappa_estimate(cuda, engine):
+    """dp_pcg_system_t.coef: a / beta of every body against the oracle's (cg.py:78,82) and the condition-number
+    estimate built from them against the dense spectrum of M A (what test.py:111-113 computes densely)."""
+    p = helpers.problem("poisson2d", 16, 0, 0.5, "net")
+    ops = gpu_operands(p, cuda)
+    A = osp.to_scipy(*p.A).toarray()
+    At = osp.to_torch_csr(*p.A)
+    for M_gpu, M_o, dense in [(dp.Identity(), operators.Identity(), np.eye(p.n)),
+                              (dp.Jacobi(ops["A"]), operators.Jacobi(A.diagonal()), np.diag(1 / A.diagonal()))]:
+        got = dp.pcg_solve(ops["A"], p.b.to(cuda), M_gpu, rtol=1e-20, max_iter=400, engine=engine, history=True)
+        want = pcg.preconditioned_conjugate_gradient(At, p.b, M_o, rtol=1e-20, max_iter=400)
+        assert len(got.alphas) == len(got.betas) == got.iterations
+        np.testing.assert_allclose(got.alphas[:12], want.alphas[:12], rtol=1e-9)
+        np.testing.assert_allclose(got.betas[:12], want.betas[:12], rtol=1e-9)
+        lam = np.linalg.eigvals(dense @ A).real
+        assert got.kappa == pytest.approx(lam.max() / lam.min(), rel=1e-6)
+    batch = dp.pcg_solve_batch([(ops["A"], p.b.to(cuda), dp.FactoredMultiply(ops["L"], ops["Lt"])),
+                                (ops["A"], p.b.to(cuda), None)], 1e-8, 3000, engine=engine, history=True)
+    assert batch[0].kappa > batch[1].kappa > 1 and len(batch[0].alphas) == batch[0].iterations
+    assert np.isnan(dp.pcg_solve(ops["A"], p.b.to(cuda), None, engine=engine).kappa)  # no history requested
+
+
 def test_pcg_is_bitwise_reproducible_and_engines_agree(cuda):
     p = helpers.problem("poisson2d", 64, 0, 0.5, "net")
     ops = gpu_operands(p, cuda)
@@ -431,6 +454,8 @@ def test_benchmark_suite_end_to_end(cuda, tmp_path):
         assert len(suite.iterations[name]) == 2 and all(0 < i < 5000 for i in suite.iterations[name])
         assert all(s == 100 for s in suite.successes[name]) and all(r < 1e-8 for r in suite.residuals[name])
     assert max(suite.iterations["incomplete_cholesky"]) < min(suite.iterations["vanilla"])
+    assert all(np.isfinite(k) and k > 1 for name in suite.techniques for k in suite.kappas[name])
+    assert max(suite.kappas["incomplete_cholesky"]) < min(suite.kappas["jacobi"]) < max(suite.kappas["vanilla"]) * 1.001
     table = (tmp_path / "table.csv").read_text().splitlines()
     assert table[0] == "technique,kappas,densities,iterations,setups,durations,totals,successes" and len(table) == 5
     assert (tmp_path / "totals.csv").read_text().splitlines()[0] == "vanilla,jacobi,incomplete_cholesky,learned"

@@ -36,9 +36,9 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_descriptor_layout_and_size_queries(lib):
-    assert ctypes.sizeof(_lib.PcgSystem) == 10 * 4 + 28 * 8
+    assert ctypes.sizeof(_lib.PcgSystem) == 10 * 4 + 29 * 8
     assert ctypes.sizeof(_lib.PcgParams) == 24
-    assert _lib.PcgSystem.a_rowptr.offset == 40 and _lib.PcgSystem.history.offset == 40 + 27 * 8
+    assert _lib.PcgSystem.a_rowptr.offset == 40 and _lib.PcgSystem.history.offset == 40 + 27 * 8 and _lib.PcgSystem.coef.offset == 40 + 28 * 8
     for n in (1, 31, 32, 33, 511, 512, 513, 99856):
         pad = (n + 31) // 32 * 32
         tiles = (n + 511) // 512

@@ -176,3 +176,29 @@ def test_synthetic_systems_are_spd_and_fp32_exact():
     assert len(a5.A[1]) == 5 * 144 - 4 * 12 and len(a5.T[1]) == 3 * 144 - 2 * 12  # SURVEY §8 nnz formulas
     a7 = helpers.problem("poisson3d", 6, 0, 0.5, None)
     assert len(a7.A[1]) == 7 * 216 - 6 * 36 and len(a7.T[1]) == 4 * 216 - 3 * 36
+
+
+def test_kappa_estimate_from_cg_coefficients_matches_the_dense_spectrum():
+    """the Lanczos tridiagonal built from a/beta of the reference loop (cg.py:78,82) has the extreme
+    eigenvalues of M A; its ratio is what replaces the dense torch.linalg.cond of test.py:111-113 (equal to it for
+    M = I, the symmetric-preconditioning condition number otherwise)."""
+    from deeppreconditioning_b200 import spectrum
+
+    p = helpers.problem("poisson2d", 16, 0, 0.5, "net")
+    A = osp.to_scipy(*p.A).toarray()
+    At = osp.to_torch_csr(*p.A)
+    L = osp.to_scipy(*p.L).toarray()
+    for M, dense, iters in [(operators.Identity(), np.eye(p.n), 400), (operators.Jacobi(A.diagonal()), np.diag(1 / A.diagonal()), 400),
+                            (operators.FactoredMultiply(*p.L), L @ L.T, 2000)]:
+        r = pcg.preconditioned_conjugate_gradient(At, p.b, M, rtol=1e-20, max_iter=iters)
+        assert len(r.alphas) == len(r.betas) == r.iterations and r.betas[0] == 0.0
+        lam = np.linalg.eigvals(dense @ A).real
+        lo, hi = spectrum.ritz_extremes(r.alphas, r.betas)
+        assert lo == pytest.approx(lam.min(), rel=1e-8) and hi == pytest.approx(lam.max(), rel=1e-8)
+        assert spectrum.kappa_estimate(r.alphas, r.betas) == pytest.approx(lam.max() / lam.min(), rel=1e-8)
+    assert spectrum.kappa_estimate(r.alphas[:1], r.betas[:1]) == 1.0  # one body: a single Ritz value
+    assert np.isnan(spectrum.kappa_estimate([], []))
+    # at the reference's tolerance the Ritz values are still inside the spectrum: a lower bound
+    r8 = pcg.preconditioned_conjugate_gradient(At, p.b, operators.Identity(), max_iter=400)
+    k8 = spectrum.kappa_estimate(r8.alphas, r8.betas)
+    assert 0.5 * np.linalg.cond(A) < k8 <= np.linalg.cond(A) * (1 + 1e-9)
