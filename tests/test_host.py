@@ -123,3 +123,43 @@ def test_gather_records_gloo_world_size_2(tmp_path):
         out, _ = proc.communicate(timeout=180)
         assert proc.returncode == 0, out.decode()
         assert f"rank {r} ok" in out.decode()
+
+
+def test_sludge_pattern_data_set_reads_the_reference_layout(tmp_path):
+    """data_set.py:73-130 restated literally on files written in the generator's layout (generate_data.py:109-111):
+    80/20 split over sorted folders, lower triangle, padding with trivial equations to the largest system."""
+    import scipy.sparse as sp
+    from deeppreconditioning_b200 import synthetic
+    from deeppreconditioning_b200.data_set import SludgePatternDataSet, write_case
+
+    root = tmp_path / "raw"
+    sides = [5, 7, 4, 6, 5, 3, 8, 4, 6, 5]
+    for k, side in enumerate(sides):
+        rows, cols, vals, rhs = synthetic.poisson2d_tril(side, 0.5, k)
+        low = sp.coo_matrix((vals.astype(np.float64), (rows, cols)), shape=(side * side,) * 2)
+        full = (low + sp.tril(low, -1).T).tocoo()
+        write_case(root / "sludge_patterns" / f"case_{k:04}", full, rhs, np.linspace(0, 1, side * side))
+    data = SludgePatternDataSet("test", 1, shuffle=False, root=root, device="cpu")
+    train = SludgePatternDataSet("train", 2, shuffle=False, root=root, device="cpu")
+    assert len(data) == 2 and len(train) == 4 and data.dof_max == train.dof_max == 64
+    for index, folder in enumerate(sorted((root / "sludge_patterns").glob("case_*"))[8:]):
+        tril, solutions, right_hand_sides, sizes = data[index]
+        # the reference's arithmetic, literally (data_set.py:84-128)
+        rows, columns, _, original_size, values = np.load(folder / "matrix.npz").values()
+        n, difference = int(original_size[0]), 64 - int(original_size[0])
+        (keep,) = np.where(rows >= columns)
+        rows, columns, values = rows[keep], columns[keep], values[keep]
+        rows = np.append(rows, np.arange(n, 64))
+        columns = np.append(columns, np.arange(n, 64))
+        values = np.append(values, np.ones((difference,)))
+        assert sizes == (n,) and tril.batch_size == 1 and list(tril.spatial_shape) == [64, 64]
+        assert tril.features.dtype == torch.float32 and tril.indices.dtype == torch.int32
+        assert np.array_equal(tril.features.numpy(), np.expand_dims(values, -1).astype(np.float32))
+        assert np.array_equal(tril.indices.numpy(), np.column_stack((np.zeros(len(values)), rows, columns)).astype(np.int32))
+        want_rhs = np.pad(np.loadtxt(folder / "right_hand_side.csv"), (0, difference), constant_values=1)
+        assert np.array_equal(right_hand_sides.numpy(), want_rhs[None, :].astype(np.float32))
+        assert solutions.shape == (1, 64) and float(solutions[0, -1]) == 1.0
+    pair = train[1]
+    assert pair[3] == (16, 36) and pair[0].batch_size == 2 and set(pair[0].indices[:, 0].tolist()) == {0, 1}
+    with pytest.raises(AssertionError):
+        SludgePatternDataSet("validation", 1, root=root, device="cpu")
