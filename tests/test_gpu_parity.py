@@ -464,6 +464,34 @@ def test_benchmark_suite_end_to_end(cuda, tmp_path):
     assert suite.densities["vanilla"][0] == pytest.approx(100 / n) and suite.densities["learned"][0] > suite.densities["incomplete_cholesky"][0]
 
 
+def test_benchmark_suite_on_the_reference_disk_layout(cuda, tmp_path):
+    """The reference's generator layout on disk (generate_data.py:109-111) -> SludgePatternDataSet -> BenchmarkSuite:
+    ragged systems padded to the largest one, only the `[0, 0, :n, :n]` block solved (test.py:61-68,124)."""
+    import scipy.sparse as sp
+    from deeppreconditioning_b200.data_set import SludgePatternDataSet, write_case
+
+    root = tmp_path / "raw"
+    sides = [9, 12, 7, 10, 8, 11, 6, 12, 9, 10]
+    for k, side in enumerate(sides):
+        rows, cols, vals, rhs = synthetic.poisson2d_tril(side, 0.5, k)
+        low = sp.coo_matrix((vals.astype(np.float64), (rows, cols)), shape=(side * side,) * 2)
+        write_case(root / "sludge_patterns" / f"case_{k:04}", (low + sp.tril(low, -1).T).tocoo(), rhs, np.zeros(side * side))
+    data = SludgePatternDataSet("test", 1, shuffle=False, root=root, device=cuda)
+    assert len(data) == 2 and data.dof_max == 144
+    torch.manual_seed(69)
+    suite = BenchmarkSuite(data, models.PreconditionerNet(models.DEFAULT_CHANNELS).to(cuda), max_iter=5000)
+    suite.run()
+    for index, side in enumerate(sides[8:]):
+        rows, cols, vals, rhs = synthetic.poisson2d_tril(side, 0.5, 8 + index)
+        low = sp.coo_matrix((vals.astype(np.float64), (rows, cols)), shape=(side * side,) * 2)
+        A = (low + sp.tril(low, -1).T).tocsr()
+        A.sort_indices()
+        want = pcg.preconditioned_conjugate_gradient(osp.to_torch_csr(A.indptr, A.indices, A.data),
+                                                     torch.from_numpy(rhs.astype(np.float64)), operators.Identity(), max_iter=5000)
+        assert abs(suite.iterations["vanilla"][index] - want.iterations) <= 1
+        assert suite.residuals["jacobi"][index] < 1e-8 and suite.successes["learned"][index] == 100
+
+
 # ---- full-size properties (BASELINE configs 2 and 4): too large for the dense/CPU oracle in seconds ------------------
 def test_config2_size_properties(cuda):
     """316^2 (N = 99 856): assembly sizes, SpMV linearity and symmetry, SpTRSV round trip, PCG true residual."""
