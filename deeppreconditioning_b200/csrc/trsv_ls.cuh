@@ -53,7 +53,8 @@ using LsPipe = PipeT<kLsCap, kLsStages>;  // 5 stages of 1536 entries over the S
 struct LsShared {
     PipeBarriers<kLsStages> bar;
     unsigned items;
-    unsigned steps;  // level steps taken so far (carried like `items`: fixes the parities of the ring below)
+    int pad;
+    unsigned long long steps;  // level steps taken so far (carried like `items`: fixes the parities of the ring below)
     alignas(8) unsigned long long level_done[kLsRing];  // step s completes phase s / kLsRing of slot s % kLsRing
     double win[kLsWindow];
     __device__ __forceinline__ void init() {  // thread 0, once per kernel, before a CTA barrier
@@ -63,7 +64,7 @@ struct LsShared {
         }
         for (int s = 0; s < kLsRing; ++s) mbar_init(&level_done[s], (unsigned)kWarpsPerBlock);
         mbar_fence_init();
-        items = 0u, steps = 0u;
+        items = 0u, steps = 0ull;
     }
 };
 
@@ -94,9 +95,10 @@ __device__ __forceinline__ void trsv_level_stream(const LsFactor& F, const doubl
     constexpr int kAhead = kLsStages - 2;      // tiles in flight; the stage issued into was released a whole tile ago
     constexpr int kProducer = kBlock - kWarp;  // lane 0 of the LAST warp: its rows come last in every tile
     const int lane = tid & 31;
-    unsigned step0 = ls.steps;  // step of the first level of the current tile
-    auto step_wait = [&](unsigned s) {  // all 16 warps have arrived at step s
-        while (!mbar_try_wait(&ls.level_done[s % kLsRing], (s / kLsRing) & 1u)) {
+    unsigned long long step0 = ls.steps;  // step of the first level of the current tile
+    const unsigned long long solve_step0 = step0;  // the first level of a solve has no dependencies
+    auto step_wait = [&](unsigned long long s) {  // all 16 warps have arrived at step s
+        while (!mbar_try_wait(&ls.level_done[s % kLsRing], (unsigned)(s / kLsRing) & 1u)) {
         }
     };
     for (int ga = 0; ga < ntiles; ga += tabcap) {
@@ -129,9 +131,9 @@ __device__ __forceinline__ void trsv_level_stream(const LsFactor& F, const doubl
         };
         load_meta(ga);
         int pre = 0;  // level steps of the upcoming tile this warp has already arrived at
-        auto step_arrive = [&](unsigned s) {
+        auto step_arrive = [&](unsigned long long s) {
             // a slot of the ring is reused every kLsRing steps: stay less than a ring ahead of the slowest warp
-            if (s % (kLsRing / 2) == 0u && s >= (unsigned)(kLsRing / 2)) step_wait(s - kLsRing / 2);
+            if (s % (kLsRing / 2) == 0ull && s >= (unsigned long long)(kLsRing / 2)) step_wait(s - kLsRing / 2);
             __syncwarp();
             if (lane == 0) mbar_arrive(&ls.level_done[s % kLsRing]);
         };
@@ -169,9 +171,9 @@ __device__ __forceinline__ void trsv_level_stream(const LsFactor& F, const doubl
             g_ls_trace_levels(ga + i, lv1 - lv0 + 1);
 #pragma unroll 1
             for (int l = lv0 + pre; l <= lv1; ++l) {
-                const unsigned s = step0 + (unsigned)(l - lv0);
+                const unsigned long long s = step0 + (unsigned long long)(l - lv0);
                 if (wl0 >= 0 && l >= wl0 && l <= wl1) {
-                    if (s > 0u) step_wait(s - 1u);  // every row of the earlier levels is solved
+                    if (s != solve_step0) step_wait(s - 1ull);  // every row of the earlier levels is solved
                     if (lvl == l) {
                         double sum = 0.0;
 #pragma unroll
@@ -183,7 +185,7 @@ __device__ __forceinline__ void trsv_level_stream(const LsFactor& F, const doubl
                 }
                 step_arrive(s);
             }
-            step0 += (unsigned)(lv1 - lv0 + 1);
+            step0 += (unsigned long long)(lv1 - lv0 + 1);
             // Before the hand-over (store, stage release, next rows into registers) the warp already arrives at the
             // steps of the next tile that come before its own first level there: nobody waits for its hand-over.
             pre = 0;
@@ -191,7 +193,7 @@ __device__ __forceinline__ void trsv_level_stream(const LsFactor& F, const doubl
                 const int lv0n = tab[i + 1].n, lv1n = tab[i + 1].nnz;
                 const int wl0n = __shfl_sync(kFull, lvl_n, 0);  // lvl_n: this thread's level in the next tile
                 pre = wl0n < 0 ? lv1n - lv0n + 1 : max(0, wl0n - lv0n);
-                for (int k = 0; k < pre; ++k) step_arrive(step0 + (unsigned)k);
+                for (int k = 0; k < pre; ++k) step_arrive(step0 + (unsigned long long)k);
             }
             // the global copy (original numbering)
             LS_TRACE(ga + i, 5);
