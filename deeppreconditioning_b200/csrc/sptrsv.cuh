@@ -119,30 +119,36 @@ __device__ __forceinline__ bool sptrsv_stream(const CsrView& T, const int* __res
                 if ((spins & 1023u) == 0 && ctl.aborted()) return false;
             }
         }
-        // resolve: every lane polls its own dependencies, consumed strictly in column order
+        // resolve: every lane polls its own dependencies, a batch of kTrsvInflight at a time, and re-reads only the ones
+        // that are still pending; a complete batch is summed in column order
         double sum = 0.0;
         unsigned idle = 0;
+        unsigned long long u[kTrsvInflight];
+#pragma unroll
+        for (int k = 0; k < kTrsvInflight; ++k) u[k] = kPending;
         for (;;) {
             const bool pending = cur.row >= 0 && cur.e < cur.end;
             if (!__any_sync(kFull, pending)) break;
             bool progress = false;
             if (pending) {
                 const int m = min(kTrsvInflight, cur.end - cur.e);
-                unsigned long long u[kTrsvInflight];
-#pragma unroll
-                for (int k = 0; k < kTrsvInflight; ++k) u[k] = k < m ? ld_relaxed_u64(x + cur.c[k]) : kPending;
-                int used = 0;
+                bool all = true;
 #pragma unroll
                 for (int k = 0; k < kTrsvInflight; ++k) {
-                    if (used == k && u[k] != kPending) {
-                        sum = __dadd_rn(sum, __dmul_rn(cur.v[k], as_double(u[k])));
-                        ++used;
+                    if (k < m && u[k] == kPending) {
+                        u[k] = ld_relaxed_u64(x + cur.c[k]);
+                        all = all && u[k] != kPending;
                     }
                 }
-                if (used) {
-                    cur.e += used;
+                if (all) {
+#pragma unroll
+                    for (int k = 0; k < kTrsvInflight; ++k)
+                        if (k < m) sum = __dadd_rn(sum, __dmul_rn(cur.v[k], as_double(u[k])));
+                    cur.e += m;
                     progress = true;
-                    if (cur.e < cur.end) {  // rows with more than kTrsvInflight dependencies: fetch the next ones
+#pragma unroll
+                    for (int k = 0; k < kTrsvInflight; ++k) u[k] = kPending;
+                    if (cur.e < cur.end) {  // rows with more than kTrsvInflight dependencies: fetch the next batch
 #pragma unroll
                         for (int k = 0; k < kTrsvInflight; ++k)
                             if (cur.e + k < cur.end) cur.c[k] = __ldg(T.col + cur.e + k), cur.v[k] = __ldg(T.val + cur.e + k);
