@@ -524,10 +524,12 @@ __device__ __forceinline__ void ensure_table(const Ctx& ctx, int cur, int ver, i
 // `next_tab` (fused engine only, -1 = none): the table the NEXT phase will stream; when it is still valid for this
 // CTA's range its first items are issued before the grid barrier (Pipe::begin_early).
 template <int kPhase, bool kInit, bool kCheckState>
-__device__ __forceinline__ void run_tiles(const Ctx& ctx, int k, int cur, int ver, Smem& sm, Pipe& pipe, int next_tab = -1) {
+__device__ __forceinline__ void run_tiles(const Ctx& ctx, int k, int cur, int ver, int total, Smem& sm, Pipe& pipe,
+                                          int next_tab = -1) {
     constexpr int kTab = kPhase == PH_APPLY1 ? TAB_P1 : kPhase == PH_APPLY2 ? TAB_P2 : TAB_A;
     constexpr bool kStream = kPhase != PH_DOTRZ;
-    const int total = __ldcg(ctx.act_meta + 2 * cur + 1);
+    // `total` = tiles of list `cur`: kept in a register by the caller (it only changes when the list is rebuilt), which
+    // saves an L2 round trip at the head of every phase
     // contiguous ranges that differ by at most one tile: the first `rem` CTAs take one more
     const int quot = total / (int)gridDim.x, rem = total % (int)gridDim.x;
     const int g0 = (int)blockIdx.x * quot + min((int)blockIdx.x, rem), g1 = g0 + quot + ((int)blockIdx.x < rem ? 1 : 0);
@@ -593,16 +595,16 @@ __device__ __forceinline__ void rebuild_active(const Ctx& ctx, int cur, Smem& sm
 // Returns false on abort. `done` = finished count of the last barrier.
 // `list_stays`: the active list (hence every table) survives this iteration, so the last phase may start table A early.
 template <bool kInit>
-__device__ __forceinline__ bool apply_preconditioner(const Ctx& ctx, int k, int cur, int ver, GridBarrier& bar, Smem& sm,
-                                                     Pipe& pipe, bool list_stays) {
+__device__ __forceinline__ bool apply_preconditioner(const Ctx& ctx, int k, int cur, int ver, int total, GridBarrier& bar,
+                                                     Smem& sm, Pipe& pipe, bool list_stays) {
     const int tab_a = list_stays ? (int)TAB_A : -1;
-    run_tiles<PH_APPLY1, kInit, false>(ctx, k, cur, ver, sm, pipe,
+    run_tiles<PH_APPLY1, kInit, false>(ctx, k, cur, ver, total, sm, pipe,
                                        ctx.has_multiply ? (int)TAB_P2 : (ctx.has_solve ? -1 : tab_a));
     trace(ctx, sm, 8 * PH_APPLY1 + 1);
     if (bar.sync() < 0) return false;
     trace(ctx, sm, 8 * PH_APPLY1 + 2);
     if (ctx.has_multiply) {
-        run_tiles<PH_APPLY2, kInit, false>(ctx, k, cur, ver, sm, pipe, ctx.has_solve ? -1 : tab_a);
+        run_tiles<PH_APPLY2, kInit, false>(ctx, k, cur, ver, total, sm, pipe, ctx.has_solve ? -1 : tab_a);
         trace(ctx, sm, 8 * PH_APPLY2 + 1);
         if (bar.sync() < 0) return false;
         trace(ctx, sm, 8 * PH_APPLY2 + 2);
@@ -614,7 +616,7 @@ __device__ __forceinline__ bool apply_preconditioner(const Ctx& ctx, int k, int 
         if (ctx.has_ls) phase_trsv_ls<true, kInit>(ctx, k, sm);
         const bool b = phase_trsv<true, kInit>(ctx, k, sm);
         if (bar.sync() < 0 || !b) return false;
-        run_tiles<PH_DOTRZ, kInit, false>(ctx, k, cur, ver, sm, pipe, tab_a);
+        run_tiles<PH_DOTRZ, kInit, false>(ctx, k, cur, ver, total, sm, pipe, tab_a);
         if (bar.sync() < 0) return false;
     }
     return true;
@@ -641,12 +643,13 @@ __global__ void __launch_bounds__(kBlock, 2) pcg_fused_kernel(Ctx ctx) {
     int cur = 0;          // active-list buffer in use
     int ver = 1;          // bumped whenever the list (hence every CTA's tile range) changes
     int done_built = 0;   // finished count the list `cur` reflects
-    run_tiles<PH_INIT, false, false>(ctx, -1, cur, ver, sm, pipe, TAB_P1);
+    int total = ctx.total_tiles;  // tiles of the active list (all systems at first)
+    run_tiles<PH_INIT, false, false>(ctx, -1, cur, ver, total, sm, pipe, TAB_P1);
     if (bar.sync() < 0) return;
-    if (!apply_preconditioner<true>(ctx, -1, cur, ver, bar, sm, pipe, true)) return;
+    if (!apply_preconditioner<true>(ctx, -1, cur, ver, total, bar, sm, pipe, true)) return;
     for (int k = 0; k <= ctx.max_iter; ++k) {
         trace(ctx, sm, 8 * PH_A + 0);
-        run_tiles<PH_A, false, false>(ctx, k, cur, ver, sm, pipe, TAB_P1);
+        run_tiles<PH_A, false, false>(ctx, k, cur, ver, total, sm, pipe, TAB_P1);
         trace(ctx, sm, 8 * PH_A + 1);
         const int done = bar.sync();
         trace(ctx, sm, 8 * PH_A + 2);
@@ -657,8 +660,11 @@ __global__ void __launch_bounds__(kBlock, 2) pcg_fused_kernel(Ctx ctx) {
         }
         const bool rebuild = done != done_built;  // same decision in every CTA
         if (rebuild && blockIdx.x == 0) rebuild_active(ctx, cur, sm);
-        if (!apply_preconditioner<false>(ctx, k, cur, ver, bar, sm, pipe, !rebuild)) return;  // >= 1 barrier: the new list is visible
-        if (rebuild) cur ^= 1, done_built = done, ++ver;
+        if (!apply_preconditioner<false>(ctx, k, cur, ver, total, bar, sm, pipe, !rebuild)) return;  // >= 1 barrier: the new list is visible
+        if (rebuild) {
+            cur ^= 1, done_built = done, ++ver;
+            total = __ldcg(ctx.act_meta + 2 * cur + 1);
+        }
     }
 }
 
@@ -676,7 +682,7 @@ __global__ void __launch_bounds__(kBlock, 2) pcg_phase_kernel(Ctx ctx, int k) {
         if (ctx.has_ls) phase_trsv_ls<true, kInit>(ctx, k, sm);
         phase_trsv<true, kInit>(ctx, k, sm);
     } else {
-        run_tiles<kPhase, kInit, true>(ctx, k, 0, 1, sm, pipe);
+        run_tiles<kPhase, kInit, true>(ctx, k, 0, 1, ctx.total_tiles, sm, pipe);
     }
 }
 
