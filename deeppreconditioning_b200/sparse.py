@@ -80,7 +80,11 @@ class CsrMatrix:
     def from_arrays(cls, rowptr, col, val, device=None) -> "CsrMatrix":
         """From host or device CSR arrays (columns must already be sorted per row)."""
         device = _cuda_device(device)
-        as_t = lambda a, dt: torch.as_tensor(np.asarray(a) if not torch.is_tensor(a) else a).to(device=device, dtype=dt)
+        def as_t(a, dt):
+            t = torch.as_tensor(np.asarray(a) if not torch.is_tensor(a) else a)
+            # pinned host operands (the e2e path) are uploaded asynchronously on the current stream: the caller keeps them
+            # alive, and every kernel that reads the copy is enqueued behind it
+            return t.to(device=device, dtype=dt, non_blocking=bool(t.device.type == "cpu" and t.is_pinned() and t.dtype == dt))
         rowptr = as_t(rowptr, torch.int32)
         return cls(rowptr, as_t(col, torch.int32), as_t(val, torch.float64), rowptr.shape[0] - 1)
 
