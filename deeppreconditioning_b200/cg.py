@@ -131,6 +131,16 @@ class PcgBatch:
         """Synchronise and collect ``PcgResult`` per system (``x_hat`` on the device the right-hand side came from)."""
         _lib.raise_on_flag(self.flag, "dp_pcg_solve_f64")
         iters, res = self.iters.cpu().tolist(), self.res.cpu().tolist()
+        # solutions that go back to the host leave through pinned buffers, all copies in flight before one wait
+        xs = []
+        for e in self.entries:
+            if e["out_device"].type == "cpu":
+                host = torch.empty(e["x"].shape, dtype=torch.float64, pin_memory=True)
+                host.copy_(e["x"], non_blocking=True)
+                xs.append(host)
+            else:
+                xs.append(e["x"].to(e["out_device"]))
+        torch.cuda.synchronize(self.device)
         out = []
         for i, e in enumerate(self.entries):
             hist = e["hist"][: iters[i] + 1].cpu().tolist() if e["hist"] is not None and iters[i] >= 0 else []
@@ -139,7 +149,7 @@ class PcgBatch:
                 c = e["coef"][: 2 * iters[i]].cpu().view(-1, 2)
                 alphas, betas = c[:, 0].tolist(), c[:, 1].tolist()
                 betas[0] = 0.0
-            out.append(PcgResult(seconds, int(iters[i]), 0, e["x"].to(e["out_device"]), float(res[i]), hist, alphas, betas))
+            out.append(PcgResult(seconds, int(iters[i]), 0, xs[i], float(res[i]), hist, alphas, betas))
         return out
 
 
