@@ -5,6 +5,7 @@
 
 #include "sptrsv.cuh"
 #include "trsv_ls.cuh"
+#include "trsv_ts.cuh"
 
 namespace dp {
 
@@ -99,6 +100,23 @@ __global__ void __launch_bounds__(kBlock, 1) sptrsv_ls_batch_kernel(const LsSysD
         else
             trsv_level_stream<false>(S.F, S.b, S.x, sm.bytes, sm.ls, sm.tab, kLsRound);
     }
+}
+
+// ---- tile-stream solve (trsv_ts.cuh): the tiles of all systems in one sequence, dealt to persistent CTAs ---------
+__global__ void arm_positions_kernel(const TsSysDev* __restrict__ sys, int nsys) {
+    for (int s = blockIdx.y; s < nsys; s += gridDim.y) {
+        unsigned long long* xp = reinterpret_cast<unsigned long long*>(sys[s].xp);
+        const int n = sys[s].F.n;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) xp[i] = kPending;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock, 2)
+sptrsv_ts_batch_kernel(const TsSysDev* __restrict__ sys, int nsys, int max_tiles, unsigned long long* word, int* flag) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TsSmem& sm = *reinterpret_cast<TsSmem*>(smem_raw);
+    const AbortCtl ctl{word, flag};
+    trsv_tile_stream(sys, nsys, max_tiles, sm, ctl);
 }
 
 // IC(0), up-looking, one lane per row, rows of a level per chunk (same plan as the forward solve of tril(A)):
@@ -314,6 +332,68 @@ int dp_sptrsv_ls_solve_batch_f64(const dp_trsv_ls_system_t* systems_host, int32_
     const int resident = sm_count();
     sptrsv_ls_batch_kernel<<<nsys < resident ? nsys : resident, kBlock, sizeof(LsSmem), s>>>(sys, nsys);
     DP_LAUNCH_CHECK();
+    return DP_OK;
+}
+
+/* ---- tile-stream batch solve ---------------------------------------------------------------------------------- */
+static size_t ts_header_bytes(int32_t nsys) { return 256 + align_up(sizeof(TsSysDev) * (size_t)(nsys > 0 ? nsys : 0), 256); }
+
+size_t dp_sptrsv_ts_workspace_bytes(const dp_trsv_ls_system_t* systems_host, int32_t nsys) {
+    size_t bytes = ts_header_bytes(nsys);
+    for (int i = 0; systems_host && i < nsys; ++i)
+        if (systems_host[i].perm) bytes += align_up(sizeof(double) * (size_t)(systems_host[i].n > 0 ? systems_host[i].n : 0), 256);
+    return bytes;
+}
+
+int dp_sptrsv_ts_solve_batch_f64(const dp_trsv_ls_system_t* systems_host, int32_t nsys, int32_t* flag_out, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+    if (!systems_host || nsys <= 0 || !flag_out || !workspace) return DP_ERR_INVALID;
+    if (workspace_bytes < dp_sptrsv_ts_workspace_bytes(systems_host, nsys)) return DP_ERR_WORKSPACE;
+    if (!aligned16(workspace)) return DP_ERR_ALIGNMENT;
+    cudaStream_t s = (cudaStream_t)stream;
+    char* ws = static_cast<char*>(workspace);
+    unsigned long long* word = reinterpret_cast<unsigned long long*>(ws);
+    TsSysDev* sys = reinterpret_cast<TsSysDev*>(ws + 256);
+    size_t off = ts_header_bytes(nsys);
+    std::vector<TsSysDev> dev((size_t)nsys);
+    int max_tiles = 0, nmax = 0;
+    for (int i = 0; i < nsys; ++i) {
+        const dp_trsv_ls_system_t& u = systems_host[i];
+        if (u.n <= 0 || !u.rowptr_p || !u.col_p || !u.val_p || !u.b || !u.x || u.b == u.x) return DP_ERR_INVALID;
+        if (!aligned16(u.col_p) || !aligned16(u.val_p) || !aligned16(u.rowptr_p) || !aligned16(u.perm ? (const void*)u.perm : (const void*)u.b))
+            return DP_ERR_ALIGNMENT;  // spans of all four arrays are moved by 16-byte granular bulk copies
+        TsSysDev d{};
+        d.F = LsFactor{u.rowptr_p, u.col_p, u.val_p, u.perm, u.level_sorted, u.n, u.nnz};
+        d.b = u.b, d.x = u.x, d.upper = u.upper ? 1 : 0;
+        if (u.perm) {
+            d.xp = reinterpret_cast<double*>(ws + off);
+            off += align_up(sizeof(double) * (size_t)u.n, 256);
+        } else {
+            d.xp = u.x;  // position space: the solution vector is the polled vector
+        }
+        d.ntiles = (u.n + kTileRows - 1) / kTileRows;
+        if (d.ntiles > max_tiles) max_tiles = d.ntiles;
+        if (u.n > nmax) nmax = u.n;
+        dev[(size_t)i] = d;
+    }
+    DP_CUDA(cudaMemsetAsync(word, 0, sizeof(unsigned long long), s));
+    // pageable source: the call returns once the bytes are staged, `dev` may go out of scope
+    DP_CUDA(cudaMemcpyAsync(sys, dev.data(), sizeof(TsSysDev) * (size_t)nsys, cudaMemcpyHostToDevice, s));
+    const int fill_x = (nmax + 255) / 256 < sm_count() * 4 ? (nmax + 255) / 256 : sm_count() * 4;
+    arm_positions_kernel<<<dim3(fill_x, nsys < 1024 ? nsys : 1024), 256, 0, s>>>(sys, nsys);
+    DP_LAUNCH_CHECK();
+    static thread_local bool smem_ok = false;
+    if (!smem_ok) {
+        DP_CUDA(cudaFuncSetAttribute((const void*)sptrsv_ts_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(TsSmem)));
+        smem_ok = true;
+    }
+    int grid = coop_grid((const void*)sptrsv_ts_batch_kernel, kBlock, sizeof(TsSmem));
+    const long long items = (long long)max_tiles * nsys;
+    if (items < grid) grid = (int)items;
+    int nsys_i = nsys;
+    void* args[] = {&sys, &nsys_i, &max_tiles, &word, &flag_out};
+    DP_CUDA(cudaLaunchCooperativeKernel((const void*)sptrsv_ts_batch_kernel, dim3(grid), dim3(kBlock), args, sizeof(TsSmem), s));
     return DP_OK;
 }
 

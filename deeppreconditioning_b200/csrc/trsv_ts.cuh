@@ -1,0 +1,315 @@
+// trsv_ts.cuh — K4, third algorithm: the TILE-STREAM triangular solve for BATCHES of factors with WIDE levels.
+//
+// No reference counterpart; same arithmetic as sptrsv.cuh / trsv_ls.cuh (plain substitution, sum in column
+// order, products and sums rounded separately, multiplication by the stored reciprocal 1 / T_ii), so the solution is
+// bit-identical to oracle_sptrsv_lower/upper.
+//
+// Why a third algorithm. The sync-free solve (sptrsv.cuh) reads the factor in its ORIGINAL order, one lane per row of
+// a level: on a 3-D stencil a level is a diagonal plane i+j+k = l, its rows are n-1 apart, so every lane of a warp
+// touches its own sectors of rowptr/col/val/b (each fetched again for the neighbouring rows of later levels) and the
+// stream is a chain of dependent scattered loads: 0.13 of the HBM peak on 16 x 128^3. The level-stream solve
+// (trsv_ls.cuh) streams a level-ordered copy but keeps a system inside ONE SM - right for 2-D factors whose levels
+// are narrower than a tile, hopeless for levels of 10^4..10^5 rows. Here the two are combined:
+//
+//   * the factor is read from its LEVEL-ORDERED copy (dp_sptrsv_permute: row r = row perm[r] of T, columns renumbered
+//     to positions, diagonal stored as reciprocal). A 512-row TILE of the copy is one contiguous span of col/val, moved
+//     by the TMA engine through the tile pipeline (tilepipe.cuh), one thread per row - the matrix stream is as
+//     coalesced as an SpMV's;
+//   * the tiles of ALL systems of the batch form one global sequence (tile-major, systems interleaved) that the
+//     persistent CTAs take round robin. All CTAs are co-resident (cooperative launch) and a dependency always lives at
+//     a lower position of the same system, i.e. in an earlier item of the sequence: forward progress by induction;
+//   * dependencies are awaited on the solution vector in POSITION space (xp, pre-armed with the kPending NaN pattern:
+//     data is its own flag, one store per row, no fences - the protocol of sptrsv.cuh). Consecutive rows of a level
+//     depend on nearly consecutive positions of the previous level, so a warp's polls are a few sectors wide;
+//   * with levels wider than the window of tiles in flight (G / nsys tiles per system) a tile's dependencies were
+//     solved long before it starts: no waiting at all, the solve streams at SpMV speed. Narrow levels (the corners
+//     of the diagonal sweep) pay one L2 hop per level, shared by all systems of the batch.
+// Everything a tile needs that is contiguous travels with its first pipeline item: the 513 row pointers, and either
+// the 512 right-hand sides (position space) or the 512 entries of perm. Nothing is prefetched through registers, so
+// the only latency a warp sees per tile is the poll of its dependencies (measured before this: the row extents
+// fetched one tile ahead through registers cost a DRAM latency per tile, 3 us per tile and CTA, 0.52 of peak).
+// The solution is also scattered to the original numbering (x[perm[r]]). A caller that keeps its vectors in LEVEL
+// ORDER (perm == nullptr: b and x are indexed by position, x doubles as the polled vector) saves the gather of b and
+// the scatter of x, whose sectors are shared by rows of 4 consecutive levels and only survive in L2 while the
+// batch's level fronts are small (measured: 8 x 256^3 0.30 of peak with perm, 0.49 in position space).
+#pragma once
+
+#include "sptrsv.cuh"
+#include "tilepipe.cuh"
+#include "trsv_ls.cuh"
+
+#ifndef DPCG_TS_CAP
+#define DPCG_TS_CAP 2048
+#endif
+#ifndef DPCG_TS_STAGES
+#define DPCG_TS_STAGES 3
+#endif
+#ifndef DPCG_TS_SLEEP
+#define DPCG_TS_SLEEP 32
+#endif
+#ifndef DPCG_TS_ROUND
+#define DPCG_TS_ROUND 96
+#endif
+
+namespace dp {
+
+constexpr int kTsCap = DPCG_TS_CAP;        // entries per stage: a 512-row tile of a 7-point factor (4 per row) is one item
+constexpr int kTsStages = DPCG_TS_STAGES;
+constexpr int kTsRound = DPCG_TS_ROUND;    // tile descriptors per table refill
+constexpr int kTsInflight = 4;             // dependencies polled per lane and round
+constexpr int kTsSlots = kTsCap + 8;       // up to 3 lead-in entries (16-byte alignment) + tail rounding
+static_assert(kTsCap % 4 == 0 && kTsCap >= 64, "stage capacity");
+
+struct TsSysDev {
+    LsFactor F;
+    const double* b;  // original numbering (position space when F.perm == nullptr)
+    double* x;        // original numbering (position space when F.perm == nullptr)
+    double* xp;       // position space, armed with kPending before the launch (== x when F.perm == nullptr)
+    int upper, ntiles;
+};
+
+// One 512-row tile of one system's level-ordered copy. rowptr == nullptr: a system with fewer tiles, nothing to do.
+struct TsTile {
+    const int* rowptr;
+    const int* col;
+    const double* val;
+    const double* b;
+    const int* perm;
+    double* x;
+    double* xp;
+    int n, cs, ce, ltile, upper, pad;
+};
+
+struct TsStage {
+    double val[kTsSlots];
+    int col[kTsSlots];
+    double b[kTileRows];          // position space only
+    int rowptr[kTileRows + 8];    // kTileRows + 1 used
+    int perm[kTileRows];          // original numbering only
+};
+static_assert(sizeof(TsStage) % 16 == 0 && (kTsSlots * 8) % 16 == 0 && (kTsSlots * 4) % 16 == 0, "bulk-copy alignment");
+
+struct TsSmem {
+    alignas(16) TsStage stage[kTsStages];
+    alignas(8) unsigned long long full[kTsStages];   // producer -> consumers: bytes have landed
+    alignas(8) unsigned long long empty[kTsStages];  // consumers -> producer: all 16 warps are done with the stage
+    int released[kTsStages];                         // warps that have released the stage's current item
+    TsTile tab[kTsRound];
+};
+
+__device__ __forceinline__ int ts_blocks(const TsTile& d) { return d.rowptr ? (d.ce - d.cs + kTsCap - 1) / kTsCap : 0; }
+
+// The pipeline of tilepipe.cuh with two changes: the tile's metadata rides on its first item, and there is no
+// producer thread - the warp that releases a stage LAST re-arms it at once with the item kTsStages further on (the
+// item after (t, j) is found by walking the round's table), so a stage is never idle while a producer is busy
+// elsewhere. Items are numbered since kernel start: item i lives in stage i % kTsStages, its (i / kTsStages)-th use.
+struct TsPipe {
+    TsSmem* sm;
+    int ntiles;
+    unsigned c_count;  // items this warp has consumed
+
+    __device__ __forceinline__ void init(TsSmem* s) {
+        sm = s, ntiles = 0, c_count = 0u;
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int k = 0; k < kTsStages; ++k) {
+                mbar_init(&sm->full[k], 1u);
+                mbar_init(&sm->empty[k], (unsigned)kWarpsPerBlock);
+                sm->released[k] = 0;
+            }
+            mbar_fence_init();
+        }
+        __syncthreads();
+    }
+    // (t, j) -> the following item of the round; false at its end. Start from (0, -1).
+    __device__ __forceinline__ bool next_item(int& t, int& j) const {
+        ++j;
+        while (t < ntiles && j >= ts_blocks(sm->tab[t])) ++t, j = 0;
+        return t < ntiles;
+    }
+    // One lane: arm `stage` (free: every warp has released its previous item) with block j of tile t.
+    __device__ __forceinline__ void issue(unsigned stage, int t, int j) {
+        const TsTile& d = sm->tab[t];
+        TsStage& st = sm->stage[stage];
+        const int bs = d.cs + j * kTsCap;
+        const int be = min(d.ce, bs + kTsCap);
+        const int as = bs & ~3;
+        const unsigned ncol = (unsigned)(((be + 3) & ~3) - as), nval = (unsigned)(((be + 1) & ~1) - as);
+        unsigned bytes = ncol * 4u + nval * 8u;
+        const int r0 = d.ltile * kTileRows;
+        const unsigned nr = (unsigned)min(kTileRows, d.n - r0);
+        const unsigned rp_bytes = ((nr + 1u) * 4u + 15u) & ~15u;
+        const unsigned pm_bytes = (nr * 4u + 15u) & ~15u, b_bytes = (nr * 8u + 15u) & ~15u;
+        if (j == 0) bytes += rp_bytes + (d.perm ? pm_bytes : b_bytes);
+        unsigned long long* bar = &sm->full[stage];
+        const unsigned long long pol = l2_policy_stream();
+        mbar_arrive_expect_tx(bar, bytes);
+        if (j == 0) {  // metadata first: it is what the consumers read first
+            bulk_g2s(st.rowptr, d.rowptr + r0, rp_bytes, bar, pol);
+            if (d.perm)
+                bulk_g2s(st.perm, d.perm + r0, pm_bytes, bar, pol);
+            else
+                bulk_g2s(st.b, d.b + r0, b_bytes, bar, pol);
+        }
+        bulk_g2s(st.val, d.val + as, nval * 8u, bar, pol);
+        bulk_g2s(st.col, d.col + as, ncol * 4u, bar, pol);
+    }
+    // All threads, after the round's table is complete and visible and every item of the previous round is consumed
+    // (so all stages are free and nobody is re-arming one).
+    __device__ __forceinline__ void begin(int count) {
+        ntiles = count;
+        if (threadIdx.x == 0) {
+            int t = 0, j = -1;
+#pragma unroll
+            for (int k = 0; k < kTsStages; ++k)
+                if (next_item(t, j)) issue((c_count + (unsigned)k) % kTsStages, t, j);
+        }
+    }
+    __device__ __forceinline__ unsigned acquire() {
+        const unsigned stage = c_count % kTsStages;
+        while (!mbar_try_wait(&sm->full[stage], (c_count / kTsStages) & 1u)) {
+        }
+        return stage;
+    }
+    // Hand back block j of tile t; the last warp to do so re-arms the stage.
+    __device__ __forceinline__ void release(int t, int j) {
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) {
+            const unsigned stage = c_count % kTsStages;
+            mbar_arrive(&sm->empty[stage]);
+            if (atomicAdd(&sm->released[stage], 1) == kWarpsPerBlock - 1) {
+                sm->released[stage] = 0;
+                bool more = true;
+#pragma unroll
+                for (int k = 0; k < kTsStages; ++k) more = more && next_item(t, j);
+                if (more) {
+                    // acquire the other warps' arrivals (their reads of the stage) before the async proxy overwrites it
+                    while (!mbar_try_wait(&sm->empty[stage], (c_count / kTsStages) & 1u)) {
+                    }
+                    issue(stage, t, j);
+                }
+            }
+        }
+        ++c_count;
+    }
+};
+
+// The whole batch. All kBlock threads of every CTA of a cooperative launch must call.
+__device__ __forceinline__ void trsv_tile_stream(const TsSysDev* __restrict__ sys, int nsys, int max_tiles, TsSmem& sm,
+                                                 const AbortCtl& ctl) {
+    TsPipe pipe;
+    pipe.init(&sm);
+    const int tid = threadIdx.x;
+    const long long G = gridDim.x;
+    const long long items = (long long)max_tiles * nsys;
+    const long long mine = items > (long long)blockIdx.x ? (items - blockIdx.x + G - 1) / G : 0;
+    bool dead = false;  // the solve was aborted: keep the pipeline moving (every item is acquired and released), solve nothing
+    for (long long j0 = 0; j0 < mine; j0 += kTsRound) {
+        const int cnt = (int)min((long long)kTsRound, mine - j0);
+        __syncthreads();  // every warp has consumed every item of the previous round: its table is free
+        for (int i = tid; i < cnt; i += kBlock) {
+            const long long g = blockIdx.x + (j0 + i) * G;
+            const int s = (int)(g % nsys), t = (int)(g / nsys);
+            const TsSysDev S = sys[s];
+            TsTile d;
+            d.rowptr = nullptr, d.col = S.F.col, d.val = S.F.val, d.b = S.b, d.perm = S.F.perm, d.x = S.x, d.xp = S.xp;
+            d.n = S.F.n, d.cs = 0, d.ce = 0, d.ltile = t, d.upper = S.upper, d.pad = 0;
+            if (t < S.ntiles) {
+                d.rowptr = S.F.rowptr;
+                d.cs = __ldg(S.F.rowptr + min(t * kTileRows, S.F.n));
+                d.ce = __ldg(S.F.rowptr + min((t + 1) * kTileRows, S.F.n));
+            }
+            sm.tab[i] = d;
+        }
+        __syncthreads();
+        pipe.begin(cnt);
+        for (int i = 0; i < cnt; ++i) {
+            const TsTile& d = sm.tab[i];
+            if (!d.rowptr) continue;
+            double* xp = d.xp;
+            double* xg = d.x;
+            const bool upper = d.upper != 0;
+            const int cs = d.cs, ce = d.ce;
+            const int r = d.ltile * kTileRows + tid;
+            const bool valid = r < d.n;
+            int orig = -1, dpos = 0, q = 0, end = 0;
+            double bi = 0.0;
+            bool done = !valid || dead, have_rcp = false;
+            double sum = 0.0, rcp = 0.0;
+            unsigned long long u[kTsInflight];
+#pragma unroll
+            for (int k = 0; k < kTsInflight; ++k) u[k] = kPending;
+            const int nb = (ce - cs + kTsCap - 1) / kTsCap;
+            for (int j = 0; j < nb; ++j) {
+                const int bs = cs + j * kTsCap;
+                const int be = min(ce, bs + kTsCap);
+                const int as = bs & ~3;
+                const unsigned stage = pipe.acquire();
+                const TsStage& st = sm.stage[stage];
+                if (j == 0 && valid) {  // the tile's metadata rides on its first item
+                    const int rs = st.rowptr[tid], re = st.rowptr[tid + 1];
+                    dpos = upper ? rs : re - 1;   // the diagonal's entry (holds 1 / T_ii)
+                    q = upper ? rs + 1 : rs;      // dependencies: entries [q, end)
+                    end = upper ? re : re - 1;
+                    if (d.perm) {
+                        orig = st.perm[tid];
+                        if (!dead) bi = ldcg_here_f64(d.b + orig);
+                    } else {
+                        orig = r;
+                        bi = st.b[tid];
+                    }
+                }
+                const double* __restrict__ sv = st.val;
+                const int* __restrict__ sc = st.col;
+                if (!done && !have_rcp && dpos >= bs && dpos < be) rcp = sv[dpos - as], have_rcp = true;
+                const int qe = min(end, be);  // this row's dependencies inside the block: [q, qe) (empty if q >= be)
+                unsigned idle = 0;
+                for (;;) {
+                    if (!done && q == end && have_rcp) {  // publish at once: rows of the same warp may wait for it
+                        const double xv = __dmul_rn(__dsub_rn(bi, sum), rcp);
+                        st_relaxed_u64(xp + r, as_bits(xv));
+                        if (xg != xp) xg[orig] = xv;
+                        done = true;
+                    }
+                    const bool pending = !done && q < qe;
+                    if (!__any_sync(kFull, pending)) break;
+                    bool progress = false;
+                    if (pending) {
+                        const int m = min(kTsInflight, qe - q);
+                        bool all = true;
+#pragma unroll
+                        for (int k = 0; k < kTsInflight; ++k) {
+                            if (k < m && u[k] == kPending) {
+                                u[k] = ld_relaxed_u64(xp + sc[q + k - as]);
+                                all = all && u[k] != kPending;
+                            }
+                        }
+                        if (all) {
+#pragma unroll
+                            for (int k = 0; k < kTsInflight; ++k) {
+                                if (k < m) sum = __dadd_rn(sum, __dmul_rn(sv[q + k - as], as_double(u[k])));
+                                u[k] = kPending;
+                            }
+                            q += m;
+                            progress = true;
+                        }
+                    }
+                    if (!__any_sync(kFull, progress)) {
+                        ++idle;
+                        if (idle > kSpinBudget) ctl.raise(DP_ERR_TIMEOUT), dead = true;
+                        if ((idle & 255u) == 0 && ctl.aborted()) dead = true;
+                        dead = __any_sync(kFull, dead);
+                        if (dead) done = true;
+#if DPCG_TS_SLEEP > 0
+                        else __nanosleep(DPCG_TS_SLEEP);
+#endif
+                    }
+                }
+                pipe.release(i, j);
+            }
+        }
+    }
+    __syncthreads();
+}
+
+}  // namespace dp

@@ -38,6 +38,7 @@ class TriangularPlan:
     max_level_chunks: int
     upper: bool
     ls: "LevelOrdered | None" = None  # level-ordered copy of the factor (narrow levels): level-stream solve
+    ts: "LevelOrdered | None" = None  # level-ordered copy of any factor, made on demand: tile-stream batch solve
 
 
 @dataclass
@@ -58,11 +59,9 @@ class LevelOrdered:
 LS_MAX_MEAN_LEVEL_ROWS = 1024  # level-stream solve when n / nlevels is at most this (one CTA must keep up)
 
 
-def level_ordered(matrix: CsrMatrix, plan: TriangularPlan) -> LevelOrdered | None:
-    """Build the level-ordered copy if the factor qualifies for the level-stream solve, else ``None``."""
+def _permute(matrix: CsrMatrix, plan: TriangularPlan):
+    """``dp_sptrsv_permute``: the level-ordered copy and its statistics (tile entries, row entries, dependency distance)."""
     lib, n, dev = _lib.lib(), matrix.n, matrix.device
-    if n == 0 or plan.nlevels == 0 or n / plan.nlevels > LS_MAX_MEAN_LEVEL_ROWS:
-        return None
     i32 = dict(dtype=torch.int32, device=dev)
     rowptr_p, level_sorted = torch.empty(n + 1, **i32), torch.empty(n, **i32)
     col_p = torch.empty(max(matrix.nnz, 1), **i32)
@@ -74,12 +73,31 @@ def level_ordered(matrix: CsrMatrix, plan: TriangularPlan) -> LevelOrdered | Non
                                          _lib.ptr(plan.perm), _lib.ptr(plan.level), _lib.ptr(rowptr_p), _lib.ptr(col_p),
                                          _lib.ptr(val_p), _lib.ptr(level_sorted), _lib.ptr(stats), _lib.ptr(ws), ws.numel(),
                                          _lib.stream_ptr(dev)), "dp_sptrsv_permute")
+    copy = LevelOrdered(rowptr_p, col_p[: matrix.nnz], val_p[: matrix.nnz], level_sorted, matrix.nnz, matrix.val.data_ptr())
+    return copy, stats
+
+
+def level_ordered(matrix: CsrMatrix, plan: TriangularPlan) -> LevelOrdered | None:
+    """Build the level-ordered copy if the factor qualifies for the level-stream solve, else ``None``."""
+    lib, n = _lib.lib(), matrix.n
+    if n == 0 or plan.nlevels == 0 or n / plan.nlevels > LS_MAX_MEAN_LEVEL_ROWS:
+        return None
+    copy, stats = _permute(matrix, plan)
     limits = np.zeros(4, np.int32)
     lib.dp_sptrsv_ls_limits(limits.ctypes.data)
     widest = int(torch.diff(plan.level_ptr).max().item())
     if widest > limits[3] or np.any(stats.cpu().numpy() > limits[:3]):  # once per matrix: tile entries, row entries, dependency distance
         return None
-    return LevelOrdered(rowptr_p, col_p[: matrix.nnz], val_p[: matrix.nnz], level_sorted, matrix.nnz, matrix.val.data_ptr())
+    return copy
+
+
+def level_ordered_any(matrix: CsrMatrix, plan: TriangularPlan) -> LevelOrdered:
+    """The level-ordered copy of ANY triangular factor: input of the tile-stream batch solve (wide levels)."""
+    if plan.ls is not None and plan.ls.matches(matrix):
+        return plan.ls
+    if plan.ts is None or not plan.ts.matches(matrix):
+        plan.ts = _permute(matrix, plan)[0]
+    return plan.ts
 
 
 def analyse(matrix: CsrMatrix, upper: bool, level_stream: bool = True) -> TriangularPlan:
@@ -163,15 +181,52 @@ def _level_stream_batch(systems, outs=None, copies=None):
     return xs
 
 
-def triangular_solve_batch(systems, outs=None, algorithm: str = "auto"):
-    """Independent solves ``T_s x_s = b_s`` in ONE launch (``dp_sptrsv_solve_batch_f64``).
+def _tile_stream_batch(systems, outs=None, copies=None, position_space=False):
+    lib = _lib.lib()
+    dev = systems[0][0].device
+    nsys = len(systems)
+    descs = (_lib.TrsvLsSystem * nsys)()
+    xs, keep = [], []
+    for i, (matrix, plan, b) in enumerate(systems):
+        n, ls = matrix.n, (copies[i] if copies is not None else level_ordered_any(matrix, plan))
+        assert b.is_cuda and b.dtype == torch.float64 and b.shape == (n,)
+        b = b.contiguous()
+        if b.data_ptr() % 16:  # spans of b are moved by 16-byte granular bulk copies
+            b = b.clone()
+        x = outs[i] if outs is not None else torch.empty(n, dtype=torch.float64, device=dev)
+        d = descs[i]
+        d.n, d.nnz, d.upper = n, ls.nnz, int(plan.upper)
+        d.rowptr_p, d.col_p, d.val_p = _lib.ptr(ls.rowptr), _lib.ptr(ls.col), _lib.ptr(ls.val)
+        d.perm, d.level_sorted, d.b, d.x = _lib.ptr(plan.perm), _lib.ptr(ls.level_sorted), _lib.ptr(b), _lib.ptr(x)
+        if position_space:
+            d.perm = None
+        xs.append(x), keep.append((b, ls))
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = _workspace(lib.dp_sptrsv_ts_workspace_bytes(descs, nsys), dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.dp_sptrsv_ts_solve_batch_f64(descs, nsys, _lib.ptr(flag), _lib.ptr(ws), ws.numel(),
+                                                    _lib.stream_ptr(dev)), "dp_sptrsv_ts_solve_batch_f64")
+    _lib.raise_on_flag(flag, "dp_sptrsv_ts_solve_batch_f64")
+    return xs
 
-    ``systems``: list of ``(matrix, plan, b)``; returns the list of solutions. The resident warps are dealt to the
-    systems so that they advance side by side (the data-parallel axis of ``BenchmarkSuite.run``, ``test.py:121``).
+
+def triangular_solve_batch(systems, outs=None, algorithm: str = "auto", copies=None, position_space: bool = False):
+    """Independent solves ``T_s x_s = b_s`` in ONE launch.
+
+    ``systems``: list of ``(matrix, plan, b)``; returns the list of solutions (the data-parallel axis of
+    ``BenchmarkSuite.run``, ``test.py:121``). Three kernels, same bits: "ls" (level-stream, one CTA per system: factors
+    with narrow levels, chosen by "auto" when every plan carries its copy), "ts" (tile-stream: the tiles of the
+    level-ordered copies of all systems dealt to persistent CTAs, for wide levels; the copies are made on demand and
+    cached in the plans, or passed as ``copies``), "syncfree" (``dp_sptrsv_solve_batch_f64``, original ordering).
+    ``position_space`` ("ts" only): ``b`` and the solutions are in LEVEL ORDER (``b_pos = b[perm]``, ``x = x_pos`` with
+    ``x_pos[r] = x[perm[r]]``) - the form a caller uses that keeps all its vectors in that order.
     """
     lib = _lib.lib()
     dev = systems[0][0].device
     nsys = len(systems)
+    if algorithm == "ts":
+        return _tile_stream_batch(systems, outs, copies, position_space)
+    assert not position_space, "position-space vectors are a feature of the tile-stream solve"
     if algorithm != "syncfree" and all(plan.ls is not None and plan.ls.matches(m) for m, plan, _ in systems):
         return _level_stream_batch(systems, outs)
     if algorithm == "ls":

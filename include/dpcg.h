@@ -176,6 +176,18 @@ size_t dp_sptrsv_ls_workspace_bytes(int32_t nsys);
 int dp_sptrsv_ls_solve_batch_f64(const dp_trsv_ls_system_t* systems_host, int32_t nsys, void* workspace,
                                  size_t workspace_bytes, void* stream);
 
+/* Tile-stream solve: the batch form for factors with WIDE levels (3-D stencils: levels of 10^4..10^5 rows). The
+ * 512-row tiles of the level-ordered copies of ALL systems form one sequence that persistent CTAs take round robin;
+ * the matrix stream goes through the TMA tile pipeline like an SpMV's, dependencies are awaited on a position-space
+ * copy of the solution (kept in the workspace). Takes the same descriptors as the level-stream solve (level_sorted
+ * may be NULL) and any level-ordered copy (no dp_sptrsv_ls_limits restriction). Bit-identical to dp_sptrsv_solve_f64.
+ * perm == NULL: b and x are indexed by POSITION (the caller keeps its vectors in level order, x_pos[r] = x[perm[r]]);
+ * this saves the per-row gather of b and scatter of x through the permutation. b and x must not alias.
+ * Cooperative launch; *flag_out receives DP_ERR_TIMEOUT if a dependency never arrives. */
+size_t dp_sptrsv_ts_workspace_bytes(const dp_trsv_ls_system_t* systems_host, int32_t nsys);
+int dp_sptrsv_ts_solve_batch_f64(const dp_trsv_ls_system_t* systems_host, int32_t nsys, int32_t* flag_out, void* workspace,
+                                 size_t workspace_bytes, void* stream);
+
 /* ---- IC(0) on the pattern of tril(A) (stands in for ilupp.ichol0, test.py:84) -------------------------------
  * Level-scheduled, sync-free numeric factorisation; uses the lower plan of the same pattern.
  * *flag_out: DP_ERR_STRUCTURE on a non-positive pivot. */

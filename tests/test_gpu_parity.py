@@ -189,6 +189,38 @@ def test_triangular_solve_batch_is_bitwise_the_single_solves(cuda):
         assert torch.equal(got, want)
 
 
+def test_tile_stream_batch_bit_exact(cuda):
+    """Tile-stream solve (trsv_ts.cuh): a ragged batch mixing 3-D and 2-D systems, lower and upper factors, stencil
+    factors (one pipeline item per tile) and CNN factors (several items per tile, rows cut by the stage boundary), with
+    more tiles than resident CTAs — every solution bit-identical to plain substitution, alone and in the batch."""
+    systems, wants = [], []
+    for kind, side, seed, net in [("poisson3d", 40, 0, None), ("poisson3d", 12, 1, "tril"), ("poisson2d", 64, 2, "net"),
+                                  ("poisson3d", 5, 3, "net"), ("poisson2d", 100, 4, None), ("poisson3d", 33, 5, None),
+                                  ("poisson2d", 3, 6, None)]:
+        p = helpers.problem(kind, side, seed, 0.5, net)
+        want = p.T if net is None else p.L
+        coo = helpers.to_device(p.systems_tril if net is None else p.learned, cuda)
+        lower = CsrMatrix.from_spconv(coo, p.n, "tril")
+        upper_m = lower.transpose()
+        b = p.b.to(cuda)
+        y_want = ckernels.sptrsv_lower(*want, p.b.numpy())
+        z_want = ckernels.sptrsv_upper(*osp.transpose_csr(*want), p.b.numpy())
+        for m, up, w in [(lower, False, y_want), (upper_m, True, z_want)]:
+            plan = precond.analyse(m, up, level_stream=False)
+            systems.append((m, plan, b)), wants.append(w)
+            alone = precond.triangular_solve_batch([(m, plan, b)], algorithm="ts")[0]
+            assert np.array_equal(alone.cpu().numpy(), w), (kind, side, net, up)
+    for got, want in zip(precond.triangular_solve_batch(systems, algorithm="ts"), wants):
+        assert np.array_equal(got.cpu().numpy(), want)
+    many = systems * 3  # 42 systems, > 1500 tiles: several table rounds per CTA
+    for got, want in zip(precond.triangular_solve_batch(many, algorithm="ts"), wants * 3):
+        assert np.array_equal(got.cpu().numpy(), want)
+    # vectors kept in level order by the caller: b_pos = b[perm] in, x_pos = x[perm] out, same bits
+    in_pos = [(m, plan, b[plan.perm.long()]) for m, plan, b in systems]
+    for got, want, (_, plan, _) in zip(precond.triangular_solve_batch(in_pos, algorithm="ts", position_space=True), wants, systems):
+        assert np.array_equal(got.cpu().numpy(), want[plan.perm.cpu().numpy()])
+
+
 def test_level_stream_eligibility(cuda):
     """Factors the level-stream solve cannot take (a dependency further back than its shared-memory window, rows too
     long for registers, tiles larger than a pipeline stage) are refused at analysis and solved sync-free; a chain of
