@@ -252,6 +252,49 @@ def triangular_solve_batch(systems, outs=None, algorithm: str = "auto", copies=N
     return xs
 
 
+@dataclass
+class LevelOrdering:
+    """Symmetric renumbering of a system by the level sets of its lower triangle (``x_level[r] = x[perm[r]]``).
+
+    Level order is a topological order of the factor's dependency graph, so ``P tril(A) P^T`` is the lower triangle of
+    ``P A P^T``, IC(0) commutes with the renumbering, and CG on the renumbered system is the same iteration up to the
+    summation order of its dot products. What it buys: a level of the factor becomes a CONTIGUOUS run of rows (and of
+    ``b`` / ``x`` entries), so the triangular solves read the factor and the vectors coalesced instead of one scattered
+    sector per row - the form the tile-stream batch solve wants (``position_space=True``), and a better layout for the
+    sync-free solves inside the fused PCG kernel as well. Natural ordering is what the reference's data has
+    (``data_set.py:85-125``); this is an opt-in for SOLVE-mode preconditioners only.
+    """
+
+    perm: torch.Tensor  # int64[n]: position -> original row
+    inv: torch.Tensor   # int32[n]: original row -> position
+    nlevels: int
+
+    def to_level(self, v: torch.Tensor) -> torch.Tensor:
+        return v[self.perm]
+
+    def from_level(self, v: torch.Tensor) -> torch.Tensor:
+        out = torch.empty_like(v)
+        out[self.perm] = v
+        return out
+
+    def renumber(self, tensor):
+        """The same COO sites ``(batch, row, col)`` with rows and columns renumbered (a ``SparseConvTensor`` stand-in)."""
+        from .model import SparseConvTensor
+
+        idx = tensor.indices.to(self.inv.device)
+        new = torch.stack([idx[:, 0], self.inv[idx[:, 1].long()], self.inv[idx[:, 2].long()]], dim=1).to(torch.int32)
+        return SparseConvTensor(tensor.features.to(self.inv.device), new.contiguous(), tensor.spatial_shape, tensor.batch_size)
+
+
+def level_ordering(tril_a: CsrMatrix, plan: TriangularPlan | None = None) -> LevelOrdering:
+    """Level analysis (K3) of ``tril(A)`` turned into a symmetric renumbering of the whole system."""
+    plan = plan or analyse(tril_a, upper=False, level_stream=False)
+    perm = plan.perm.long()
+    inv = torch.empty(tril_a.n, dtype=torch.int32, device=tril_a.device)
+    inv[perm] = torch.arange(tril_a.n, dtype=torch.int32, device=tril_a.device)
+    return LevelOrdering(perm, inv, plan.nlevels)
+
+
 def incomplete_cholesky0(tril_a: CsrMatrix, plan: TriangularPlan | None = None) -> CsrMatrix:
     """IC(0) factor on the pattern of ``tril(A)`` (``dp_ic0_f64``) — stands in for ``ilupp.ichol0`` (``test.py:84``)."""
     lib, n, dev = _lib.lib(), tril_a.n, tril_a.device

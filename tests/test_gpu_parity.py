@@ -221,6 +221,55 @@ def test_tile_stream_batch_bit_exact(cuda):
         assert np.array_equal(got.cpu().numpy(), want[plan.perm.cpu().numpy()])
 
 
+@pytest.mark.parametrize("kind,side", [("poisson3d", 12), ("poisson2d", 37)])
+def test_level_ordered_system_is_the_same_solve(cuda, kind, side):
+    """precond.LevelOrdering: P A P^T assembled from the renumbered COO sites is bitwise the permuted matrix, its lower
+    triangle is P tril(A) P^T with levels ascending along the rows (perm of the renumbered factor = identity), IC(0)
+    commutes with the renumbering (bitwise on stencils: no row pair shares two neighbours), a triangular solve in level
+    order is bitwise the natural-order solve, and IC(0)-PCG on the renumbered system is the same iteration (counts +-1,
+    solution to 1e-8) as on the natural one and as the oracle's."""
+    import scipy.sparse as sp
+
+    p = helpers.problem(kind, side, 0, 0.5, None)
+    st = helpers.to_device(p.systems_tril, cuda)
+    A, T = CsrMatrix.from_spconv(st, p.n, "symmetrise"), CsrMatrix.from_spconv(st, p.n, "tril")
+    order = precond.level_ordering(T)
+    st_l = order.renumber(st)
+    A_l, T_l = CsrMatrix.from_spconv(st_l, p.n, "symmetrise"), CsrMatrix.from_spconv(st_l, p.n, "tril")
+    perm = order.perm.cpu().numpy()
+    want = osp.to_scipy(*p.A)[perm][:, perm].tocsr()
+    want.sort_indices()
+    helpers.assert_csr_equal(A_l, (want.indptr, want.indices, want.data))
+    want_t = sp.tril(want).tocsr()
+    want_t.sort_indices()
+    helpers.assert_csr_equal(T_l, (want_t.indptr, want_t.indices, want_t.data))
+    plan_l = precond.analyse(T_l, False, level_stream=False)
+    assert plan_l.nlevels == order.nlevels
+    assert np.array_equal(plan_l.perm.cpu().numpy(), np.arange(p.n)), "levels ascend along the rows of the renumbered factor"
+    # IC(0) commutes with the renumbering
+    F, F_l = precond.incomplete_cholesky0(T), precond.incomplete_cholesky0(T_l, plan_l)
+    f = sp.csr_matrix((F.val.cpu().numpy(), F.col.cpu().numpy(), F.rowptr.cpu().numpy()), shape=(p.n, p.n))
+    f_l = f[perm][:, perm].tocsr()
+    f_l.sort_indices()
+    helpers.assert_csr_equal(F_l, (f_l.indptr, f_l.indices, f_l.data))
+    # triangular solves: level order in, level order out, same bits (sync-free and tile-stream in position space)
+    b = p.b.to(cuda)
+    y = precond.triangular_solve(F, precond.analyse(F, False, level_stream=False), b, algorithm="syncfree")
+    y_l = precond.triangular_solve(F_l, plan_l, order.to_level(b), algorithm="syncfree")
+    assert torch.equal(order.from_level(y_l), y)
+    y_ts = precond.triangular_solve_batch([(F_l, plan_l, order.to_level(b))], algorithm="ts", position_space=True)[0]
+    assert torch.equal(y_ts, y_l)
+    # PCG with the IC(0) factor in solve mode
+    got = dp.pcg_solve(A, b, dp.FactoredSolve(F), max_iter=3000)
+    got_l = dp.pcg_solve(A_l, order.to_level(b), dp.FactoredSolve(F_l), max_iter=3000)
+    ref = pcg.preconditioned_conjugate_gradient(osp.to_torch_csr(*p.A), p.b, operators.FactoredSolve(*helpers.ic0_factor(p)),
+                                                max_iter=3000)
+    assert abs(got_l.iterations - got.iterations) <= 1 and abs(got_l.iterations - ref.iterations) <= 1
+    x_l = order.from_level(got_l.x_hat).cpu()
+    tol = 1e-8 if got_l.iterations == ref.iterations else 1e-3  # one more body moves x by about the residual tolerance
+    assert torch.linalg.vector_norm(x_l - ref.x_hat) <= tol * torch.linalg.vector_norm(ref.x_hat)
+
+
 def test_level_stream_eligibility(cuda):
     """Factors the level-stream solve cannot take (a dependency further back than its shared-memory window, rows too
     long for registers, tiles larger than a pipeline stage) are refused at analysis and solved sync-free; a chain of
