@@ -32,7 +32,7 @@ class PcgSystem(C.Structure):
 
     _fields_ = [(name, _i32) for name in (
         "n", "precond", "a_nnz", "m_nnz", "mt_nnz", "fwd_nchunks", "bwd_nchunks",
-        "fwd_max_level_chunks", "bwd_max_level_chunks", "reserved")] + [(name, _p) for name in (
+        "fwd_max_level_chunks", "bwd_max_level_chunks", "solve_algorithm")] + [(name, _p) for name in (
             "a_rowptr", "a_col", "a_val", "m_rowptr", "m_col", "m_val", "mt_rowptr", "mt_col", "mt_val",
             "dinv", "fwd_plan", "bwd_plan",
             "fwd_ls_rowptr", "fwd_ls_col", "fwd_ls_val", "fwd_ls_perm", "fwd_ls_level",
@@ -50,7 +50,7 @@ class TrsvSystem(C.Structure):
 class TrsvLsSystem(C.Structure):
     """``dp_trsv_ls_system_t``."""
 
-    _fields_ = [("n", _i32), ("nnz", _i32), ("upper", _i32), ("reserved", _i32)] + [
+    _fields_ = [("n", _i32), ("nnz", _i32), ("upper", _i32), ("flags", _i32)] + [
         (name, _p) for name in ("rowptr_p", "col_p", "val_p", "perm", "level_sorted", "b", "x")]
 
 

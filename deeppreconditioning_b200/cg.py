@@ -91,6 +91,9 @@ class PcgBatch:
             coef = torch.full((2 * (self.max_iter + 1),), float("nan"), **f64) if history else None
             self.entries.append(dict(A=A, M=M, b=b_dev, x=x, work=work, hist=hist, coef=coef, out_device=b.device))
         nsys = len(self.entries)
+        if any(getattr(e["M"], "tile_stream", False) for e in self.entries):
+            # tile-stream solves are separate launches between the phases: a feature of the stepped engine
+            self.params = _lib.PcgParams(self.rtol, self.max_iter, _ENGINES["stepped"], int(check_every), 0)
         self.iters = torch.full((nsys,), -1, dtype=torch.int32, device=self.device)
         self.res = torch.full((nsys,), float("nan"), dtype=torch.float64, device=self.device)
         self.flag = torch.zeros(1, dtype=torch.int32, device=self.device)

@@ -33,6 +33,7 @@
 #include <vector>
 
 #include "sptrsv.cuh"
+#include "trsv_ts.cuh"
 #include "tilepipe.cuh"
 #include "trsv_ls.cuh"
 
@@ -692,7 +693,7 @@ static inline int ntiles_of(int n) { return (n + kTileRows - 1) / kTileRows; }
 constexpr int kTraceCap = 4096;
 
 struct WsLayout {
-    size_t word, n_done, meta, sys, state, tile_ofs, fwd_ofs, bwd_ofs, act_sys[2], act_ofs[2], trace, total;
+    size_t word, n_done, meta, sys, state, tile_ofs, fwd_ofs, bwd_ofs, act_sys[2], act_ofs[2], trace, ts_word, ts_sys[4], total;
 };
 static WsLayout ws_layout(int nsys) {
     WsLayout w{};
@@ -709,6 +710,8 @@ static WsLayout ws_layout(int nsys) {
     w.bwd_ofs = take(ints);
     for (int i = 0; i < 2; ++i) w.act_sys[i] = take(ints), w.act_ofs[i] = take(ints);
     w.trace = take(sizeof(long long) * 2 * kTraceCap);
+    w.ts_word = take(8);
+    for (int i = 0; i < 4; ++i) w.ts_sys[i] = take(sizeof(TsSysDev) * (size_t)nsys);  // fwd/bwd x parity of (k + 1)
     w.total = off;
     return w;
 }
@@ -741,14 +744,29 @@ static int launch_phase(const Ctx& ctx, int k, int grid, bool cooperative, cudaS
     return DP_OK;
 }
 
+// Tile-stream solves of the stepped engine (DP_SOLVE_TILE_STREAM): device descriptor arrays of the SOLVE systems,
+// forward (r_new -> y) and backward (y -> z_new), one pair per parity of k + 1 (r and z are double buffered).
+struct TsPhases {
+    const TsSysDev* fwd[2];
+    const TsSysDev* bwd[2];
+    int nsys, max_tiles, nmax;
+    unsigned long long* word;
+};
+
 template <bool kInit>
-static int launch_apply(const Ctx& ctx, int k, int tile_grid, int coop, cudaStream_t s) {
+static int launch_apply(const Ctx& ctx, int k, int tile_grid, int coop, const TsPhases* ts, cudaStream_t s) {
     int st;
     if ((st = launch_phase<PH_APPLY1, kInit>(ctx, k, tile_grid, false, s)) != DP_OK) return st;
     if (ctx.has_multiply && (st = launch_phase<PH_APPLY2, kInit>(ctx, k, tile_grid, false, s)) != DP_OK) return st;
     if (ctx.has_solve) {
-        if ((st = launch_phase<PH_FWD, kInit>(ctx, k, coop, true, s)) != DP_OK) return st;
-        if ((st = launch_phase<PH_BWD, kInit>(ctx, k, coop, true, s)) != DP_OK) return st;
+        if (ts) {  // finished systems are solved along (their vectors are scratch by then): no host round trip
+            const int par = (k + 1) & 1;
+            if ((st = ts_solve_launch(ts->fwd[par], ts->nsys, ts->max_tiles, ts->nmax, ts->word, ctx.flag, s)) != DP_OK) return st;
+            if ((st = ts_solve_launch(ts->bwd[par], ts->nsys, ts->max_tiles, ts->nmax, ts->word, ctx.flag, s)) != DP_OK) return st;
+        } else {
+            if ((st = launch_phase<PH_FWD, kInit>(ctx, k, coop, true, s)) != DP_OK) return st;
+            if ((st = launch_phase<PH_BWD, kInit>(ctx, k, coop, true, s)) != DP_OK) return st;
+        }
         if ((st = launch_phase<PH_DOTRZ, kInit>(ctx, k, tile_grid, false, s)) != DP_OK) return st;
     }
     return DP_OK;
@@ -803,8 +821,9 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
     std::vector<SysDev> sys((size_t)nsys);
     std::vector<int> tile_ofs((size_t)nsys + 1, 0), fwd_ofs((size_t)nsys + 1, 0), bwd_ofs((size_t)nsys + 1, 0);
     std::vector<int> ident((size_t)nsys + 1, 0);
-    int has_multiply = 0, has_solve = 0, has_ls = 0;
+    int has_multiply = 0, has_solve = 0, has_ls = 0, n_solve = 0, n_ts = 0;
     long long sum_fwd_lvl = 0, sum_bwd_lvl = 0;
+    std::vector<TsSysDev> ts_sys[4];
     for (int i = 0; i < nsys; ++i) {
         const dp_pcg_system_t& u = systems_host[i];
         if (u.n <= 0 || !u.a_rowptr || !u.a_col || !u.a_val || !u.b || !u.x || !u.work || !u.iters_out || !u.res_out)
@@ -822,7 +841,16 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
         d.bwd_plan = u.bwd_plan;
         d.fwd_ls = LsFactor{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
         d.bwd_ls = d.fwd_ls;
-        if (u.precond == DP_PRECOND_SOLVE) {
+        const bool tile_stream = u.precond == DP_PRECOND_SOLVE && u.solve_algorithm == DP_SOLVE_TILE_STREAM;
+        if (u.precond == DP_PRECOND_SOLVE) ++n_solve;
+        if (tile_stream) {
+            if (!u.fwd_ls_rowptr || !u.fwd_ls_col || !u.fwd_ls_val || !u.bwd_ls_rowptr || !u.bwd_ls_col || !u.bwd_ls_val)
+                return DP_ERR_INVALID;
+            if (!aligned16(u.fwd_ls_rowptr) || !aligned16(u.fwd_ls_col) || !aligned16(u.fwd_ls_val) ||
+                !aligned16(u.bwd_ls_rowptr) || !aligned16(u.bwd_ls_col) || !aligned16(u.bwd_ls_val))
+                return DP_ERR_ALIGNMENT;
+            ++n_ts;
+        } else if (u.precond == DP_PRECOND_SOLVE) {
             if (u.fwd_ls_rowptr && u.fwd_ls_col && u.fwd_ls_val && u.fwd_ls_perm && u.fwd_ls_level) {
                 if (!aligned16(u.fwd_ls_col) || !aligned16(u.fwd_ls_val)) return DP_ERR_ALIGNMENT;
                 d.fwd_ls = LsFactor{u.fwd_ls_rowptr, u.fwd_ls_col, u.fwd_ls_val, u.fwd_ls_perm, u.fwd_ls_level, u.n, u.m_nnz};
@@ -877,6 +905,17 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
         d.res_out = u.res_out;
         d.history = u.history;
         d.coef = u.coef;
+        if (tile_stream) {  // y = t, z double buffered like r: the vectors are the iteration's own (position space)
+            for (int par = 0; par < 2; ++par) {
+                TsSysDev f{}, g{};
+                f.F = LsFactor{u.fwd_ls_rowptr, u.fwd_ls_col, u.fwd_ls_val, nullptr, nullptr, u.n, u.m_nnz};
+                f.b = d.r[par], f.x = d.t, f.xp = d.t, f.upper = 0, f.ntiles = d.ntiles, f.rev = 0;
+                g.F = LsFactor{u.bwd_ls_rowptr, u.bwd_ls_col, u.bwd_ls_val, nullptr, nullptr, u.n, u.mt_nnz};
+                g.b = d.t, g.x = d.z[par], g.xp = d.z[par], g.upper = 1, g.ntiles = d.ntiles, g.rev = 1;
+                ts_sys[par].push_back(f);
+                ts_sys[2 + par].push_back(g);
+            }
+        }
         sys[(size_t)i] = d;
         ident[(size_t)i] = i;
         tile_ofs[(size_t)i + 1] = tile_ofs[(size_t)i] + d.ntiles;
@@ -884,6 +923,8 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
         bwd_ofs[(size_t)i + 1] = bwd_ofs[(size_t)i] + bwd_chunks;
     }
 
+    // the tile-stream solves replace the FWD/BWD phases of the stepped engine for ALL solve-mode systems of the batch
+    if (n_ts && (n_ts != n_solve || params_host->engine != DP_ENGINE_STEPPED)) return DP_ERR_INVALID;
     if (allow_smem(pcg_fused_kernel) != DP_OK || allow_smem(pcg_phase_kernel<PH_FWD, false>) != DP_OK) return DP_ERR_CUDA;
     const int coop = coop_grid((const void*)pcg_fused_kernel, kBlock, sizeof(Smem));
     const int coop_phase = coop_grid((const void*)pcg_phase_kernel<PH_FWD, false>, kBlock, sizeof(Smem));
@@ -954,11 +995,29 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
 
     ctx.pw_fwd = clamp_pw(sum_fwd_lvl, coop_phase);
     ctx.pw_bwd = clamp_pw(sum_bwd_lvl, coop_phase);
+    TsPhases ts_phases{};
+    const TsPhases* ts = nullptr;
+    if (n_ts) {
+        DP_CUDA(cudaMemsetAsync(ws + lay.ts_word, 0, 8, s));
+        for (int i = 0; i < 4; ++i)
+            DP_CUDA(cudaMemcpyAsync(ws + lay.ts_sys[i], ts_sys[i].data(), sizeof(TsSysDev) * (size_t)n_ts, cudaMemcpyHostToDevice, s));
+        for (int par = 0; par < 2; ++par) {
+            ts_phases.fwd[par] = reinterpret_cast<const TsSysDev*>(ws + lay.ts_sys[par]);
+            ts_phases.bwd[par] = reinterpret_cast<const TsSysDev*>(ws + lay.ts_sys[2 + par]);
+        }
+        ts_phases.nsys = n_ts;
+        ts_phases.word = reinterpret_cast<unsigned long long*>(ws + lay.ts_word);
+        for (const TsSysDev& f : ts_sys[0]) {
+            if (f.ntiles > ts_phases.max_tiles) ts_phases.max_tiles = f.ntiles;
+            if (f.F.n > ts_phases.nmax) ts_phases.nmax = f.F.n;
+        }
+        ts = &ts_phases;
+    }
     const int tile_grid = ctx.total_tiles < coop * 4 ? ctx.total_tiles : coop * 4;
     const int every = params_host->check_every > 0 ? params_host->check_every : 1;
     int st;
     if ((st = launch_phase<PH_INIT, false>(ctx, -1, tile_grid, false, s)) != DP_OK) return st;
-    if ((st = launch_apply<true>(ctx, -1, tile_grid, coop_phase, s)) != DP_OK) return st;
+    if ((st = launch_apply<true>(ctx, -1, tile_grid, coop_phase, ts, s)) != DP_OK) return st;
     for (int k = 0; k <= ctx.max_iter; ++k) {
         if ((st = launch_phase<PH_A, false>(ctx, k, tile_grid, false, s)) != DP_OK) return st;
         if (k % every == 0 || k == ctx.max_iter) {  // the one host sync per convergence check
@@ -967,7 +1026,7 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
             DP_CUDA(cudaStreamSynchronize(s));
             if (done >= nsys) break;
         }
-        if ((st = launch_apply<false>(ctx, k, tile_grid, coop_phase, s)) != DP_OK) return st;
+        if ((st = launch_apply<false>(ctx, k, tile_grid, coop_phase, ts, s)) != DP_OK) return st;
     }
     return DP_OK;
 }

@@ -207,6 +207,27 @@ static int participating_warps(int max_level_chunks, int grid) {
     return pw > w ? w : (int)pw;
 }
 
+int ts_solve_launch(const TsSysDev* sys_dev, int nsys, int max_tiles, int nmax, unsigned long long* word, int* flag,
+                    cudaStream_t s) {
+    const int fill_x = (nmax + 255) / 256 < sm_count() * 4 ? (nmax + 255) / 256 : sm_count() * 4;
+    arm_positions_kernel<<<dim3(fill_x, nsys < 1024 ? nsys : 1024), 256, 0, s>>>(sys_dev, nsys);
+    DP_LAUNCH_CHECK();
+    static thread_local bool smem_ok = false;
+    if (!smem_ok) {
+        DP_CUDA(cudaFuncSetAttribute((const void*)sptrsv_ts_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(TsSmem)));
+        smem_ok = true;
+    }
+    static thread_local int resident = 0;
+    if (!resident) resident = coop_grid((const void*)sptrsv_ts_batch_kernel, kBlock, sizeof(TsSmem));
+    int grid = resident;
+    const long long items = (long long)max_tiles * nsys;
+    if (items < grid) grid = (int)items;
+    void* args[] = {&sys_dev, &nsys, &max_tiles, &word, &flag};
+    DP_CUDA(cudaLaunchCooperativeKernel((const void*)sptrsv_ts_batch_kernel, dim3(grid), dim3(kBlock), args, sizeof(TsSmem), s));
+    return DP_OK;
+}
+
 }  // namespace dp
 
 using namespace dp;
@@ -365,6 +386,8 @@ int dp_sptrsv_ts_solve_batch_f64(const dp_trsv_ls_system_t* systems_host, int32_
         TsSysDev d{};
         d.F = LsFactor{u.rowptr_p, u.col_p, u.val_p, u.perm, u.level_sorted, u.n, u.nnz};
         d.b = u.b, d.x = u.x, d.upper = u.upper ? 1 : 0;
+        d.rev = (u.flags & DP_TRSV_REVERSED) ? 1 : 0;
+        if (d.rev && u.perm) return DP_ERR_INVALID;  // reversed positions are a form of position space
         if (u.perm) {
             d.xp = reinterpret_cast<double*>(ws + off);
             off += align_up(sizeof(double) * (size_t)u.n, 256);
@@ -379,22 +402,7 @@ int dp_sptrsv_ts_solve_batch_f64(const dp_trsv_ls_system_t* systems_host, int32_
     DP_CUDA(cudaMemsetAsync(word, 0, sizeof(unsigned long long), s));
     // pageable source: the call returns once the bytes are staged, `dev` may go out of scope
     DP_CUDA(cudaMemcpyAsync(sys, dev.data(), sizeof(TsSysDev) * (size_t)nsys, cudaMemcpyHostToDevice, s));
-    const int fill_x = (nmax + 255) / 256 < sm_count() * 4 ? (nmax + 255) / 256 : sm_count() * 4;
-    arm_positions_kernel<<<dim3(fill_x, nsys < 1024 ? nsys : 1024), 256, 0, s>>>(sys, nsys);
-    DP_LAUNCH_CHECK();
-    static thread_local bool smem_ok = false;
-    if (!smem_ok) {
-        DP_CUDA(cudaFuncSetAttribute((const void*)sptrsv_ts_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)sizeof(TsSmem)));
-        smem_ok = true;
-    }
-    int grid = coop_grid((const void*)sptrsv_ts_batch_kernel, kBlock, sizeof(TsSmem));
-    const long long items = (long long)max_tiles * nsys;
-    if (items < grid) grid = (int)items;
-    int nsys_i = nsys;
-    void* args[] = {&sys, &nsys_i, &max_tiles, &word, &flag_out};
-    DP_CUDA(cudaLaunchCooperativeKernel((const void*)sptrsv_ts_batch_kernel, dim3(grid), dim3(kBlock), args, sizeof(TsSmem), s));
-    return DP_OK;
+    return ts_solve_launch(sys, nsys, max_tiles, nmax, word, flag_out, s);
 }
 
 int dp_ic0_f64(int32_t n, const int32_t* rowptr, const int32_t* col, const double* a_val, double* l_val,

@@ -32,6 +32,10 @@
 // ORDER (perm == nullptr: b and x are indexed by position, x doubles as the polled vector) saves the gather of b and
 // the scatter of x, whose sectors are shared by rows of 4 consecutive levels and only survive in L2 while the
 // batch's level fronts are small (measured: 8 x 256^3 0.30 of peak with perm, 0.49 in position space).
+// REVERSED position space (rev): position p is row n - 1 - p of b and x. This is the backward solve (L^T) of a system
+// that is kept in the level order of its FORWARD solve: walking its rows from the last to the first is a valid order
+// for L^T (every dependency of row i is a row j > i), and a row's dependencies sit one forward level further on, as
+// far away as in the forward solve - so one ordering of the system serves both solves of a PCG iteration.
 #pragma once
 
 #include "sptrsv.cuh"
@@ -78,6 +82,7 @@ struct TsSysDev {
     double* x;        // original numbering (position space when F.perm == nullptr)
     double* xp;       // position space, armed with kPending before the launch (== x when F.perm == nullptr)
     int upper, ntiles;
+    int rev, pad;     // F.perm == nullptr only: position p is row n - 1 - p of b / x (see below)
 };
 
 // One 512-row tile of one system's level-ordered copy. rowptr == nullptr: a system with fewer tiles, nothing to do.
@@ -89,13 +94,13 @@ struct TsTile {
     const int* perm;
     double* x;
     double* xp;
-    int n, cs, ce, ltile, upper, pad;
+    int n, cs, ce, ltile, upper, rev;
 };
 
 struct TsStage {
     double val[kTsSlots];
     int col[kTsSlots];
-    double b[kTileRows];          // position space only
+    double b[kTileRows + 2];      // position space only (reversed slices start at an even row: one lead-in entry)
     int rowptr[kTileRows + 8];    // kTileRows + 1 used
     int perm[kTileRows];          // original numbering only
 };
@@ -151,7 +156,10 @@ struct TsPipe {
         const int r0 = d.ltile * kTileRows;
         const unsigned nr = (unsigned)min(kTileRows, d.n - r0);
         const unsigned rp_bytes = ((nr + 1u) * 4u + 15u) & ~15u;
-        const unsigned pm_bytes = (nr * 4u + 15u) & ~15u, b_bytes = (nr * 8u + 15u) & ~15u;
+        // right-hand sides of the tile: rows [r0, r0 + nr), or - reversed - rows [n - r0 - nr, n - r0) from the even row below
+        const int b0 = d.rev ? (d.n - r0 - (int)nr) & ~1 : r0;
+        const unsigned pm_bytes = (nr * 4u + 15u) & ~15u;
+        const unsigned b_bytes = ((unsigned)((d.rev ? d.n - r0 : r0 + (int)nr) - b0) * 8u + 15u) & ~15u;
         if (j == 0) bytes += rp_bytes + (d.perm ? pm_bytes : b_bytes);
         unsigned long long* bar = &sm->full[stage];
         const unsigned long long pol = l2_policy_stream();
@@ -161,7 +169,7 @@ struct TsPipe {
             if (d.perm)
                 bulk_g2s(st.perm, d.perm + r0, pm_bytes, bar, pol);
             else
-                bulk_g2s(st.b, d.b + r0, b_bytes, bar, pol);
+                bulk_g2s(st.b, d.b + b0, b_bytes, bar, pol);
         }
         bulk_g2s(st.val, d.val + as, nval * 8u, bar, pol);
         bulk_g2s(st.col, d.col + as, ncol * 4u, bar, pol);
@@ -226,7 +234,7 @@ __device__ __forceinline__ void trsv_tile_stream(const TsSysDev* __restrict__ sy
             const TsSysDev S = sys[s];
             TsTile d;
             d.rowptr = nullptr, d.col = S.F.col, d.val = S.F.val, d.b = S.b, d.perm = S.F.perm, d.x = S.x, d.xp = S.xp;
-            d.n = S.F.n, d.cs = 0, d.ce = 0, d.ltile = t, d.upper = S.upper, d.pad = 0;
+            d.n = S.F.n, d.cs = 0, d.ce = 0, d.ltile = t, d.upper = S.upper, d.rev = S.rev;
             if (t < S.ntiles) {
                 d.rowptr = S.F.rowptr;
                 d.cs = __ldg(S.F.rowptr + min(t * kTileRows, S.F.n));
@@ -245,6 +253,9 @@ __device__ __forceinline__ void trsv_tile_stream(const TsSysDev* __restrict__ sy
             const int cs = d.cs, ce = d.ce;
             const int r = d.ltile * kTileRows + tid;
             const bool valid = r < d.n;
+            // where position p lives in xp: p, or n - 1 - p when the caller's vectors are in the REVERSE of this
+            // factor's position order (the backward solve of a system kept in the forward solve's level order)
+            const int xm = d.rev ? -1 : 1, xo = d.rev ? d.n - 1 : 0;
             int orig = -1, dpos = 0, q = 0, end = 0;
             double bi = 0.0;
             bool done = !valid || dead, have_rcp = false;
@@ -269,7 +280,8 @@ __device__ __forceinline__ void trsv_tile_stream(const TsSysDev* __restrict__ sy
                         if (!dead) bi = ldcg_here_f64(d.b + orig);
                     } else {
                         orig = r;
-                        bi = st.b[tid];
+                        const int r0 = d.ltile * kTileRows;
+                        bi = d.rev ? st.b[(d.n - 1 - r) - ((d.n - r0 - min(kTileRows, d.n - r0)) & ~1)] : st.b[tid];
                     }
                 }
                 const double* __restrict__ sv = st.val;
@@ -285,7 +297,7 @@ __device__ __forceinline__ void trsv_tile_stream(const TsSysDev* __restrict__ sy
                     bool ready = true;
 #pragma unroll
                     for (int k = 0; k < kTsInflight; ++k)
-                        if (k < m) u[k] = ld_relaxed_u64(xp + sc[q + k - as]);
+                        if (k < m) u[k] = ld_relaxed_u64(xp + (xo + xm * sc[q + k - as]));
 #pragma unroll
                     for (int k = 0; k < kTsInflight; ++k)
                         if (k < m) ready = ready && u[k] != kPending;
@@ -295,7 +307,7 @@ __device__ __forceinline__ void trsv_tile_stream(const TsSysDev* __restrict__ sy
                             for (int k = 0; k < kTsInflight; ++k)
                                 if (k < m) sum = __dadd_rn(sum, __dmul_rn(sv[q + k - as], as_double(u[k])));
                             const double xv = __dmul_rn(__dsub_rn(bi, sum), rcp);
-                            st_relaxed_u64(xp + r, as_bits(xv));
+                            st_relaxed_u64(xp + (xo + xm * r), as_bits(xv));
                             if (xg != xp) xg[orig] = xv;
                         }
                         pipe.release(i, j);
@@ -306,7 +318,7 @@ __device__ __forceinline__ void trsv_tile_stream(const TsSysDev* __restrict__ sy
                 for (;;) {
                     if (!done && q == end && have_rcp) {  // publish at once: rows of the same warp may wait for it
                         const double xv = __dmul_rn(__dsub_rn(bi, sum), rcp);
-                        st_relaxed_u64(xp + r, as_bits(xv));
+                        st_relaxed_u64(xp + (xo + xm * r), as_bits(xv));
                         if (xg != xp) xg[orig] = xv;
                         done = true;
                     }
@@ -319,7 +331,7 @@ __device__ __forceinline__ void trsv_tile_stream(const TsSysDev* __restrict__ sy
 #pragma unroll
                         for (int k = 0; k < kTsInflight; ++k) {
                             if (k < m && u[k] == kPending) {
-                                u[k] = ld_relaxed_u64(xp + sc[q + k - as]);
+                                u[k] = ld_relaxed_u64(xp + (xo + xm * sc[q + k - as]));
                                 all = all && u[k] != kPending;
                             }
                         }
@@ -350,5 +362,10 @@ __device__ __forceinline__ void trsv_tile_stream(const TsSysDev* __restrict__ sy
     }
     __syncthreads();
 }
+
+// Host side (sptrsv.cu): arm the polled vectors of a device-resident descriptor array and launch the solve. `word`
+// (8 bytes, zeroed by the caller once) carries the abort bit. No host synchronisation.
+int ts_solve_launch(const TsSysDev* sys_dev, int nsys, int max_tiles, int nmax, unsigned long long* word, int* flag,
+                    cudaStream_t s);
 
 }  // namespace dp

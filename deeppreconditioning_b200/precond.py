@@ -59,9 +59,11 @@ class LevelOrdered:
 LS_MAX_MEAN_LEVEL_ROWS = 1024  # level-stream solve when n / nlevels is at most this (one CTA must keep up)
 
 
-def _permute(matrix: CsrMatrix, plan: TriangularPlan):
-    """``dp_sptrsv_permute``: the level-ordered copy and its statistics (tile entries, row entries, dependency distance)."""
+def _permute(matrix: CsrMatrix, plan: TriangularPlan, perm: torch.Tensor | None = None):
+    """``dp_sptrsv_permute``: the level-ordered copy and its statistics (tile entries, row entries, dependency distance).
+    ``perm`` overrides the plan's level order with another valid solve order (``reversed_copy``)."""
     lib, n, dev = _lib.lib(), matrix.n, matrix.device
+    perm = plan.perm if perm is None else perm
     i32 = dict(dtype=torch.int32, device=dev)
     rowptr_p, level_sorted = torch.empty(n + 1, **i32), torch.empty(n, **i32)
     col_p = torch.empty(max(matrix.nnz, 1), **i32)
@@ -70,7 +72,7 @@ def _permute(matrix: CsrMatrix, plan: TriangularPlan):
     ws = _workspace(lib.dp_sptrsv_permute_workspace_bytes(n), dev)
     with torch.cuda.device(dev):
         _lib.check(lib.dp_sptrsv_permute(n, int(plan.upper), _lib.ptr(matrix.rowptr), _lib.ptr(matrix.col), _lib.ptr(matrix.val),
-                                         _lib.ptr(plan.perm), _lib.ptr(plan.level), _lib.ptr(rowptr_p), _lib.ptr(col_p),
+                                         _lib.ptr(perm), _lib.ptr(plan.level), _lib.ptr(rowptr_p), _lib.ptr(col_p),
                                          _lib.ptr(val_p), _lib.ptr(level_sorted), _lib.ptr(stats), _lib.ptr(ws), ws.numel(),
                                          _lib.stream_ptr(dev)), "dp_sptrsv_permute")
     copy = LevelOrdered(rowptr_p, col_p[: matrix.nnz], val_p[: matrix.nnz], level_sorted, matrix.nnz, matrix.val.data_ptr())
@@ -98,6 +100,17 @@ def level_ordered_any(matrix: CsrMatrix, plan: TriangularPlan) -> LevelOrdered:
     if plan.ts is None or not plan.ts.matches(matrix):
         plan.ts = _permute(matrix, plan)[0]
     return plan.ts
+
+
+def reversed_copy(upper_matrix: CsrMatrix, plan: TriangularPlan) -> LevelOrdered:
+    """Copy of ``U = L^T`` for the tile-stream solve in REVERSED position space (``DP_TRSV_REVERSED``): row ``r`` of the
+    copy is row ``n-1-r`` of ``U``. For a system kept in the level order of its forward solve (``LevelOrdering``) that is
+    a valid backward order whose dependencies sit one forward level away, so the system's own ``b`` / ``x`` serve both
+    solves without a gather."""
+    assert plan.upper
+    n = upper_matrix.n
+    perm = torch.arange(n - 1, -1, -1, dtype=torch.int32, device=upper_matrix.device)
+    return _permute(upper_matrix, plan, perm)[0]
 
 
 def analyse(matrix: CsrMatrix, upper: bool, level_stream: bool = True) -> TriangularPlan:
@@ -181,7 +194,7 @@ def _level_stream_batch(systems, outs=None, copies=None):
     return xs
 
 
-def _tile_stream_batch(systems, outs=None, copies=None, position_space=False):
+def _tile_stream_batch(systems, outs=None, copies=None, position_space=False, reverse=None):
     lib = _lib.lib()
     dev = systems[0][0].device
     nsys = len(systems)
@@ -200,6 +213,7 @@ def _tile_stream_batch(systems, outs=None, copies=None, position_space=False):
         d.perm, d.level_sorted, d.b, d.x = _lib.ptr(plan.perm), _lib.ptr(ls.level_sorted), _lib.ptr(b), _lib.ptr(x)
         if position_space:
             d.perm = None
+            d.flags = 1 if (reverse is not None and reverse[i]) else 0  # DP_TRSV_REVERSED
         xs.append(x), keep.append((b, ls))
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
     ws = _workspace(lib.dp_sptrsv_ts_workspace_bytes(descs, nsys), dev)
@@ -210,7 +224,8 @@ def _tile_stream_batch(systems, outs=None, copies=None, position_space=False):
     return xs
 
 
-def triangular_solve_batch(systems, outs=None, algorithm: str = "auto", copies=None, position_space: bool = False):
+def triangular_solve_batch(systems, outs=None, algorithm: str = "auto", copies=None, position_space: bool = False,
+                           reverse=None):
     """Independent solves ``T_s x_s = b_s`` in ONE launch.
 
     ``systems``: list of ``(matrix, plan, b)``; returns the list of solutions (the data-parallel axis of
@@ -219,13 +234,14 @@ def triangular_solve_batch(systems, outs=None, algorithm: str = "auto", copies=N
     level-ordered copies of all systems dealt to persistent CTAs, for wide levels; the copies are made on demand and
     cached in the plans, or passed as ``copies``), "syncfree" (``dp_sptrsv_solve_batch_f64``, original ordering).
     ``position_space`` ("ts" only): ``b`` and the solutions are in LEVEL ORDER (``b_pos = b[perm]``, ``x = x_pos`` with
-    ``x_pos[r] = x[perm[r]]``) - the form a caller uses that keeps all its vectors in that order.
+    ``x_pos[r] = x[perm[r]]``) - the form a caller uses that keeps all its vectors in that order. ``reverse[i]``: system
+    ``i``'s copy is a ``reversed_copy`` and its vectors are in the reverse of the copy's position order.
     """
     lib = _lib.lib()
     dev = systems[0][0].device
     nsys = len(systems)
     if algorithm == "ts":
-        return _tile_stream_batch(systems, outs, copies, position_space)
+        return _tile_stream_batch(systems, outs, copies, position_space, reverse)
     assert not position_space, "position-space vectors are a feature of the tile-stream solve"
     if algorithm != "syncfree" and all(plan.ls is not None and plan.ls.matches(m) for m, plan, _ in systems):
         return _level_stream_batch(systems, outs)
@@ -393,16 +409,31 @@ class FactoredSolve(FactoredMultiply):
     precond = _lib.PRECOND_SOLVE
 
     def __init__(self, L: CsrMatrix, Lt: CsrMatrix | None = None, fwd: TriangularPlan | None = None,
-                 bwd: TriangularPlan | None = None, level_stream: bool = True) -> None:
+                 bwd: TriangularPlan | None = None, level_stream: bool = True, tile_stream: bool = False) -> None:
+        """``tile_stream``: the system is kept in the level order of ``L`` (``LevelOrdering``: checked); both solves of
+        a PCG iteration then run as tile-stream batch solves (``DP_SOLVE_TILE_STREAM``; stepped engine, picked by
+        ``PcgBatch``) on the iteration's own vectors - the form for batches of 3-D factors."""
         super().__init__(L, Lt)
         self.fwd = fwd or analyse(self.L, upper=False, level_stream=False)
         self.bwd = bwd or analyse(self.Lt, upper=True, level_stream=False)
+        self.tile_stream = bool(tile_stream)
+        if self.tile_stream:
+            n = self.L.n
+            if not torch.equal(self.fwd.perm, torch.arange(n, dtype=torch.int32, device=self.L.device)):
+                raise _lib.DpcgError("tile_stream=True needs the system in the level order of L (precond.level_ordering)")
+            self.fwd_ls = level_ordered_any(self.L, self.fwd)   # identity order: the copy only stores 1 / diagonal
+            self.bwd_ls = reversed_copy(self.Lt, self.bwd)
+            return
         # level-ordered copies of THIS factor's values (a plan may have been made on another matrix of the same pattern)
         own = lambda plan, m: plan.ls if (plan.ls is not None and plan.ls.matches(m)) else level_ordered(m, plan)
         self.fwd_ls = own(self.fwd, self.L) if level_stream else None
         self.bwd_ls = own(self.bwd, self.Lt) if level_stream else None
 
     def _apply(self, r):
+        if self.tile_stream:
+            y = _tile_stream_batch([(self.L, self.fwd, r)], None, [self.fwd_ls], True, [False])[0]
+            return _tile_stream_batch([(self.Lt, self.bwd, y)], None, [self.bwd_ls], True, [True])[0]
+
         def one(m, plan, copy, b):
             if copy is not None:
                 return _level_stream_batch([(m, plan, b)], None, [copy])[0]
@@ -416,6 +447,7 @@ class FactoredSolve(FactoredMultiply):
         system.fwd_plan, system.bwd_plan = _lib.ptr(self.fwd.plan), _lib.ptr(self.bwd.plan)
         system.fwd_nchunks, system.bwd_nchunks = self.fwd.nchunks, self.bwd.nchunks
         system.fwd_max_level_chunks, system.bwd_max_level_chunks = self.fwd.max_level_chunks, self.bwd.max_level_chunks
+        system.solve_algorithm = 1 if self.tile_stream else 0  # DP_SOLVE_TILE_STREAM
         for tag, plan, ls in (("fwd", self.fwd, self.fwd_ls), ("bwd", self.bwd, self.bwd_ls)):
             if ls is not None:
                 for name, t in (("rowptr", ls.rowptr), ("col", ls.col), ("val", ls.val), ("perm", plan.perm),

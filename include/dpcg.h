@@ -164,7 +164,7 @@ typedef struct dp_trsv_ls_system {
     int32_t n;
     int32_t nnz;
     int32_t upper;   /* 0: lower (diagonal last in each row), 1: upper (diagonal first) */
-    int32_t reserved;
+    int32_t flags;   /* tile-stream solve only: DP_TRSV_REVERSED */
     const int32_t* rowptr_p; const int32_t* col_p; const double* val_p; /* dp_sptrsv_permute outputs */
     const int32_t* perm;
     const int32_t* level_sorted;
@@ -183,7 +183,11 @@ int dp_sptrsv_ls_solve_batch_f64(const dp_trsv_ls_system_t* systems_host, int32_
  * may be NULL) and any level-ordered copy (no dp_sptrsv_ls_limits restriction). Bit-identical to dp_sptrsv_solve_f64.
  * perm == NULL: b and x are indexed by POSITION (the caller keeps its vectors in level order, x_pos[r] = x[perm[r]]);
  * this saves the per-row gather of b and scatter of x through the permutation. b and x must not alias.
+ * flags & DP_TRSV_REVERSED (perm == NULL only): position r is row n-1-r of b and x - the backward solve of a system
+ * kept in the level order of its forward solve (the copy is dp_sptrsv_permute of L^T with perm[r] = n-1-r).
+ * rowptr_p and b (or perm) must be 16-byte aligned like col_p / val_p: their spans travel by bulk copy too.
  * Cooperative launch; *flag_out receives DP_ERR_TIMEOUT if a dependency never arrives. */
+#define DP_TRSV_REVERSED 1
 size_t dp_sptrsv_ts_workspace_bytes(const dp_trsv_ls_system_t* systems_host, int32_t nsys);
 int dp_sptrsv_ts_solve_batch_f64(const dp_trsv_ls_system_t* systems_host, int32_t nsys, int32_t* flag_out, void* workspace,
                                  size_t workspace_bytes, void* stream);
@@ -207,7 +211,8 @@ typedef struct dp_pcg_system {
     int32_t a_nnz, m_nnz, mt_nnz;
     int32_t fwd_nchunks, bwd_nchunks;       /* SOLVE: plan sizes */
     int32_t fwd_max_level_chunks, bwd_max_level_chunks;
-    int32_t reserved;
+    int32_t solve_algorithm; /* SOLVE: 0 = level-stream where the copies below are given, else sync-free;
+                              * DP_SOLVE_TILE_STREAM = the tile-stream batch solve (see below) */
     const int32_t* a_rowptr; const int32_t* a_col; const double* a_val;     /* A (full symmetric CSR) */
     const int32_t* m_rowptr; const int32_t* m_col; const double* m_val;     /* L (MULTIPLY/SOLVE) or M (CSR) */
     const int32_t* mt_rowptr; const int32_t* mt_col; const double* mt_val;  /* L^T (MULTIPLY/SOLVE) */
@@ -219,6 +224,11 @@ typedef struct dp_pcg_system {
     const int32_t* fwd_ls_perm; const int32_t* fwd_ls_level;
     const int32_t* bwd_ls_rowptr; const int32_t* bwd_ls_col; const double* bwd_ls_val;
     const int32_t* bwd_ls_perm; const int32_t* bwd_ls_level;
+    /* solve_algorithm == DP_SOLVE_TILE_STREAM (STEPPED engine, every SOLVE system of the batch): the system is kept in
+     * the level order of its forward solve (levels ascend along the rows). fwd_ls_{rowptr,col,val} = dp_sptrsv_permute
+     * of L with the identity order, bwd_ls_{rowptr,col,val} = dp_sptrsv_permute of L^T with perm[r] = n-1-r
+     * (DP_TRSV_REVERSED); the perm / level pointers are ignored. Both solves of an iteration then run as tile-stream
+     * batch solves over all systems, directly on the iteration's vectors. */
     const double* b;   /* right-hand side, n */
     double* x;         /* in: x0, out: x_hat, n */
     double* work;      /* dp_pcg_work_doubles(n) doubles of scratch, contents ignored on entry */
@@ -230,6 +240,8 @@ typedef struct dp_pcg_system {
                            * tridiagonal of M*A: the host turns them into the condition-number estimate that replaces
                            * the dense torch.linalg.cond of test.py:111-113. */
 } dp_pcg_system_t;
+
+#define DP_SOLVE_TILE_STREAM 1
 
 typedef struct dp_pcg_params {
     double rtol;          /* cg.py:51 default 1e-8, compared with the SQUARED relative residual */

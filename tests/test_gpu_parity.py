@@ -11,6 +11,7 @@ import torch
 import helpers
 import deeppreconditioning_b200 as dp
 from deeppreconditioning_b200 import precond, utils
+from deeppreconditioning_b200 import _lib as dp_lib
 from deeppreconditioning_b200.sparse import CsrMatrix
 from deeppreconditioning_b200.test import BenchmarkSuite
 from deeppreconditioning_b200 import model as models, synthetic
@@ -259,12 +260,30 @@ def test_level_ordered_system_is_the_same_solve(cuda, kind, side):
     assert torch.equal(order.from_level(y_l), y)
     y_ts = precond.triangular_solve_batch([(F_l, plan_l, order.to_level(b))], algorithm="ts", position_space=True)[0]
     assert torch.equal(y_ts, y_l)
+    # the backward solve of the SAME ordering: rows walked from the last to the first (DP_TRSV_REVERSED)
+    U_l = F_l.transpose()
+    bwd_l = precond.analyse(U_l, True, level_stream=False)
+    z_l = precond.triangular_solve(U_l, bwd_l, y_l, algorithm="syncfree")
+    z_ts = precond.triangular_solve_batch([(U_l, bwd_l, y_l)] * 3, algorithm="ts", position_space=True, reverse=[True] * 3,
+                                          copies=[precond.reversed_copy(U_l, bwd_l)] * 3)
+    assert all(torch.equal(z, z_l) for z in z_ts)
+    z = precond.triangular_solve(F.transpose(), precond.analyse(F.transpose(), True, level_stream=False), y, algorithm="syncfree")
+    assert torch.equal(order.from_level(z_l), z)
     # PCG with the IC(0) factor in solve mode
     got = dp.pcg_solve(A, b, dp.FactoredSolve(F), max_iter=3000)
     got_l = dp.pcg_solve(A_l, order.to_level(b), dp.FactoredSolve(F_l), max_iter=3000)
     ref = pcg.preconditioned_conjugate_gradient(osp.to_torch_csr(*p.A), p.b, operators.FactoredSolve(*helpers.ic0_factor(p)),
                                                 max_iter=3000)
     assert abs(got_l.iterations - got.iterations) <= 1 and abs(got_l.iterations - ref.iterations) <= 1
+    # ... and with both solves of every iteration run by the tile-stream batch kernel (stepped engine): the solves are
+    # bit-exact and every other phase is the same code, so the whole solve is bitwise the sync-free one
+    M_ts = dp.FactoredSolve(F_l, tile_stream=True)
+    assert torch.equal(M_ts @ order.to_level(b), dp.FactoredSolve(F_l, level_stream=False) @ order.to_level(b))
+    got_ts = dp.pcg_solve_batch([(A_l, order.to_level(b), M_ts)] * 2, max_iter=3000)
+    for g in got_ts:
+        assert g.iterations == got_l.iterations and torch.equal(g.x_hat, got_l.x_hat) and g.res == got_l.res
+    with pytest.raises(dp_lib.DpcgError):
+        dp.FactoredSolve(F, tile_stream=True)  # natural order: refused
     x_l = order.from_level(got_l.x_hat).cpu()
     tol = 1e-8 if got_l.iterations == ref.iterations else 1e-3  # one more body moves x by about the residual tolerance
     assert torch.linalg.vector_norm(x_l - ref.x_hat) <= tol * torch.linalg.vector_norm(ref.x_hat)

@@ -27,7 +27,7 @@ peak = bench.peaks()[0]
 ev = lambda: torch.cuda.Event(enable_timing=True)
 
 
-def build(index, level):
+def build(index, level, tile_stream=False):
     st, _, rhs, sizes = synthetic.make_batch(a.kind, a.side, [index], device=dev)
     n = sizes[0]
     b = rhs[0, :n].to(torch.float64)
@@ -41,13 +41,13 @@ def build(index, level):
     A = CsrMatrix.from_spconv(st, n, "symmetrise")
     plan = precond.analyse(T, False, level_stream=False)
     F = precond.incomplete_cholesky0(T, plan)
-    return A, b, dp.FactoredSolve(F, None, plan, level_stream=False), order
+    return A, b, dp.FactoredSolve(F, None, plan, level_stream=False, tile_stream=tile_stream), order
 
 
-for level in (False, True):
+for level, tile_stream in ((False, False), (True, False), (True, True)):
     systems, orders = [], []
     for i in range(a.batch):
-        A, b, M, order = build(i, level)
+        A, b, M, order = build(i, level, tile_stream)
         systems.append((A, b, M)), orders.append(order)
     n, nnz_a, nnz_l = systems[0][0].n, systems[0][0].nnz, systems[0][2].L.nnz
     for nb in sorted({1, a.batch}):
@@ -61,7 +61,7 @@ for level in (False, True):
         res = batch.results()
         its = sum(r.iterations for r in res)
         gbs = bench.iter_bytes(n, nnz_a, nnz_l) * its / best / 1e6
-        print(f"{'level' if level else 'natural'} order, {nb} x {a.side}^3 IC(0) solve-mode PCG: {best:.1f} ms, iterations "
+        print(f"{'level' if level else 'natural'} order{' + tile-stream solves (stepped engine)' if tile_stream else ''}, {nb} x {a.side}^3 IC(0) solve-mode PCG: {best:.1f} ms, iterations "
               f"{[r.iterations for r in res]}, {1e3 * best / max(r.iterations for r in res):.0f} us per iteration, "
               f"{gbs:.0f} GB/s = {gbs / peak:.3f} of peak", flush=True)
         del batch
