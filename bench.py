@@ -421,6 +421,89 @@ def extras(device, host0):
                                    "frac_of_hbm_peak": nb * trsv_bytes / ms / 1e6 / peak,
                                    "note": "16 copies of the factor in distinct memory, warps dealt to the systems"}
     del batch3d, outs
+    # the same batch through the tile-stream solve (trsv_ts.cuh): level-ordered copies, TMA tile pipeline
+    base3 = precond.level_ordered_any(T3, fwd3)
+
+    def ts_batch(T, plan, base, rhs_vec, nb, position_space):
+        systems, copies, outs = [], [], []
+        for _ in range(nb):  # distinct memory per system
+            c = _copy.copy(base)
+            c.rowptr, c.col, c.val = base.rowptr.clone(), base.col.clone(), base.val.clone()
+            p = _copy.copy(plan)
+            p.perm = plan.perm.clone()
+            rhs_s = rhs_vec[plan.perm.long()] if position_space else rhs_vec.clone()
+            systems.append((T, p, rhs_s)), copies.append(c), outs.append(torch.empty_like(rhs_vec))
+        return timed(lambda: precond.triangular_solve_batch(systems, outs, algorithm="ts", copies=copies,
+                                                            position_space=position_space), reps=3)
+
+    ts = {}
+    for key, pos in [("original_numbering", False), ("level_order_vectors", True)]:
+        ms = ts_batch(T3, fwd3, base3, x, nb, pos)
+        ts[key] = {"ms": ms, "algorithmic_gbs": nb * trsv_bytes / ms / 1e6, "frac_of_hbm_peak": nb * trsv_bytes / ms / 1e6 / peak}
+    out["sptrsv_batch16_128^3"]["tile_stream"] = ts
+    del base3
+    torch.cuda.empty_cache()
+    # config 5, one GPU's share: 8 independent 256^3 factors (1.14 GB each), vectors in level order
+    try:
+        st5, _, rhs5, sizes5 = synthetic.make_batch("poisson3d", 256, [0], device=device)
+        n5 = sizes5[0]
+        T5 = CsrMatrix.from_spconv(st5, n5, "tril")
+        del st5
+        x5 = rhs5[0, :n5].to(torch.float64)
+        del rhs5
+        fwd5 = precond.analyse(T5, False, level_stream=False)
+        base5 = precond.level_ordered_any(T5, fwd5)
+        bytes5 = 12 * T5.nnz + 4 * (n5 + 1) + 16 * n5
+        widths = torch.diff(fwd5.level_ptr)
+        entry = {"n": n5, "nnz": T5.nnz, "levels": fwd5.nlevels, "widest_level_rows": int(widths.max())}
+        for nb5 in (1, 8):
+            ms = ts_batch(T5, fwd5, base5, x5, nb5, True)
+            entry[f"{nb5}_systems"] = {"ms": ms, "algorithmic_gbs": nb5 * bytes5 / ms / 1e6,
+                                       "frac_of_hbm_peak": nb5 * bytes5 / ms / 1e6 / peak}
+        entry["note"] = ("tile-stream solve, vectors in level order, 8 distinct copies of the factor; the time includes arming "
+                         "the solution vectors (8 B per row on top of the algorithmic bytes)")
+        out["sptrsv_tile_stream_256^3"] = entry
+        del T5, x5, fwd5, base5
+        torch.cuda.empty_cache()
+    except Exception as exc:  # an extra must never take the bench line down
+        out["sptrsv_tile_stream_256^3"] = {"skipped": repr(exc)[:200]}
+    # IC(0)-PCG on a batch of 8 x 128^3 (solve mode): natural order, level order, level order + tile-stream solves
+    try:
+        pcg8 = {}
+        for key, level, tile_stream in [("natural_order", False, False), ("level_order", True, False),
+                                        ("level_order_tile_stream", True, True)]:
+            systems8 = []
+            for i in range(8):
+                st8, _, rhs8, sizes8 = synthetic.make_batch("poisson3d", 128, [i], device=device)
+                n8 = sizes8[0]
+                b8 = rhs8[0, :n8].to(torch.float64)
+                T8 = CsrMatrix.from_spconv(st8, n8, "tril")
+                if level:
+                    order = precond.level_ordering(T8)
+                    st8 = order.renumber(st8)
+                    T8 = CsrMatrix.from_spconv(st8, n8, "tril")
+                    b8 = order.to_level(b8)
+                A8 = CsrMatrix.from_spconv(st8, n8, "symmetrise")
+                plan8 = precond.analyse(T8, False, level_stream=False)
+                F8 = precond.incomplete_cholesky0(T8, plan8)
+                systems8.append((A8, b8, dp.FactoredSolve(F8, None, plan8, level_stream=False, tile_stream=tile_stream)))
+            batch8 = dp.PcgBatch(systems8, RTOL, MAX_ITER)
+
+            def go8():
+                batch8.reset()
+                batch8.solve()
+
+            ms = timed(go8, reps=2)
+            res8 = batch8.results()
+            its = [r.iterations for r in res8]
+            gbs = iter_bytes(n8, A8.nnz, T8.nnz) * sum(its) / ms / 1e6
+            pcg8[key] = {"ms_to_tol": ms, "iterations": its, "us_per_iteration": 1e3 * ms / max(its),
+                         "algorithmic_gbs": gbs, "frac_of_hbm_peak": gbs / peak}
+            del batch8, systems8
+            torch.cuda.empty_cache()
+        out["pcg_ic0_batch8_128^3"] = pcg8
+    except Exception as exc:
+        out["pcg_ic0_batch8_128^3"] = {"skipped": repr(exc)[:200]}
     return out
 
 
