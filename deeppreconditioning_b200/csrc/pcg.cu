@@ -750,6 +750,7 @@ struct TsPhases {
     const TsSysDev* fwd[2];
     const TsSysDev* bwd[2];
     int nsys, max_tiles, nmax;
+    bool short_rows;  // every system promises DP_TRSV_SHORT_ROWS (solve_algorithm bit 1)
     unsigned long long* word;
 };
 
@@ -761,8 +762,8 @@ static int launch_apply(const Ctx& ctx, int k, int tile_grid, int coop, const Ts
     if (ctx.has_solve) {
         if (ts) {  // finished systems are solved along (their vectors are scratch by then): no host round trip
             const int par = (k + 1) & 1;
-            if ((st = ts_solve_launch(ts->fwd[par], ts->nsys, ts->max_tiles, ts->nmax, ts->word, ctx.flag, s)) != DP_OK) return st;
-            if ((st = ts_solve_launch(ts->bwd[par], ts->nsys, ts->max_tiles, ts->nmax, ts->word, ctx.flag, s)) != DP_OK) return st;
+            if ((st = ts_solve_launch(ts->fwd[par], ts->nsys, ts->max_tiles, ts->nmax, ts->short_rows, ts->word, ctx.flag, s)) != DP_OK) return st;
+            if ((st = ts_solve_launch(ts->bwd[par], ts->nsys, ts->max_tiles, ts->nmax, ts->short_rows, ts->word, ctx.flag, s)) != DP_OK) return st;
         } else {
             if ((st = launch_phase<PH_FWD, kInit>(ctx, k, coop, true, s)) != DP_OK) return st;
             if ((st = launch_phase<PH_BWD, kInit>(ctx, k, coop, true, s)) != DP_OK) return st;
@@ -824,6 +825,7 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
     int has_multiply = 0, has_solve = 0, has_ls = 0, n_solve = 0, n_ts = 0;
     long long sum_fwd_lvl = 0, sum_bwd_lvl = 0;
     std::vector<TsSysDev> ts_sys[4];
+    bool ts_short = true;
     for (int i = 0; i < nsys; ++i) {
         const dp_pcg_system_t& u = systems_host[i];
         if (u.n <= 0 || !u.a_rowptr || !u.a_col || !u.a_val || !u.b || !u.x || !u.work || !u.iters_out || !u.res_out)
@@ -841,7 +843,8 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
         d.bwd_plan = u.bwd_plan;
         d.fwd_ls = LsFactor{nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
         d.bwd_ls = d.fwd_ls;
-        const bool tile_stream = u.precond == DP_PRECOND_SOLVE && u.solve_algorithm == DP_SOLVE_TILE_STREAM;
+        const bool tile_stream = u.precond == DP_PRECOND_SOLVE && (u.solve_algorithm & DP_SOLVE_TILE_STREAM) != 0;
+        if (tile_stream && !(u.solve_algorithm & DP_SOLVE_SHORT_ROWS)) ts_short = false;
         if (u.precond == DP_PRECOND_SOLVE) ++n_solve;
         if (tile_stream) {
             if (!u.fwd_ls_rowptr || !u.fwd_ls_col || !u.fwd_ls_val || !u.bwd_ls_rowptr || !u.bwd_ls_col || !u.bwd_ls_val)
@@ -1006,6 +1009,7 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
             ts_phases.bwd[par] = reinterpret_cast<const TsSysDev*>(ws + lay.ts_sys[2 + par]);
         }
         ts_phases.nsys = n_ts;
+        ts_phases.short_rows = ts_short;
         ts_phases.word = reinterpret_cast<unsigned long long*>(ws + lay.ts_word);
         for (const TsSysDev& f : ts_sys[0]) {
             if (f.ntiles > ts_phases.max_tiles) ts_phases.max_tiles = f.ntiles;

@@ -111,12 +111,13 @@ __global__ void arm_positions_kernel(const TsSysDev* __restrict__ sys, int nsys)
     }
 }
 
+template <bool kShort>
 __global__ void __launch_bounds__(kBlock, 2)
 sptrsv_ts_batch_kernel(const TsSysDev* __restrict__ sys, int nsys, int max_tiles, unsigned long long* word, int* flag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TsSmem& sm = *reinterpret_cast<TsSmem*>(smem_raw);
     const AbortCtl ctl{word, flag};
-    trsv_tile_stream(sys, nsys, max_tiles, sm, ctl);
+    trsv_tile_stream<kShort>(sys, nsys, max_tiles, sm, ctl);
 }
 
 // IC(0), up-looking, one lane per row, rows of a level per chunk (same plan as the forward solve of tril(A)):
@@ -207,24 +208,24 @@ static int participating_warps(int max_level_chunks, int grid) {
     return pw > w ? w : (int)pw;
 }
 
-int ts_solve_launch(const TsSysDev* sys_dev, int nsys, int max_tiles, int nmax, unsigned long long* word, int* flag,
-                    cudaStream_t s) {
+int ts_solve_launch(const TsSysDev* sys_dev, int nsys, int max_tiles, int nmax, bool short_rows, unsigned long long* word,
+                    int* flag, cudaStream_t s) {
     const int fill_x = (nmax + 255) / 256 < sm_count() * 4 ? (nmax + 255) / 256 : sm_count() * 4;
     arm_positions_kernel<<<dim3(fill_x, nsys < 1024 ? nsys : 1024), 256, 0, s>>>(sys_dev, nsys);
     DP_LAUNCH_CHECK();
-    static thread_local bool smem_ok = false;
-    if (!smem_ok) {
-        DP_CUDA(cudaFuncSetAttribute((const void*)sptrsv_ts_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)sizeof(TsSmem)));
-        smem_ok = true;
+    const void* kernel = short_rows ? (const void*)sptrsv_ts_batch_kernel<true> : (const void*)sptrsv_ts_batch_kernel<false>;
+    static thread_local int resident_of[2] = {0, 0};
+    int& resident = resident_of[short_rows ? 1 : 0];
+    if (!resident) {
+        DP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TsSmem)));
+        resident = coop_grid(kernel, kBlock, sizeof(TsSmem));
     }
-    static thread_local int resident = 0;
-    if (!resident) resident = coop_grid((const void*)sptrsv_ts_batch_kernel, kBlock, sizeof(TsSmem));
     int grid = resident;
     const long long items = (long long)max_tiles * nsys;
+    if (items >= (1ll << 31) - 1024) return DP_ERR_INVALID;  // the kernel counts items in 32 bits
     if (items < grid) grid = (int)items;
     void* args[] = {&sys_dev, &nsys, &max_tiles, &word, &flag};
-    DP_CUDA(cudaLaunchCooperativeKernel((const void*)sptrsv_ts_batch_kernel, dim3(grid), dim3(kBlock), args, sizeof(TsSmem), s));
+    DP_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kBlock), args, sizeof(TsSmem), s));
     return DP_OK;
 }
 
@@ -359,6 +360,11 @@ int dp_sptrsv_ls_solve_batch_f64(const dp_trsv_ls_system_t* systems_host, int32_
 /* ---- tile-stream batch solve ---------------------------------------------------------------------------------- */
 static size_t ts_header_bytes(int32_t nsys) { return 256 + align_up(sizeof(TsSysDev) * (size_t)(nsys > 0 ? nsys : 0), 256); }
 
+void dp_sptrsv_ts_limits(int32_t* limits_host) {
+    limits_host[0] = kTsCap;       // entries of a 512-row tile that fit one pipeline item
+    limits_host[1] = kTsFast + 1;  // entries per row (diagonal included) of the register path: DP_TRSV_SHORT_ROWS
+}
+
 size_t dp_sptrsv_ts_workspace_bytes(const dp_trsv_ls_system_t* systems_host, int32_t nsys) {
     size_t bytes = ts_header_bytes(nsys);
     for (int i = 0; systems_host && i < nsys; ++i)
@@ -378,9 +384,11 @@ int dp_sptrsv_ts_solve_batch_f64(const dp_trsv_ls_system_t* systems_host, int32_
     size_t off = ts_header_bytes(nsys);
     std::vector<TsSysDev> dev((size_t)nsys);
     int max_tiles = 0, nmax = 0;
+    bool short_rows = true;
     for (int i = 0; i < nsys; ++i) {
         const dp_trsv_ls_system_t& u = systems_host[i];
         if (u.n <= 0 || !u.rowptr_p || !u.col_p || !u.val_p || !u.b || !u.x || u.b == u.x) return DP_ERR_INVALID;
+        short_rows = short_rows && (u.flags & DP_TRSV_SHORT_ROWS) != 0;
         if (!aligned16(u.col_p) || !aligned16(u.val_p) || !aligned16(u.rowptr_p) || !aligned16(u.perm ? (const void*)u.perm : (const void*)u.b))
             return DP_ERR_ALIGNMENT;  // spans of all four arrays are moved by 16-byte granular bulk copies
         TsSysDev d{};
@@ -402,7 +410,7 @@ int dp_sptrsv_ts_solve_batch_f64(const dp_trsv_ls_system_t* systems_host, int32_
     DP_CUDA(cudaMemsetAsync(word, 0, sizeof(unsigned long long), s));
     // pageable source: the call returns once the bytes are staged, `dev` may go out of scope
     DP_CUDA(cudaMemcpyAsync(sys, dev.data(), sizeof(TsSysDev) * (size_t)nsys, cudaMemcpyHostToDevice, s));
-    return ts_solve_launch(sys, nsys, max_tiles, nmax, word, flag_out, s);
+    return ts_solve_launch(sys, nsys, max_tiles, nmax, short_rows, word, flag_out, s);
 }
 
 int dp_ic0_f64(int32_t n, const int32_t* rowptr, const int32_t* col, const double* a_val, double* l_val,

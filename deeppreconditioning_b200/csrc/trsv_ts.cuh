@@ -61,6 +61,10 @@ constexpr int kTsCap = DPCG_TS_CAP;        // entries per stage: a 512-row tile 
 constexpr int kTsStages = DPCG_TS_STAGES;
 constexpr int kTsRound = DPCG_TS_ROUND;    // tile descriptors per table refill
 constexpr int kTsInflight = 4;             // dependencies polled per lane and round
+#ifndef DPCG_TS_FAST
+#define DPCG_TS_FAST 3
+#endif
+constexpr int kTsFast = DPCG_TS_FAST;      // register path: rows with at most this many dependencies (5-/7-point factors: 2 / 3)
 constexpr int kTsSlots = kTsCap + 8;       // up to 3 lead-in entries (16-byte alignment) + tail rounding
 static_assert(kTsCap % 4 == 0 && kTsCap >= 64, "stage capacity");
 
@@ -215,21 +219,200 @@ struct TsPipe {
     }
 };
 
-// The whole batch. All kBlock threads of every CTA of a cooperative launch must call.
+// One tile whose rows have at most kTsFast dependencies each (so the tile is ONE pipeline item): the row moves to
+// registers (dependency positions, coefficients, 1 / diagonal), the STAGE IS HANDED BACK BEFORE ANY POLL, and the row is
+// finished from registers. The stage is held for a few shared-memory reads instead of an L2 round trip (or a whole
+// level of waiting), so its next item is on its way while this tile still polls; where all dependencies are long
+// solved (levels wider than the batch's window of tiles in flight) the code is straight-line. A kernel of its own
+// (kShort): sharing registers with the general loop below spilled, and the spill traffic cost more than the early
+// hand-back won (profiles/README.md).
+__device__ __forceinline__ void ts_tile_short(const TsTile& d, int i, TsSmem& sm, TsPipe& pipe, const AbortCtl& ctl, bool& dead) {
+    const int tid = threadIdx.x;
+    double* xp = d.xp;
+    double* xg = d.x;
+    const int r = d.ltile * kTileRows + tid;
+    const bool valid = r < d.n;
+    const int xm = d.rev ? -1 : 1, xo = d.rev ? d.n - 1 : 0;
+    const int as = d.cs & ~3;
+    int orig = r, m = 0;
+    double bi = 0.0, rcp = 0.0;
+    int c[kTsFast];
+    double v[kTsFast];
+#pragma unroll
+    for (int k = 0; k < kTsFast; ++k) c[k] = 0, v[k] = 0.0;
+    const unsigned stage = pipe.acquire();
+    const TsStage& st = sm.stage[stage];
+    bool done = !valid || dead;
+    bool bad = false;  // the caller's DP_TRSV_SHORT_ROWS promise does not hold for this row
+    if (valid) {
+        const int rs = st.rowptr[tid], re = st.rowptr[tid + 1];
+        const int q = (d.upper ? rs + 1 : rs) - as;  // dependencies: stage entries [q, q + m)
+        m = re - rs - 1;
+        bad = m > kTsFast || m < 0 || re - as > kTsSlots;
+        if (bad) m = 0;
+        else rcp = st.val[(d.upper ? rs : re - 1) - as];  // the diagonal's entry holds 1 / T_ii
+        if (d.perm) {
+            orig = st.perm[tid];
+            if (!dead) bi = ldcg_here_f64(d.b + orig);
+        } else {
+            const int r0 = d.ltile * kTileRows;
+            bi = d.rev ? st.b[(d.n - 1 - r) - ((d.n - r0 - min(kTileRows, d.n - r0)) & ~1)] : st.b[tid];
+        }
+#pragma unroll
+        for (int k = 0; k < kTsFast; ++k)
+            if (k < m) c[k] = xo + xm * st.col[q + k], v[k] = st.val[q + k];
+    }
+    if (bad) ctl.raise(DP_ERR_STRUCTURE), dead = true;
+    dead = __any_sync(kFull, dead);
+    if (dead) done = true;
+    pipe.release(i, 0);
+    unsigned long long u[kTsFast];
+#pragma unroll
+    for (int k = 0; k < kTsFast; ++k) {
+        u[k] = 0ull;
+        if (!done && k < m) u[k] = ld_relaxed_u64(xp + c[k]);
+    }
+    unsigned idle = 0;
+    for (;;) {
+        if (!done) {
+            bool ready = true;
+#pragma unroll
+            for (int k = 0; k < kTsFast; ++k) ready = ready && (k >= m || u[k] != kPending);
+            if (ready) {  // publish at once: rows of the same warp may wait for it
+                double sum = 0.0;
+#pragma unroll
+                for (int k = 0; k < kTsFast; ++k)
+                    if (k < m) sum = __dadd_rn(sum, __dmul_rn(v[k], as_double(u[k])));
+                const double xv = __dmul_rn(__dsub_rn(bi, sum), rcp);
+                st_relaxed_u64(xp + (xo + xm * r), as_bits(xv));
+                if (xg != xp) xg[orig] = xv;
+                done = true;
+            }
+        }
+        if (__all_sync(kFull, done)) break;
+        if (!done) {
+#pragma unroll
+            for (int k = 0; k < kTsFast; ++k)
+                if (k < m && u[k] == kPending) u[k] = ld_relaxed_u64(xp + c[k]);
+        }
+        ++idle;
+        if (idle > kSpinBudget) ctl.raise(DP_ERR_TIMEOUT), dead = true;
+        if ((idle & 255u) == 0 && ctl.aborted()) dead = true;
+        dead = __any_sync(kFull, dead);
+        if (dead) done = true;
+#if DPCG_TS_SLEEP > 0
+        else if (idle > 1) __nanosleep(DPCG_TS_SLEEP);
+#endif
+    }
+}
+
+// One tile of any shape: rows of any length, tiles of several pipeline items, rows cut by an item boundary.
+__device__ __forceinline__ void ts_tile_general(const TsTile& d, int i, TsSmem& sm, TsPipe& pipe, const AbortCtl& ctl, bool& dead) {
+    const int tid = threadIdx.x;
+    double* xp = d.xp;
+    double* xg = d.x;
+    const bool upper = d.upper != 0;
+    const int cs = d.cs, ce = d.ce;
+    const int r = d.ltile * kTileRows + tid;
+    const bool valid = r < d.n;
+    // where position p lives in xp: p, or n - 1 - p when the caller's vectors are in the REVERSE of this
+    // factor's position order (the backward solve of a system kept in the forward solve's level order)
+    const int xm = d.rev ? -1 : 1, xo = d.rev ? d.n - 1 : 0;
+    int orig = -1, dpos = 0, q = 0, end = 0;
+    double bi = 0.0;
+    bool done = !valid || dead, have_rcp = false;
+    double sum = 0.0, rcp = 0.0;
+    unsigned long long u[kTsInflight];
+#pragma unroll
+    for (int k = 0; k < kTsInflight; ++k) u[k] = kPending;
+    const int nb = (ce - cs + kTsCap - 1) / kTsCap;
+    for (int j = 0; j < nb; ++j) {
+        const int bs = cs + j * kTsCap;
+        const int be = min(ce, bs + kTsCap);
+        const int as = bs & ~3;
+        const unsigned stage = pipe.acquire();
+        const TsStage& st = sm.stage[stage];
+        if (j == 0 && valid) {  // the tile's metadata rides on its first item
+            const int rs = st.rowptr[tid], re = st.rowptr[tid + 1];
+            dpos = upper ? rs : re - 1;   // the diagonal's entry (holds 1 / T_ii)
+            q = upper ? rs + 1 : rs;      // dependencies: entries [q, end)
+            end = upper ? re : re - 1;
+            if (d.perm) {
+                orig = st.perm[tid];
+                if (!dead) bi = ldcg_here_f64(d.b + orig);
+            } else {
+                orig = r;
+                const int r0 = d.ltile * kTileRows;
+                bi = d.rev ? st.b[(d.n - 1 - r) - ((d.n - r0 - min(kTileRows, d.n - r0)) & ~1)] : st.b[tid];
+            }
+        }
+        const double* __restrict__ sv = st.val;
+        const int* __restrict__ sc = st.col;
+        if (!done && !have_rcp && dpos >= bs && dpos < be) rcp = sv[dpos - as], have_rcp = true;
+        const int qe = min(end, be);  // this row's dependencies inside the block: [q, qe) (empty if q >= be)
+        unsigned idle = 0;
+        for (;;) {
+            if (!done && q == end && have_rcp) {  // publish at once: rows of the same warp may wait for it
+                const double xv = __dmul_rn(__dsub_rn(bi, sum), rcp);
+                st_relaxed_u64(xp + (xo + xm * r), as_bits(xv));
+                if (xg != xp) xg[orig] = xv;
+                done = true;
+            }
+            const bool pending = !done && q < qe;
+            if (!__any_sync(kFull, pending)) break;
+            bool progress = false;
+            if (pending) {
+                const int m = min(kTsInflight, qe - q);
+                bool all = true;
+#pragma unroll
+                for (int k = 0; k < kTsInflight; ++k) {
+                    if (k < m && u[k] == kPending) {
+                        u[k] = ld_relaxed_u64(xp + (xo + xm * sc[q + k - as]));
+                        all = all && u[k] != kPending;
+                    }
+                }
+                if (all) {
+#pragma unroll
+                    for (int k = 0; k < kTsInflight; ++k) {
+                        if (k < m) sum = __dadd_rn(sum, __dmul_rn(sv[q + k - as], as_double(u[k])));
+                        u[k] = kPending;
+                    }
+                    q += m;
+                    progress = true;
+                }
+            }
+            if (!__any_sync(kFull, progress)) {
+                ++idle;
+                if (idle > kSpinBudget) ctl.raise(DP_ERR_TIMEOUT), dead = true;
+                if ((idle & 255u) == 0 && ctl.aborted()) dead = true;
+                dead = __any_sync(kFull, dead);
+                if (dead) done = true;
+#if DPCG_TS_SLEEP > 0
+                else __nanosleep(DPCG_TS_SLEEP);
+#endif
+            }
+        }
+        pipe.release(i, j);
+    }
+}
+
+// The whole batch. All kBlock threads of every CTA of a cooperative launch must call. kShort: every system of the
+// batch carries DP_TRSV_SHORT_ROWS (no row with more than kTsFast dependencies; violations raise DP_ERR_STRUCTURE).
+template <bool kShort>
 __device__ __forceinline__ void trsv_tile_stream(const TsSysDev* __restrict__ sys, int nsys, int max_tiles, TsSmem& sm,
                                                  const AbortCtl& ctl) {
     TsPipe pipe;
     pipe.init(&sm);
     const int tid = threadIdx.x;
-    const long long G = gridDim.x;
-    const long long items = (long long)max_tiles * nsys;
-    const long long mine = items > (long long)blockIdx.x ? (items - blockIdx.x + G - 1) / G : 0;
+    const int G = gridDim.x;
+    const int items = max_tiles * nsys;  // < 2^31: checked by the host
+    const int mine = items > (int)blockIdx.x ? (items - (int)blockIdx.x + G - 1) / G : 0;
     bool dead = false;  // the solve was aborted: keep the pipeline moving (every item is acquired and released), solve nothing
-    for (long long j0 = 0; j0 < mine; j0 += kTsRound) {
-        const int cnt = (int)min((long long)kTsRound, mine - j0);
+    for (int j0 = 0; j0 < mine; j0 += kTsRound) {
+        const int cnt = min(kTsRound, mine - j0);
         __syncthreads();  // every warp has consumed every item of the previous round: its table is free
         for (int i = tid; i < cnt; i += kBlock) {
-            const long long g = blockIdx.x + (j0 + i) * G;
+            const long long g = blockIdx.x + (long long)(j0 + i) * G;
             const int s = (int)(g % nsys), t = (int)(g / nsys);
             const TsSysDev S = sys[s];
             TsTile d;
@@ -239,6 +422,7 @@ __device__ __forceinline__ void trsv_tile_stream(const TsSysDev* __restrict__ sy
                 d.rowptr = S.F.rowptr;
                 d.cs = __ldg(S.F.rowptr + min(t * kTileRows, S.F.n));
                 d.ce = __ldg(S.F.rowptr + min((t + 1) * kTileRows, S.F.n));
+                if (kShort && d.ce - d.cs > kTsCap) d.ce = d.cs + kTsCap;  // keeps the tile ONE item; reported by ts_tile_short
             }
             sm.tab[i] = d;
         }
@@ -247,117 +431,10 @@ __device__ __forceinline__ void trsv_tile_stream(const TsSysDev* __restrict__ sy
         for (int i = 0; i < cnt; ++i) {
             const TsTile& d = sm.tab[i];
             if (!d.rowptr) continue;
-            double* xp = d.xp;
-            double* xg = d.x;
-            const bool upper = d.upper != 0;
-            const int cs = d.cs, ce = d.ce;
-            const int r = d.ltile * kTileRows + tid;
-            const bool valid = r < d.n;
-            // where position p lives in xp: p, or n - 1 - p when the caller's vectors are in the REVERSE of this
-            // factor's position order (the backward solve of a system kept in the forward solve's level order)
-            const int xm = d.rev ? -1 : 1, xo = d.rev ? d.n - 1 : 0;
-            int orig = -1, dpos = 0, q = 0, end = 0;
-            double bi = 0.0;
-            bool done = !valid || dead, have_rcp = false;
-            double sum = 0.0, rcp = 0.0;
-            unsigned long long u[kTsInflight];
-#pragma unroll
-            for (int k = 0; k < kTsInflight; ++k) u[k] = kPending;
-            const int nb = (ce - cs + kTsCap - 1) / kTsCap;
-            for (int j = 0; j < nb; ++j) {
-                const int bs = cs + j * kTsCap;
-                const int be = min(ce, bs + kTsCap);
-                const int as = bs & ~3;
-                const unsigned stage = pipe.acquire();
-                const TsStage& st = sm.stage[stage];
-                if (j == 0 && valid) {  // the tile's metadata rides on its first item
-                    const int rs = st.rowptr[tid], re = st.rowptr[tid + 1];
-                    dpos = upper ? rs : re - 1;   // the diagonal's entry (holds 1 / T_ii)
-                    q = upper ? rs + 1 : rs;      // dependencies: entries [q, end)
-                    end = upper ? re : re - 1;
-                    if (d.perm) {
-                        orig = st.perm[tid];
-                        if (!dead) bi = ldcg_here_f64(d.b + orig);
-                    } else {
-                        orig = r;
-                        const int r0 = d.ltile * kTileRows;
-                        bi = d.rev ? st.b[(d.n - 1 - r) - ((d.n - r0 - min(kTileRows, d.n - r0)) & ~1)] : st.b[tid];
-                    }
-                }
-                const double* __restrict__ sv = st.val;
-                const int* __restrict__ sc = st.col;
-                if (!done && !have_rcp && dpos >= bs && dpos < be) rcp = sv[dpos - as], have_rcp = true;
-                const int qe = min(end, be);  // this row's dependencies inside the block: [q, qe) (empty if q >= be)
-                // Straight-line attempt for the common case - the tile is one item, no row of the warp has more than
-                // kTsInflight dependencies and all of them are already solved (always true where the levels are wider
-                // than the batch's window of tiles in flight): one poll per dependency, no loop, ~4x fewer instructions
-                // than the general loop below (the kernel is issue bound before it is HBM bound: profiles/README.md).
-                if (nb == 1 && __all_sync(kFull, done || end - q <= kTsInflight)) {
-                    const int m = done ? 0 : end - q;
-                    bool ready = true;
-#pragma unroll
-                    for (int k = 0; k < kTsInflight; ++k)
-                        if (k < m) u[k] = ld_relaxed_u64(xp + (xo + xm * sc[q + k - as]));
-#pragma unroll
-                    for (int k = 0; k < kTsInflight; ++k)
-                        if (k < m) ready = ready && u[k] != kPending;
-                    if (__all_sync(kFull, ready)) {
-                        if (!done) {
-#pragma unroll
-                            for (int k = 0; k < kTsInflight; ++k)
-                                if (k < m) sum = __dadd_rn(sum, __dmul_rn(sv[q + k - as], as_double(u[k])));
-                            const double xv = __dmul_rn(__dsub_rn(bi, sum), rcp);
-                            st_relaxed_u64(xp + (xo + xm * r), as_bits(xv));
-                            if (xg != xp) xg[orig] = xv;
-                        }
-                        pipe.release(i, j);
-                        continue;
-                    }
-                }
-                unsigned idle = 0;
-                for (;;) {
-                    if (!done && q == end && have_rcp) {  // publish at once: rows of the same warp may wait for it
-                        const double xv = __dmul_rn(__dsub_rn(bi, sum), rcp);
-                        st_relaxed_u64(xp + (xo + xm * r), as_bits(xv));
-                        if (xg != xp) xg[orig] = xv;
-                        done = true;
-                    }
-                    const bool pending = !done && q < qe;
-                    if (!__any_sync(kFull, pending)) break;
-                    bool progress = false;
-                    if (pending) {
-                        const int m = min(kTsInflight, qe - q);
-                        bool all = true;
-#pragma unroll
-                        for (int k = 0; k < kTsInflight; ++k) {
-                            if (k < m && u[k] == kPending) {
-                                u[k] = ld_relaxed_u64(xp + (xo + xm * sc[q + k - as]));
-                                all = all && u[k] != kPending;
-                            }
-                        }
-                        if (all) {
-#pragma unroll
-                            for (int k = 0; k < kTsInflight; ++k) {
-                                if (k < m) sum = __dadd_rn(sum, __dmul_rn(sv[q + k - as], as_double(u[k])));
-                                u[k] = kPending;
-                            }
-                            q += m;
-                            progress = true;
-                        }
-                    }
-                    if (!__any_sync(kFull, progress)) {
-                        ++idle;
-                        if (idle > kSpinBudget) ctl.raise(DP_ERR_TIMEOUT), dead = true;
-                        if ((idle & 255u) == 0 && ctl.aborted()) dead = true;
-                        dead = __any_sync(kFull, dead);
-                        if (dead) done = true;
-#if DPCG_TS_SLEEP > 0
-                        else __nanosleep(DPCG_TS_SLEEP);
-#endif
-                    }
-                }
-                pipe.release(i, j);
-            }
+            if (kShort)
+                ts_tile_short(d, i, sm, pipe, ctl, dead);
+            else
+                ts_tile_general(d, i, sm, pipe, ctl, dead);
         }
     }
     __syncthreads();
@@ -365,7 +442,7 @@ __device__ __forceinline__ void trsv_tile_stream(const TsSysDev* __restrict__ sy
 
 // Host side (sptrsv.cu): arm the polled vectors of a device-resident descriptor array and launch the solve. `word`
 // (8 bytes, zeroed by the caller once) carries the abort bit. No host synchronisation.
-int ts_solve_launch(const TsSysDev* sys_dev, int nsys, int max_tiles, int nmax, unsigned long long* word, int* flag,
-                    cudaStream_t s);
+int ts_solve_launch(const TsSysDev* sys_dev, int nsys, int max_tiles, int nmax, bool short_rows, unsigned long long* word,
+                    int* flag, cudaStream_t s);
 
 }  // namespace dp

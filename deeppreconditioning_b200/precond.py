@@ -51,9 +51,20 @@ class LevelOrdered:
     level_sorted: torch.Tensor  # int32[n]
     nnz: int
     source: int                 # data_ptr of the values it was copied from (a plan may serve several factors)
+    stats: torch.Tensor | None = None  # device int32[3]: most entries in a tile / in a row, largest dependency distance
+    _short: bool | None = None
 
     def matches(self, matrix: CsrMatrix) -> bool:
         return self.source == matrix.val.data_ptr()
+
+    @property
+    def short_rows(self) -> bool:
+        """``DP_TRSV_SHORT_ROWS``: rows short enough for the register path of the tile-stream solve (one read-back per copy)."""
+        if self._short is None:
+            limits = np.zeros(2, np.int32)
+            _lib.lib().dp_sptrsv_ts_limits(limits.ctypes.data)
+            self._short = self.stats is not None and int(self.stats[1].item()) <= int(limits[1])
+        return self._short
 
 
 LS_MAX_MEAN_LEVEL_ROWS = 1024  # level-stream solve when n / nlevels is at most this (one CTA must keep up)
@@ -75,7 +86,8 @@ def _permute(matrix: CsrMatrix, plan: TriangularPlan, perm: torch.Tensor | None 
                                          _lib.ptr(perm), _lib.ptr(plan.level), _lib.ptr(rowptr_p), _lib.ptr(col_p),
                                          _lib.ptr(val_p), _lib.ptr(level_sorted), _lib.ptr(stats), _lib.ptr(ws), ws.numel(),
                                          _lib.stream_ptr(dev)), "dp_sptrsv_permute")
-    copy = LevelOrdered(rowptr_p, col_p[: matrix.nnz], val_p[: matrix.nnz], level_sorted, matrix.nnz, matrix.val.data_ptr())
+    copy = LevelOrdered(rowptr_p, col_p[: matrix.nnz], val_p[: matrix.nnz], level_sorted, matrix.nnz, matrix.val.data_ptr(),
+                        stats)
     return copy, stats
 
 
@@ -211,9 +223,10 @@ def _tile_stream_batch(systems, outs=None, copies=None, position_space=False, re
         d.n, d.nnz, d.upper = n, ls.nnz, int(plan.upper)
         d.rowptr_p, d.col_p, d.val_p = _lib.ptr(ls.rowptr), _lib.ptr(ls.col), _lib.ptr(ls.val)
         d.perm, d.level_sorted, d.b, d.x = _lib.ptr(plan.perm), _lib.ptr(ls.level_sorted), _lib.ptr(b), _lib.ptr(x)
+        d.flags = 2 if ls.short_rows else 0  # DP_TRSV_SHORT_ROWS
         if position_space:
             d.perm = None
-            d.flags = 1 if (reverse is not None and reverse[i]) else 0  # DP_TRSV_REVERSED
+            d.flags |= 1 if (reverse is not None and reverse[i]) else 0  # DP_TRSV_REVERSED
         xs.append(x), keep.append((b, ls))
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
     ws = _workspace(lib.dp_sptrsv_ts_workspace_bytes(descs, nsys), dev)
@@ -447,7 +460,9 @@ class FactoredSolve(FactoredMultiply):
         system.fwd_plan, system.bwd_plan = _lib.ptr(self.fwd.plan), _lib.ptr(self.bwd.plan)
         system.fwd_nchunks, system.bwd_nchunks = self.fwd.nchunks, self.bwd.nchunks
         system.fwd_max_level_chunks, system.bwd_max_level_chunks = self.fwd.max_level_chunks, self.bwd.max_level_chunks
-        system.solve_algorithm = 1 if self.tile_stream else 0  # DP_SOLVE_TILE_STREAM
+        system.solve_algorithm = 0
+        if self.tile_stream:  # DP_SOLVE_TILE_STREAM | DP_SOLVE_SHORT_ROWS
+            system.solve_algorithm = 1 | (2 if (self.fwd_ls.short_rows and self.bwd_ls.short_rows) else 0)
         for tag, plan, ls in (("fwd", self.fwd, self.fwd_ls), ("bwd", self.bwd, self.bwd_ls)):
             if ls is not None:
                 for name, t in (("rowptr", ls.rowptr), ("col", ls.col), ("val", ls.val), ("perm", plan.perm),

@@ -188,6 +188,11 @@ int dp_sptrsv_ls_solve_batch_f64(const dp_trsv_ls_system_t* systems_host, int32_
  * rowptr_p and b (or perm) must be 16-byte aligned like col_p / val_p: their spans travel by bulk copy too.
  * Cooperative launch; *flag_out receives DP_ERR_TIMEOUT if a dependency never arrives. */
 #define DP_TRSV_REVERSED 1
+/* flags & DP_TRSV_SHORT_ROWS: no row of the copy has more entries than dp_sptrsv_ts_limits()[1] (5-/7-point stencil
+ * factors; stats_out[1] of dp_sptrsv_permute). When every system of the batch says so the solve runs a leaner kernel
+ * that finishes rows from registers after handing its pipeline stage back; a violated promise raises DP_ERR_STRUCTURE. */
+#define DP_TRSV_SHORT_ROWS 2
+void dp_sptrsv_ts_limits(int32_t* limits_host /* [2]: entries per pipeline item, row entries of the register path */);
 size_t dp_sptrsv_ts_workspace_bytes(const dp_trsv_ls_system_t* systems_host, int32_t nsys);
 int dp_sptrsv_ts_solve_batch_f64(const dp_trsv_ls_system_t* systems_host, int32_t nsys, int32_t* flag_out, void* workspace,
                                  size_t workspace_bytes, void* stream);
@@ -212,7 +217,7 @@ typedef struct dp_pcg_system {
     int32_t fwd_nchunks, bwd_nchunks;       /* SOLVE: plan sizes */
     int32_t fwd_max_level_chunks, bwd_max_level_chunks;
     int32_t solve_algorithm; /* SOLVE: 0 = level-stream where the copies below are given, else sync-free;
-                              * DP_SOLVE_TILE_STREAM = the tile-stream batch solve (see below) */
+                              * DP_SOLVE_TILE_STREAM (| DP_SOLVE_SHORT_ROWS) = the tile-stream batch solve (see below) */
     const int32_t* a_rowptr; const int32_t* a_col; const double* a_val;     /* A (full symmetric CSR) */
     const int32_t* m_rowptr; const int32_t* m_col; const double* m_val;     /* L (MULTIPLY/SOLVE) or M (CSR) */
     const int32_t* mt_rowptr; const int32_t* mt_col; const double* mt_val;  /* L^T (MULTIPLY/SOLVE) */
@@ -242,6 +247,7 @@ typedef struct dp_pcg_system {
 } dp_pcg_system_t;
 
 #define DP_SOLVE_TILE_STREAM 1
+#define DP_SOLVE_SHORT_ROWS 2 /* with DP_SOLVE_TILE_STREAM: L and L^T keep the DP_TRSV_SHORT_ROWS promise */
 
 typedef struct dp_pcg_params {
     double rtol;          /* cg.py:51 default 1e-8, compared with the SQUARED relative residual */
