@@ -81,7 +81,9 @@ for side in [int(s) for s in a.sides.split(",")]:
             systems = [(m, p, b[plan.perm.long()]) for m, p, b in systems]
         got = precond.triangular_solve_batch(systems, outs, algorithm="ts", copies=copies, position_space=pos)
         torch.cuda.synchronize()
-        if ref is not None:
+        if os.environ.get("DPCG_NO_CHECK"):
+            pass
+        elif ref is not None:
             want = ref[plan.perm.long()] if pos else ref
             assert all(torch.equal(g, want) for g in got), "tile-stream differs from sync-free"
         elif nb > 1:
