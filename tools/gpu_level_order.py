@@ -13,6 +13,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--side", type=int, default=128)
 ap.add_argument("--batch", type=int, default=8)
 ap.add_argument("--kind", default="poisson3d")
+ap.add_argument("--modes", default="natural,level,level_ts")
 a = ap.parse_args()
 
 import numpy as np, torch
@@ -44,8 +45,10 @@ def build(index, level, tile_stream=False):
     return A, b, dp.FactoredSolve(F, None, plan, level_stream=False, tile_stream=tile_stream), order
 
 
-for level, tile_stream in ((False, False), (True, False), (True, True)):
+MODES = {"natural": (False, False), "level": (True, False), "level_ts": (True, True)}
+for level, tile_stream in [MODES[m] for m in a.modes.split(",")]:
     systems, orders = [], []
+    torch.cuda.empty_cache()
     for i in range(a.batch):
         A, b, M, order = build(i, level, tile_stream)
         systems.append((A, b, M)), orders.append(order)
