@@ -825,6 +825,7 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
     int has_multiply = 0, has_solve = 0, has_ls = 0, n_solve = 0, n_ts = 0;
     long long sum_fwd_lvl = 0, sum_bwd_lvl = 0;
     std::vector<TsSysDev> ts_sys[4];
+    std::vector<int> ts_owner;  // system index of each tile-stream descriptor
     bool ts_short = true;
     for (int i = 0; i < nsys; ++i) {
         const dp_pcg_system_t& u = systems_host[i];
@@ -918,6 +919,7 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
                 ts_sys[par].push_back(f);
                 ts_sys[2 + par].push_back(g);
             }
+            ts_owner.push_back(i);
         }
         sys[(size_t)i] = d;
         ident[(size_t)i] = i;
@@ -1000,21 +1002,33 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
     ctx.pw_bwd = clamp_pw(sum_bwd_lvl, coop_phase);
     TsPhases ts_phases{};
     const TsPhases* ts = nullptr;
+    auto ts_upload = [&](const std::vector<int>& keep) -> int {  // descriptors of the systems still iterating
+        std::vector<TsSysDev> act;
+        ts_phases.nsys = (int)keep.size(), ts_phases.max_tiles = 0, ts_phases.nmax = 0;
+        for (int q = 0; q < 4; ++q) {
+            act.clear();
+            for (int idx : keep) act.push_back(ts_sys[q][(size_t)idx]);
+            // pageable source: the call returns once the bytes are staged
+            DP_CUDA(cudaMemcpyAsync(ws + lay.ts_sys[q], act.data(), sizeof(TsSysDev) * act.size(), cudaMemcpyHostToDevice, s));
+        }
+        for (int idx : keep) {
+            const TsSysDev& f = ts_sys[0][(size_t)idx];
+            if (f.ntiles > ts_phases.max_tiles) ts_phases.max_tiles = f.ntiles;
+            if (f.F.n > ts_phases.nmax) ts_phases.nmax = f.F.n;
+        }
+        return DP_OK;
+    };
+    std::vector<int> ts_keep;
     if (n_ts) {
         DP_CUDA(cudaMemsetAsync(ws + lay.ts_word, 0, 8, s));
-        for (int i = 0; i < 4; ++i)
-            DP_CUDA(cudaMemcpyAsync(ws + lay.ts_sys[i], ts_sys[i].data(), sizeof(TsSysDev) * (size_t)n_ts, cudaMemcpyHostToDevice, s));
+        for (int q = 0; q < n_ts; ++q) ts_keep.push_back(q);
+        if (ts_upload(ts_keep) != DP_OK) return DP_ERR_CUDA;
         for (int par = 0; par < 2; ++par) {
             ts_phases.fwd[par] = reinterpret_cast<const TsSysDev*>(ws + lay.ts_sys[par]);
             ts_phases.bwd[par] = reinterpret_cast<const TsSysDev*>(ws + lay.ts_sys[2 + par]);
         }
-        ts_phases.nsys = n_ts;
         ts_phases.short_rows = ts_short;
         ts_phases.word = reinterpret_cast<unsigned long long*>(ws + lay.ts_word);
-        for (const TsSysDev& f : ts_sys[0]) {
-            if (f.ntiles > ts_phases.max_tiles) ts_phases.max_tiles = f.ntiles;
-            if (f.F.n > ts_phases.nmax) ts_phases.nmax = f.F.n;
-        }
         ts = &ts_phases;
     }
     const int tile_grid = ctx.total_tiles < coop * 4 ? ctx.total_tiles : coop * 4;
@@ -1029,6 +1043,18 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
             DP_CUDA(cudaMemcpyAsync(&done, ctx.n_done, sizeof(int), cudaMemcpyDeviceToHost, s));
             DP_CUDA(cudaStreamSynchronize(s));
             if (done >= nsys) break;
+            if (ts && done > nsys - (int)ts_keep.size()) {  // some systems finished: stop solving them along
+                std::vector<int> state((size_t)nsys);
+                DP_CUDA(cudaMemcpyAsync(state.data(), ctx.state, sizeof(int) * (size_t)nsys, cudaMemcpyDeviceToHost, s));
+                DP_CUDA(cudaStreamSynchronize(s));
+                std::vector<int> keep;
+                for (int idx : ts_keep)
+                    if (state[(size_t)ts_owner[(size_t)idx]] == 0) keep.push_back(idx);
+                if (!keep.empty() && keep.size() < ts_keep.size()) {
+                    ts_keep.swap(keep);
+                    if (ts_upload(ts_keep) != DP_OK) return DP_ERR_CUDA;
+                }
+            }
         }
         if ((st = launch_apply<false>(ctx, k, tile_grid, coop_phase, ts, s)) != DP_OK) return st;
     }

@@ -289,6 +289,26 @@ def test_level_ordered_system_is_the_same_solve(cuda, kind, side):
     assert torch.linalg.vector_norm(x_l - ref.x_hat) <= tol * torch.linalg.vector_norm(ref.x_hat)
 
 
+def test_pcg_tile_stream_batch_drops_finished_systems(cuda):
+    """Stepped engine with tile-stream solves on a ragged batch of level-ordered systems that converge at different
+    iterations, polled every iteration: systems that finished are dropped from the batch solves, and every system is
+    bitwise its own single solve (fused engine, sync-free solves)."""
+    systems, singles = [], []
+    for kind, side, seed in [("poisson3d", 14, 0), ("poisson3d", 6, 1), ("poisson2d", 40, 2), ("poisson3d", 10, 3)]:
+        p = helpers.problem(kind, side, seed, 0.5, None)
+        st = helpers.to_device(p.systems_tril, cuda)
+        order = precond.level_ordering(CsrMatrix.from_spconv(st, p.n, "tril"))
+        st_l = order.renumber(st)
+        A_l, T_l = CsrMatrix.from_spconv(st_l, p.n, "symmetrise"), CsrMatrix.from_spconv(st_l, p.n, "tril")
+        F_l = precond.incomplete_cholesky0(T_l)
+        b_l = order.to_level(p.b.to(cuda))
+        systems.append((A_l, b_l, dp.FactoredSolve(F_l, tile_stream=True)))
+        singles.append(dp.pcg_solve(A_l, b_l, dp.FactoredSolve(F_l, level_stream=False), max_iter=3000))
+    assert len({r.iterations for r in singles}) > 1, "the batch must be ragged in iterations for this test to bite"
+    for got, want in zip(dp.pcg_solve_batch(systems, max_iter=3000, check_every=1), singles):
+        assert got.iterations == want.iterations and got.res == want.res and torch.equal(got.x_hat, want.x_hat)
+
+
 def test_level_stream_eligibility(cuda):
     """Factors the level-stream solve cannot take (a dependency further back than its shared-memory window, rows too
     long for registers, tiles larger than a pipeline stage) are refused at analysis and solved sync-free; a chain of

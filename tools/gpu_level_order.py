@@ -14,6 +14,7 @@ ap.add_argument("--side", type=int, default=128)
 ap.add_argument("--batch", type=int, default=8)
 ap.add_argument("--kind", default="poisson3d")
 ap.add_argument("--modes", default="natural,level,level_ts")
+ap.add_argument("--max-iter", type=int, default=0, help="cap the iterations (profiling runs)")
 a = ap.parse_args()
 
 import numpy as np, torch
@@ -54,7 +55,7 @@ for level, tile_stream in [MODES[m] for m in a.modes.split(",")]:
         systems.append((A, b, M)), orders.append(order)
     n, nnz_a, nnz_l = systems[0][0].n, systems[0][0].nnz, systems[0][2].L.nnz
     for nb in sorted({1, a.batch}):
-        batch = dp.PcgBatch(systems[:nb], bench.RTOL, bench.MAX_ITER)
+        batch = dp.PcgBatch(systems[:nb], bench.RTOL, a.max_iter or bench.MAX_ITER)
         best = float("inf")
         for _ in range(2):
             batch.reset()
