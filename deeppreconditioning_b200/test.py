@@ -26,7 +26,7 @@ import numpy as np
 import torch
 
 from .cg import PcgBatch
-from .precond import FactoredMultiply, FactoredSolve, Identity, Jacobi, incomplete_cholesky0
+from .precond import FactoredMultiply, FactoredSolve, Identity, Jacobi, incomplete_cholesky0, level_ordering
 from .sparse import CsrMatrix
 
 RESULTS_DIRECTORY: Path = Path("./assets/results/")
@@ -46,6 +46,7 @@ class BenchmarkSuite:
     techniques: tuple[str, ...] = ("vanilla", "jacobi", "incomplete_cholesky", "learned")
     rtol: float = 1e-8       # cg.py:51
     max_iter: int = 1024     # cg.py:51
+    level_order_ic: bool = False  # solve the IC(0) comparator on the system renumbered by the factor's level sets
     kappas: dict = field(default_factory=dict)
     densities: dict = field(default_factory=dict)
     iterations: dict = field(default_factory=dict)
@@ -132,8 +133,22 @@ class BenchmarkSuite:
                 torch.cuda.synchronize()
                 setup = time.perf_counter() - start_time if name != "vanilla" else 0.0  # test.py:135
 
+                system, b_sys = matrix, rhs
+                if name == "incomplete_cholesky" and self.level_order_ic:
+                    # same solve, rows renumbered so that a level of the factor is a contiguous run (precond.LevelOrdering):
+                    # the triangular solves read the factor and the vectors coalesced. Counted as set-up time.
+                    torch.cuda.synchronize()
+                    start_time = time.perf_counter()
+                    order = level_ordering(self._current_tril)
+                    renumbered = order.renumber(system_tril)
+                    system = CsrMatrix.from_spconv(renumbered, n, mode="symmetrise")
+                    preconditioner = FactoredSolve(incomplete_cholesky0(CsrMatrix.from_spconv(renumbered, n, mode="tril")))
+                    b_sys = order.to_level(rhs)
+                    torch.cuda.synchronize()
+                    setup += time.perf_counter() - start_time
+
                 density = self._compute_sparsity(preconditioner)
-                batch = PcgBatch([(matrix, rhs, preconditioner)], self.rtol, self.max_iter, history=True)
+                batch = PcgBatch([(system, b_sys, preconditioner)], self.rtol, self.max_iter, history=True)
                 torch.cuda.synchronize()
                 start_time = time.perf_counter()
                 batch.solve()

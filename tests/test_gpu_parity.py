@@ -582,6 +582,12 @@ def test_benchmark_suite_end_to_end(cuda, tmp_path):
     # density column: explicit nnz(M)/n^2 like test.py:107-109
     n = 24 * 24
     assert suite.densities["vanilla"][0] == pytest.approx(100 / n) and suite.densities["learned"][0] > suite.densities["incomplete_cholesky"][0]
+    # the IC(0) comparator on the level-ordered system: the same iteration (counts +-1, density unchanged)
+    ordered = BenchmarkSuite(data, net, techniques=("incomplete_cholesky",), max_iter=5000, level_order_ic=True)
+    ordered.run()
+    for got, want in zip(ordered.iterations["incomplete_cholesky"], suite.iterations["incomplete_cholesky"]):
+        assert abs(got - want) <= 1
+    assert ordered.densities["incomplete_cholesky"] == pytest.approx(suite.densities["incomplete_cholesky"])
 
 
 def test_benchmark_suite_on_the_reference_disk_layout(cuda, tmp_path):
