@@ -51,6 +51,12 @@
 #ifndef DPCG_TS_SLEEP
 #define DPCG_TS_SLEEP 32
 #endif
+#ifndef DPCG_TS_TWO_POLLS
+#define DPCG_TS_TWO_POLLS 0
+#endif
+#ifndef DPCG_TS_HALF_TRIP
+#define DPCG_TS_HALF_TRIP 200
+#endif
 #ifndef DPCG_TS_ROUND
 #define DPCG_TS_ROUND 96
 #endif
@@ -272,38 +278,66 @@ __device__ __forceinline__ void ts_tile_short(const TsTile& d, int i, TsSmem& sm
         u[k] = 0ull;
         if (!done && k < m) u[k] = ld_relaxed_u64(xp + c[k]);
     }
-    unsigned idle = 0;
-    for (;;) {
-        if (!done) {
-            bool ready = true;
+    // finish the row from one snapshot of its dependencies; publishes at once (rows of the same warp may wait for it)
+    auto try_finish = [&](const unsigned long long (&w)[kTsFast]) {
+        bool ready = true;
 #pragma unroll
-            for (int k = 0; k < kTsFast; ++k) ready = ready && (k >= m || u[k] != kPending);
-            if (ready) {  // publish at once: rows of the same warp may wait for it
-                double sum = 0.0;
-#pragma unroll
-                for (int k = 0; k < kTsFast; ++k)
-                    if (k < m) sum = __dadd_rn(sum, __dmul_rn(v[k], as_double(u[k])));
-                const double xv = __dmul_rn(__dsub_rn(bi, sum), rcp);
-                st_relaxed_u64(xp + (xo + xm * r), as_bits(xv));
-                if (xg != xp) xg[orig] = xv;
-                done = true;
-            }
-        }
-        if (__all_sync(kFull, done)) break;
-        if (!done) {
+        for (int k = 0; k < kTsFast; ++k) ready = ready && (k >= m || w[k] != kPending);
+        if (ready) {
+            double sum = 0.0;
 #pragma unroll
             for (int k = 0; k < kTsFast; ++k)
-                if (k < m && u[k] == kPending) u[k] = ld_relaxed_u64(xp + c[k]);
+                if (k < m) sum = __dadd_rn(sum, __dmul_rn(v[k], as_double(w[k])));
+            const double xv = __dmul_rn(__dsub_rn(bi, sum), rcp);
+            st_relaxed_u64(xp + (xo + xm * r), as_bits(xv));
+            if (xg != xp) xg[orig] = xv;
+            done = true;
         }
+    };
+    auto repoll = [&](unsigned long long (&w)[kTsFast]) {
+#pragma unroll
+        for (int k = 0; k < kTsFast; ++k)
+            if (k < m && w[k] == kPending) w[k] = ld_relaxed_u64(xp + c[k]);
+    };
+    if (!done) try_finish(u);
+    if (__all_sync(kFull, done)) return;  // the streaming regime: every dependency was solved long ago
+#if DPCG_TS_TWO_POLLS
+    // Waiting for a level: keep TWO polls per dependency in flight, half an L2 round trip apart (the first sleep sets the
+    // phase, after that each wait returns when its own set does), so a store is seen on average a quarter of a round
+    // trip after it lands instead of half - the level-by-level critical path of a narrow level is made of these.
+    unsigned long long w[kTsFast];
+#pragma unroll
+    for (int k = 0; k < kTsFast; ++k) w[k] = u[k];
+    if (!done) repoll(u);
+    __nanosleep(DPCG_TS_HALF_TRIP);
+    for (unsigned idle = 0;;) {
+        if (!done) repoll(w);
+        if (!done) try_finish(u);
+        if (__all_sync(kFull, done)) break;
+        if (!done) repoll(u);
+        if (!done) try_finish(w);
+        if (__all_sync(kFull, done)) break;
+        ++idle;
+        if (idle > kSpinBudget) ctl.raise(DP_ERR_TIMEOUT), dead = true;
+        if ((idle & 255u) == 0 && ctl.aborted()) dead = true;
+        dead = __any_sync(kFull, dead);
+        if (dead) done = true;
+    }
+#else
+    for (unsigned idle = 0;;) {
+        if (!done) repoll(u);
+        if (!done) try_finish(u);
+        if (__all_sync(kFull, done)) break;
         ++idle;
         if (idle > kSpinBudget) ctl.raise(DP_ERR_TIMEOUT), dead = true;
         if ((idle & 255u) == 0 && ctl.aborted()) dead = true;
         dead = __any_sync(kFull, dead);
         if (dead) done = true;
 #if DPCG_TS_SLEEP > 0
-        else if (idle > 1) __nanosleep(DPCG_TS_SLEEP);
+        else __nanosleep(DPCG_TS_SLEEP);
 #endif
     }
+#endif
 }
 
 // One tile of any shape: rows of any length, tiles of several pipeline items, rows cut by an item boundary.
