@@ -51,12 +51,6 @@
 #ifndef DPCG_TS_SLEEP
 #define DPCG_TS_SLEEP 32
 #endif
-#ifndef DPCG_TS_TWO_POLLS
-#define DPCG_TS_TWO_POLLS 0
-#endif
-#ifndef DPCG_TS_HALF_TRIP
-#define DPCG_TS_HALF_TRIP 200
-#endif
 #ifndef DPCG_TS_ROUND
 #define DPCG_TS_ROUND 96
 #endif
@@ -301,29 +295,8 @@ __device__ __forceinline__ void ts_tile_short(const TsTile& d, int i, TsSmem& sm
     };
     if (!done) try_finish(u);
     if (__all_sync(kFull, done)) return;  // the streaming regime: every dependency was solved long ago
-#if DPCG_TS_TWO_POLLS
-    // Waiting for a level: keep TWO polls per dependency in flight, half an L2 round trip apart (the first sleep sets the
-    // phase, after that each wait returns when its own set does), so a store is seen on average a quarter of a round
-    // trip after it lands instead of half - the level-by-level critical path of a narrow level is made of these.
-    unsigned long long w[kTsFast];
-#pragma unroll
-    for (int k = 0; k < kTsFast; ++k) w[k] = u[k];
-    if (!done) repoll(u);
-    __nanosleep(DPCG_TS_HALF_TRIP);
-    for (unsigned idle = 0;;) {
-        if (!done) repoll(w);
-        if (!done) try_finish(u);
-        if (__all_sync(kFull, done)) break;
-        if (!done) repoll(u);
-        if (!done) try_finish(w);
-        if (__all_sync(kFull, done)) break;
-        ++idle;
-        if (idle > kSpinBudget) ctl.raise(DP_ERR_TIMEOUT), dead = true;
-        if ((idle & 255u) == 0 && ctl.aborted()) dead = true;
-        dead = __any_sync(kFull, dead);
-        if (dead) done = true;
-    }
-#else
+    // Waiting for a level: one poll per dependency in flight. Two polls half a round trip apart were measured SLOWER
+    // (0.97 -> 1.05 us per level, profiles/r1/ts_two_polls_negative.log): the L2 traffic of the pollers is part of the hop.
     for (unsigned idle = 0;;) {
         if (!done) repoll(u);
         if (!done) try_finish(u);
@@ -337,7 +310,6 @@ __device__ __forceinline__ void ts_tile_short(const TsTile& d, int i, TsSmem& sm
         else __nanosleep(DPCG_TS_SLEEP);
 #endif
     }
-#endif
 }
 
 // One tile of any shape: rows of any length, tiles of several pipeline items, rows cut by an item boundary.
