@@ -80,6 +80,7 @@ struct Ctx {
     int nsys, total_tiles, total_fwd, total_bwd;
     int pw_fwd, pw_bwd;
     int has_multiply, has_solve, has_ls;
+    int rearm_t;  // tile-stream solves (stepped engine): PH_DOTRZ re-arms y for the next forward solve
     double rtol;
     int max_iter;
     unsigned long long* word;  // grid barrier (+ finished count in the upper half)
@@ -405,6 +406,8 @@ __device__ __forceinline__ void phase_dotrz(const Ctx& ctx, const SysDev& S, con
     if (row < S.n) {
         rn = S.r[(k + 1) & 1][row];
         zi = S.z[(k + 1) & 1][row];
+        // the tile-stream backward solve reads y by bulk copy and cannot re-arm it on the way like the sync-free one
+        if (ctx.rearm_t) st_relaxed_u64(S.t + row, kPending);
     }
     double v[2] = {__dmul_rn(rn, zi), __dmul_rn(zi, zi)};
     tile_reduce<2>(v, sm.scratch, pipe);
@@ -762,8 +765,10 @@ static int launch_apply(const Ctx& ctx, int k, int tile_grid, int coop, const Ts
     if (ctx.has_solve) {
         if (ts) {  // finished systems are solved along (their vectors are scratch by then): no host round trip
             const int par = (k + 1) & 1;
-            if ((st = ts_solve_launch(ts->fwd[par], ts->nsys, ts->max_tiles, ts->nmax, ts->short_rows, ts->word, ctx.flag, s)) != DP_OK) return st;
-            if ((st = ts_solve_launch(ts->bwd[par], ts->nsys, ts->max_tiles, ts->nmax, ts->short_rows, ts->word, ctx.flag, s)) != DP_OK) return st;
+            // no arming launches: y is armed by PH_INIT and re-armed by PH_DOTRZ, z_new by APPLY1 (the lines the sync-free
+            // solves rely on as well)
+            if ((st = ts_solve_launch(ts->fwd[par], ts->nsys, ts->max_tiles, ts->nmax, ts->short_rows, false, ts->word, ctx.flag, s)) != DP_OK) return st;
+            if ((st = ts_solve_launch(ts->bwd[par], ts->nsys, ts->max_tiles, ts->nmax, ts->short_rows, false, ts->word, ctx.flag, s)) != DP_OK) return st;
         } else {
             if ((st = launch_phase<PH_FWD, kInit>(ctx, k, coop, true, s)) != DP_OK) return st;
             if ((st = launch_phase<PH_BWD, kInit>(ctx, k, coop, true, s)) != DP_OK) return st;
@@ -958,6 +963,7 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
     ctx.has_multiply = has_multiply;
     ctx.has_solve = has_solve;
     ctx.has_ls = has_ls;
+    ctx.rearm_t = n_ts ? 1 : 0;
     ctx.rtol = params_host->rtol;
     ctx.max_iter = params_host->max_iter;
     ctx.word = reinterpret_cast<unsigned long long*>(ws + lay.word);

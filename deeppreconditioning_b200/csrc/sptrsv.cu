@@ -208,11 +208,13 @@ static int participating_warps(int max_level_chunks, int grid) {
     return pw > w ? w : (int)pw;
 }
 
-int ts_solve_launch(const TsSysDev* sys_dev, int nsys, int max_tiles, int nmax, bool short_rows, unsigned long long* word,
-                    int* flag, cudaStream_t s) {
-    const int fill_x = (nmax + 255) / 256 < sm_count() * 4 ? (nmax + 255) / 256 : sm_count() * 4;
-    arm_positions_kernel<<<dim3(fill_x, nsys < 1024 ? nsys : 1024), 256, 0, s>>>(sys_dev, nsys);
-    DP_LAUNCH_CHECK();
+int ts_solve_launch(const TsSysDev* sys_dev, int nsys, int max_tiles, int nmax, bool short_rows, bool arm,
+                    unsigned long long* word, int* flag, cudaStream_t s) {
+    if (arm) {
+        const int fill_x = (nmax + 255) / 256 < sm_count() * 4 ? (nmax + 255) / 256 : sm_count() * 4;
+        arm_positions_kernel<<<dim3(fill_x, nsys < 1024 ? nsys : 1024), 256, 0, s>>>(sys_dev, nsys);
+        DP_LAUNCH_CHECK();
+    }
     const void* kernel = short_rows ? (const void*)sptrsv_ts_batch_kernel<true> : (const void*)sptrsv_ts_batch_kernel<false>;
     static thread_local int resident_of[2] = {0, 0};
     int& resident = resident_of[short_rows ? 1 : 0];
@@ -410,7 +412,7 @@ int dp_sptrsv_ts_solve_batch_f64(const dp_trsv_ls_system_t* systems_host, int32_
     DP_CUDA(cudaMemsetAsync(word, 0, sizeof(unsigned long long), s));
     // pageable source: the call returns once the bytes are staged, `dev` may go out of scope
     DP_CUDA(cudaMemcpyAsync(sys, dev.data(), sizeof(TsSysDev) * (size_t)nsys, cudaMemcpyHostToDevice, s));
-    return ts_solve_launch(sys, nsys, max_tiles, nmax, short_rows, word, flag_out, s);
+    return ts_solve_launch(sys, nsys, max_tiles, nmax, short_rows, true, word, flag_out, s);
 }
 
 int dp_ic0_f64(int32_t n, const int32_t* rowptr, const int32_t* col, const double* a_val, double* l_val,

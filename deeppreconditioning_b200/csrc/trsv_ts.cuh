@@ -446,9 +446,10 @@ __device__ __forceinline__ void trsv_tile_stream(const TsSysDev* __restrict__ sy
     __syncthreads();
 }
 
-// Host side (sptrsv.cu): arm the polled vectors of a device-resident descriptor array and launch the solve. `word`
-// (8 bytes, zeroed by the caller once) carries the abort bit. No host synchronisation.
-int ts_solve_launch(const TsSysDev* sys_dev, int nsys, int max_tiles, int nmax, bool short_rows, unsigned long long* word,
-                    int* flag, cudaStream_t s);
+// Host side (sptrsv.cu): arm the polled vectors of a device-resident descriptor array (`arm`; a caller whose own
+// kernels leave them armed passes false) and launch the solve. `word` (8 bytes, zeroed by the caller once) carries the
+// abort bit. No host synchronisation.
+int ts_solve_launch(const TsSysDev* sys_dev, int nsys, int max_tiles, int nmax, bool short_rows, bool arm,
+                    unsigned long long* word, int* flag, cudaStream_t s);
 
 }  // namespace dp
