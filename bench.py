@@ -499,7 +499,17 @@ def extras(device, host0):
             gbs = iter_bytes(n8, A8.nnz, T8.nnz) * sum(its) / ms / 1e6
             pcg8[key] = {"ms_to_tol": ms, "iterations": its, "us_per_iteration": 1e3 * ms / max(its),
                          "algorithmic_gbs": gbs, "frac_of_hbm_peak": gbs / peak}
-            del batch8, systems8
+            del batch8
+            batch1 = dp.PcgBatch(systems8[:1], RTOL, MAX_ITER)  # config 4 in this form: one 128^3 system
+
+            def go1():
+                batch1.reset()
+                batch1.solve()
+
+            ms1 = timed(go1, reps=2)
+            it1 = batch1.results()[0].iterations
+            pcg8[key]["single_system"] = {"ms_to_tol": ms1, "iterations": it1, "us_per_iteration": 1e3 * ms1 / max(it1, 1)}
+            del batch1, systems8
             torch.cuda.empty_cache()
         out["pcg_ic0_batch8_128^3"] = pcg8
     except Exception as exc:
