@@ -918,9 +918,9 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
             for (int par = 0; par < 2; ++par) {
                 TsSysDev f{}, g{};
                 f.F = LsFactor{u.fwd_ls_rowptr, u.fwd_ls_col, u.fwd_ls_val, nullptr, nullptr, u.n, u.m_nnz};
-                f.b = d.r[par], f.x = d.t, f.xp = d.t, f.upper = 0, f.ntiles = d.ntiles, f.rev = 0;
+                f.b = d.r[par], f.x = d.t, f.upper = 0, f.ntiles = d.ntiles, f.rev = 0;
                 g.F = LsFactor{u.bwd_ls_rowptr, u.bwd_ls_col, u.bwd_ls_val, nullptr, nullptr, u.n, u.mt_nnz};
-                g.b = d.t, g.x = d.z[par], g.xp = d.z[par], g.upper = 1, g.ntiles = d.ntiles, g.rev = 1;
+                g.b = d.t, g.x = d.z[par], g.upper = 1, g.ntiles = d.ntiles, g.rev = 1;
                 ts_sys[par].push_back(f);
                 ts_sys[2 + par].push_back(g);
             }

@@ -105,9 +105,37 @@ __global__ void __launch_bounds__(kBlock, 1) sptrsv_ls_batch_kernel(const LsSysD
 // ---- tile-stream solve (trsv_ts.cuh): the tiles of all systems in one sequence, dealt to persistent CTAs ---------
 __global__ void arm_positions_kernel(const TsSysDev* __restrict__ sys, int nsys) {
     for (int s = blockIdx.y; s < nsys; s += gridDim.y) {
-        unsigned long long* xp = reinterpret_cast<unsigned long long*>(sys[s].xp);
+        unsigned long long* x = reinterpret_cast<unsigned long long*>(sys[s].x);
         const int n = sys[s].F.n;
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) xp[i] = kPending;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) x[i] = kPending;
+    }
+}
+
+// Vectors in the ORIGINAL numbering: b_pos = b[perm] before the solve, x[perm] = x_pos after it, in passes of their own
+// and one system after the other (blockIdx.y would interleave the systems: the point is that the 4 consecutive levels
+// which share a sector of b / x stay in L2 between their visits - true for one system's fronts, not for a batch's).
+struct TsPermDev {
+    const int* perm;
+    const double* b;  // original numbering
+    double* x;        // original numbering
+    double* b_pos;    // workspace
+    double* x_pos;    // workspace
+    int n, pad;
+};
+// (One row per thread and step: eight rows in flight per thread, a grid stride apart, were measured 40 % SLOWER -
+// neighbouring positions of a level are neighbouring rows of a plane, and the unrolled form visits them far apart.)
+__global__ void ts_gather_kernel(const TsPermDev* __restrict__ sys, int nsys) {
+    for (int s = 0; s < nsys; ++s) {
+        const TsPermDev S = sys[s];
+        for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < S.n; p += gridDim.x * blockDim.x)
+            S.b_pos[p] = __ldg(S.b + __ldg(S.perm + p));
+    }
+}
+__global__ void ts_scatter_kernel(const TsPermDev* __restrict__ sys, int nsys) {
+    for (int s = 0; s < nsys; ++s) {
+        const TsPermDev S = sys[s];
+        for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < S.n; p += gridDim.x * blockDim.x)
+            S.x[__ldg(S.perm + p)] = S.x_pos[p];
     }
 }
 
@@ -368,9 +396,9 @@ void dp_sptrsv_ts_limits(int32_t* limits_host) {
 }
 
 size_t dp_sptrsv_ts_workspace_bytes(const dp_trsv_ls_system_t* systems_host, int32_t nsys) {
-    size_t bytes = ts_header_bytes(nsys);
-    for (int i = 0; systems_host && i < nsys; ++i)
-        if (systems_host[i].perm) bytes += align_up(sizeof(double) * (size_t)(systems_host[i].n > 0 ? systems_host[i].n : 0), 256);
+    size_t bytes = ts_header_bytes(nsys) + align_up(sizeof(TsPermDev) * (size_t)(nsys > 0 ? nsys : 0), 256);
+    for (int i = 0; systems_host && i < nsys; ++i)  // b_pos and x_pos of the systems that come in the original numbering
+        if (systems_host[i].perm) bytes += 2 * align_up(sizeof(double) * (size_t)(systems_host[i].n > 0 ? systems_host[i].n : 0), 256);
     return bytes;
 }
 
@@ -384,25 +412,29 @@ int dp_sptrsv_ts_solve_batch_f64(const dp_trsv_ls_system_t* systems_host, int32_
     unsigned long long* word = reinterpret_cast<unsigned long long*>(ws);
     TsSysDev* sys = reinterpret_cast<TsSysDev*>(ws + 256);
     size_t off = ts_header_bytes(nsys);
+    TsPermDev* perm_sys = reinterpret_cast<TsPermDev*>(ws + off);
+    off += align_up(sizeof(TsPermDev) * (size_t)nsys, 256);
     std::vector<TsSysDev> dev((size_t)nsys);
+    std::vector<TsPermDev> perms;
     int max_tiles = 0, nmax = 0;
     bool short_rows = true;
     for (int i = 0; i < nsys; ++i) {
         const dp_trsv_ls_system_t& u = systems_host[i];
         if (u.n <= 0 || !u.rowptr_p || !u.col_p || !u.val_p || !u.b || !u.x || u.b == u.x) return DP_ERR_INVALID;
         short_rows = short_rows && (u.flags & DP_TRSV_SHORT_ROWS) != 0;
-        if (!aligned16(u.col_p) || !aligned16(u.val_p) || !aligned16(u.rowptr_p) || !aligned16(u.perm ? (const void*)u.perm : (const void*)u.b))
+        if (!aligned16(u.col_p) || !aligned16(u.val_p) || !aligned16(u.rowptr_p) || (!u.perm && !aligned16(u.b)))
             return DP_ERR_ALIGNMENT;  // spans of all four arrays are moved by 16-byte granular bulk copies
         TsSysDev d{};
-        d.F = LsFactor{u.rowptr_p, u.col_p, u.val_p, u.perm, u.level_sorted, u.n, u.nnz};
+        d.F = LsFactor{u.rowptr_p, u.col_p, u.val_p, nullptr, nullptr, u.n, u.nnz};
         d.b = u.b, d.x = u.x, d.upper = u.upper ? 1 : 0;
         d.rev = (u.flags & DP_TRSV_REVERSED) ? 1 : 0;
         if (d.rev && u.perm) return DP_ERR_INVALID;  // reversed positions are a form of position space
-        if (u.perm) {
-            d.xp = reinterpret_cast<double*>(ws + off);
-            off += align_up(sizeof(double) * (size_t)u.n, 256);
-        } else {
-            d.xp = u.x;  // position space: the solution vector is the polled vector
+        if (u.perm) {  // original numbering: the solve runs on position-space copies in the workspace
+            const size_t vec = align_up(sizeof(double) * (size_t)u.n, 256);
+            TsPermDev g{u.perm, u.b, u.x, reinterpret_cast<double*>(ws + off), reinterpret_cast<double*>(ws + off + vec), u.n, 0};
+            off += 2 * vec;
+            d.b = g.b_pos, d.x = g.x_pos;
+            perms.push_back(g);
         }
         d.ntiles = (u.n + kTileRows - 1) / kTileRows;
         if (d.ntiles > max_tiles) max_tiles = d.ntiles;
@@ -410,9 +442,22 @@ int dp_sptrsv_ts_solve_batch_f64(const dp_trsv_ls_system_t* systems_host, int32_
         dev[(size_t)i] = d;
     }
     DP_CUDA(cudaMemsetAsync(word, 0, sizeof(unsigned long long), s));
-    // pageable source: the call returns once the bytes are staged, `dev` may go out of scope
+    // pageable sources: the calls return once the bytes are staged, the vectors may go out of scope
     DP_CUDA(cudaMemcpyAsync(sys, dev.data(), sizeof(TsSysDev) * (size_t)nsys, cudaMemcpyHostToDevice, s));
-    return ts_solve_launch(sys, nsys, max_tiles, nmax, short_rows, true, word, flag_out, s);
+    const int np = (int)perms.size();
+    const int pass_grid = (nmax + 255) / 256 < sm_count() * 8 ? (nmax + 255) / 256 : sm_count() * 8;
+    if (np) {
+        DP_CUDA(cudaMemcpyAsync(perm_sys, perms.data(), sizeof(TsPermDev) * (size_t)np, cudaMemcpyHostToDevice, s));
+        ts_gather_kernel<<<pass_grid, 256, 0, s>>>(perm_sys, np);
+        DP_LAUNCH_CHECK();
+    }
+    const int st = ts_solve_launch(sys, nsys, max_tiles, nmax, short_rows, true, word, flag_out, s);
+    if (st != DP_OK) return st;
+    if (np) {
+        ts_scatter_kernel<<<pass_grid, 256, 0, s>>>(perm_sys, np);
+        DP_LAUNCH_CHECK();
+    }
+    return DP_OK;
 }
 
 int dp_ic0_f64(int32_t n, const int32_t* rowptr, const int32_t* col, const double* a_val, double* l_val,

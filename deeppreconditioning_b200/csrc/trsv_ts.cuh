@@ -24,14 +24,16 @@
 //   * with levels wider than the window of tiles in flight (G / nsys tiles per system) a tile's dependencies were
 //     solved long before it starts: no waiting at all, the solve streams at SpMV speed. Narrow levels (the corners
 //     of the diagonal sweep) pay one L2 hop per level, shared by all systems of the batch.
-// Everything a tile needs that is contiguous travels with its first pipeline item: the 513 row pointers, and either
-// the 512 right-hand sides (position space) or the 512 entries of perm. Nothing is prefetched through registers, so
-// the only latency a warp sees per tile is the poll of its dependencies (measured before this: the row extents
-// fetched one tile ahead through registers cost a DRAM latency per tile, 3 us per tile and CTA, 0.52 of peak).
-// The solution is also scattered to the original numbering (x[perm[r]]). A caller that keeps its vectors in LEVEL
-// ORDER (perm == nullptr: b and x are indexed by position, x doubles as the polled vector) saves the gather of b and
-// the scatter of x, whose sectors are shared by rows of 4 consecutive levels and only survive in L2 while the
-// batch's level fronts are small (measured: 8 x 256^3 0.30 of peak with perm, 0.49 in position space).
+// Everything a tile needs that is contiguous travels with its first pipeline item: the 513 row pointers and the 512
+// right-hand sides. Nothing is prefetched through registers, so the only latency a warp sees per tile is the poll of
+// its dependencies (measured before this: the row extents fetched one tile ahead through registers cost a DRAM
+// latency per tile, 3 us per tile and CTA, 0.52 of peak).
+// The kernel works in POSITION SPACE only: b and x are indexed by position, x doubles as the polled vector. A caller
+// that keeps its vectors in level order (dp_trsv_ls_system_t.perm == NULL, precond.LevelOrdering) gets exactly that.
+// For vectors in the original numbering the host side (sptrsv.cu) brackets the solve with a gather b_pos = b[perm]
+// and a scatter x[perm] = x_pos, one system after the other: a row's b / x sector is shared by rows of 4 consecutive
+// levels, which survives in L2 inside one system's pass but not inside the batch solve, where the level fronts of all
+// systems compete for it (measured with the gather/scatter inside the solve: 8 x 256^3 0.30 of peak against 0.49).
 // REVERSED position space (rev): position p is row n - 1 - p of b and x. This is the backward solve (L^T) of a system
 // that is kept in the level order of its FORWARD solve: walking its rows from the last to the first is a valid order
 // for L^T (every dependency of row i is a row j > i), and a row's dependencies sit one forward level further on, as
@@ -81,12 +83,11 @@ __device__ __forceinline__ bool mbar_try_wait_hint(unsigned long long* bar, unsi
 }
 
 struct TsSysDev {
-    LsFactor F;
-    const double* b;  // original numbering (position space when F.perm == nullptr)
-    double* x;        // original numbering (position space when F.perm == nullptr)
-    double* xp;       // position space, armed with kPending before the launch (== x when F.perm == nullptr)
+    LsFactor F;       // level-ordered copy (perm / lvl unused here)
+    const double* b;  // position space
+    double* x;        // position space: solution AND polled vector, armed with kPending before the launch
     int upper, ntiles;
-    int rev, pad;     // F.perm == nullptr only: position p is row n - 1 - p of b / x (see below)
+    int rev, pad;     // position p is row n - 1 - p of b / x (see above)
 };
 
 // One 512-row tile of one system's level-ordered copy. rowptr == nullptr: a system with fewer tiles, nothing to do.
@@ -95,18 +96,15 @@ struct TsTile {
     const int* col;
     const double* val;
     const double* b;
-    const int* perm;
     double* x;
-    double* xp;
     int n, cs, ce, ltile, upper, rev;
 };
 
 struct TsStage {
     double val[kTsSlots];
     int col[kTsSlots];
-    double b[kTileRows + 2];      // position space only (reversed slices start at an even row: one lead-in entry)
+    double b[kTileRows + 2];      // (reversed slices start at an even row: one lead-in entry)
     int rowptr[kTileRows + 8];    // kTileRows + 1 used
-    int perm[kTileRows];          // original numbering only
 };
 static_assert(sizeof(TsStage) % 16 == 0 && (kTsSlots * 8) % 16 == 0 && (kTsSlots * 4) % 16 == 0, "bulk-copy alignment");
 
@@ -162,18 +160,14 @@ struct TsPipe {
         const unsigned rp_bytes = ((nr + 1u) * 4u + 15u) & ~15u;
         // right-hand sides of the tile: rows [r0, r0 + nr), or - reversed - rows [n - r0 - nr, n - r0) from the even row below
         const int b0 = d.rev ? (d.n - r0 - (int)nr) & ~1 : r0;
-        const unsigned pm_bytes = (nr * 4u + 15u) & ~15u;
         const unsigned b_bytes = ((unsigned)((d.rev ? d.n - r0 : r0 + (int)nr) - b0) * 8u + 15u) & ~15u;
-        if (j == 0) bytes += rp_bytes + (d.perm ? pm_bytes : b_bytes);
+        if (j == 0) bytes += rp_bytes + b_bytes;
         unsigned long long* bar = &sm->full[stage];
         const unsigned long long pol = l2_policy_stream();
         mbar_arrive_expect_tx(bar, bytes);
         if (j == 0) {  // metadata first: it is what the consumers read first
             bulk_g2s(st.rowptr, d.rowptr + r0, rp_bytes, bar, pol);
-            if (d.perm)
-                bulk_g2s(st.perm, d.perm + r0, pm_bytes, bar, pol);
-            else
-                bulk_g2s(st.b, d.b + b0, b_bytes, bar, pol);
+            bulk_g2s(st.b, d.b + b0, b_bytes, bar, pol);
         }
         bulk_g2s(st.val, d.val + as, nval * 8u, bar, pol);
         bulk_g2s(st.col, d.col + as, ncol * 4u, bar, pol);
@@ -228,13 +222,12 @@ struct TsPipe {
 // hand-back won (profiles/README.md).
 __device__ __forceinline__ void ts_tile_short(const TsTile& d, int i, TsSmem& sm, TsPipe& pipe, const AbortCtl& ctl, bool& dead) {
     const int tid = threadIdx.x;
-    double* xp = d.xp;
-    double* xg = d.x;
+    double* xp = d.x;
     const int r = d.ltile * kTileRows + tid;
     const bool valid = r < d.n;
     const int xm = d.rev ? -1 : 1, xo = d.rev ? d.n - 1 : 0;
     const int as = d.cs & ~3;
-    int orig = r, m = 0;
+    int m = 0;
     double bi = 0.0, rcp = 0.0;
     int c[kTsFast];
     double v[kTsFast];
@@ -251,13 +244,8 @@ __device__ __forceinline__ void ts_tile_short(const TsTile& d, int i, TsSmem& sm
         bad = m > kTsFast || m < 0 || re - as > kTsSlots;
         if (bad) m = 0;
         else rcp = st.val[(d.upper ? rs : re - 1) - as];  // the diagonal's entry holds 1 / T_ii
-        if (d.perm) {
-            orig = st.perm[tid];
-            if (!dead) bi = ldcg_here_f64(d.b + orig);
-        } else {
-            const int r0 = d.ltile * kTileRows;
-            bi = d.rev ? st.b[(d.n - 1 - r) - ((d.n - r0 - min(kTileRows, d.n - r0)) & ~1)] : st.b[tid];
-        }
+        const int r0 = d.ltile * kTileRows;
+        bi = d.rev ? st.b[(d.n - 1 - r) - ((d.n - r0 - min(kTileRows, d.n - r0)) & ~1)] : st.b[tid];
 #pragma unroll
         for (int k = 0; k < kTsFast; ++k)
             if (k < m) c[k] = xo + xm * st.col[q + k], v[k] = st.val[q + k];
@@ -284,7 +272,6 @@ __device__ __forceinline__ void ts_tile_short(const TsTile& d, int i, TsSmem& sm
                 if (k < m) sum = __dadd_rn(sum, __dmul_rn(v[k], as_double(w[k])));
             const double xv = __dmul_rn(__dsub_rn(bi, sum), rcp);
             st_relaxed_u64(xp + (xo + xm * r), as_bits(xv));
-            if (xg != xp) xg[orig] = xv;
             done = true;
         }
     };
@@ -315,8 +302,7 @@ __device__ __forceinline__ void ts_tile_short(const TsTile& d, int i, TsSmem& sm
 // One tile of any shape: rows of any length, tiles of several pipeline items, rows cut by an item boundary.
 __device__ __forceinline__ void ts_tile_general(const TsTile& d, int i, TsSmem& sm, TsPipe& pipe, const AbortCtl& ctl, bool& dead) {
     const int tid = threadIdx.x;
-    double* xp = d.xp;
-    double* xg = d.x;
+    double* xp = d.x;
     const bool upper = d.upper != 0;
     const int cs = d.cs, ce = d.ce;
     const int r = d.ltile * kTileRows + tid;
@@ -324,7 +310,7 @@ __device__ __forceinline__ void ts_tile_general(const TsTile& d, int i, TsSmem& 
     // where position p lives in xp: p, or n - 1 - p when the caller's vectors are in the REVERSE of this
     // factor's position order (the backward solve of a system kept in the forward solve's level order)
     const int xm = d.rev ? -1 : 1, xo = d.rev ? d.n - 1 : 0;
-    int orig = -1, dpos = 0, q = 0, end = 0;
+    int dpos = 0, q = 0, end = 0;
     double bi = 0.0;
     bool done = !valid || dead, have_rcp = false;
     double sum = 0.0, rcp = 0.0;
@@ -343,14 +329,8 @@ __device__ __forceinline__ void ts_tile_general(const TsTile& d, int i, TsSmem& 
             dpos = upper ? rs : re - 1;   // the diagonal's entry (holds 1 / T_ii)
             q = upper ? rs + 1 : rs;      // dependencies: entries [q, end)
             end = upper ? re : re - 1;
-            if (d.perm) {
-                orig = st.perm[tid];
-                if (!dead) bi = ldcg_here_f64(d.b + orig);
-            } else {
-                orig = r;
-                const int r0 = d.ltile * kTileRows;
-                bi = d.rev ? st.b[(d.n - 1 - r) - ((d.n - r0 - min(kTileRows, d.n - r0)) & ~1)] : st.b[tid];
-            }
+            const int r0 = d.ltile * kTileRows;
+            bi = d.rev ? st.b[(d.n - 1 - r) - ((d.n - r0 - min(kTileRows, d.n - r0)) & ~1)] : st.b[tid];
         }
         const double* __restrict__ sv = st.val;
         const int* __restrict__ sc = st.col;
@@ -361,7 +341,6 @@ __device__ __forceinline__ void ts_tile_general(const TsTile& d, int i, TsSmem& 
             if (!done && q == end && have_rcp) {  // publish at once: rows of the same warp may wait for it
                 const double xv = __dmul_rn(__dsub_rn(bi, sum), rcp);
                 st_relaxed_u64(xp + (xo + xm * r), as_bits(xv));
-                if (xg != xp) xg[orig] = xv;
                 done = true;
             }
             const bool pending = !done && q < qe;
@@ -422,7 +401,7 @@ __device__ __forceinline__ void trsv_tile_stream(const TsSysDev* __restrict__ sy
             const int s = (int)(g % nsys), t = (int)(g / nsys);
             const TsSysDev S = sys[s];
             TsTile d;
-            d.rowptr = nullptr, d.col = S.F.col, d.val = S.F.val, d.b = S.b, d.perm = S.F.perm, d.x = S.x, d.xp = S.xp;
+            d.rowptr = nullptr, d.col = S.F.col, d.val = S.F.val, d.b = S.b, d.x = S.x;
             d.n = S.F.n, d.cs = 0, d.ce = 0, d.ltile = t, d.upper = S.upper, d.rev = S.rev;
             if (t < S.ntiles) {
                 d.rowptr = S.F.rowptr;

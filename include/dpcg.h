@@ -178,11 +178,12 @@ int dp_sptrsv_ls_solve_batch_f64(const dp_trsv_ls_system_t* systems_host, int32_
 
 /* Tile-stream solve: the batch form for factors with WIDE levels (3-D stencils: levels of 10^4..10^5 rows). The
  * 512-row tiles of the level-ordered copies of ALL systems form one sequence that persistent CTAs take round robin;
- * the matrix stream goes through the TMA tile pipeline like an SpMV's, dependencies are awaited on a position-space
- * copy of the solution (kept in the workspace). Takes the same descriptors as the level-stream solve (level_sorted
- * may be NULL) and any level-ordered copy (no dp_sptrsv_ls_limits restriction). Bit-identical to dp_sptrsv_solve_f64.
- * perm == NULL: b and x are indexed by POSITION (the caller keeps its vectors in level order, x_pos[r] = x[perm[r]]);
- * this saves the per-row gather of b and scatter of x through the permutation. b and x must not alias.
+ * the matrix stream goes through the TMA tile pipeline like an SpMV's, dependencies are awaited on the solution
+ * vector in position space. Takes the same descriptors as the level-stream solve (level_sorted may be NULL) and any
+ * level-ordered copy (no dp_sptrsv_ls_limits restriction). Bit-identical to dp_sptrsv_solve_f64.
+ * perm == NULL: b and x are indexed by POSITION (the caller keeps its vectors in level order, x_pos[r] = x[perm[r]]).
+ * perm != NULL: b and x are in the original numbering; the call brackets the solve with a gather and a scatter pass
+ * through position-space copies in the workspace (40 B per row of extra traffic). b and x must not alias.
  * flags & DP_TRSV_REVERSED (perm == NULL only): position r is row n-1-r of b and x - the backward solve of a system
  * kept in the level order of its forward solve (the copy is dp_sptrsv_permute of L^T with perm[r] = n-1-r).
  * rowptr_p and b (or perm) must be 16-byte aligned like col_p / val_p: their spans travel by bulk copy too.
