@@ -58,6 +58,44 @@ def test_argument_validation_without_a_gpu(lib):
     assert lib.dp_pcg_solve_f64(None, 1, ctypes.byref(params), None, None, 0, None) == 1
 
 
+def test_tile_stream_descriptors_limits_and_validation(lib):
+    """dp_sptrsv_ts_*: size queries, limits and argument checks that run before any CUDA call."""
+    limits = np.zeros(2, np.int32)
+    lib.dp_sptrsv_ts_limits(limits.ctypes.data)
+    assert limits[0] >= 4 * 512 and limits[1] == 4, "a 512-row tile of a 7-point factor is one pipeline item; rows of <= 4 entries"
+    assert ctypes.sizeof(_lib.TrsvLsSystem) == 4 * 4 + 7 * 8 and _lib.TrsvLsSystem.flags.offset == 12
+    descs = (_lib.TrsvLsSystem * 2)()
+    for d, n, perm in zip(descs, (1000, 513), (None, 64)):
+        d.n, d.nnz, d.upper, d.flags = n, 4 * n, 0, 0
+        d.rowptr_p, d.col_p, d.val_p, d.perm, d.b, d.x = 16, 32, 48, perm, 64, 80
+    base = lib.dp_sptrsv_ts_workspace_bytes(descs, 0)
+    # position space: no vectors in the workspace; original numbering: b_pos and x_pos (two padded vectors)
+    assert lib.dp_sptrsv_ts_workspace_bytes(descs, 1) - base < 4096
+    assert lib.dp_sptrsv_ts_workspace_bytes(descs, 2) - lib.dp_sptrsv_ts_workspace_bytes(descs, 1) >= 2 * 513 * 8
+    flag = ctypes.c_void_p(256)
+    assert lib.dp_sptrsv_ts_solve_batch_f64(descs, 2, flag, None, 0, None) == 1          # no workspace
+    assert lib.dp_sptrsv_ts_solve_batch_f64(descs, 2, flag, ctypes.c_void_p(4096), 64, None) == 3  # workspace too small
+    assert lib.dp_sptrsv_ts_solve_batch_f64(None, 2, flag, ctypes.c_void_p(4096), 1 << 30, None) == 1
+
+
+def test_level_ordering_helpers_on_the_host():
+    """precond.LevelOrdering is index plumbing around the K3 analysis: to_level / from_level are inverse gathers and
+    renumber() maps the COO sites (batch column untouched) - checked on CPU tensors with a hand-made permutation."""
+    from deeppreconditioning_b200 import model as models
+    from deeppreconditioning_b200.precond import LevelOrdering
+
+    perm = torch.tensor([2, 0, 3, 1])
+    inv = torch.empty(4, dtype=torch.int32)
+    inv[perm] = torch.arange(4, dtype=torch.int32)
+    order = LevelOrdering(perm, inv, 3)
+    v = torch.tensor([10.0, 11.0, 12.0, 13.0], dtype=torch.float64)
+    assert order.to_level(v).tolist() == [12.0, 10.0, 13.0, 11.0] and torch.equal(order.from_level(order.to_level(v)), v)
+    st = models.SparseConvTensor(torch.ones(3, 1), torch.tensor([[0, 0, 0], [0, 2, 0], [0, 3, 1]], dtype=torch.int32), [4, 4], 1)
+    got = order.renumber(st)
+    assert got.indices.tolist() == [[0, 1, 1], [0, 0, 1], [0, 2, 3]] and got.indices.dtype == torch.int32
+    assert torch.equal(got.features, st.features) and got.spatial_shape == [4, 4] and got.batch_size == 1
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the behaviour on a box WITHOUT a GPU")
 def test_no_cpu_fallback():
     """The product path raises instead of computing on the CPU."""

@@ -202,3 +202,57 @@ def test_kappa_estimate_from_cg_coefficients_matches_the_dense_spectrum():
     r8 = pcg.preconditioned_conjugate_gradient(At, p.b, operators.Identity(), max_iter=400)
     k8 = spectrum.kappa_estimate(r8.alphas, r8.betas)
     assert 0.5 * np.linalg.cond(A) < k8 <= np.linalg.cond(A) * (1 + 1e-9)
+
+
+@pytest.mark.parametrize("kind,side", [("poisson3d", 9), ("poisson2d", 23)])
+def test_level_ordering_commutes_with_the_path_on_the_oracle(kind, side):
+    """The claims behind precond.LevelOrdering, checked with the CPU restatement only: level order is a topological
+    order of tril(A)'s graph, so P tril(A) P^T is the lower triangle of P A P^T and its own levels ascend along the rows
+    (level-sorted permutation = identity); IC(0) commutes with the renumbering (bitwise on stencils: no row pair shares two
+    neighbours); forward substitution in level order is bitwise the natural one; walking the rows of L^T from the last to
+    the first is a valid backward order; and PCG on the renumbered system is the same iteration as cg.py's on the
+    natural one (same count, same solution to 1e-8)."""
+    p = helpers.problem(kind, side, 0, 0.5, None)
+    level, perm, level_ptr = ckernels.levels(p.T[0], p.T[1], False)
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(p.n, dtype=perm.dtype)
+    A = osp.to_scipy(*p.A)
+    T = osp.to_scipy(*p.T)
+    A_l = A[perm][:, perm].tocsr()
+    T_l = T[perm][:, perm].tocsr()
+    for m in (A_l, T_l):
+        m.sort_indices()
+    assert (sp.triu(T_l, 1)).nnz == 0 and (sp.tril(A_l) != T_l).nnz == 0
+    level_l, perm_l, level_ptr_l = ckernels.levels(T_l.indptr, T_l.indices, False)
+    assert np.array_equal(perm_l, np.arange(p.n)) and np.array_equal(level_ptr_l, level_ptr)
+    assert np.array_equal(level_l, level[perm])
+    # IC(0)
+    f = ckernels.ic0(*p.T)
+    f_l = ckernels.ic0(T_l.indptr, T_l.indices, T_l.data)
+    F = sp.csr_matrix((f, p.T[1], p.T[0]), shape=(p.n, p.n))
+    want = F[perm][:, perm].tocsr()
+    want.sort_indices()
+    assert np.array_equal(want.indices, T_l.indices) and np.array_equal(want.data.view(np.int64), f_l.view(np.int64))
+    # triangular solves
+    b = p.b.numpy()
+    y = ckernels.sptrsv_lower(p.T[0], p.T[1], f, b)
+    y_l = ckernels.sptrsv_lower(T_l.indptr, T_l.indices, f_l, b[perm])
+    assert np.array_equal(y_l, y[perm])
+    U_l = sp.csr_matrix((f_l, T_l.indices, T_l.indptr), shape=(p.n, p.n)).T.tocsr()
+    U_l.sort_indices()
+    z_l = ckernels.sptrsv_upper(U_l.indptr, U_l.indices, U_l.data, y_l)
+    Ut = F.T.tocsr()
+    Ut.sort_indices()
+    z = ckernels.sptrsv_upper(Ut.indptr, Ut.indices, Ut.data, y)
+    assert np.array_equal(z_l, z[perm])
+    rows = np.repeat(np.arange(p.n), np.diff(U_l.indptr))
+    assert np.all(U_l.indices >= rows), "every dependency of row i of L^T is a row j > i: last-to-first is a valid order"
+    # the loop itself
+    nat = pcg.preconditioned_conjugate_gradient(osp.to_torch_csr(*p.A), p.b, operators.FactoredSolve(p.T[0], p.T[1], f),
+                                                max_iter=3000)
+    lvl = pcg.preconditioned_conjugate_gradient(osp.to_torch_csr(A_l.indptr, A_l.indices, A_l.data), p.b[torch.from_numpy(perm).long()],
+                                                operators.FactoredSolve(T_l.indptr, T_l.indices, f_l), max_iter=3000)
+    assert lvl.iterations == nat.iterations
+    x_back = torch.empty_like(lvl.x_hat)
+    x_back[torch.from_numpy(perm).long()] = lvl.x_hat
+    assert torch.linalg.vector_norm(x_back - nat.x_hat) <= 1e-8 * torch.linalg.vector_norm(nat.x_hat)
