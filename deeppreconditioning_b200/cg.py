@@ -92,8 +92,11 @@ class PcgBatch:
             self.entries.append(dict(A=A, M=M, b=b_dev, x=x, work=work, hist=hist, coef=coef, out_device=b.device))
         nsys = len(self.entries)
         if any(getattr(e["M"], "tile_stream", False) for e in self.entries):
-            # tile-stream solves are separate launches between the phases: a feature of the stepped engine
-            self.params = _lib.PcgParams(self.rtol, self.max_iter, _ENGINES["stepped"], int(check_every), 0)
+            # tile-stream solves are separate launches between the phases: a feature of the stepped engine. The host
+            # polls the done counter every other iteration: these are systems whose iteration takes a millisecond, so a
+            # poll costs ~1 % while every iteration enqueued past convergence (up to check_every - 1) is pure loss, and
+            # finished systems leave the batch solves only at a poll.
+            self.params = _lib.PcgParams(self.rtol, self.max_iter, _ENGINES["stepped"], min(int(check_every), 2), 0)
         self.iters = torch.full((nsys,), -1, dtype=torch.int32, device=self.device)
         self.res = torch.full((nsys,), float("nan"), dtype=torch.float64, device=self.device)
         self.flag = torch.zeros(1, dtype=torch.int32, device=self.device)
