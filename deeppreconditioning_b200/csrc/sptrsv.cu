@@ -251,6 +251,10 @@ int ts_solve_launch(const TsSysDev* sys_dev, int nsys, int max_tiles, int nmax, 
         resident = coop_grid(kernel, kBlock, sizeof(TsSmem));
     }
     int grid = resident;
+    if (const char* e = getenv("DPCG_TS_GRID")) {  // experiments: fewer CTAs = fewer pollers
+        const int g = atoi(e);
+        if (g > 0 && g < grid) grid = g;
+    }
     const long long items = (long long)max_tiles * nsys;
     if (items >= (1ll << 31) - 1024) return DP_ERR_INVALID;  // the kernel counts items in 32 bits
     if (items < grid) grid = (int)items;
