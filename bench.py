@@ -1,22 +1,31 @@
 #!/usr/bin/env python
 """Benchmark of the PCG hot path (BASELINE.json metric: PCG solves/sec + ms-to-tol per system; HBM roofline).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--config c3|c5]
 
-Workload (config.workload): every GPU holds a batch of independent 316x316 5-point variable-coefficient pressure
-systems (N = 99 856 unknowns each, BASELINE config 2 shape) with the factor L of a random-init PreconditionerNet
-(multiply mode, the reference's `learned` technique). 128 systems per GPU: at 8 GPUs that is exactly BASELINE config 3
-(1024 systems sharded over 8 B200). A step = one fused-PCG solve of the rank's whole batch to rtol=1e-8
-(squared criterion, cg.py:17), max_iter 20000 (the default 1024 saturates).
+Workload c3 (default; BASELINE config 3, config.workload): the TEST SET of 1024 independent 316x316 5-point
+variable-coefficient pressure systems (N = 99 856 unknowns each, the config-2 shape) with the factor L of a random-init
+PreconditionerNet (multiply mode, the reference's `learned` technique), sharded over the N GPUs by interleaved index
+(rank r holds systems r, r+N, ...: 1024/N per GPU, resident in HBM). A STEP is one fused-PCG solve (one kernel launch
+per GPU) of the next 128 systems of the set (128/N per GPU) to rtol=1e-8 (squared criterion, cg.py:17), max_iter 20000
+(the default 1024 saturates); eight steps are one pass over the set. The work of a step does not depend on N:
+"scaling": "strong". (A whole-set step is 68 s on one GPU; the driver's 25 steps would not fit its time limit.)
+
+Workload c5 (BASELINE config 5): 64 systems 256^3 (7-point, N = 16 777 216) on 8 GPUs = 8 per GPU, IC(0) in solve mode,
+systems kept in the level order of the factor, tile-stream triangular solves. A step = one PCG solve of the GPU's 8
+systems; "scaling": "weak" (8 per GPU at any N: 64 systems need the HBM of 8 GPUs).
 
 value   : solves/s with operands resident in HBM (CUDA events, max over ranks).
-e2e     : the same through the reference-facing call with HOST operands (pinned CSR of A and L, b): H2D copies, L^T
-          assembly, workspace setup, solve, D2H of x/iterations inside the timed region.
-roofline: fused PCG kernel, algorithmic bytes per launch (12 nnzA + 24 nnzL + 132 N + 12 per iteration and system,
+e2e     : the same through the reference-facing call with HOST operands (c3: pinned CSR of A and L, b - what
+          preconditioned_conjugate_gradient receives from test.py:138; c5: the pinned COO lower triangle and b - what
+          the data set yields): H2D copies, L^T assembly / analysis, workspace setup, solve, D2H of x/iterations inside
+          the timed region.
+roofline: the solve kernels, algorithmic bytes per launch (12 nnzA + 24 nnzL + 132 N + 12 per iteration and system,
           SURVEY §8d) / CUDA-event duration, against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
-cpu_baseline / --impl reference: the CPU restatement of the reference loop (oracle/pcg.py, torch CPU CSR operands,
-          all host threads) on a bounded sample of the same workload. The reference itself is Python and cannot
-          travel to the GPU box; tests pin the restatement to it.
+cpu_baseline / --impl reference: the CPU restatement of the reference loop (oracle/pcg.py, `as_is`: including the second
+          `A @` of cg.py:87), torch CPU CSR operands built on the CPU by oracle/sparse.py (the process never loads
+          libdpcg.so), all host threads, on a bounded sample of the same workload. The reference itself is Python and
+          cannot travel to the GPU box; tests pin the restatement to it.
 """
 from __future__ import annotations
 
@@ -48,20 +57,31 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--systems-per-gpu", type=int, default=64)
+    ap.add_argument("--config", default="c3", choices=["c3", "c5"])
+    ap.add_argument("--systems-total", type=int, default=1024, help="c3: size of the test set (sharded over the GPUs)")
+    ap.add_argument("--step-systems", type=int, default=128, help="c3: systems of the set solved per step (all GPUs together)")
+    ap.add_argument("--c5-side", type=int, default=256)
+    ap.add_argument("--c5-per-gpu", type=int, default=8)
     ap.add_argument("--side", type=int, default=316)
     ap.add_argument("--net", default="net", choices=["net", "tril"])
     ap.add_argument("--max-iter", type=int, default=MAX_ITER, help="profiling only: cap the bodies per solve")
     ap.add_argument("--no-extras", action="store_true", help="skip single-system latency and 128^3 kernel numbers")
     args = ap.parse_args()
     MAX_ITER = args.max_iter
+    world = max(1, args.gpus)
+    if args.systems_total % args.step_systems or args.step_systems % world:
+        ap.error("--systems-total must be a multiple of --step-systems, and --step-systems of --gpus")
     return args
 
 
 def workload_name(args):
-    return (f"{args.systems_per_gpu} x poisson2d {args.side}x{args.side} (N={args.side ** 2}) per GPU, "
+    if args.config == "c5":
+        world = max(1, args.gpus)
+        return (f"{args.c5_per_gpu * world} x poisson3d {args.c5_side}^3 (N={args.c5_side ** 3}), {args.c5_per_gpu} per GPU, "
+                f"IC(0) solve mode, level-ordered systems, tile-stream SpTRSV, rtol=1e-8 (squared), max_iter={MAX_ITER}")
+    return (f"{args.systems_total} x poisson2d {args.side}x{args.side} (N={args.side ** 2}) test set sharded over the GPUs, "
             f"random-init Preconditioner{'Net' if args.net == 'net' else 'TrilNet'} L, multiply mode, "
-            f"rtol=1e-8 (squared), max_iter={MAX_ITER}")
+            f"rtol=1e-8 (squared), max_iter={MAX_ITER}; step = next {args.step_systems} systems of the set")
 
 
 def iter_bytes(n, nnz_a, nnz_l):
@@ -113,49 +133,51 @@ class ClockSampler:
 
 
 # ---- workload -----------------------------------------------------------------------------------------------------------
-def build_host_systems(args, rank, world, device):
-    """Synthetic systems of this rank (interleaved shard of the global list) as pinned HOST CSR operands.
+CNN_BATCH = 8  # systems per CNN forward (the model is batched like data_set.py's loader; assembly picks one batch element)
 
-    Assembly of A and L runs on the GPU (K1 kernels) once, then the operands are read back to pinned host memory so
-    that the e2e leg can start from host buffers like the reference's harness does (everything `.cpu()`, test.py:68,105).
-    """
-    from deeppreconditioning_b200 import model as models
+
+def step_indices(args, step, rank, world):
+    """Global indices of the systems this rank solves in step `step`: the step takes the next `step_systems` systems of
+    the set (cyclically); rank r holds the systems with index % world == r (distributed.shard_indices)."""
+    nchunks = args.systems_total // args.step_systems
+    base = (step % nchunks) * args.step_systems
+    return [i for i in range(base, base + args.step_systems) if i % world == rank]
+
+
+def build_chunk(args, indices, net, device, keep_host):
+    """Device operands (A, b, FactoredMultiply(L, L^T)) of the systems `indices`; with keep_host also their pinned HOST
+    CSR copies for the e2e leg (what the reference's harness hands to cg.py after `.cpu()`, test.py:68,105)."""
+    import deeppreconditioning_b200 as dp
     from deeppreconditioning_b200 import synthetic
-    from deeppreconditioning_b200.distributed import shard_indices
     from deeppreconditioning_b200.sparse import CsrMatrix
 
-    n_global = args.systems_per_gpu * world
-    mine = shard_indices(n_global, rank, world)
-    torch.manual_seed(69)  # test.py:205
-    cls = models.PreconditionerNet if args.net == "net" else models.PreconditionerTrilNet
-    net = cls(models.DEFAULT_CHANNELS).to(device)
-    host = []
-    for index in mine:
-        st, _, rhs, sizes = synthetic.make_batch("poisson2d", args.side, [index], device=device)
-        n = sizes[0]
+    systems, host = [], []
+    for at in range(0, len(indices), CNN_BATCH):
+        group = indices[at:at + CNN_BATCH]
+        st, _, rhs, sizes = synthetic.make_batch("poisson2d", args.side, group, device=device)
         with torch.no_grad():
             learned = net(st)
-        A = CsrMatrix.from_spconv(st, n, "symmetrise")
-        L = CsrMatrix.from_spconv(learned, n, "tril")
-        pin = lambda t: t.cpu().pin_memory()
-        host.append(dict(index=index, n=n, a=tuple(pin(t) for t in (A.rowptr, A.col, A.val)),
-                         l=tuple(pin(t) for t in (L.rowptr, L.col, L.val)),
-                         b=pin(rhs[0, :n].to(torch.float64))))
-        del st, learned, A, L
-    torch.cuda.empty_cache()
-    return mine, host
+        for k, index in enumerate(group):
+            n = sizes[k]
+            A = CsrMatrix.from_spconv(st, n, "symmetrise", batch=k)
+            L = CsrMatrix.from_spconv(learned, n, "tril", batch=k)
+            Lt = CsrMatrix.from_spconv(learned, n, "tril_t", batch=k)
+            b = rhs[k, :n].to(torch.float64)
+            systems.append((A, b, dp.FactoredMultiply(L, Lt)))
+            if keep_host:
+                pin = lambda t: t.cpu().pin_memory()
+                host.append(dict(index=index, n=n, a=tuple(pin(t) for t in (A.rowptr, A.col, A.val)),
+                                 l=tuple(pin(t) for t in (L.rowptr, L.col, L.val)), b=pin(b)))
+        del st, learned
+    return systems, host
 
 
-def device_batch(host, device):
-    import deeppreconditioning_b200 as dp
-    from deeppreconditioning_b200.sparse import CsrMatrix
+def make_net(args, device):
+    from deeppreconditioning_b200 import model as models
 
-    systems = []
-    for h in host:
-        A = CsrMatrix.from_arrays(*h["a"], device=device)
-        L = CsrMatrix.from_arrays(*h["l"], device=device)
-        systems.append((A, h["b"].to(device, non_blocking=True), dp.FactoredMultiply(L)))
-    return dp.PcgBatch(systems, RTOL, MAX_ITER, engine="fused", device=device)
+    torch.manual_seed(69)  # test.py:205
+    cls = models.PreconditionerNet if args.net == "net" else models.PreconditionerTrilNet
+    return cls(models.DEFAULT_CHANNELS).to(device)
 
 
 def dist_setup(args):
@@ -203,16 +225,40 @@ def sum_over_ranks(value, world, device):
     return float(t.item())
 
 
-def cpu_solve_sample(host_system, threads):
-    """One system through the CPU restatement of the reference loop (oracle/pcg.py), reference operand types."""
-    from oracle import operators, pcg
+def cpu_operands(args, index, net, cnn_device):
+    """One system of the c3 set as CPU operands, built WITHOUT libdpcg: the synthetic generator (numpy), the CNN forward
+    in PyTorch (on the GPU when there is one, as the reference runs its model, test.py:102,217), and the CSR assembly of
+    oracle/sparse.py (the literal test.py:65-68,103-105 arithmetic) on the CPU."""
+    from deeppreconditioning_b200 import synthetic
+    from oracle import operators
     from oracle import sparse as osp
 
+    st, _, rhs, sizes = synthetic.make_batch("poisson2d", args.side, [index], device=cnn_device)
+    n = sizes[0]
+    with torch.no_grad():
+        learned = net(st)
+    ind, feat = st.indices.cpu().numpy(), st.features.cpu().numpy()
+    a = osp.symmetrise_tril(ind, feat, 0, n)
+    l = osp.tril_coo_to_csr(learned.indices.cpu().numpy(), learned.features.cpu().numpy(), 0, n)
+    return osp.to_torch_csr(*a), operators.FactoredMultiply(*l), rhs[0, :n].cpu().to(torch.float64)
+
+
+def cpu_solve(a, m, b, threads):
+    """One system through the CPU restatement of the reference loop, executed as the reference executes it (as_is)."""
+    from oracle import pcg
+
     torch.set_num_threads(threads)
+    return pcg.preconditioned_conjugate_gradient(a, b.clone(), m, rtol=RTOL, max_iter=MAX_ITER, as_is=True)
+
+
+def cpu_solve_sample(host_system, threads):
+    """c3 cpu_baseline leg of the GPU arm: the rank's own host CSR operands through the same loop."""
+    from oracle import operators
+    from oracle import sparse as osp
+
     a = osp.to_torch_csr(*(t.numpy() for t in host_system["a"]))
     m = operators.FactoredMultiply(*(t.numpy() for t in host_system["l"]))
-    result = pcg.preconditioned_conjugate_gradient(a, host_system["b"].clone(), m, rtol=RTOL, max_iter=MAX_ITER)
-    return result
+    return cpu_solve(a, m, host_system["b"], threads)
 
 
 def peaks():
@@ -224,33 +270,79 @@ def peaks():
 
 # ---- reference arm ---------------------------------------------------------------------------------------------------
 def run_reference(args):
+    """The reference's CPU implementation of the path on the box's host cores (rank 0 only): one system of the set per
+    step, distinct systems. Nothing of libdpcg is loaded in this process."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    device = torch.device("cuda", 0) if torch.cuda.is_available() else None
     threads = os.cpu_count() or 1
-    one = argparse.Namespace(**{**vars(args), "systems_per_gpu": max(args.steps + args.warmup, 1)})
-    if device is not None:
-        _, host = build_host_systems(one, 0, 1, device)
-    else:
-        raise SystemExit("the reference arm builds its operands with the same GPU assembly path; no GPU found")
+    if args.config == "c5":
+        return run_reference_c5(args, threads)
+    cnn_device = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+    net = make_net(args, cnn_device)
     times, iters = [], []
     for step in range(args.warmup + args.steps):
-        h = host[step % len(host)]
+        index = (step * 41) % args.systems_total  # distinct systems spread over the set
+        a, m, b = cpu_operands(args, index, net, cnn_device)
         t0 = time.perf_counter()
-        r = cpu_solve_sample(h, threads)
+        r = cpu_solve(a, m, b, threads)
         dt = time.perf_counter() - t0
         if step >= args.warmup:
             times.append(dt), iters.append(r.iterations)
     total = float(np.sum(times))
     value = len(times) / total
-    sample = (f"1 system per step ({len(times)} timed, distinct seeds) of the {args.systems_per_gpu}-system per-GPU batch; "
+    sample = (f"1 system of the {args.systems_total}-system set per step ({len(times)} timed, distinct systems), cg.py:70-88 "
+              f"as is (second A@ of cg.py:87 included), torch CPU CSR operands built by oracle/sparse.py; "
               f"mean {np.mean(iters):.0f} iterations")
+    assert not any("libdpcg" in line for line in open("/proc/self/maps")), "the reference arm must not load libdpcg.so"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": workload_name(args)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def c5_iterations_hint():
+    path = ROOT / "profiles" / "c5_iterations.json"
+    return json.loads(path.read_text()) if path.exists() else {}
+
+
+def run_reference_c5(args, threads):
+    """c5 on the CPU: one 256^3 IC(0)-PCG solve is minutes of host time (two sequential triangular solves of 67 M entries
+    per iteration), so a step is a bounded sample: the first `sample_iters` bodies of one system. solves/s is quoted
+    for the iteration count the GPU arm needs on that system (profiles/c5_iterations.json)."""
+    from deeppreconditioning_b200 import synthetic
+    from oracle import ckernels, operators, pcg
+    from oracle import sparse as osp
+
+    ckernels.build()
+    sample_iters = 3
+    st, _, rhs, sizes = synthetic.make_batch("poisson3d", args.c5_side, [0])
+    n = sizes[0]
+    ind, feat = st.indices.numpy(), st.features.numpy()
+    a = osp.to_torch_csr(*osp.symmetrise_tril(ind, feat, 0, n))
+    t = osp.tril_coo_to_csr(ind, feat, 0, n)
+    m = operators.FactoredSolve(t[0], t[1], ckernels.ic0(*t))
+    b = rhs[0, :n].to(torch.float64)
+    torch.set_num_threads(threads)
+    times = []
+    for step in range(args.warmup + args.steps):
+        r = pcg.preconditioned_conjugate_gradient(a, b.clone(), m, rtol=RTOL, max_iter=sample_iters, as_is=True)
+        if step >= args.warmup:
+            times.append(r.seconds)
+    per_iter = float(np.mean(times)) / sample_iters
+    need = int(c5_iterations_hint().get(str(args.c5_side), 0)) or None
+    value = 1.0 / (per_iter * need) if need else None
+    sample = (f"{sample_iters} PCG bodies of one {args.c5_side}^3 system per step ({1e3 * per_iter:.0f} ms per iteration, oracle IC(0) "
+              f"+ sequential C triangular solves); solves/s extrapolated to the {need} iterations the GPU arm needs")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": workload_name(args)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "ms_per_iteration": 1e3 * per_iter},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -519,19 +611,50 @@ def extras(device, host0):
 
 def run_ours(args):
     from deeppreconditioning_b200 import build as dp_build
-    from deeppreconditioning_b200.distributed import gather_records, make_records
 
     rank, world, local = dist_setup(args)
     if rank == 0:
         dp_build.build()
     barrier(world)
     device = torch.device("cuda", local)
-    mine, host = build_host_systems(args, rank, world, device)
-    batch = device_batch(host, device)
-    n_sys_global = args.systems_per_gpu * world
+    if args.config == "c5":
+        line = run_c5(args, rank, world, device)
+    else:
+        line = run_c3(args, rank, world, device)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+def run_c3(args, rank, world, device):
+    """BASELINE config 3: the 1024-system test set, sharded; a step = one fused solve of the next 128 systems."""
+    import deeppreconditioning_b200 as dp
+    from deeppreconditioning_b200.distributed import gather_records, make_records
+    from deeppreconditioning_b200.sparse import CsrMatrix
+
+    local = device.index
+    nsteps = args.warmup + args.steps
+    nchunks = min(args.systems_total // args.step_systems, nsteps)  # chunks of the set the run touches
+    net = make_net(args, device)
+    t_setup = time.perf_counter()
+    chunk_idx, batches, host = [], [], None
+    for c in range(nchunks):
+        mine = step_indices(args, c, rank, world)
+        systems, h = build_chunk(args, mine, net, device, keep_host=(c == 0))
+        if c == 0:
+            host = h
+        chunk_idx.append(mine)
+        batches.append(dp.PcgBatch(systems, RTOL, MAX_ITER, engine="fused", device=device))
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t_setup
+    resident_gb = torch.cuda.memory_allocated(device) / 1e9
 
     # ---- resident-operand measurement -----------------------------------------------------------------------------
-    for _ in range(args.warmup):
+    for step in range(args.warmup):
+        batch = batches[step % nchunks]
         batch.reset()
         batch.solve()
     barrier(world)
@@ -539,42 +662,46 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = []
+    launches = []  # (chunk, start event, stop event) of every timed launch
     barrier(world)
     start.record()
-    for _ in range(args.steps):
-        batch.reset()
+    for step in range(args.warmup, nsteps):
+        c = step % nchunks
+        batches[c].reset()
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         k0.record()
-        batch.solve()  # ONE kernel launch: pcg_fused_kernel
+        batches[c].solve()  # ONE kernel launch: pcg_fused_kernel
         k1.record()
-        kernel_ms.append((k0, k1))
+        launches.append((c, k0, k1))
     stop.record()
     barrier(world)
     elapsed_ms = max_over_ranks(start.elapsed_time(stop), world, device)
     clocks = sampler.stop() if rank == 0 else None
-    results = batch.results()
-    kernel_ms = [a.elapsed_time(b) for a, b in kernel_ms]
-    value = n_sys_global * args.steps / (elapsed_ms / 1e3)
+    value = args.step_systems * args.steps / (elapsed_ms / 1e3)
 
-    # per-system records: the only collective of the path (SURVEY §8e)
-    records = gather_records(make_records(mine, results, [np.mean(kernel_ms)] * len(mine)), n_sys_global)
-    iterations = records[:, 1].numpy()
-
-    # roofline of the dominant (only) kernel, rank-local bytes / rank-local kernel time, summed over ranks
-    local_bytes = sum(iter_bytes(h["n"], h["a"][1].numel(), h["l"][1].numel()) * r.iterations for h, r in zip(host, results))
-    local_gbs = local_bytes / (np.mean(kernel_ms) / 1e3) / 1e9
+    # results of every chunk that was solved (warm-up or timed): iteration statistics of the set
+    solved = sorted({s % nchunks for s in range(nsteps)})
+    results = {c: batches[c].results() for c in solved}
+    kernel_ms = [k0.elapsed_time(k1) for _, k0, k1 in launches]
+    chunk_bytes = {c: sum(iter_bytes(e["A"].n, e["A"].nnz, e["M"].L.nnz) * r.iterations
+                          for e, r in zip(batches[c].entries, results[c])) for c in solved}
+    local_bytes = float(sum(chunk_bytes[c] for c, _, _ in launches))
+    local_gbs = local_bytes / (sum(kernel_ms) / 1e3) / 1e9
     peak, peak_source = peaks()
     mean_gbs = sum_over_ranks(local_gbs, world, device) / world
 
-    # ---- e2e: host operands through the public call ------------------------------------------------------------------
-    import deeppreconditioning_b200 as dp
-    from deeppreconditioning_b200.sparse import CsrMatrix
+    # per-system records: the only collective of the path (SURVEY §8e)
+    idx = [i for c in solved for i in chunk_idx[c]]
+    res = [r for c in solved for r in results[c]]
+    ms_of = {c: [m for (cc, _, _), m in zip(launches, kernel_ms) if cc == c] for c in solved}
+    ms = [float(np.mean(ms_of[c])) if ms_of[c] else 0.0 for c in solved for _ in chunk_idx[c]]
+    # (the gather wants one record per index 0..n-1: chunks are contiguous index ranges starting at 0)
+    records = gather_records(make_records(idx, res, ms), len(solved) * args.step_systems)
+    iterations = records[:, 1].numpy()
 
+    # ---- e2e: host operands through the public call ------------------------------------------------------------------
     h2d = sum(sum(t.numel() * t.element_size() for t in h["a"] + h["l"]) + h["b"].numel() * 8 for h in host)
     d2h = sum(h["n"] * 8 + 12 for h in host)
-    del batch
-    torch.cuda.empty_cache()
 
     def e2e_step():
         systems = []
@@ -582,10 +709,9 @@ def run_ours(args):
             A = CsrMatrix.from_arrays(*h["a"], device=device)
             L = CsrMatrix.from_arrays(*h["l"], device=device)
             systems.append((A, h["b"], dp.FactoredMultiply(L)))  # b stays a (pinned) host tensor: x_hat returns to host
-        out = dp.pcg_solve_batch(systems, RTOL, MAX_ITER, device=device)
-        return out
+        return dp.pcg_solve_batch(systems, RTOL, MAX_ITER, device=device)
 
-    e2e_steps = max(1, min(args.steps, 2))
+    e2e_steps = max(1, min(args.steps, 3))
     e2e_step()
     barrier(world)
     t0 = time.perf_counter()
@@ -593,12 +719,12 @@ def run_ours(args):
         out = e2e_step()
     barrier(world)
     e2e_s = max_over_ranks(time.perf_counter() - t0, world, device)
-    assert [r.iterations for r in out] == [r.iterations for r in results], "e2e and resident runs disagree"
-    e2e_value = n_sys_global * e2e_steps / e2e_s
+    assert [r.iterations for r in out] == [r.iterations for r in results[0]], "e2e and resident runs disagree"
+    e2e_value = args.step_systems * e2e_steps / e2e_s
+    h2d_all, d2h_all = int(sum_over_ranks(h2d, world, device)), int(sum_over_ranks(d2h, world, device))
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only) -----------------------------------------------------------
-    cpu = None
-    extra = None
+    cpu = extra = None
     if rank == 0 and world == 1:
         threads = os.cpu_count() or 1
         nsample = min(3, len(host))  # bounded sample: ~10-15 s of CPU work
@@ -607,51 +733,165 @@ def run_ours(args):
         dt = time.perf_counter() - t0
         cpu_iters = [r.iterations for r in cpu_runs]
         cpu = {"value": nsample / dt, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"systems {[h['index'] for h in host[:nsample]]} of the batch, one after the other: {cpu_iters} "
-                         f"iterations in {dt:.2f} s (GPU: {[r.iterations for r in results[:nsample]]} iterations)",
+               "sample": f"systems {[h['index'] for h in host[:nsample]]} of the set, one after the other, cg.py:70-88 as is "
+                         f"(second A@ of cg.py:87 included): {cpu_iters} iterations in {dt:.2f} s "
+                         f"(GPU, same operands: {[r.iterations for r in results[0][:nsample]]} iterations)",
                "ms_per_iteration": 1e3 * dt / max(sum(cpu_iters), 1)}
         if not args.no_extras:
+            del batches[1:]
+            torch.cuda.empty_cache()
             extra = extras(device, host[0])
+    if rank != 0:
+        return None
+    # DRAM traffic of the fused kernel: ncu (--set full) measured dram__bytes_read+write on a short launch of the same
+    # kernel and workload shape; profiles/traffic.json keeps it per system-iteration, scaled here to the mean launch.
+    traffic, traffic_source = None, None
+    tpath = ROOT / "profiles" / "traffic.json"
+    if tpath.exists():
+        tj = json.loads(tpath.read_text())
+        per_iter = tj.get("pcg_fused_kernel_dram_bytes_per_system_iteration")
+        if per_iter:
+            its = [sum(r.iterations for r in results[c]) for c, _, _ in launches]
+            traffic = float(per_iter) * float(np.mean(its))
+            traffic_source = tj.get("source", "profiles/traffic.json (ncu --set full capture of a short launch, scaled by iterations)")
+    per_gpu = args.step_systems // world
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "systems_total": args.systems_total, "systems_per_step": args.step_systems,
+                   "systems_per_gpu_per_step": per_gpu, "systems_resident_per_gpu": nchunks * per_gpu,
+                   "l2": f"per-GPU working set of a step {per_gpu * 0.057:.1f} GB >> 126 MB L2 (no flush needed); "
+                         f"{resident_gb:.0f} GB resident per GPU",
+                   "iterations_mean": float(iterations.mean()), "iterations_min": int(iterations.min()),
+                   "iterations_max": int(iterations.max()), "systems_measured": int(len(iterations)),
+                   "engine": "fused persistent cooperative kernel", "setup_s_untimed": setup_s},
+        "ms_to_tol_per_system": elapsed_ms / args.steps / per_gpu,
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all, "steps": e2e_steps},
+        "gpu_launches": args.steps * world,
+        "roofline": {"bound": "hbm", "kernel": "pcg_fused_kernel", "achieved": mean_gbs, "peak": peak, "unit": "GB/s",
+                     "frac": mean_gbs / peak, "traffic": traffic, "traffic_source": traffic_source, "peak_source": peak_source,
+                     "bytes_per_launch": local_bytes / len(launches), "ms_per_launch": float(np.mean(kernel_ms))},
+        "cpu_baseline": cpu,
+    }
+    if extra:
+        line["extras"] = extra
+    return line
 
+
+def run_c5(args, rank, world, device):
+    """BASELINE config 5: 8 systems 256^3 per GPU (64 on 8 GPUs), IC(0) solve mode on level-ordered systems with
+    tile-stream triangular solves. A step = one PCG solve of the GPU's batch."""
+    import deeppreconditioning_b200 as dp
+    from deeppreconditioning_b200 import model as models
+    from deeppreconditioning_b200 import precond, synthetic
+    from deeppreconditioning_b200.sparse import CsrMatrix
+
+    local = device.index
+    side, per_gpu = args.c5_side, args.c5_per_gpu
+    mine = [rank * per_gpu + i for i in range(per_gpu)]
+
+    def prepare(st, rhs, n):
+        """From the data set's item (COO lower triangle + rhs, on the device) to a batch entry: level ordering (K3),
+        assembly of A and tril(A) in that order (K1), IC(0), L^T, level-ordered copies of both factors."""
+        T = CsrMatrix.from_spconv(st, n, "tril")
+        order = precond.level_ordering(T)
+        del T
+        st = order.renumber(st)
+        T = CsrMatrix.from_spconv(st, n, "tril")
+        A = CsrMatrix.from_spconv(st, n, "symmetrise")
+        plan = precond.analyse(T, False, level_stream=False)
+        F = precond.incomplete_cholesky0(T, plan)
+        b = order.to_level(rhs[0, :n].to(device=device, dtype=torch.float64))
+        return (A, b, dp.FactoredSolve(F, None, plan, level_stream=False, tile_stream=True)), order
+
+    t_setup = time.perf_counter()
+    systems, host = [], None
+    for index in mine:
+        st, _, rhs, sizes = synthetic.make_batch("poisson3d", side, [index])
+        n = sizes[0]
+        if host is None:  # the e2e leg runs on pinned host buffers of the rank's first system
+            host = (st.features.pin_memory(), st.indices.pin_memory(), rhs.pin_memory(), n)
+        dev_st = models.SparseConvTensor(st.features.to(device), st.indices.to(device), st.spatial_shape, 1)
+        entry, _ = prepare(dev_st, rhs, n)
+        systems.append(entry)
+        del st, dev_st
+    batch = dp.PcgBatch(systems, RTOL, MAX_ITER, device=device)
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t_setup
+    resident_gb = torch.cuda.memory_allocated(device) / 1e9
+    nnz_a, nnz_l = systems[0][0].nnz, systems[0][2].L.nnz
+
+    for _ in range(args.warmup):
+        batch.reset()
+        batch.solve()
+    barrier(world)
+    sampler = ClockSampler(local)
     if rank == 0:
-        # DRAM traffic of the fused kernel: ncu (--set full) measured dram__bytes_read+write on a short launch of the same
-        # kernel and workload shape; profiles/traffic.json keeps it per system-iteration, scaled here to this launch.
-        traffic = None
-        tpath = ROOT / "profiles" / "traffic.json"
-        if tpath.exists():
-            per_iter = json.loads(tpath.read_text()).get("pcg_fused_kernel_dram_bytes_per_system_iteration")
-            if per_iter:
-                traffic = float(per_iter) * float(sum(r.iterations for r in results))
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args), "systems_total": n_sys_global, "l2": "per-GPU working set "
-                       f"{sum(sum(t.numel() * t.element_size() for t in h['a'] + h['l']) for h in host) * 1.5 / 1e9:.1f} GB >> 126 MB L2 (no flush needed)",
-                       "iterations_mean": float(iterations.mean()), "iterations_min": int(iterations.min()),
-                       "iterations_max": int(iterations.max()), "engine": "fused persistent cooperative kernel"},
-            "ms_to_tol_per_system": elapsed_ms / args.steps / args.systems_per_gpu,
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(sum_over_ranks(h2d, world, device)) if world > 1 else h2d,
-                    "d2h_bytes_per_step": int(sum_over_ranks(d2h, world, device)) if world > 1 else d2h, "steps": e2e_steps},
-            "gpu_launches": args.steps * world,
-            "roofline": {"bound": "hbm", "kernel": "pcg_fused_kernel", "achieved": mean_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": mean_gbs / peak, "traffic": traffic, "peak_source": peak_source,
-                         "bytes_per_launch": local_bytes, "ms_per_launch": float(np.mean(kernel_ms))},
-            "cpu_baseline": cpu,
-        }
-        if extra:
-            line["extras"] = extra
-        print(json.dumps(line))
-    else:
-        # keep collectives matched on the other ranks
-        if world > 1:
-            sum_over_ranks(h2d, world, device)
-            sum_over_ranks(d2h, world, device)
-    if world > 1:
-        import torch.distributed as dist
+        sampler.start()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(world)
+    start.record()
+    for _ in range(args.steps):
+        batch.reset()
+        batch.solve()
+    stop.record()
+    barrier(world)
+    elapsed_ms = max_over_ranks(start.elapsed_time(stop), world, device)
+    local_ms = start.elapsed_time(stop)
+    clocks = sampler.stop() if rank == 0 else None
+    results = batch.results()
+    its = [r.iterations for r in results]
+    value = per_gpu * world * args.steps / (elapsed_ms / 1e3)
+    local_bytes = float(sum(iter_bytes(n, nnz_a, nnz_l) * i for i in its))
+    local_gbs = local_bytes * args.steps / (local_ms / 1e3) / 1e9
+    peak, peak_source = peaks()
+    mean_gbs = sum_over_ranks(local_gbs, world, device) / world
+    all_its = sum_over_ranks(float(sum(its)), world, device)
 
-        dist.destroy_process_group()
+    # e2e: one system from HOST COO (what the data set yields) through set-up and solve, solution back to the host
+    feats, inds, rhs_h, n = host
+    del batch, systems
+    torch.cuda.empty_cache()
+
+    def e2e_step():
+        dev_st = models.SparseConvTensor(feats.to(device, non_blocking=True), inds.to(device, non_blocking=True), [n, n], 1)
+        entry, order = prepare(dev_st, rhs_h.to(device, non_blocking=True), n)
+        out = dp.pcg_solve_batch([entry], RTOL, MAX_ITER, device=device)[0]
+        return order.from_level(out.x_hat).cpu(), out.iterations
+
+    e2e_step()
+    barrier(world)
+    t0 = time.perf_counter()
+    _, e2e_its = e2e_step()
+    barrier(world)
+    e2e_s = max_over_ranks(time.perf_counter() - t0, world, device)
+    e2e_value = world / e2e_s
+    h2d = feats.numel() * 4 + inds.numel() * 4 + n * 4
+    if rank != 0:
+        return None
+    return {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "systems_total": per_gpu * world, "systems_per_gpu": per_gpu,
+                   "l2": f"{resident_gb:.0f} GB resident per GPU, 5.2 GB per system-iteration >> 126 MB L2 (no flush needed)",
+                   "iterations": its, "iterations_mean_all_ranks": all_its / (per_gpu * world),
+                   "engine": "stepped (tile-stream SpTRSV launches between the fused phases)", "setup_s_untimed": setup_s},
+        "ms_to_tol_per_system": elapsed_ms / args.steps / per_gpu,
+        "us_per_iteration": 1e3 * elapsed_ms / args.steps / max(its),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": (n * 8 + 12) * world,
+                "steps": 1, "note": f"one system per GPU from the pinned host COO lower triangle: level analysis, assembly, IC(0), "
+                                    f"solve ({e2e_its} iterations), x back in the original numbering"},
+        "gpu_launches": int(args.steps * world * (5 * max(its) + 8)),
+        "roofline": {"bound": "hbm", "kernel": "sptrsv_ts_batch_kernel + pcg_phase_kernel (whole iteration)", "achieved": mean_gbs,
+                     "peak": peak, "unit": "GB/s", "frac": mean_gbs / peak, "traffic": None, "peak_source": peak_source,
+                     "bytes_per_launch": local_bytes, "ms_per_launch": local_ms / args.steps,
+                     "note": "launch = one whole solve of the batch (the stepped engine's kernels together)"},
+        "cpu_baseline": None,
+    }
 
 
 def main():

@@ -74,6 +74,7 @@ _SIGNATURES = {
     "dp_csr_transpose_workspace_bytes": (C.c_size_t, [_i32, _i32]),
     "dp_csr_transpose": (C.c_int, [_i32, _i32, _p, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
     "dp_csr_inv_diagonal": (C.c_int, [_i32, _p, _p, _p, _p, _p, _p]),
+    "dp_csr_aat_nnz": (C.c_int, [_i32, _p, _p, _p, _p, _p, _p]),
     "dp_spmv_csr_f64": (C.c_int, [_i32, _i32, _p, _p, _p, _p, _p, _p]),
     "dp_coo_spmv_batch_f32": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _i32, _p, _p]),
     "dp_sptrsv_analyse_workspace_bytes": (C.c_size_t, [_i32]),

@@ -129,6 +129,45 @@ __global__ void inv_diagonal_kernel(int n, const int* __restrict__ rowptr, const
     }
 }
 
+
+// nnz(L L^T) without forming the product (test.py:107-109 reports the density of the explicit M = L L^T that
+// test.py:104-105 stores): entry (i, j) is structurally non-zero iff rows i and j of L share a column, i.e.
+//   row i of L L^T  =  union over the columns c of row i of { rows j with L_jc != 0 }  =  union of rows c of L^T.
+// One warp per row: candidate j from the k-th list counts iff it is in none of the lists 0..k-1 (binary search, every
+// row of L^T is sorted). Integer work, exact; a 64-bit total by atomics.
+__global__ void __launch_bounds__(256) aat_nnz_kernel(int n, const int* __restrict__ rowptr, const int* __restrict__ col,
+                                                      const int* __restrict__ rowptr_t, const int* __restrict__ col_t,
+                                                      unsigned long long* __restrict__ total) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    unsigned long long mine = 0;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+        const int rs = rowptr[i], re = rowptr[i + 1];
+        for (int k = rs; k < re; ++k) {
+            const int c = col[k];
+            const int ts = rowptr_t[c], te = rowptr_t[c + 1];
+            for (int q = ts + lane; q < te; q += 32) {
+                const int j = col_t[q];
+                bool seen = false;
+                for (int k2 = rs; k2 < k && !seen; ++k2) {
+                    const int c2 = col[k2];
+                    int lo = rowptr_t[c2], hi = rowptr_t[c2 + 1];
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        const int v = col_t[mid];
+                        if (v == j) { seen = true; break; }
+                        if (v < j) lo = mid + 1; else hi = mid;
+                    }
+                }
+                mine += seen ? 0ull : 1ull;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(kFull, mine, o);
+    if (lane == 0 && mine) atomicAdd(total, mine);
+}
+
 static int grid_for(long long items, int threads) {
     long long b = (items + threads - 1) / threads;
     long long cap = (long long)sm_count() * 16;
@@ -222,6 +261,18 @@ int dp_csr_inv_diagonal(int32_t n, const int32_t* rowptr, const int32_t* col, co
     if (n < 0 || !rowptr || !dinv || !flag_out) return DP_ERR_INVALID;
     if (n == 0) return DP_OK;
     inv_diagonal_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(n, rowptr, col, val, dinv, flag_out);
+    DP_LAUNCH_CHECK();
+    return DP_OK;
+}
+
+int dp_csr_aat_nnz(int32_t n, const int32_t* rowptr, const int32_t* col, const int32_t* rowptr_t, const int32_t* col_t,
+                   int64_t* nnz_out, void* stream) {
+    if (n < 0 || !nnz_out || (n > 0 && (!rowptr || !col || !rowptr_t || !col_t))) return DP_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    DP_CUDA(cudaMemsetAsync(nnz_out, 0, sizeof(int64_t), s));
+    if (n == 0) return DP_OK;
+    aat_nnz_kernel<<<grid_for((long long)n * 32, 256), 256, 0, s>>>(n, rowptr, col, rowptr_t, col_t,
+                                                                    reinterpret_cast<unsigned long long*>(nnz_out));
     DP_LAUNCH_CHECK();
     return DP_OK;
 }

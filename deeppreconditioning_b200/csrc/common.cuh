@@ -22,7 +22,11 @@ constexpr unsigned long long kPending = 0xFFFBADC0FFEE0B20ull;
 constexpr unsigned kSpinBudget = 1u << 24;
 
 const char* set_cuda_error(cudaError_t e);
-int sm_count();
+// Per-DEVICE host-side caches (spmv.cu): a process may solve on cuda:0 and then on cuda:1, and function attributes,
+// occupancy and SM counts belong to the current device, not to the process or the host thread.
+int sm_count();                                              // SMs of the current device
+int allow_dynamic_smem(const void* kernel, size_t bytes);    // opt `kernel` into > 48 KB of dynamic shared memory (DP_OK / DP_ERR_CUDA)
+int coop_grid(const void* kernel, int threads, size_t smem); // co-resident CTAs of `kernel` on the current device
 
 #define DP_CUDA(call)                                   \
     do {                                                \

@@ -39,11 +39,11 @@
 
 namespace dp {
 
-int coop_grid(const void* kernel, int threads, size_t smem);  // sptrsv.cu
 int trsv_lookahead();                                          // sptrsv.cu
 
 struct SysDev {
-    int n, precond, ntiles, pad;
+    int n, precond, ntiles;
+    int rearm_t;  // SOLVE: PH_DOTRZ re-arms y (= t) for the next forward solve (see dp_pcg_solve_f64)
     int fwd_look, bwd_look;  // SOLVE: chunks of the widest level (parking distance of the sync-free solves)
     CsrView A, M, Mt;
     const double* dinv;
@@ -80,7 +80,6 @@ struct Ctx {
     int nsys, total_tiles, total_fwd, total_bwd;
     int pw_fwd, pw_bwd;
     int has_multiply, has_solve, has_ls;
-    int rearm_t;  // tile-stream solves (stepped engine): PH_DOTRZ re-arms y for the next forward solve
     double rtol;
     int max_iter;
     unsigned long long* word;  // grid barrier (+ finished count in the upper half)
@@ -406,8 +405,9 @@ __device__ __forceinline__ void phase_dotrz(const Ctx& ctx, const SysDev& S, con
     if (row < S.n) {
         rn = S.r[(k + 1) & 1][row];
         zi = S.z[(k + 1) & 1][row];
-        // the tile-stream backward solve reads y by bulk copy and cannot re-arm it on the way like the sync-free one
-        if (ctx.rearm_t) st_relaxed_u64(S.t + row, kPending);
+        // a sync-free forward solve polls y and needs it armed before every application; the sync-free backward solve
+        // re-arms it on the way (RhsConsume), the level-stream and tile-stream ones read it plainly and cannot
+        if (S.rearm_t) st_relaxed_u64(S.t + row, kPending);
     }
     double v[2] = {__dmul_rn(rn, zi), __dmul_rn(zi, zi)};
     tile_reduce<2>(v, sm.scratch, pipe);
@@ -722,13 +722,7 @@ static WsLayout ws_layout(int nsys) {
 // Every PCG kernel carries the tile pipeline's stages in dynamic shared memory (> 48 KB: opt in once per kernel).
 template <class Kernel>
 static int allow_smem(Kernel kernel) {
-    static thread_local const void* done[16];
-    static thread_local int ndone = 0;
-    for (int i = 0; i < ndone; ++i)
-        if (done[i] == (const void*)kernel) return DP_OK;
-    DP_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-    if (ndone < 16) done[ndone++] = (const void*)kernel;
-    return DP_OK;
+    return allow_dynamic_smem((const void*)kernel, sizeof(Smem));  // cached per (device, kernel)
 }
 
 template <int kPhase, bool kInit>
@@ -871,6 +865,9 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
                 has_ls = 1;
             }
         }
+        // y is polled by a forward solve that is sync-free (or tile-stream) and must be re-armed after every backward
+        // solve that does not consume-and-re-arm it itself (level-stream, tile-stream)
+        d.rearm_t = tile_stream || (u.precond == DP_PRECOND_SOLVE && !d.fwd_ls.rowptr && d.bwd_ls.rowptr) ? 1 : 0;
         d.fwd_look = u.fwd_max_level_chunks > 0 ? u.fwd_max_level_chunks : 1;
         d.bwd_look = u.bwd_max_level_chunks > 0 ? u.bwd_max_level_chunks : 1;
         int fwd_chunks = 0, bwd_chunks = 0;
@@ -963,7 +960,6 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
     ctx.has_multiply = has_multiply;
     ctx.has_solve = has_solve;
     ctx.has_ls = has_ls;
-    ctx.rearm_t = n_ts ? 1 : 0;
     ctx.rtol = params_host->rtol;
     ctx.max_iter = params_host->max_iter;
     ctx.word = reinterpret_cast<unsigned long long*>(ws + lay.word);

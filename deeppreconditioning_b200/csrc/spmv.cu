@@ -2,6 +2,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
+#include <vector>
+
 #include "tilepipe.cuh"
 
 namespace dp {
@@ -71,14 +74,65 @@ __global__ void coo_spmv_batch_kernel(const int* __restrict__ ind, const float* 
     }
 }
 
+namespace {
+constexpr int kMaxDevices = 64;
+struct KernelEntry {
+    int device;
+    const void* kernel;
+    size_t smem;     // dynamic shared memory the kernel has been opted into on that device
+    int threads;     // occupancy query the cached grid belongs to (0: none yet)
+    size_t occ_smem;
+    int grid;
+};
+std::mutex g_cache_mutex;
+std::vector<KernelEntry> g_kernels;
+int g_sm_count[kMaxDevices];
+
+int current_device() {
+    int dev = 0;
+    return cudaGetDevice(&dev) == cudaSuccess ? dev : 0;
+}
+KernelEntry& kernel_entry(int dev, const void* kernel) {  // caller holds g_cache_mutex
+    for (KernelEntry& e : g_kernels)
+        if (e.device == dev && e.kernel == kernel) return e;
+    g_kernels.push_back(KernelEntry{dev, kernel, 0, 0, 0, 0});
+    return g_kernels.back();
+}
+}  // namespace
+
 int sm_count() {
-    static int cached = 0;
-    if (!cached) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        if (cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) cached = 148;
-    }
-    return cached;
+    const int dev = current_device();
+    const bool cacheable = dev >= 0 && dev < kMaxDevices;
+    if (cacheable && g_sm_count[dev]) return g_sm_count[dev];
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) return 148;
+    if (cacheable) g_sm_count[dev] = sms;
+    return sms;
+}
+
+int allow_dynamic_smem(const void* kernel, size_t bytes) {
+    const int dev = current_device();
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    KernelEntry& e = kernel_entry(dev, kernel);
+    if (e.smem >= bytes && e.smem > 0) return DP_OK;
+    DP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    e.smem = bytes;
+    e.threads = 0;  // occupancy depends on the attribute
+    return DP_OK;
+}
+
+int coop_grid(const void* kernel, int threads, size_t smem) {
+    const int dev = current_device();
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    KernelEntry& e = kernel_entry(dev, kernel);
+    if (e.threads == threads && e.occ_smem == smem && e.grid > 0) return e.grid;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
+    e.threads = threads, e.occ_smem = smem, e.grid = per_sm * sms;
+    return e.grid;
 }
 
 }  // namespace dp
@@ -109,12 +163,7 @@ int dp_spmv_csr_f64(int32_t n, int32_t nnz, const int32_t* rowptr, const int32_t
     if (n < 0 || nnz < 0 || !rowptr || !y || (nnz > 0 && (!col || !val || !x))) return DP_ERR_INVALID;
     if (!aligned16(col) || !aligned16(val)) return DP_ERR_ALIGNMENT;
     if (n == 0) return DP_OK;
-    static thread_local bool smem_ok = false;
-    if (!smem_ok) {
-        DP_CUDA(cudaFuncSetAttribute((const void*)spmv_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)sizeof(SpmvSmem)));
-        smem_ok = true;
-    }
+    if (allow_dynamic_smem((const void*)spmv_csr_kernel, sizeof(SpmvSmem)) != DP_OK) return DP_ERR_CUDA;
     const int tiles = (n + kTileRows - 1) / kTileRows;
     const int resident = 2 * sm_count();
     const int grid = tiles < resident ? tiles : resident;

@@ -212,13 +212,6 @@ ic0_kernel(CsrView A, double* l, const int* __restrict__ plan, long long nchunks
     }
 }
 
-int coop_grid(const void* kernel, int threads, size_t smem) {
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1)
-        per_sm = 1;
-    return per_sm * sm_count();
-}
-
 int trsv_lookahead() {  // levels' worth of warps that take part in a solve (DPCG_TRSV_LOOKAHEAD: experiments)
     static int cached = 0;
     if (!cached) {
@@ -244,13 +237,8 @@ int ts_solve_launch(const TsSysDev* sys_dev, int nsys, int max_tiles, int nmax, 
         DP_LAUNCH_CHECK();
     }
     const void* kernel = short_rows ? (const void*)sptrsv_ts_batch_kernel<true> : (const void*)sptrsv_ts_batch_kernel<false>;
-    static thread_local int resident_of[2] = {0, 0};
-    int& resident = resident_of[short_rows ? 1 : 0];
-    if (!resident) {
-        DP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TsSmem)));
-        resident = coop_grid(kernel, kBlock, sizeof(TsSmem));
-    }
-    int grid = resident;
+    if (allow_dynamic_smem(kernel, sizeof(TsSmem)) != DP_OK) return DP_ERR_CUDA;
+    int grid = coop_grid(kernel, kBlock, sizeof(TsSmem));  // cached per device
     if (const char* e = getenv("DPCG_TS_GRID")) {  // experiments: fewer CTAs = fewer pollers
         const int g = atoi(e);
         if (g > 0 && g < grid) grid = g;
@@ -344,6 +332,13 @@ int dp_sptrsv_solve_batch_f64(const dp_trsv_system_t* systems_host, int32_t nsys
     return DP_OK;
 }
 
+#ifdef DPCG_TS_TRACE
+int dp_debug_ts_trace(long long* out_host) {
+    DP_CUDA(cudaMemcpyFromSymbol(out_host, g_ts_trace, sizeof(long long) * 2 * kTsTraceTiles * 8));
+    return DP_OK;
+}
+#endif
+
 #ifdef DPCG_LS_TRACE
 int dp_debug_ls_trace(long long* out_host) {
     DP_CUDA(cudaMemcpyFromSymbol(out_host, g_ls_trace, sizeof(long long) * 8 * 256));
@@ -379,12 +374,7 @@ int dp_sptrsv_ls_solve_batch_f64(const dp_trsv_ls_system_t* systems_host, int32_
     LsSysDev* sys = static_cast<LsSysDev*>(workspace);
     DP_CUDA(cudaMemcpyAsync(sys, dev.data(), sizeof(LsSysDev) * (size_t)nsys, cudaMemcpyHostToDevice, s));
     DP_CUDA(cudaStreamSynchronize(s));  // `dev` is a stack-lifetime staging buffer
-    static thread_local bool smem_ok = false;
-    if (!smem_ok) {
-        DP_CUDA(cudaFuncSetAttribute((const void*)sptrsv_ls_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)sizeof(LsSmem)));
-        smem_ok = true;
-    }
+    if (allow_dynamic_smem((const void*)sptrsv_ls_batch_kernel, sizeof(LsSmem)) != DP_OK) return DP_ERR_CUDA;
     const int resident = sm_count();
     sptrsv_ls_batch_kernel<<<nsys < resident ? nsys : resident, kBlock, sizeof(LsSmem), s>>>(sys, nsys);
     DP_LAUNCH_CHECK();

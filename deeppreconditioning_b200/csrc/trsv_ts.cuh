@@ -59,6 +59,18 @@
 
 namespace dp {
 
+// Timeline of the short-row kernel (experiments, -DDPCG_TS_TRACE): thread 0 of CTA 0 and of the middle CTA record
+// clock64 at five points of each of their first kTsTraceTiles tiles; read back with dp_debug_ts_trace.
+#ifdef DPCG_TS_TRACE
+constexpr int kTsTraceTiles = 1024;
+__device__ long long g_ts_trace[2 * kTsTraceTiles * 8];
+#define TS_TRACE(slot)                                                                                      \
+    if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2) && pipe.c_count < kTsTraceTiles) \
+    g_ts_trace[((blockIdx.x ? 1 : 0) * kTsTraceTiles + pipe.c_count) * 8 + (slot)] = clock64()
+#else
+#define TS_TRACE(slot)
+#endif
+
 constexpr int kTsCap = DPCG_TS_CAP;        // entries per stage: a 512-row tile of a 7-point factor (4 per row) is one item
 constexpr int kTsStages = DPCG_TS_STAGES;
 constexpr int kTsRound = DPCG_TS_ROUND;    // tile descriptors per table refill
@@ -233,7 +245,9 @@ __device__ __forceinline__ void ts_tile_short(const TsTile& d, int i, TsSmem& sm
     double v[kTsFast];
 #pragma unroll
     for (int k = 0; k < kTsFast; ++k) c[k] = 0, v[k] = 0.0;
+    TS_TRACE(0);
     const unsigned stage = pipe.acquire();
+    TS_TRACE(1);
     const TsStage& st = sm.stage[stage];
     bool done = !valid || dead;
     bool bad = false;  // the caller's DP_TRSV_SHORT_ROWS promise does not hold for this row
@@ -253,7 +267,17 @@ __device__ __forceinline__ void ts_tile_short(const TsTile& d, int i, TsSmem& sm
     if (bad) ctl.raise(DP_ERR_STRUCTURE), dead = true;
     dead = __any_sync(kFull, dead);
     if (dead) done = true;
+    TS_TRACE(2);
+#ifdef DPCG_TS_TRACE
+    const unsigned trace_item = pipe.c_count;
+#define TS_TRACE_AFTER(slot)                                                                                 \
+    if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2) && trace_item < kTsTraceTiles)  \
+    g_ts_trace[((blockIdx.x ? 1 : 0) * kTsTraceTiles + trace_item) * 8 + (slot)] = clock64()
+#else
+#define TS_TRACE_AFTER(slot)
+#endif
     pipe.release(i, 0);
+    TS_TRACE_AFTER(3);
     unsigned long long u[kTsFast];
 #pragma unroll
     for (int k = 0; k < kTsFast; ++k) {
@@ -281,7 +305,11 @@ __device__ __forceinline__ void ts_tile_short(const TsTile& d, int i, TsSmem& sm
             if (k < m && w[k] == kPending) w[k] = ld_relaxed_u64(xp + c[k]);
     };
     if (!done) try_finish(u);
-    if (__all_sync(kFull, done)) return;  // the streaming regime: every dependency was solved long ago
+    TS_TRACE_AFTER(4);
+    if (__all_sync(kFull, done)) {  // the streaming regime: every dependency was solved long ago
+        TS_TRACE_AFTER(5);
+        return;
+    }
     // Waiting for a level: one poll per dependency in flight. Two polls half a round trip apart were measured SLOWER
     // (0.97 -> 1.05 us per level, profiles/r1/ts_two_polls_negative.log): the L2 traffic of the pollers is part of the hop.
     for (unsigned idle = 0;;) {
@@ -297,6 +325,7 @@ __device__ __forceinline__ void ts_tile_short(const TsTile& d, int i, TsSmem& sm
         else __nanosleep(DPCG_TS_SLEEP);
 #endif
     }
+    TS_TRACE_AFTER(5);
 }
 
 // One tile of any shape: rows of any length, tiles of several pipeline items, rows cut by an item boundary.

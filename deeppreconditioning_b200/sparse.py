@@ -74,7 +74,10 @@ class CsrMatrix:
                        "dp_csr_from_coo")
         nnz = int(nnz_out.item())  # one sync per assembled matrix
         _lib.raise_on_flag(flag, "dp_csr_from_coo (duplicate (row, col) in the COO input)")
-        return cls(rowptr, col[:nnz], val[:nnz], n)
+        col, val = col[:nnz], val[:nnz]
+        if cap > nnz + nnz // 4:  # one element of a batched tensor: do not pin the whole batch's capacity behind a view
+            col, val = col.clone(), val.clone()
+        return cls(rowptr, col, val, n)
 
     @classmethod
     def from_arrays(cls, rowptr, col, val, device=None) -> "CsrMatrix":

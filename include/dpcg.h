@@ -85,6 +85,12 @@ int dp_csr_transpose(int32_t n, int32_t nnz, const int32_t* rowptr, const int32_
 int dp_csr_inv_diagonal(int32_t n, const int32_t* rowptr, const int32_t* col, const double* val, double* dinv,
                         int32_t* flag_out, void* stream);
 
+/* Structural nnz of M = L L^T without forming it: the count behind BenchmarkSuite._compute_sparsity (test.py:107-109:
+ * `100 * len(matrix.values()) / n^2` of the explicit product test.py:104-105 stores). rowptr/col = L, rowptr_t/col_t =
+ * L^T (dp_csr_transpose / TRIL_T), both with sorted rows. *nnz_out is a DEVICE int64. Exact integer work. */
+int dp_csr_aat_nnz(int32_t n, const int32_t* rowptr, const int32_t* col, const int32_t* rowptr_t, const int32_t* col_t,
+                   int64_t* nnz_out, void* stream);
+
 /* ---- K2: CSR SpMV fp64 ---------------------------------------------------------------------------------
  * y = A x. Replaces `A @ p` / `M @ r` (cg.py:60,61,75,81). Row sums are sequential in column order with
  * separately rounded products and sums, i.e. bit-identical to scipy's csr_matvec. */

@@ -31,8 +31,12 @@ class PcgResult:
     betas: list = field(default_factory=list)   # beta behind every body's p (cg.py:82 of the previous body; 0 first)
 
 
-def preconditioned_conjugate_gradient(A, b, M, x0=None, x_true=None, rtol=1e-8, max_iter=1024) -> PcgResult:
-    """cg.py:50-90. ``M`` is applied by ``@`` (an approximate inverse)."""
+def preconditioned_conjugate_gradient(A, b, M, x0=None, x_true=None, rtol=1e-8, max_iter=1024, as_is=False) -> PcgResult:
+    """cg.py:50-90. ``M`` is applied by ``@`` (an approximate inverse).
+
+    ``as_is``: also execute the work the reference does and drops every iteration - the error vector (all zeros when
+    ``x_true`` is None) and its A-norm ``<e, A e>``, a second ``A @`` per body (cg.py:85,87). It never influences the
+    iteration; the timed CPU baseline of ``bench.py`` switches it on so that the loop is timed as the reference runs it."""
     x_hat = x0 if x0 is not None else torch.zeros_like(b, dtype=torch.float64)  # cg.py:58
 
     rk = b - A @ x_hat  # cg.py:60
@@ -56,8 +60,12 @@ def preconditioned_conjugate_gradient(A, b, M, x0=None, x_true=None, rtol=1e-8, 
         zk = M @ rk  # cg.py:81
         beta = torch.inner(rk, zk) / rz  # cg.py:82
         pk = zk + beta * pk  # cg.py:83
+        if as_is:
+            error_i = (x_hat - x_true) if x_true is not None else torch.zeros_like(b, requires_grad=False)  # cg.py:85
         res = stopping_criterion(A, rk, b)  # cg.py:86
-        history.append(res.item())  # cg.py:87 (the A-norm error term is dropped: x_true is None on the path)
+        if as_is:
+            torch.inner(error_i, A @ error_i)  # cg.py:87: the A-norm error the reference appends and never reads
+        history.append(res.item())  # cg.py:87
     end_time = time.perf_counter()  # cg.py:88
 
     return PcgResult(end_time - start_time, len(history) - 1, 0, x_hat, float(history[-1]), history, alphas, betas)  # cg.py:90

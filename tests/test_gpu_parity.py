@@ -660,3 +660,101 @@ def test_config4_size_spmv_and_levels(cuda):
     b = rhs[0, :n].to(device=cuda, dtype=torch.float64)
     yv = precond.triangular_solve(T, fwd, b)
     assert torch.allclose(T.matvec(yv), b, rtol=1e-9, atol=1e-11)
+
+
+# ---- BASELINE sizes against the oracle and the reference's own spread (configs 2/3 and 4) -----------------------------
+SPREAD_PATH = Path(__file__).parent / "golden" / "pcg_spread.json"
+SPREAD = json.loads(SPREAD_PATH.read_text())["cases"] if SPREAD_PATH.exists() else []
+
+
+def spread_margin(case) -> int:
+    """The reference loop, unmodified, gives iterations_min..iterations_max on these operands depending on thread count,
+    storage of A and form of M (tests/golden/make_spread.py). A CUDA run is one more summation order: it is held to the
+    band widened by its own width on either side, which is +-1 (the north_star tolerance) where the reference is
+    reproducible, i.e. where the band is a single value."""
+    return max(1, case["iterations_max"] - case["iterations_min"])
+
+
+@pytest.mark.parametrize("case", SPREAD, ids=lambda c: f"{c['kind']}{c['side']}-sys{c['index']}-{c['net']}-{c['precond']}")
+def test_pcg_at_baseline_sizes(cuda, case):
+    """PCG at the sizes the bench quotes (316x316 with the PreconditionerNet factor in multiply mode = configs 2/3;
+    128^3 with Jacobi, the tril-pattern CNN factor and IC(0)-solve = config 4) against (a) the iteration counts of the
+    UNMODIFIED reference (committed fixture), (b) the oracle run here on the same operands: history, x, criterion."""
+    p = helpers.problem(case["kind"], case["side"], case["index"], 0.5, case["net"])
+    assert p.n == case["n"] and len(p.A[1]) == case["nnz_a"]
+    assert float(p.b.sum()) == case["b_checksum"] and float(np.sum(p.A[2])) == case["a_checksum"]
+    ops = gpu_operands(p, cuda)
+    helpers.assert_csr_equal(ops["A"], p.A)
+    helpers.assert_csr_equal(ops["L"], p.L)
+    name = case["precond"]
+    oracle = pcg.preconditioned_conjugate_gradient(osp.to_torch_csr(*p.A), p.b, build_operator(p, name),
+                                                   max_iter=case["max_iter"])
+    result = dp.pcg_solve(ops["A"], p.b.to(cuda), gpu_operator(name, ops, p, cuda), max_iter=case["max_iter"], history=True)
+    lo, hi, margin = case["iterations_min"], case["iterations_max"], spread_margin(case)
+    assert lo - margin <= result.iterations <= hi + margin, (result.iterations, lo, hi)
+    assert lo - margin <= oracle.iterations <= hi + margin, (oracle.iterations, lo, hi)  # the oracle is one of those runs
+    assert result.info == 0 and result.res < 1e-8 <= result.history[-2]
+    x, xo = result.x_hat.cpu(), oracle.x_hat
+    head = min(result.iterations, oracle.iterations, 10) + 1
+    np.testing.assert_allclose(result.history[:head], oracle.history[:head], rtol=1e-8)  # same recurrence
+    if lo == hi:  # the reference is reproducible here: north_star bar
+        assert abs(result.iterations - lo) <= 1
+        if result.iterations == oracle.iterations:
+            assert torch.linalg.vector_norm(x - xo) <= 1e-8 * torch.linalg.vector_norm(xo)
+            assert abs(result.res - oracle.res) <= 1e-8 * oracle.res
+    a = osp.to_scipy(*p.A)
+    bn = p.b.numpy()
+    true_rel = np.linalg.norm(a @ x.numpy() - bn) / np.linalg.norm(bn)
+    true_rel_oracle = np.linalg.norm(a @ xo.numpy() - bn) / np.linalg.norm(bn)
+    assert true_rel < 2e-4 and true_rel < 2 * true_rel_oracle + 1e-6
+    assert torch.linalg.vector_norm(x - xo) <= 1e-3 * torch.linalg.vector_norm(xo)  # both within sqrt(rtol) of A^-1 b
+
+
+def test_pcg_mixed_level_stream_directions(cuda):
+    """SOLVE mode where only ONE direction qualifies for the level-stream solve: a few 5-entry rows in L (too long for
+    its registers) whose transposed entries fall into the last, partly filled tile of L^T's level order (a full tile of
+    a 5-point factor is exactly at the stage capacity). The sync-free forward solve polls y, so y must be re-armed
+    after every level-stream backward solve (dp_pcg_solve_f64: rearm_t). Same bits as the all-sync-free solve, both
+    engines, and the oracle's iterations / solution. Then the mirrored case (long rows in L^T)."""
+    import scipy.sparse as sp
+
+    side = 40
+    p = helpers.problem("poisson2d", side, 3, 0.5, None)
+    lr, lc, lv = helpers.ic0_factor(p)
+    ops = gpu_operands(p, cuda)
+    b = p.b.to(cuda)
+    for long_rows_in, sites in (("L", ((2, 4), (3, 5), (1, 6))), ("U", ((37, 33), (36, 32), (38, 31)))):
+        L = osp.to_scipy(lr, lc, lv).tolil()
+        for y, x in sites:
+            i = y * side + x
+            if long_rows_in == "L":
+                L[i, i - 2], L[i, i - 3] = -0.01, 0.005
+            else:
+                L[i + 2, i], L[i + 3, i] = -0.01, 0.005
+        L = sp.csr_matrix(L)
+        L.sort_indices()
+        assert max(np.diff(L.indptr).max(), np.diff(sp.csr_matrix(L.T).indptr).max()) == 5
+        lower = CsrMatrix.from_scipy(L, cuda)
+        mixed = dp.FactoredSolve(lower)
+        plain = dp.FactoredSolve(lower, level_stream=False)
+        if long_rows_in == "L":
+            assert mixed.fwd_ls is None and mixed.bwd_ls is not None
+        else:
+            assert mixed.fwd_ls is not None and mixed.bwd_ls is None
+        assert plain.fwd_ls is None and plain.bwd_ls is None
+        want = pcg.preconditioned_conjugate_gradient(osp.to_torch_csr(*p.A), p.b,
+                                                     operators.FactoredSolve(L.indptr, L.indices, L.data), max_iter=3000)
+        for engine in ("fused", "stepped"):
+            got = dp.pcg_solve(ops["A"], b, mixed, max_iter=3000, engine=engine)
+            ref = dp.pcg_solve(ops["A"], b, plain, max_iter=3000, engine=engine)
+            assert got.iterations == ref.iterations == want.iterations, (long_rows_in, engine)
+            assert torch.equal(got.x_hat, ref.x_hat), (long_rows_in, engine)
+            assert torch.linalg.vector_norm(got.x_hat.cpu() - want.x_hat) <= 1e-8 * torch.linalg.vector_norm(want.x_hat)
+        # inside a batch next to a plain multiply system
+        pn = helpers.problem("poisson2d", 37, 0, 0.5, "net")
+        on = gpu_operands(pn, cuda)
+        extra = (on["A"], pn.b.to(cuda), dp.FactoredMultiply(on["L"], on["Lt"]))
+        got = dp.pcg_solve_batch([(ops["A"], b, mixed), extra], 1e-8, 3000)
+        ref = dp.pcg_solve_batch([(ops["A"], b, plain), extra], 1e-8, 3000)
+        for g, w in zip(got, ref):
+            assert g.iterations == w.iterations and torch.equal(g.x_hat, w.x_hat)
