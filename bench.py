@@ -400,7 +400,7 @@ def extras(device, host0):
                         "res": r.res, "algorithmic_gbs": iter_bytes(n, A.nnz, nnz_l) * r.iterations / ms / 1e6}
     single["ic0_solve"]["setup_ms_analysis_plus_factorisation"] = ic_setup_ms
     single["ic0_solve"]["levels"] = fwd.nlevels
-    single["ic0_solve"]["triangular_solves"] = "level-stream (one CTA, shared-memory dependencies)"
+    single["ic0_solve"]["triangular_solves"] = "level-stream (one CTA, dependencies polled in a shared-memory window)"
     single["ic0_solve_sync_free"]["triangular_solves"] = "sync-free (dependencies polled through L2)"
     out["single_system_316x316"] = single
 
@@ -421,7 +421,7 @@ def extras(device, host0):
         p.ls = copy.copy(fplan.ls)
         for field in ("rowptr", "col", "val", "level_sorted"):
             setattr(p.ls, field, getattr(fplan.ls, field).clone())
-        p.ls.source = f.val.data_ptr()
+        p.ls.source = type(p.ls).key(f)
         return (f, p, r0.clone())
 
     nb2 = 128
@@ -430,9 +430,52 @@ def extras(device, host0):
     ms = timed(lambda: precond.triangular_solve_batch(batch2, outs2, algorithm="ls"), reps=3)
     trsv2["level_stream_batch128"] = {"ms": ms, "algorithmic_gbs": nb2 * trsv_bytes2 / ms / 1e6,
                                       "frac_of_hbm_peak": nb2 * trsv_bytes2 / ms / 1e6 / peaks()[0],
-                                      "note": "128 copies of the factor in distinct memory, one CTA per system"}
+                                      "note": "128 copies of the factor in distinct memory, one CTA per system, vectors in the "
+                                              "original numbering (b gathered / x scattered through the level permutation)"}
     del batch2, outs2
+    # the same factor of the system kept in LEVEL ORDER (precond.LevelOrdering: perm = identity, vectors coalesced)
+    order = precond.level_ordering(T)
+    st_lo = order.renumber(st)
+    T_lo = CsrMatrix.from_spconv(st_lo, n, "tril")
+    A_lo = CsrMatrix.from_spconv(st_lo, n, "symmetrise")
+    b_lo = order.to_level(b)
+    factor_lo = precond.incomplete_cholesky0(T_lo)
+    fplan_lo = precond.analyse(factor_lo, False)
+    y_lo = torch.empty_like(b_lo)
+    ms = timed(lambda: precond.triangular_solve(factor_lo, fplan_lo, b_lo, y_lo, algorithm="ls"), reps=5)
+    trsv2["level_stream_level_order"] = {"ms": ms, "us_per_level": 1e3 * ms / fplan_lo.nlevels, "algorithmic_gbs": trsv_bytes2 / ms / 1e6}
+
+    def clone_lo():
+        f = CsrMatrix(factor_lo.rowptr.clone(), factor_lo.col.clone(), factor_lo.val.clone(), factor_lo.n)
+        p = copy.copy(fplan_lo)
+        p.perm = fplan_lo.perm.clone()
+        p.ls = copy.copy(fplan_lo.ls)
+        for field in ("rowptr", "col", "val", "level_sorted"):
+            setattr(p.ls, field, getattr(fplan_lo.ls, field).clone())
+        p.ls.source = type(p.ls).key(f)
+        return (f, p, b_lo.clone())
+
+    batch_lo = [clone_lo() for _ in range(nb2)]
+    outs_lo = [torch.empty_like(b_lo) for _ in range(nb2)]
+    ms = timed(lambda: precond.triangular_solve_batch(batch_lo, outs_lo, algorithm="ls"), reps=3)
+    trsv2["level_stream_batch128_level_order"] = {"ms": ms, "algorithmic_gbs": nb2 * trsv_bytes2 / ms / 1e6,
+                                                  "frac_of_hbm_peak": nb2 * trsv_bytes2 / ms / 1e6 / peaks()[0],
+                                                  "note": "same, systems renumbered by the factor's level sets: vectors coalesced"}
+    del batch_lo, outs_lo
     out["sptrsv_316x316_ic0"] = trsv2
+    # IC(0)-PCG on the level-ordered system (config 2's comparator in its fastest form)
+    batch = dp.PcgBatch([(A_lo, b_lo, dp.FactoredSolve(factor_lo, None, fplan_lo))], RTOL, MAX_ITER)
+
+    def go_lo():
+        batch.reset()
+        batch.solve()
+
+    ms = timed(go_lo)
+    r = batch.results()[0]
+    single["ic0_solve_level_order"] = {"ms_to_tol": ms, "iterations": r.iterations, "us_per_iteration": 1e3 * ms / max(r.iterations, 1),
+                                       "res": r.res, "algorithmic_gbs": iter_bytes(n, A.nnz, T.nnz) * r.iterations / ms / 1e6,
+                                       "triangular_solves": "level-stream on the system renumbered by the factor's level sets"}
+    del batch
 
     # config 4: 128^3, HBM-bound SpMV and SpTRSV
     st, _, rhs, sizes = synthetic.make_batch("poisson3d", 128, [0], device=device)

@@ -92,11 +92,10 @@ class PcgBatch:
             self.entries.append(dict(A=A, M=M, b=b_dev, x=x, work=work, hist=hist, coef=coef, out_device=b.device))
         nsys = len(self.entries)
         if any(getattr(e["M"], "tile_stream", False) for e in self.entries):
-            # tile-stream solves are separate launches between the phases: a feature of the stepped engine. The host
-            # polls the done counter every other iteration: these are systems whose iteration takes a millisecond, so a
-            # poll costs ~1 % while every iteration enqueued past convergence (up to check_every - 1) is pure loss, and
-            # finished systems leave the batch solves only at a poll.
-            self.params = _lib.PcgParams(self.rtol, self.max_iter, _ENGINES["stepped"], min(int(check_every), 2), 0)
+            # tile-stream solves are separate launches between the phases: a feature of the stepped engine. Converged
+            # systems drop out of every launch on the device (state flags), so an iteration enqueued past the batch's
+            # convergence is a handful of empty launches and the host polls the done counter only every 8 iterations.
+            self.params = _lib.PcgParams(self.rtol, self.max_iter, _ENGINES["stepped"], min(int(check_every), 8), 0)
         self.iters = torch.full((nsys,), -1, dtype=torch.int32, device=self.device)
         self.res = torch.full((nsys,), float("nan"), dtype=torch.float64, device=self.device)
         self.flag = torch.zeros(1, dtype=torch.int32, device=self.device)
@@ -190,13 +189,23 @@ def preconditioned_conjugate_gradient(A, b: torch.Tensor, M, x0=None, x_true=Non
 def conjugate_gradient(A, b, x0=None, x_true=None, rtol=1e-8, max_iter=1024):
     """Unpreconditioned CG (cg.py:20-47): returns ``(errors, x_hat)``, ``errors`` a list of ``(A-norm error, res)``.
 
-    With ``M = I`` the preconditioned recurrence is the same arithmetic as cg.py:31-45 (``z = r``, so
-    ``<r,z> = <r,r>``); the A-norm error entry is evaluated only when ``x_true`` is given, for the final iterate.
+    With ``M = I`` the preconditioned recurrence is the same arithmetic as cg.py:31-45 (``z = r``, so ``<r,z> = <r,r>``).
+    The A-norm error column (``<e_k, A e_k>`` with ``e_k = x_k - x_true``, cg.py:28-30,42-44; zero without ``x_true``) is
+    evaluated on the device for the final iterate (one SpMV) and carried back through the iterations by the CG identity
+    ``||e_k||_A^2 - ||e_{k+1}||_A^2 = a_k <r_k, r_k>`` (Hestenes-Stiefel; numerically stable in finite precision, Strakos &
+    Tichy 2002) from the step lengths and residual norms the solve records - no iterate history, no SpMV per iteration.
     """
     result = pcg_solve(A, b, Identity(), x0, rtol, max_iter, history=True)
-    zero = torch.zeros((), dtype=torch.float64)
-    errors = [(zero, torch.tensor(r, dtype=torch.float64)) for r in result.history]
-    if x_true is not None and errors:
-        e = (result.x_hat - x_true).to(torch.float64)
-        errors[-1] = (torch.inner(e, as_csr(A) @ e), errors[-1][1])
+    f64 = torch.float64
+    tail = torch.zeros(len(result.history), dtype=f64)
+    if x_true is not None and result.history:
+        A_dev = as_csr(A)
+        e = result.x_hat.to(device=A_dev.device, dtype=f64) - x_true.to(device=A_dev.device, dtype=f64)
+        last = float(torch.inner(e, A_dev.matvec(e)))
+        b64 = b.detach().to(f64)
+        bb = float(torch.inner(b64, b64))
+        drops = torch.tensor([a * r * bb for a, r in zip(result.alphas, result.history[:-1])], dtype=f64)  # a_k <r_k, r_k>
+        tail[:-1] = torch.flip(torch.cumsum(torch.flip(drops, [0]), 0), [0])
+        tail = tail + last
+    errors = [(tail[k], torch.tensor(r, dtype=f64)) for k, r in enumerate(result.history)]
     return errors, result.x_hat

@@ -80,6 +80,7 @@ struct Ctx {
     int nsys, total_tiles, total_fwd, total_bwd;
     int pw_fwd, pw_bwd;
     int has_multiply, has_solve, has_ls;
+    int keep_l2;  // the batch's matrices and vectors fit the L2 (a single small system): stream them without evict-first
     double rtol;
     int max_iter;
     unsigned long long* word;  // grid barrier (+ finished count in the upper half)
@@ -112,7 +113,7 @@ struct Smem {
     TileDesc tab[3][kMaxRoundTiles];
     double scratch[2][3 * kWarpsPerBlock];  // tile_reduce (double buffered)
     TileRed red;                            // tile_reduce_async (tiles that went through the pipeline)
-    LsShared ls;                            // level-stream solves: barriers of their pipeline geometry, window
+    LsShared ls;                            // level-stream solves: barriers of their pipeline geometry
     double scratch2[3 * kWarpsPerBlock];    // block_sum* of the per-system scalar evaluation
     SysDev sys;  // descriptor of the system this CTA is working on (survives across phases)
     int sys_id;
@@ -424,15 +425,14 @@ __device__ __forceinline__ void phase_dotrz(const Ctx& ctx, const SysDev& S, con
 // persistent kernel it would push the SpMV phases into register spills.
 template <bool kUpper>
 __device__ __noinline__ void trsv_level_stream_outlined(const LsFactor* F, const double* rhs, double* x,
-                                                        unsigned char* stage_bytes, LsShared* ls, TileDesc* tab) {
-    trsv_level_stream<kUpper>(*F, rhs, x, stage_bytes, *ls, tab, kMaxRoundTiles);
+                                                        unsigned char* stage_bytes, LsShared* ls) {
+    trsv_level_stream<kUpper, kLsStagesFused>(*F, rhs, x, stage_bytes, *ls);
 }
 
-// Systems that come with a level-ordered copy of the factor are solved by ONE CTA each (trsv_ls.cuh); they borrow table
-// P2 for their tile descriptors (a SOLVE system never streams in APPLY2).
+// Systems that come with a level-ordered copy of the factor are solved by ONE CTA each (trsv_ls.cuh), on the bytes of
+// the SpMV pipeline (idle between the phases).
 template <bool kUpper, bool kInit>
 __device__ __forceinline__ void phase_trsv_ls(const Ctx& ctx, int k, Smem& sm) {
-    bool used = false;
     for (int s = blockIdx.x; s < ctx.nsys; s += gridDim.x) {
         const SysDev* S = ctx.sys + s;
         if (S->precond != DP_PRECOND_SOLVE) continue;
@@ -441,13 +441,7 @@ __device__ __forceinline__ void phase_trsv_ls(const Ctx& ctx, int k, Smem& sm) {
         if (!kInit && ld_relaxed_s32(ctx.state + s) != 0) continue;
         const double* rhs = kUpper ? S->t : S->r[(k + 1) & 1];
         double* x = kUpper ? S->z[(k + 1) & 1] : S->t;
-        trsv_level_stream_outlined<kUpper>(&F, rhs, x, sm.pipe.bytes, &sm.ls, sm.tab[TAB_P2]);
-        used = true;
-    }
-    if (used) {
-        __syncthreads();
-        if (threadIdx.x == 0) sm.tab_ver[TAB_P2] = 0;
-        __syncthreads();
+        trsv_level_stream_outlined<kUpper>(&F, rhs, x, sm.pipe.bytes, &sm.ls);
     }
 }
 
@@ -598,22 +592,22 @@ __device__ __forceinline__ void rebuild_active(const Ctx& ctx, int cur, Smem& sm
 
 // Returns false on abort. `done` = finished count of the last barrier.
 // `list_stays`: the active list (hence every table) survives this iteration, so the last phase may start table A early.
-template <bool kInit>
+template <bool kInit, bool kSolve>
 __device__ __forceinline__ bool apply_preconditioner(const Ctx& ctx, int k, int cur, int ver, int total, GridBarrier& bar,
                                                      Smem& sm, Pipe& pipe, bool list_stays) {
     const int tab_a = list_stays ? (int)TAB_A : -1;
     run_tiles<PH_APPLY1, kInit, false>(ctx, k, cur, ver, total, sm, pipe,
-                                       ctx.has_multiply ? (int)TAB_P2 : (ctx.has_solve ? -1 : tab_a));
+                                       ctx.has_multiply ? (int)TAB_P2 : (kSolve ? -1 : tab_a));
     trace(ctx, sm, 8 * PH_APPLY1 + 1);
     if (bar.sync() < 0) return false;
     trace(ctx, sm, 8 * PH_APPLY1 + 2);
     if (ctx.has_multiply) {
-        run_tiles<PH_APPLY2, kInit, false>(ctx, k, cur, ver, total, sm, pipe, ctx.has_solve ? -1 : tab_a);
+        run_tiles<PH_APPLY2, kInit, false>(ctx, k, cur, ver, total, sm, pipe, kSolve ? -1 : tab_a);
         trace(ctx, sm, 8 * PH_APPLY2 + 1);
         if (bar.sync() < 0) return false;
         trace(ctx, sm, 8 * PH_APPLY2 + 2);
     }
-    if (ctx.has_solve) {
+    if (kSolve) {
         if (ctx.has_ls) phase_trsv_ls<false, kInit>(ctx, k, sm);
         const bool f = phase_trsv<false, kInit>(ctx, k, sm);
         if (bar.sync() < 0 || !f) return false;
@@ -639,10 +633,15 @@ __device__ __forceinline__ Smem& smem_init(unsigned char* raw, Pipe& pipe) {
 }
 
 // The whole solve in one persistent cooperative launch: device-side loop control, no host round trips.
+// kSolve: the batch holds SOLVE-mode systems. Two instantiations, so that the triangular-solve code (two inlined sync-free
+// streams, the level-stream call) does not weigh on the register allocation of the batches that never run it - the
+// benchmarked multiply-mode batches among them.
+template <bool kSolve>
 __global__ void __launch_bounds__(kBlock, 2) pcg_fused_kernel(Ctx ctx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Pipe pipe;
     Smem& sm = smem_init(smem_raw, pipe);
+    pipe.keep_l2 = ctx.keep_l2;
     GridBarrier bar{ctx.word, ctx.flag, &sm.bcast, 0u, gridDim.x};
     int cur = 0;          // active-list buffer in use
     int ver = 1;          // bumped whenever the list (hence every CTA's tile range) changes
@@ -650,7 +649,7 @@ __global__ void __launch_bounds__(kBlock, 2) pcg_fused_kernel(Ctx ctx) {
     int total = ctx.total_tiles;  // tiles of the active list (all systems at first)
     run_tiles<PH_INIT, false, false>(ctx, -1, cur, ver, total, sm, pipe, TAB_P1);
     if (bar.sync() < 0) return;
-    if (!apply_preconditioner<true>(ctx, -1, cur, ver, total, bar, sm, pipe, true)) return;
+    if (!apply_preconditioner<true, kSolve>(ctx, -1, cur, ver, total, bar, sm, pipe, true)) return;
     for (int k = 0; k <= ctx.max_iter; ++k) {
         trace(ctx, sm, 8 * PH_A + 0);
         run_tiles<PH_A, false, false>(ctx, k, cur, ver, total, sm, pipe, TAB_P1);
@@ -664,7 +663,7 @@ __global__ void __launch_bounds__(kBlock, 2) pcg_fused_kernel(Ctx ctx) {
         }
         const bool rebuild = done != done_built;  // same decision in every CTA
         if (rebuild && blockIdx.x == 0) rebuild_active(ctx, cur, sm);
-        if (!apply_preconditioner<false>(ctx, k, cur, ver, total, bar, sm, pipe, !rebuild)) return;  // >= 1 barrier: the new list is visible
+        if (!apply_preconditioner<false, kSolve>(ctx, k, cur, ver, total, bar, sm, pipe, !rebuild)) return;  // >= 1 barrier: the new list is visible
         if (rebuild) {
             cur ^= 1, done_built = done, ++ver;
             total = __ldcg(ctx.act_meta + 2 * cur + 1);
@@ -679,6 +678,7 @@ __global__ void __launch_bounds__(kBlock, 2) pcg_phase_kernel(Ctx ctx, int k) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Pipe pipe;
     Smem& sm = smem_init(smem_raw, pipe);
+    pipe.keep_l2 = ctx.keep_l2;
     if (kPhase == PH_FWD) {
         if (ctx.has_ls) phase_trsv_ls<false, kInit>(ctx, k, sm);
         phase_trsv<false, kInit>(ctx, k, sm);
@@ -793,8 +793,8 @@ int dp_device_info(int* sm_count_host, int* pcg_ctas_per_sm_host, int* l2_bytes_
     if (sm_count_host) *sm_count_host = sms;
     if (l2_bytes_host) *l2_bytes_host = l2;
     if (pcg_ctas_per_sm_host) {
-        if (allow_smem(pcg_fused_kernel) != DP_OK) return DP_ERR_CUDA;
-        *pcg_ctas_per_sm_host = coop_grid((const void*)pcg_fused_kernel, kBlock, sizeof(Smem)) / (sms > 0 ? sms : 1);
+        if (allow_smem(pcg_fused_kernel<false>) != DP_OK) return DP_ERR_CUDA;
+        *pcg_ctas_per_sm_host = coop_grid((const void*)pcg_fused_kernel<false>, kBlock, sizeof(Smem)) / (sms > 0 ? sms : 1);
     }
     return DP_OK;
 }
@@ -822,6 +822,7 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
     std::vector<int> tile_ofs((size_t)nsys + 1, 0), fwd_ofs((size_t)nsys + 1, 0), bwd_ofs((size_t)nsys + 1, 0);
     std::vector<int> ident((size_t)nsys + 1, 0);
     int has_multiply = 0, has_solve = 0, has_ls = 0, n_solve = 0, n_ts = 0;
+    long long working_set_bytes = 0;
     long long sum_fwd_lvl = 0, sum_bwd_lvl = 0;
     std::vector<TsSysDev> ts_sys[4];
     std::vector<int> ts_owner;  // system index of each tile-stream descriptor
@@ -854,13 +855,13 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
                 return DP_ERR_ALIGNMENT;
             ++n_ts;
         } else if (u.precond == DP_PRECOND_SOLVE) {
-            if (u.fwd_ls_rowptr && u.fwd_ls_col && u.fwd_ls_val && u.fwd_ls_perm && u.fwd_ls_level) {
-                if (!aligned16(u.fwd_ls_col) || !aligned16(u.fwd_ls_val)) return DP_ERR_ALIGNMENT;
+            if (u.fwd_ls_rowptr && u.fwd_ls_col && u.fwd_ls_val) {  // perm == NULL: the system is in this solve's level order
+                if (!aligned16(u.fwd_ls_col) || !aligned16(u.fwd_ls_val) || !aligned16(u.fwd_ls_rowptr)) return DP_ERR_ALIGNMENT;
                 d.fwd_ls = LsFactor{u.fwd_ls_rowptr, u.fwd_ls_col, u.fwd_ls_val, u.fwd_ls_perm, u.fwd_ls_level, u.n, u.m_nnz};
                 has_ls = 1;
             }
-            if (u.bwd_ls_rowptr && u.bwd_ls_col && u.bwd_ls_val && u.bwd_ls_perm && u.bwd_ls_level) {
-                if (!aligned16(u.bwd_ls_col) || !aligned16(u.bwd_ls_val)) return DP_ERR_ALIGNMENT;
+            if (u.bwd_ls_rowptr && u.bwd_ls_col && u.bwd_ls_val) {
+                if (!aligned16(u.bwd_ls_col) || !aligned16(u.bwd_ls_val) || !aligned16(u.bwd_ls_rowptr)) return DP_ERR_ALIGNMENT;
                 d.bwd_ls = LsFactor{u.bwd_ls_rowptr, u.bwd_ls_col, u.bwd_ls_val, u.bwd_ls_perm, u.bwd_ls_level, u.n, u.mt_nnz};
                 has_ls = 1;
             }
@@ -898,6 +899,9 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
         }
         d.b = u.b;
         d.x = u.x;
+        working_set_bytes += 12ll * ((long long)u.a_nnz + (u.precond >= DP_PRECOND_MULTIPLY ? u.m_nnz : 0) +
+                                     (u.precond == DP_PRECOND_MULTIPLY || u.precond == DP_PRECOND_SOLVE ? u.mt_nnz : 0)) +
+                             8ll * 10 * u.n;
         const int64_t np = pad32(u.n), tp = pad32(d.ntiles);
         double* w = u.work;
         d.r[0] = w; d.r[1] = w + np; d.p[0] = w + 2 * np; d.p[1] = w + 3 * np;
@@ -916,6 +920,7 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
                 TsSysDev f{}, g{};
                 f.F = LsFactor{u.fwd_ls_rowptr, u.fwd_ls_col, u.fwd_ls_val, nullptr, nullptr, u.n, u.m_nnz};
                 f.b = d.r[par], f.x = d.t, f.upper = 0, f.ntiles = d.ntiles, f.rev = 0;
+                f.skip = g.skip = reinterpret_cast<const int*>(ws + lay.state) + i;  // converged systems leave the solves at once
                 g.F = LsFactor{u.bwd_ls_rowptr, u.bwd_ls_col, u.bwd_ls_val, nullptr, nullptr, u.n, u.mt_nnz};
                 g.b = d.t, g.x = d.z[par], g.upper = 1, g.ntiles = d.ntiles, g.rev = 1;
                 ts_sys[par].push_back(f);
@@ -932,8 +937,9 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
 
     // the tile-stream solves replace the FWD/BWD phases of the stepped engine for ALL solve-mode systems of the batch
     if (n_ts && (n_ts != n_solve || params_host->engine != DP_ENGINE_STEPPED)) return DP_ERR_INVALID;
-    if (allow_smem(pcg_fused_kernel) != DP_OK || allow_smem(pcg_phase_kernel<PH_FWD, false>) != DP_OK) return DP_ERR_CUDA;
-    const int coop = coop_grid((const void*)pcg_fused_kernel, kBlock, sizeof(Smem));
+    const void* fused = has_solve ? (const void*)pcg_fused_kernel<true> : (const void*)pcg_fused_kernel<false>;
+    if (allow_dynamic_smem(fused, sizeof(Smem)) != DP_OK || allow_smem(pcg_phase_kernel<PH_FWD, false>) != DP_OK) return DP_ERR_CUDA;
+    const int coop = coop_grid(fused, kBlock, sizeof(Smem));
     const int coop_phase = coop_grid((const void*)pcg_phase_kernel<PH_FWD, false>, kBlock, sizeof(Smem));
     auto clamp_pw = [](long long lvl_chunks, int grid) {
         long long pw = (long long)trsv_lookahead() * lvl_chunks;
@@ -960,6 +966,13 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
     ctx.has_multiply = has_multiply;
     ctx.has_solve = has_solve;
     ctx.has_ls = has_ls;
+    {   // bytes one iteration touches: matrices (12 B per entry) + the 8 work vectors, b and x
+        int dev = 0, l2 = 0;
+        DP_CUDA(cudaGetDevice(&dev));
+        DP_CUDA(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev));
+        const char* e = getenv("DPCG_KEEP_L2");  // experiments: 0 / 1 forces the policy
+        ctx.keep_l2 = e ? (e[0] == '1') : (working_set_bytes * 10 < (long long)l2 * 6);
+    }
     ctx.rtol = params_host->rtol;
     ctx.max_iter = params_host->max_iter;
     ctx.word = reinterpret_cast<unsigned long long*>(ws + lay.word);
@@ -995,7 +1008,7 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
         ctx.pw_fwd = clamp_pw(sum_fwd_lvl, grid);
         ctx.pw_bwd = clamp_pw(sum_bwd_lvl, grid);
         void* args[] = {&ctx};
-        DP_CUDA(cudaLaunchCooperativeKernel((const void*)pcg_fused_kernel, dim3(grid), dim3(kBlock), args, sizeof(Smem), s));
+        DP_CUDA(cudaLaunchCooperativeKernel(fused, dim3(grid), dim3(kBlock), args, sizeof(Smem), s));
         return DP_OK;
     }
     if (params_host->engine != DP_ENGINE_STEPPED) return DP_ERR_INVALID;

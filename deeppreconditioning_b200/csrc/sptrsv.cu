@@ -71,8 +71,6 @@ sptrsv_batch_kernel(const TrsvSysDev* __restrict__ sys, int nsys, int wps, unsig
 }
 
 // ---- level-stream solve (trsv_ls.cuh): one CTA per system, systems dealt round robin -----------------------------
-constexpr int kLsRound = 16;  // tile descriptors per table refill
-
 struct LsSysDev {
     LsFactor F;
     const double* b;
@@ -81,14 +79,13 @@ struct LsSysDev {
 };
 
 struct LsSmem {
-    alignas(16) unsigned char bytes[PipeGeom<kLsCap, kLsStages>::kBytes];
-    LsShared ls;
-    TileDesc tab[kLsRound];
+    alignas(16) unsigned char bytes[LsGeom<kLsStagesAlone>::kBytes];
+    LsSharedT<kLsStagesAlone> ls;
 };
+constexpr int kLsThreads = kBlock + kWarp;  // 16 warps of rows + the producer warp
 
-// One CTA per SM: a solve is latency bound and wants its registers; two systems per SM were measured slower per
-// solve AND in aggregate (profiles/r1/tune26.log, tune27.log), so bigger batches loop.
-__global__ void __launch_bounds__(kBlock, 1) sptrsv_ls_batch_kernel(const LsSysDev* __restrict__ sys, int nsys) {
+// One CTA per SM: a solve is latency bound and wants the whole SM's shared memory for a deep pipeline; bigger batches loop.
+__global__ void __launch_bounds__(kLsThreads, 1) sptrsv_ls_batch_kernel(const LsSysDev* __restrict__ sys, int nsys) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LsSmem& sm = *reinterpret_cast<LsSmem*>(smem_raw);
     if (threadIdx.x == 0) sm.ls.init();
@@ -96,9 +93,9 @@ __global__ void __launch_bounds__(kBlock, 1) sptrsv_ls_batch_kernel(const LsSysD
     for (int s = blockIdx.x; s < nsys; s += gridDim.x) {
         const LsSysDev S = sys[s];
         if (S.upper)
-            trsv_level_stream<true>(S.F, S.b, S.x, sm.bytes, sm.ls, sm.tab, kLsRound);
+            trsv_level_stream<true, kLsStagesAlone>(S.F, S.b, S.x, sm.bytes, sm.ls);
         else
-            trsv_level_stream<false>(S.F, S.b, S.x, sm.bytes, sm.ls, sm.tab, kLsRound);
+            trsv_level_stream<false, kLsStagesAlone>(S.F, S.b, S.x, sm.bytes, sm.ls);
     }
 }
 
@@ -140,7 +137,7 @@ __global__ void ts_scatter_kernel(const TsPermDev* __restrict__ sys, int nsys) {
 }
 
 template <bool kShort>
-__global__ void __launch_bounds__(kBlock, 2)
+__global__ void __launch_bounds__(kTsThreads, 2)
 sptrsv_ts_batch_kernel(const TsSysDev* __restrict__ sys, int nsys, int max_tiles, unsigned long long* word, int* flag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TsSmem& sm = *reinterpret_cast<TsSmem*>(smem_raw);
@@ -238,7 +235,7 @@ int ts_solve_launch(const TsSysDev* sys_dev, int nsys, int max_tiles, int nmax, 
     }
     const void* kernel = short_rows ? (const void*)sptrsv_ts_batch_kernel<true> : (const void*)sptrsv_ts_batch_kernel<false>;
     if (allow_dynamic_smem(kernel, sizeof(TsSmem)) != DP_OK) return DP_ERR_CUDA;
-    int grid = coop_grid(kernel, kBlock, sizeof(TsSmem));  // cached per device
+    int grid = coop_grid(kernel, kTsThreads, sizeof(TsSmem));  // cached per device
     if (const char* e = getenv("DPCG_TS_GRID")) {  // experiments: fewer CTAs = fewer pollers
         const int g = atoi(e);
         if (g > 0 && g < grid) grid = g;
@@ -247,7 +244,7 @@ int ts_solve_launch(const TsSysDev* sys_dev, int nsys, int max_tiles, int nmax, 
     if (items >= (1ll << 31) - 1024) return DP_ERR_INVALID;  // the kernel counts items in 32 bits
     if (items < grid) grid = (int)items;
     void* args[] = {&sys_dev, &nsys, &max_tiles, &word, &flag};
-    DP_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kBlock), args, sizeof(TsSmem), s));
+    DP_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kTsThreads), args, sizeof(TsSmem), s));
     return DP_OK;
 }
 
@@ -349,7 +346,7 @@ int dp_debug_ls_trace(long long* out_host) {
 void dp_sptrsv_ls_limits(int32_t* limits_host) {
     limits_host[0] = kLsCap;                  // one pipeline item per 512-row tile
     limits_host[1] = kLsRowEntries;           // a row's entries live in registers
-    limits_host[2] = kLsWindow - kTileRows;   // every dependency is still in the shared-memory window
+    limits_host[2] = kLsDepDistance;          // every dependency is still in the shared-memory window
     limits_host[3] = kTileRows;               // rows of the widest level: a window slot is never rewritten by a row of
                                               // the level that still reads it
 }
@@ -364,8 +361,10 @@ int dp_sptrsv_ls_solve_batch_f64(const dp_trsv_ls_system_t* systems_host, int32_
     std::vector<LsSysDev> dev((size_t)nsys);
     for (int i = 0; i < nsys; ++i) {
         const dp_trsv_ls_system_t& u = systems_host[i];
-        if (u.n <= 0 || !u.rowptr_p || !u.col_p || !u.val_p || !u.perm || !u.level_sorted || !u.b || !u.x) return DP_ERR_INVALID;
-        if (!aligned16(u.col_p) || !aligned16(u.val_p)) return DP_ERR_ALIGNMENT;
+        if (u.n <= 0 || !u.rowptr_p || !u.col_p || !u.val_p || !u.b || !u.x) return DP_ERR_INVALID;
+        if (!u.perm && u.b == u.x) return DP_ERR_INVALID;
+        if (!aligned16(u.col_p) || !aligned16(u.val_p) || !aligned16(u.rowptr_p) || (!u.perm && !aligned16(u.b)))
+            return DP_ERR_ALIGNMENT;  // their tiles travel by 16-byte granular bulk copies
         LsSysDev d{};
         d.F = LsFactor{u.rowptr_p, u.col_p, u.val_p, u.perm, u.level_sorted, u.n, u.nnz};
         d.b = u.b, d.x = u.x, d.upper = u.upper ? 1 : 0;
@@ -376,7 +375,7 @@ int dp_sptrsv_ls_solve_batch_f64(const dp_trsv_ls_system_t* systems_host, int32_
     DP_CUDA(cudaStreamSynchronize(s));  // `dev` is a stack-lifetime staging buffer
     if (allow_dynamic_smem((const void*)sptrsv_ls_batch_kernel, sizeof(LsSmem)) != DP_OK) return DP_ERR_CUDA;
     const int resident = sm_count();
-    sptrsv_ls_batch_kernel<<<nsys < resident ? nsys : resident, kBlock, sizeof(LsSmem), s>>>(sys, nsys);
+    sptrsv_ls_batch_kernel<<<nsys < resident ? nsys : resident, kLsThreads, sizeof(LsSmem), s>>>(sys, nsys);
     DP_LAUNCH_CHECK();
     return DP_OK;
 }

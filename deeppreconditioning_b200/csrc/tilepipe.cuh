@@ -86,6 +86,13 @@ __device__ __forceinline__ unsigned long long l2_policy_stream() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
+// A working set that fits the L2 (one small system: 55 MB against 126 MB) should stay there instead: the next iteration
+// streams the same matrices again.
+__device__ __forceinline__ unsigned long long l2_policy_keep() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar,
                                          unsigned long long policy) {
 #if DPCG_PIPE_EVICT_FIRST
@@ -126,13 +133,13 @@ struct PipeBarriers {
     alignas(8) unsigned long long full[kStages];   // producer -> consumers: bytes have landed
     alignas(8) unsigned long long empty[kStages];  // consumers -> producer: all 16 warps are done with the stage
 };
-// The level-stream triangular solve (trsv_ls.cuh) lays a finer, deeper geometry over the same bytes: its tiles are
-// small (a stencil factor has 3 entries per row) and its stream is latency bound, so it wants many items in flight.
+// The level-stream triangular solve (trsv_ls.cuh) lays a finer geometry (stages of kLsCap entries: a stencil factor has 3
+// entries per row) plus its shared-memory solution window over the same bytes (checked there).
 constexpr int kLsCap = 1536;
-constexpr int kLsStages = 5;
-constexpr size_t kPipeRawBytes = PipeGeom<kPipeCap, kPipeStages>::kBytes > PipeGeom<kLsCap, kLsStages>::kBytes
-                                     ? PipeGeom<kPipeCap, kPipeStages>::kBytes
-                                     : PipeGeom<kLsCap, kLsStages>::kBytes;
+// (3 level-stream stages: matrix 3 * 18 528, row pointers 3 * 2 080, right-hand sides 3 * 4 096, a window of 5 tiles)
+constexpr size_t kLsFusedBytes = 3 * ((size_t)(kLsCap + 8) * 12 + (kTileRows + 8) * 4 + kTileRows * 8) + 5 * kTileRows * 8;
+constexpr size_t kPipeRawBytes = PipeGeom<kPipeCap, kPipeStages>::kBytes > kLsFusedBytes ? PipeGeom<kPipeCap, kPipeStages>::kBytes
+                                                                                          : kLsFusedBytes;
 struct PipeShared {
     alignas(16) unsigned char bytes[kPipeRawBytes];
     PipeBarriers<kPipeStages> bar;
@@ -173,6 +180,7 @@ struct PipeT {
     unsigned t_count;   // streaming tiles this warp has reduced (ring index of tile_reduce_async)
     int flip;           // tile_reduce scratch buffer in use next
     int early;          // 1 + id of the table whose first items are already in flight (begin_early), else 0
+    int keep_l2;        // the matrices fit the L2 together with the vectors: do not mark their lines evict-first
 
     static __device__ __forceinline__ int blocks(const TileDesc& d) { return (d.ce - d.cs + kCap - 1) / kCap; }
     __device__ __forceinline__ const double* stage_val(unsigned s) const { return val0 + (size_t)s * kSlots; }
@@ -185,7 +193,7 @@ struct PipeT {
         full = bar->full, empty = bar->empty;
         tab = nullptr;
         ntiles = 0;
-        c_count = 0u, p_count = 0u, p_tile = 0, p_blk = 0, t_count = 0u, flip = 0, early = 0;
+        c_count = 0u, p_count = 0u, p_tile = 0, p_blk = 0, t_count = 0u, flip = 0, early = 0, keep_l2 = 0;
         if (fresh) {
             if (threadIdx.x == 0) {
 #pragma unroll
@@ -227,7 +235,7 @@ struct PipeT {
         const int as = bs & ~3;
         const unsigned ncol = (unsigned)(((be + 3) & ~3) - as), nval = (unsigned)(((be + 1) & ~1) - as);
         unsigned long long* bar = &full[stage];
-        const unsigned long long pol = l2_policy_stream();
+        const unsigned long long pol = keep_l2 ? l2_policy_keep() : l2_policy_stream();
         mbar_arrive_expect_tx(bar, ncol * 4u + nval * 8u);
         bulk_g2s(val0 + (size_t)stage * kSlots, d.val + as, nval * 8u, bar, pol);
         bulk_g2s(col0 + (size_t)stage * kSlots, d.col + as, ncol * 4u, bar, pol);

@@ -60,15 +60,16 @@
 namespace dp {
 
 // Timeline of the short-row kernel (experiments, -DDPCG_TS_TRACE): thread 0 of CTA 0 and of the middle CTA record
-// clock64 at five points of each of their first kTsTraceTiles tiles; read back with dp_debug_ts_trace.
+// clock64 at six points of each of their first kTsTraceTiles tiles (look: before / after the stage wait, loads issued;
+// finish: coefficients read, first try done, tile done); read back with dp_debug_ts_trace.
 #ifdef DPCG_TS_TRACE
 constexpr int kTsTraceTiles = 1024;
 __device__ long long g_ts_trace[2 * kTsTraceTiles * 8];
-#define TS_TRACE(slot)                                                                                      \
-    if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2) && pipe.c_count < kTsTraceTiles) \
-    g_ts_trace[((blockIdx.x ? 1 : 0) * kTsTraceTiles + pipe.c_count) * 8 + (slot)] = clock64()
+#define TS_TRACE_AT(item, slot)                                                                          \
+    if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2) && (item) < kTsTraceTiles)  \
+    g_ts_trace[((blockIdx.x ? 1 : 0) * kTsTraceTiles + (item)) * 8 + (slot)] = clock64()
 #else
-#define TS_TRACE(slot)
+#define TS_TRACE_AT(item, slot)
 #endif
 
 constexpr int kTsCap = DPCG_TS_CAP;        // entries per stage: a 512-row tile of a 7-point factor (4 per row) is one item
@@ -100,6 +101,7 @@ struct TsSysDev {
     double* x;        // position space: solution AND polled vector, armed with kPending before the launch
     int upper, ntiles;
     int rev, pad;     // position p is row n - 1 - p of b / x (see above)
+    const int* skip;  // optional device flag, read at launch: non-zero = leave this system out (PCG: it has converged)
 };
 
 // One 512-row tile of one system's level-ordered copy. rowptr == nullptr: a system with fewer tiles, nothing to do.
@@ -124,29 +126,33 @@ struct TsSmem {
     alignas(16) TsStage stage[kTsStages];
     alignas(8) unsigned long long full[kTsStages];   // producer -> consumers: bytes have landed
     alignas(8) unsigned long long empty[kTsStages];  // consumers -> producer: all 16 warps are done with the stage
-    int released[kTsStages];                         // warps that have released the stage's current item
     TsTile tab[kTsRound];
 };
 
 __device__ __forceinline__ int ts_blocks(const TsTile& d) { return d.rowptr ? (d.ce - d.cs + kTsCap - 1) / kTsCap : 0; }
 
-// The pipeline of tilepipe.cuh with two changes: the tile's metadata rides on its first item, and there is no
-// producer thread - the warp that releases a stage LAST re-arms it at once with the item kTsStages further on (the
-// item after (t, j) is found by walking the round's table), so a stage is never idle while a producer is busy
-// elsewhere. Items are numbered since kernel start: item i lives in stage i % kTsStages, its (i / kTsStages)-th use.
+// The pipeline of tilepipe.cuh with two changes: the tile's metadata rides on its first item, and the producer is a
+// WARP OF ITS OWN (warp kWarpsPerBlock of a kTsThreads-thread CTA; lane 0 issues). Round 1 let the warp that released a
+// stage last re-arm it; the per-tile timeline (tools/trace_ts.py, profiles/r2/ts_trace_r1_kernel.log) showed what that
+// costs: under load the four bulk copies of an item block their issuing thread for ~2000 cycles (TMA back-pressure), the
+// warp that paid them was late for its next tile, hence last again, and its serial path - bytes, stage -> registers, issue,
+// poll - became the period of the whole CTA (4700 cycles per 512 rows). The producer warp takes the issue off every
+// consumer's path. Items are numbered since kernel start: item i lives in stage i % kTsStages, its (i / kTsStages)-th use.
+constexpr int kTsThreads = kBlock + kWarp;  // 16 consumer warps (one thread per row of a tile) + the producer warp
+
 struct TsPipe {
     TsSmem* sm;
     int ntiles;
-    unsigned c_count;  // items this warp has consumed
+    unsigned c_count;  // consumers: items this warp has released; producer lane: items issued
+    unsigned a_count;  // consumers: items this warp has acquired (the short-row kernel holds two at a time)
 
     __device__ __forceinline__ void init(TsSmem* s) {
-        sm = s, ntiles = 0, c_count = 0u;
+        sm = s, ntiles = 0, c_count = 0u, a_count = 0u;
         if (threadIdx.x == 0) {
 #pragma unroll
             for (int k = 0; k < kTsStages; ++k) {
                 mbar_init(&sm->full[k], 1u);
                 mbar_init(&sm->empty[k], (unsigned)kWarpsPerBlock);
-                sm->released[k] = 0;
             }
             mbar_fence_init();
         }
@@ -158,8 +164,11 @@ struct TsPipe {
         while (t < ntiles && j >= ts_blocks(sm->tab[t])) ++t, j = 0;
         return t < ntiles;
     }
-    // One lane: arm `stage` (free: every warp has released its previous item) with block j of tile t.
+    // The producer warp (all lanes): arm `stage` (free: every consumer warp has released its previous item) with block j
+    // of tile t. Under load a bulk copy blocks its issuing thread for ~400 cycles whatever its size, so the item's four
+    // copies go out from four lanes at once; lane 0 arms the barrier with the total first.
     __device__ __forceinline__ void issue(unsigned stage, int t, int j) {
+        const int lane = threadIdx.x & 31;
         const TsTile& d = sm->tab[t];
         TsStage& st = sm->stage[stage];
         const int bs = d.cs + j * kTsCap;
@@ -176,51 +185,48 @@ struct TsPipe {
         if (j == 0) bytes += rp_bytes + b_bytes;
         unsigned long long* bar = &sm->full[stage];
         const unsigned long long pol = l2_policy_stream();
-        mbar_arrive_expect_tx(bar, bytes);
-        if (j == 0) {  // metadata first: it is what the consumers read first
-            bulk_g2s(st.rowptr, d.rowptr + r0, rp_bytes, bar, pol);
-            bulk_g2s(st.b, d.b + b0, b_bytes, bar, pol);
-        }
-        bulk_g2s(st.val, d.val + as, nval * 8u, bar, pol);
-        bulk_g2s(st.col, d.col + as, ncol * 4u, bar, pol);
-    }
-    // All threads, after the round's table is complete and visible and every item of the previous round is consumed
-    // (so all stages are free and nobody is re-arming one).
-    __device__ __forceinline__ void begin(int count) {
-        ntiles = count;
-        if (threadIdx.x == 0) {
-            int t = 0, j = -1;
-#pragma unroll
-            for (int k = 0; k < kTsStages; ++k)
-                if (next_item(t, j)) issue((c_count + (unsigned)k) % kTsStages, t, j);
-        }
-    }
-    __device__ __forceinline__ unsigned acquire() {
-        const unsigned stage = c_count % kTsStages;
-        // suspend instead of spinning: warps that wait for bytes must not take issue slots from the warps that work
-        while (!mbar_try_wait_hint(&sm->full[stage], (c_count / kTsStages) & 1u, 2000u)) {
-        }
-        return stage;
-    }
-    // Hand back block j of tile t; the last warp to do so re-arms the stage.
-    __device__ __forceinline__ void release(int t, int j) {
+        if (lane == 0) mbar_arrive_expect_tx(bar, bytes);
         __syncwarp();
-        if ((threadIdx.x & 31) == 0) {
-            const unsigned stage = c_count % kTsStages;
-            mbar_arrive(&sm->empty[stage]);
-            if (atomicAdd(&sm->released[stage], 1) == kWarpsPerBlock - 1) {
-                sm->released[stage] = 0;
-                bool more = true;
-#pragma unroll
-                for (int k = 0; k < kTsStages; ++k) more = more && next_item(t, j);
-                if (more) {
-                    // acquire the other warps' arrivals (their reads of the stage) before the async proxy overwrites it
-                    while (!mbar_try_wait(&sm->empty[stage], (c_count / kTsStages) & 1u)) {
-                    }
-                    issue(stage, t, j);
+        if (lane == 0) bulk_g2s(st.val, d.val + as, nval * 8u, bar, pol);
+        if (lane == 1) bulk_g2s(st.col, d.col + as, ncol * 4u, bar, pol);
+        if (lane == 2 && j == 0) bulk_g2s(st.rowptr, d.rowptr + r0, rp_bytes, bar, pol);
+        if (lane == 3 && j == 0) bulk_g2s(st.b, d.b + b0, b_bytes, bar, pol);
+    }
+    // Producer warp, once per round (after the round's table is complete and visible): every item of the round, in
+    // order, each as soon as its stage has been released by all consumer warps.
+    __device__ __forceinline__ void produce(int count) {
+        ntiles = count;
+        int t = 0, j = -1;
+        while (next_item(t, j)) {
+            const unsigned stage = c_count % kTsStages, use = c_count / kTsStages;
+            if (use > 0 && (threadIdx.x & 31) == 0) {
+                while (!mbar_try_wait_hint(&sm->empty[stage], (use - 1u) & 1u, 2000u)) {
                 }
             }
+            __syncwarp();
+            issue(stage, t, j);
+            ++c_count;
         }
+    }
+    __device__ __forceinline__ void begin(int count) { ntiles = count; }  // consumers
+    __device__ __forceinline__ unsigned acquire() {
+        const unsigned stage = a_count % kTsStages;
+        // suspend instead of spinning: warps that wait for bytes must not take issue slots from the warps that work
+        while (!mbar_try_wait_hint(&sm->full[stage], (a_count / kTsStages) & 1u, 2000u)) {
+        }
+        ++a_count;
+        return stage;
+    }
+    // Wait for the bytes of the item after the one just released, without taking it (acquire() then returns at once).
+    __device__ __forceinline__ void await_next() {
+        const unsigned stage = a_count % kTsStages;
+        while (!mbar_try_wait_hint(&sm->full[stage], (a_count / kTsStages) & 1u, 2000u)) {
+        }
+    }
+    // Hand back the stage of the oldest item this warp still holds.
+    __device__ __forceinline__ void release(int, int) {
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&sm->empty[c_count % kTsStages]);
         ++c_count;
     }
 };
@@ -232,7 +238,14 @@ struct TsPipe {
 // solved (levels wider than the batch's window of tiles in flight) the code is straight-line. A kernel of its own
 // (kShort): sharing registers with the general loop below spilled, and the spill traffic cost more than the early
 // hand-back won (profiles/README.md).
-__device__ __forceinline__ void ts_tile_short(const TsTile& d, int i, TsSmem& sm, TsPipe& pipe, const AbortCtl& ctl, bool& dead) {
+// `more`: another tile follows in this round. Its bytes are awaited WHILE this tile's dependency loads are in flight
+// (they are an L2 round trip of 1000-1600 cycles under load, tools/trace_ts.py): the two longest waits of a warp's path
+// through a tile overlap, at no cost in registers.
+// Measured and rejected in round 2 (profiles/r2/README.md): a full look/finish software pipeline over two tiles (the
+// stage must then be held across the next tile's look, which leaves one of three stages for the stream: 0.67 -> 0.65
+// on 8 x 256^3) and conflict-free rotated stage reads (the 4-way bank conflicts of 4-entry rows are real - 53 % of the
+// wavefronts - but the phase is latency bound: no gain).
+__device__ __forceinline__ void ts_tile_short(const TsTile& d, bool more, TsSmem& sm, TsPipe& pipe, const AbortCtl& ctl, bool& dead) {
     const int tid = threadIdx.x;
     double* xp = d.x;
     const int r = d.ltile * kTileRows + tid;
@@ -245,9 +258,11 @@ __device__ __forceinline__ void ts_tile_short(const TsTile& d, int i, TsSmem& sm
     double v[kTsFast];
 #pragma unroll
     for (int k = 0; k < kTsFast; ++k) c[k] = 0, v[k] = 0.0;
-    TS_TRACE(0);
+    const unsigned trace_item = pipe.c_count;
+    (void)trace_item;
+    TS_TRACE_AT(trace_item, 0);
     const unsigned stage = pipe.acquire();
-    TS_TRACE(1);
+    TS_TRACE_AT(trace_item, 1);
     const TsStage& st = sm.stage[stage];
     bool done = !valid || dead;
     bool bad = false;  // the caller's DP_TRSV_SHORT_ROWS promise does not hold for this row
@@ -267,23 +282,16 @@ __device__ __forceinline__ void ts_tile_short(const TsTile& d, int i, TsSmem& sm
     if (bad) ctl.raise(DP_ERR_STRUCTURE), dead = true;
     dead = __any_sync(kFull, dead);
     if (dead) done = true;
-    TS_TRACE(2);
-#ifdef DPCG_TS_TRACE
-    const unsigned trace_item = pipe.c_count;
-#define TS_TRACE_AFTER(slot)                                                                                 \
-    if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2) && trace_item < kTsTraceTiles)  \
-    g_ts_trace[((blockIdx.x ? 1 : 0) * kTsTraceTiles + trace_item) * 8 + (slot)] = clock64()
-#else
-#define TS_TRACE_AFTER(slot)
-#endif
-    pipe.release(i, 0);
-    TS_TRACE_AFTER(3);
+    TS_TRACE_AT(trace_item, 2);
+    pipe.release(0, 0);
+    TS_TRACE_AT(trace_item, 3);
     unsigned long long u[kTsFast];
 #pragma unroll
     for (int k = 0; k < kTsFast; ++k) {
         u[k] = 0ull;
         if (!done && k < m) u[k] = ld_relaxed_u64(xp + c[k]);
     }
+    if (more) pipe.await_next();  // the next tile's bytes land while the loads above are in flight
     // finish the row from one snapshot of its dependencies; publishes at once (rows of the same warp may wait for it)
     auto try_finish = [&](const unsigned long long (&w)[kTsFast]) {
         bool ready = true;
@@ -305,9 +313,9 @@ __device__ __forceinline__ void ts_tile_short(const TsTile& d, int i, TsSmem& sm
             if (k < m && w[k] == kPending) w[k] = ld_relaxed_u64(xp + c[k]);
     };
     if (!done) try_finish(u);
-    TS_TRACE_AFTER(4);
+    TS_TRACE_AT(trace_item, 4);
     if (__all_sync(kFull, done)) {  // the streaming regime: every dependency was solved long ago
-        TS_TRACE_AFTER(5);
+        TS_TRACE_AT(trace_item, 5);
         return;
     }
     // Waiting for a level: one poll per dependency in flight. Two polls half a round trip apart were measured SLOWER
@@ -325,7 +333,7 @@ __device__ __forceinline__ void ts_tile_short(const TsTile& d, int i, TsSmem& sm
         else __nanosleep(DPCG_TS_SLEEP);
 #endif
     }
-    TS_TRACE_AFTER(5);
+    TS_TRACE_AT(trace_item, 5);
 }
 
 // One tile of any shape: rows of any length, tiles of several pipeline items, rows cut by an item boundary.
@@ -410,7 +418,7 @@ __device__ __forceinline__ void ts_tile_general(const TsTile& d, int i, TsSmem& 
     }
 }
 
-// The whole batch. All kBlock threads of every CTA of a cooperative launch must call. kShort: every system of the
+// The whole batch. All kTsThreads threads of every CTA of a cooperative launch must call. kShort: every system of the
 // batch carries DP_TRSV_SHORT_ROWS (no row with more than kTsFast dependencies; violations raise DP_ERR_STRUCTURE).
 template <bool kShort>
 __device__ __forceinline__ void trsv_tile_stream(const TsSysDev* __restrict__ sys, int nsys, int max_tiles, TsSmem& sm,
@@ -418,6 +426,7 @@ __device__ __forceinline__ void trsv_tile_stream(const TsSysDev* __restrict__ sy
     TsPipe pipe;
     pipe.init(&sm);
     const int tid = threadIdx.x;
+    const bool producer = tid >= kBlock;  // the last warp
     const int G = gridDim.x;
     const int items = max_tiles * nsys;  // < 2^31: checked by the host
     const int mine = items > (int)blockIdx.x ? (items - (int)blockIdx.x + G - 1) / G : 0;
@@ -425,14 +434,14 @@ __device__ __forceinline__ void trsv_tile_stream(const TsSysDev* __restrict__ sy
     for (int j0 = 0; j0 < mine; j0 += kTsRound) {
         const int cnt = min(kTsRound, mine - j0);
         __syncthreads();  // every warp has consumed every item of the previous round: its table is free
-        for (int i = tid; i < cnt; i += kBlock) {
+        for (int i = tid; i < cnt; i += kTsThreads) {
             const long long g = blockIdx.x + (long long)(j0 + i) * G;
             const int s = (int)(g % nsys), t = (int)(g / nsys);
             const TsSysDev S = sys[s];
             TsTile d;
             d.rowptr = nullptr, d.col = S.F.col, d.val = S.F.val, d.b = S.b, d.x = S.x;
             d.n = S.F.n, d.cs = 0, d.ce = 0, d.ltile = t, d.upper = S.upper, d.rev = S.rev;
-            if (t < S.ntiles) {
+            if (t < S.ntiles && !(S.skip && ld_relaxed_s32(S.skip) != 0)) {  // (the flag does not change during the launch)
                 d.rowptr = S.F.rowptr;
                 d.cs = __ldg(S.F.rowptr + min(t * kTileRows, S.F.n));
                 d.ce = __ldg(S.F.rowptr + min((t + 1) * kTileRows, S.F.n));
@@ -441,14 +450,26 @@ __device__ __forceinline__ void trsv_tile_stream(const TsSysDev* __restrict__ sy
             sm.tab[i] = d;
         }
         __syncthreads();
+        if (producer) {
+            pipe.produce(cnt);
+            continue;
+        }
         pipe.begin(cnt);
-        for (int i = 0; i < cnt; ++i) {
-            const TsTile& d = sm.tab[i];
-            if (!d.rowptr) continue;
-            if (kShort)
-                ts_tile_short(d, i, sm, pipe, ctl, dead);
-            else
+        if (kShort) {
+            int nxt = 0;  // next tile of the round that has rows
+            while (nxt < cnt && !sm.tab[nxt].rowptr) ++nxt;
+            while (nxt < cnt) {
+                const int i = nxt;
+                for (++nxt; nxt < cnt && !sm.tab[nxt].rowptr; ++nxt) {
+                }
+                ts_tile_short(sm.tab[i], nxt < cnt, sm, pipe, ctl, dead);
+            }
+        } else {
+            for (int i = 0; i < cnt; ++i) {
+                const TsTile& d = sm.tab[i];
+                if (!d.rowptr) continue;
                 ts_tile_general(d, i, sm, pipe, ctl, dead);
+            }
         }
     }
     __syncthreads();

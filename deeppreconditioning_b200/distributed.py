@@ -26,7 +26,8 @@ def make_records(indices, results, milliseconds) -> torch.Tensor:
 
 
 def gather_records(local: torch.Tensor, n_systems: int, group=None) -> torch.Tensor:
-    """All-gather the per-system records and return them ordered by system index: ``[n_systems, 4]`` on every rank.
+    """All-gather the per-system records and return them ordered by system index: ``[n_systems, width]`` on every rank
+    (column 0 is the system index; ``bench.py`` uses the 4 columns of :func:`make_records`, ``BenchmarkSuite.run`` 8).
 
     Uses the process group's backend (NCCL over NVLink/NVSwitch on GPUs, gloo in the CPU tests); the payload is
     ``n_systems * 32`` bytes — latency-only. Works without an initialised process group (single process).
@@ -37,9 +38,10 @@ def gather_records(local: torch.Tensor, n_systems: int, group=None) -> torch.Ten
         world = dist.get_world_size(group)
         per_rank = (n_systems + world - 1) // world
         device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
-        padded = torch.full((per_rank, RECORD_WIDTH), -1.0, dtype=torch.float64, device=device)
+        width = local.shape[1]
+        padded = torch.full((per_rank, width), -1.0, dtype=torch.float64, device=device)
         padded[: local.shape[0]] = local.to(device)
-        out = torch.empty((world * per_rank, RECORD_WIDTH), dtype=torch.float64, device=device)
+        out = torch.empty((world * per_rank, width), dtype=torch.float64, device=device)
         dist.all_gather_into_tensor(out, padded, group=group)
         gathered = out[out[:, 0] >= 0].cpu()
     order = torch.argsort(gathered[:, 0])

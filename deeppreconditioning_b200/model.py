@@ -56,19 +56,24 @@ class SparseConvTensor:
 class SparseConv2d(nn.Module):
     """Regular sparse convolution (stride 1): an output site is active iff its window holds an active input.
 
-    ``out[y, x] = bias + sum_{ky,kx} in[y + ky - ph, x + kx - pw] @ W[ky, kx]``. Output spatial shape is
-    ``(H + 2*ph - k + 1, W + 2*pw - k + 1)`` as for the dense convolution.
+    ``out[y, x] = bias + sum_{ky,kx} in[y + ky - ph, x + kx - pw] @ W[:, ky, kx, :].T`` - the dense ``conv2d``
+    (cross-correlation) restricted to the active output sites (``tests/test_host.py::test_sparse_conv_is_the_dense_conv``).
+    Output spatial shape is ``(H + 2*ph - k + 1, W + 2*pw - k + 1)``. ``weight`` has spconv 2.x's layout
+    ``[out, k, k, in]`` and the parameter names are spconv's (``weight``, ``bias``), so a state dict saved from the
+    reference's ``spconv.SparseConv2d`` layers loads unchanged (``test.py:216``).
     """
 
     def __init__(self, in_channels: int, out_channels: int, kernel_size: int, padding=(0, 0), bias: bool = True) -> None:
         super().__init__()
         self.k = int(kernel_size)
         self.padding = (padding, padding) if isinstance(padding, int) else tuple(padding)
-        self.weight = nn.Parameter(torch.empty(self.k, self.k, in_channels, out_channels))
         self.bias = nn.Parameter(torch.zeros(out_channels)) if bias else None
         fan_in = in_channels * self.k * self.k
         bound = (1.0 / fan_in) ** 0.5
-        nn.init.uniform_(self.weight, -bound * 3**0.5, bound * 3**0.5)
+        # drawn in (k, k, in, out) order, stored in spconv's [out, k, k, in]: the random-init factors of the committed
+        # golden vectors (tests/golden) were made with this draw order
+        drawn = nn.init.uniform_(torch.empty(self.k, self.k, in_channels, out_channels), -bound * 3**0.5, bound * 3**0.5)
+        self.weight = nn.Parameter(drawn.permute(3, 0, 1, 2).contiguous())
         if bias:
             nn.init.uniform_(self.bias, -bound, bound)
 
@@ -77,7 +82,7 @@ class SparseConv2d(nn.Module):
         h, w = x.spatial_shape
         ho, wo = h + 2 * ph - k + 1, w + 2 * pw - k + 1
         if k == 1 and ph == 0 and pw == 0:
-            out = x.features @ self.weight[0, 0]
+            out = x.features @ self.weight[:, 0, 0, :].t()
             if self.bias is not None:
                 out = out + self.bias
             return SparseConvTensor(out, x.indices, [ho, wo], x.batch_size)
@@ -91,25 +96,29 @@ class SparseConv2d(nn.Module):
                 srcs.append(ok.nonzero().squeeze(1))
                 taps.append((ky, kx))
         uniq, inverse = torch.unique(torch.cat(keys), return_inverse=True)
-        out = x.features.new_zeros(uniq.shape[0], self.weight.shape[-1])
+        out = x.features.new_zeros(uniq.shape[0], self.weight.shape[0])
         start = 0
         for key, src, (ky, kx) in zip(keys, srcs, taps):
             dst = inverse[start:start + key.shape[0]]
             start += key.shape[0]
-            out.index_add_(0, dst, x.features[src] @ self.weight[ky, kx])
+            out.index_add_(0, dst, x.features[src] @ self.weight[:, ky, kx, :].t())
         if self.bias is not None:
             out = out + self.bias
         indices = torch.stack((uniq // (ho * wo), (uniq // wo) % ho, uniq % wo), dim=1).int()
         return SparseConvTensor(out, indices, [ho, wo], x.batch_size)
 
 
-class _Activation(nn.Module):
-    def __init__(self, act: nn.Module) -> None:
-        super().__init__()
-        self.act = act
+class PReLU(nn.PReLU):
+    """``nn.PReLU`` on the features of a sparse tensor. A subclass, not a wrapper: inside ``nn.Sequential`` its parameter is
+    ``layers.N.weight`` exactly as in the reference's ``spconv.SparseSequential(..., nn.PReLU())`` (``model.py:27-37``)."""
 
-    def forward(self, x: SparseConvTensor) -> SparseConvTensor:
-        return x.replace_feature(self.act(x.features))
+    def forward(self, x: SparseConvTensor) -> SparseConvTensor:  # type: ignore[override]
+        return x.replace_feature(super().forward(x.features))
+
+
+class LeakyReLU(nn.LeakyReLU):
+    def forward(self, x: SparseConvTensor) -> SparseConvTensor:  # type: ignore[override]
+        return x.replace_feature(super().forward(x.features))
 
 
 def _lower_triangular_tail(interim: SparseConvTensor) -> SparseConvTensor:
@@ -123,15 +132,19 @@ def _lower_triangular_tail(interim: SparseConvTensor) -> SparseConvTensor:
 
 
 class PreconditionerNet(nn.Module):
-    """Fully convolutional network mapping ``tril(A)`` to a lower-triangular ``L`` (``model.py:13-59``)."""
+    """Fully convolutional network mapping ``tril(A)`` to a lower-triangular ``L`` (``model.py:13-59``).
+
+    Same module tree as the reference (``self.layers``: conv, PReLU, 4 x (2x2 conv, PReLU), conv), hence the same
+    ``state_dict`` keys and tensor shapes: ``load_state_dict(torch.load("best.pt"))`` of a reference checkpoint works
+    (``test.py:216``; ``tests/test_host.py::test_reference_checkpoint_layout_loads``)."""
 
     def __init__(self, channels: list[int]) -> None:
         super().__init__()
         assert len(channels) % 2
-        layers: list[nn.Module] = [SparseConv2d(channels[0], channels[1], 1), _Activation(nn.PReLU())]
+        layers: list[nn.Module] = [SparseConv2d(channels[0], channels[1], 1), PReLU()]
         for index, (cin, cout) in enumerate(zip(channels[1:-2], channels[2:-1], strict=True)):
             padding = (1, 0) if index < (len(channels) - 2) // 2 else (0, 1)
-            layers += [SparseConv2d(cin, cout, 2, padding=padding), _Activation(nn.PReLU())]
+            layers += [SparseConv2d(cin, cout, 2, padding=padding), PReLU()]
         layers.append(SparseConv2d(channels[-2], channels[-1], 1))
         self.layers = nn.Sequential(*layers)
 
@@ -150,7 +163,7 @@ class PreconditionerTrilNet(nn.Module):
         super().__init__()
         layers: list[nn.Module] = []
         for cin, cout in zip(channels[:-2], channels[1:-1], strict=True):
-            layers += [SparseConv2d(cin, cout, 1), _Activation(nn.LeakyReLU())]
+            layers += [SparseConv2d(cin, cout, 1), LeakyReLU()]
         layers.append(SparseConv2d(channels[-2], channels[-1], 1))
         self.layers = nn.Sequential(*layers)
 

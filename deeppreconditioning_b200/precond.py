@@ -39,6 +39,16 @@ class TriangularPlan:
     upper: bool
     ls: "LevelOrdered | None" = None  # level-ordered copy of the factor (narrow levels): level-stream solve
     ts: "LevelOrdered | None" = None  # level-ordered copy of any factor, made on demand: tile-stream batch solve
+    _identity: bool | None = None
+
+    @property
+    def perm_is_identity(self) -> bool:
+        """The matrix is already in the level order of this solve (``precond.LevelOrdering``): the level-stream solve then
+        takes its vectors by position (bulk copies instead of a gather through ``perm``). One read-back per plan."""
+        if self._identity is None:
+            n = self.perm.shape[0]
+            self._identity = bool(torch.equal(self.perm, torch.arange(n, dtype=torch.int32, device=self.perm.device)))
+        return self._identity
 
 
 @dataclass
@@ -50,12 +60,17 @@ class LevelOrdered:
     val: torch.Tensor           # fp64[nnz], entries in the factor's order inside each row
     level_sorted: torch.Tensor  # int32[n]
     nnz: int
-    source: int                 # data_ptr of the values it was copied from (a plan may serve several factors)
+    source: tuple               # (data_ptr, version counter) of the values it was copied from (a plan may serve several
+                                # factors; an in-place refactorisation bumps the tensor's version and invalidates the copy)
     stats: torch.Tensor | None = None  # device int32[3]: most entries in a tile / in a row, largest dependency distance
     _short: bool | None = None
 
+    @staticmethod
+    def key(matrix: CsrMatrix) -> tuple:
+        return (matrix.val.data_ptr(), matrix.val._version)
+
     def matches(self, matrix: CsrMatrix) -> bool:
-        return self.source == matrix.val.data_ptr()
+        return self.source == self.key(matrix)
 
     @property
     def short_rows(self) -> bool:
@@ -86,8 +101,8 @@ def _permute(matrix: CsrMatrix, plan: TriangularPlan, perm: torch.Tensor | None 
                                          _lib.ptr(perm), _lib.ptr(plan.level), _lib.ptr(rowptr_p), _lib.ptr(col_p),
                                          _lib.ptr(val_p), _lib.ptr(level_sorted), _lib.ptr(stats), _lib.ptr(ws), ws.numel(),
                                          _lib.stream_ptr(dev)), "dp_sptrsv_permute")
-    copy = LevelOrdered(rowptr_p, col_p[: matrix.nnz], val_p[: matrix.nnz], level_sorted, matrix.nnz, matrix.val.data_ptr(),
-                        stats)
+    copy = LevelOrdered(rowptr_p, col_p[: matrix.nnz], val_p[: matrix.nnz], level_sorted, matrix.nnz,
+                        LevelOrdered.key(matrix), stats)
     return copy, stats
 
 
@@ -197,7 +212,9 @@ def _level_stream_batch(systems, outs=None, copies=None):
         d = descs[i]
         d.n, d.nnz, d.upper = n, ls.nnz, int(plan.upper)
         d.rowptr_p, d.col_p, d.val_p = _lib.ptr(ls.rowptr), _lib.ptr(ls.col), _lib.ptr(ls.val)
-        d.perm, d.level_sorted, d.b, d.x = _lib.ptr(plan.perm), _lib.ptr(ls.level_sorted), _lib.ptr(b), _lib.ptr(x)
+        by_position = plan.perm_is_identity and b.data_ptr() % 16 == 0 and b.data_ptr() != x.data_ptr()
+        d.perm = None if by_position else _lib.ptr(plan.perm)
+        d.level_sorted, d.b, d.x = _lib.ptr(ls.level_sorted), _lib.ptr(b), _lib.ptr(x)
         xs.append(x), keep.append(b)
     ws = _workspace(lib.dp_sptrsv_ls_workspace_bytes(nsys), dev)
     with torch.cuda.device(dev):
@@ -339,6 +356,23 @@ def incomplete_cholesky0(tril_a: CsrMatrix, plan: TriangularPlan | None = None) 
     return CsrMatrix(tril_a.rowptr, tril_a.col, l_val[: tril_a.nnz], n)
 
 
+def incomplete_cholesky_threshold(tril_a: CsrMatrix, fill_in: int = 1, threshold: float = 0.1) -> CsrMatrix:
+    """Threshold incomplete Cholesky ICT(p, tau) of ``tril(A)`` (``dp_icholt_host``) - stands in for the reference's default
+    comparator ``ilupp.icholt(A, add_fill_in=fill_in, threshold=threshold)`` (``test.py:81-86``). A sequential host
+    algorithm (as in the reference): the pattern travels to the host and the factor back; set-up work, not the solve."""
+    lib, n, dev = _lib.lib(), tril_a.n, tril_a.device
+    rowptr, col, val = (np.ascontiguousarray(a) for a in tril_a.to_host())
+    capacity = int(len(col)) + n * max(int(fill_in), 0) + 1
+    rowptr_out = np.empty(n + 1, np.int32)
+    col_out, val_out = np.empty(capacity, np.int32), np.empty(capacity, np.float64)
+    nnz = np.zeros(1, np.int64)
+    _lib.check(lib.dp_icholt_host(n, rowptr.ctypes.data, col.ctypes.data, val.ctypes.data, int(fill_in), float(threshold),
+                                  rowptr_out.ctypes.data, col_out.ctypes.data, val_out.ctypes.data, capacity,
+                                  nnz.ctypes.data), "dp_icholt_host (missing diagonal or non-positive pivot)")
+    k = int(nnz[0])
+    return CsrMatrix.from_arrays(rowptr_out, col_out[:k].copy(), val_out[:k].copy(), device=dev)
+
+
 class _Operator:
     precond: int = _lib.PRECOND_IDENTITY
 
@@ -468,6 +502,8 @@ class FactoredSolve(FactoredMultiply):
                 for name, t in (("rowptr", ls.rowptr), ("col", ls.col), ("val", ls.val), ("perm", plan.perm),
                                 ("level", ls.level_sorted)):
                     setattr(system, f"{tag}_ls_{name}", _lib.ptr(t))
+                if not self.tile_stream and plan.perm_is_identity:
+                    setattr(system, f"{tag}_ls_perm", None)  # level-ordered system: vectors by position (bulk copies)
 
 
 def as_operator(M, device=None) -> _Operator:

@@ -148,6 +148,17 @@ class CsrMatrix:
     def T(self) -> "CsrMatrix":
         return self.transpose()
 
+    def tril(self) -> "CsrMatrix":
+        """Lower triangle, diagonal included (the ``tril(A)`` the incomplete factorisations start from). Set-up work in
+        plain tensor ops; ``BenchmarkSuite`` normally keeps the stored lower triangle it rebuilt ``A`` from instead."""
+        counts = torch.diff(self.rowptr).long()
+        rows = torch.repeat_interleave(torch.arange(self.n, device=self.device), counts)
+        keep = self.col.long() <= rows
+        per_row = torch.bincount(rows[keep], minlength=self.n)
+        rowptr = torch.zeros(self.n + 1, dtype=torch.int32, device=self.device)
+        rowptr[1:] = torch.cumsum(per_row, 0).to(torch.int32)
+        return CsrMatrix(rowptr, self.col[keep].contiguous(), self.val[keep].contiguous(), self.n)
+
     def matvec(self, x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         """``y = A x`` on the device (``dp_spmv_csr_f64``)."""
         assert x.is_cuda and x.dtype == torch.float64 and x.shape == (self.n,)

@@ -161,11 +161,14 @@ size_t dp_sptrsv_batch_workspace_bytes(int32_t nsys);
 int dp_sptrsv_solve_batch_f64(const dp_trsv_system_t* systems_host, int32_t nsys, int32_t* flag_out, void* workspace,
                               size_t workspace_bytes, void* stream);
 
-/* Level-stream solve: ONE CTA per system walks the level-ordered copy through the TMA tile pipeline and releases the
- * rows level by level through a ring of shared-memory mbarriers; dependencies are picked up from a shared-memory
- * window instead of polling L2. For factors with narrow levels (2-D stencils: 2n-1 levels of <= n rows) this replaces
- * an L2 hop per level by an mbarrier hand-off; a batch keeps one SM busy per system. Bit-identical to dp_sptrsv_solve_f64.
- * b and x are in the ORIGINAL numbering. No cooperative launch, no device flag: nothing spins. */
+/* Level-stream solve: ONE CTA per system walks the level-ordered copy through the TMA tile pipeline; a row's
+ * dependencies are awaited on a shared-memory window of the solution (the pending-NaN protocol of the sync-free solve
+ * with a shared-memory round trip in place of the L2 hop), there is no barrier per level. For factors with narrow levels
+ * (2-D stencils: 2n-1 levels of <= n rows); a batch keeps one SM busy per system. Bit-identical to dp_sptrsv_solve_f64.
+ * perm != NULL: b and x are in the ORIGINAL numbering (gathered / scattered through perm). perm == NULL: the matrix is
+ * in this solve's level order already (row r of the copy is row r of T) and b / x are indexed by position: b must be
+ * 16-byte aligned and must not alias x. level_sorted is not read. rowptr_p, col_p, val_p must be 16-byte aligned.
+ * No cooperative launch, no device flag: the only spins are on shared memory and bounded. */
 typedef struct dp_trsv_ls_system {
     int32_t n;
     int32_t nnz;
@@ -211,6 +214,16 @@ int dp_ic0_f64(int32_t n, const int32_t* rowptr, const int32_t* col, const doubl
                const int32_t* plan, int64_t nchunks, int32_t max_level_chunks, int32_t* flag_out, void* workspace,
                size_t workspace_bytes, void* stream);
 
+/* Threshold incomplete Cholesky ICT(p, tau) on the HOST (every pointer is a host pointer): the reference's default
+ * comparator `ilupp.icholt(A, add_fill_in=1, threshold=0.1)` (test.py:81-86) is a sequential C++ CPU routine, and so is
+ * this stand-in (ilupp is not in the image: values "parity unpinned", scheme and dropping rules in csrc/icholt.cu).
+ * Input: CSR of tril(A), rows sorted, diagonal last. Output: CSR of L in the same form; col_out/val_out have `capacity`
+ * entries (nnz + n * fill_in is always enough), *nnz_out_host receives the stored count.
+ * DP_ERR_STRUCTURE: missing diagonal / entry above the diagonal / non-positive pivot; DP_ERR_WORKSPACE: capacity. */
+int dp_icholt_host(int32_t n, const int32_t* rowptr_host, const int32_t* col_host, const double* val_host, int32_t fill_in,
+                   double threshold, int32_t* rowptr_out_host, int32_t* col_out_host, double* val_out_host,
+                   int64_t capacity, int64_t* nnz_out_host);
+
 /* ---- K5: the whole PCG loop ----------------------------------------------------------------------------------
  * Replaces preconditioned_conjugate_gradient (cg.py:50-90) with its exact semantics: iteration-0 check on
  * <z0,z0>/<b,b> (cg.py:66), later checks on <r,r>/<b,b> < rtol (cg.py:15-17,71,86), at most max_iter bodies,
@@ -230,8 +243,9 @@ typedef struct dp_pcg_system {
     const int32_t* mt_rowptr; const int32_t* mt_col; const double* mt_val;  /* L^T (MULTIPLY/SOLVE) */
     const double* dinv;                                                     /* JACOBI */
     const int32_t* fwd_plan; const int32_t* bwd_plan;                       /* SOLVE */
-    /* SOLVE, optional: level-ordered copies of L and L^T (dp_sptrsv_permute). When all five pointers of a direction
-     * are set that solve runs as a level-stream solve (one CTA per system) instead of the sync-free one. */
+    /* SOLVE, optional: level-ordered copies of L and L^T (dp_sptrsv_permute). When rowptr / col / val of a direction are
+     * set that solve runs as a level-stream solve (one CTA per system) instead of the sync-free one; perm == NULL there
+     * says the system is already in that solve's level order (vectors taken by position). */
     const int32_t* fwd_ls_rowptr; const int32_t* fwd_ls_col; const double* fwd_ls_val;
     const int32_t* fwd_ls_perm; const int32_t* fwd_ls_level;
     const int32_t* bwd_ls_rowptr; const int32_t* bwd_ls_col; const double* bwd_ls_val;

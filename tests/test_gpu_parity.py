@@ -563,15 +563,16 @@ def test_pcg_is_bitwise_reproducible_and_engines_agree(cuda):
 
 
 def test_benchmark_suite_end_to_end(cuda, tmp_path):
-    """BenchmarkSuite.run()/dump_csv() (test.py:119-198) on a synthetic test set, all four techniques."""
+    """BenchmarkSuite.run()/dump_csv() (test.py:119-198) on a synthetic test set, all four techniques, with the
+    reference's default comparator arguments (icholt(1, 0.1)) and with IC(0)."""
     torch.manual_seed(69)
     net = models.PreconditionerNet(models.DEFAULT_CHANNELS).to(cuda)
-    data = synthetic.SyntheticPressureDataSet("poisson2d", 24, number_samples=2, batch_size=1, device=cuda)
+    data = synthetic.SyntheticPressureDataSet("poisson2d", 24, number_samples=3, batch_size=1, device=cuda)
     suite = BenchmarkSuite(data, net, max_iter=5000)
     suite.run()
     suite.dump_csv(tmp_path)
     for name in suite.techniques:
-        assert len(suite.iterations[name]) == 2 and all(0 < i < 5000 for i in suite.iterations[name])
+        assert len(suite.iterations[name]) == 3 and all(0 < i < 5000 for i in suite.iterations[name])
         assert all(s == 100 for s in suite.successes[name]) and all(r < 1e-8 for r in suite.residuals[name])
     assert max(suite.iterations["incomplete_cholesky"]) < min(suite.iterations["vanilla"])
     assert all(np.isfinite(k) and k > 1 for name in suite.techniques for k in suite.kappas[name])
@@ -579,15 +580,72 @@ def test_benchmark_suite_end_to_end(cuda, tmp_path):
     table = (tmp_path / "table.csv").read_text().splitlines()
     assert table[0] == "technique,kappas,densities,iterations,setups,durations,totals,successes" and len(table) == 5
     assert (tmp_path / "totals.csv").read_text().splitlines()[0] == "vanilla,jacobi,incomplete_cholesky,learned"
-    # density column: explicit nnz(M)/n^2 like test.py:107-109
+    assert "icholt(add_fill_in=1, threshold=0.1)" in (tmp_path / "variants.csv").read_text()
+    # the serial walk of the reference (one system per launch) gives the same records: a system's arithmetic is bitwise the
+    # same alone or in a batch
+    serial = BenchmarkSuite(data, net, max_iter=5000, batch_systems=1)
+    serial.run()
+    for name in suite.techniques:
+        assert serial.iterations[name] == suite.iterations[name] and serial.residuals[name] == suite.residuals[name]
+        assert serial.densities[name] == suite.densities[name]
+    # density column (a10): exactly what the reference reports, 100 * len(M.values()) / n^2 of the explicit M it stores
+    # (test.py:104-109): identity / diagonal / the fp32 product L @ L.T of the model output with exact zeros dropped
     n = 24 * 24
-    assert suite.densities["vanilla"][0] == pytest.approx(100 / n) and suite.densities["learned"][0] > suite.densities["incomplete_cholesky"][0]
-    # the IC(0) comparator on the level-ordered system: the same iteration (counts +-1, density unchanged)
+    assert suite.densities["vanilla"][0] == 100 * n / n ** 2 == suite.densities["jacobi"][0]
+    for k in range(3):
+        p = helpers.problem("poisson2d", 24, k, 0.5, "net")
+        explicit = osp.explicit_product(*p.L)
+        assert suite.densities["learned"][k] == 100 * len(explicit.values()) / (n * n)
+    # the comparator's own factor: icholt on the host == its restatement; IC(0) variant and its level-ordered form
+    from oracle import icholt as oict
+
+    p0 = helpers.problem("poisson2d", 24, 0, 0.5, None)
+    want = oict.icholt(*p0.T, 1, 0.1)
+    ll = osp.to_scipy(*want)
+    assert suite.densities["incomplete_cholesky"][0] == 100 * (ll @ ll.T).nnz / (n * n)
+    ic0 = BenchmarkSuite(data, net, techniques=("incomplete_cholesky",), max_iter=5000, ic_fill_in=0, ic_threshold=0.0)
+    ic0.run()
     ordered = BenchmarkSuite(data, net, techniques=("incomplete_cholesky",), max_iter=5000, level_order_ic=True)
     ordered.run()
-    for got, want in zip(ordered.iterations["incomplete_cholesky"], suite.iterations["incomplete_cholesky"]):
-        assert abs(got - want) <= 1
-    assert ordered.densities["incomplete_cholesky"] == pytest.approx(suite.densities["incomplete_cholesky"])
+    for got, want_it in zip(ordered.iterations["incomplete_cholesky"], ic0.iterations["incomplete_cholesky"]):
+        assert abs(got - want_it) <= 1
+    assert ordered.densities["incomplete_cholesky"] == pytest.approx(ic0.densities["incomplete_cholesky"])
+    for k in range(3):  # IC(0) iteration counts against the oracle loop with the oracle's factor
+        pk = helpers.problem("poisson2d", 24, k, 0.5, None)
+        o = pcg.preconditioned_conjugate_gradient(osp.to_torch_csr(*pk.A), pk.b, operators.FactoredSolve(*helpers.ic0_factor(pk)), max_iter=5000)
+        assert ic0.iterations["incomplete_cholesky"][k] == o.iterations
+    # the reference's literal application of the comparator, (L L^T) @ r (test.py:88), also runs (and is what it is)
+    literal = BenchmarkSuite(data, net, techniques=("incomplete_cholesky",), max_iter=300, ic_apply="multiply")
+    literal.run()
+    assert all(i > 0 for i in literal.iterations["incomplete_cholesky"])
+
+
+def test_conjugate_gradient_error_history(cuda):
+    """conjugate_gradient(A, b, x_true=...) (cg.py:20-47): (A-norm error, res) per iteration against the oracle."""
+    import scipy.sparse.linalg as spla
+
+    p = helpers.problem("poisson2d", 37, 1, 0.5, None)
+    ops = gpu_operands(p, cuda)
+    x_true = torch.from_numpy(spla.spsolve(osp.to_scipy(*p.A).tocsc(), p.b.numpy()))
+    want_errors, want_x = pcg.conjugate_gradient(osp.to_torch_csr(*p.A), p.b, x_true=x_true, max_iter=3000)
+    errors, x = dp.conjugate_gradient(ops["A"], p.b.to(cuda), x_true=x_true.to(cuda), max_iter=3000)
+    assert abs(len(errors) - len(want_errors)) <= 1
+    # the same recurrence: identical early history (later on the two runs drift by a fraction of an iteration - the
+    # reference's own runs do, tests/golden/pcg_spread.json - and an error that falls by orders of magnitude shows it)
+    np.testing.assert_allclose([float(e) for e, _ in errors[:30]], [float(e) for e, _ in want_errors[:30]], rtol=1e-6)
+    np.testing.assert_allclose([float(r) for _, r in errors[:10]], [float(r) for _, r in want_errors[:10]], rtol=1e-8)
+    k = min(len(errors), len(want_errors)) - 1
+    np.testing.assert_allclose([float(e) for e, _ in errors[:k]], [float(e) for e, _ in want_errors[:k]], rtol=0.5)
+    assert torch.linalg.vector_norm(x.cpu() - want_x) <= 1e-4 * torch.linalg.vector_norm(want_x)  # both at sqrt(rtol)
+    # every entry of the column against its literal evaluation: a run stopped after j bodies ends on the same iterate
+    # x_j (solves are bitwise reproducible), whose error is computed directly, <e_j, A e_j> with one SpMV
+    for j in (1, 17, 40, 75):
+        stopped, _ = dp.conjugate_gradient(ops["A"], p.b.to(cuda), x_true=x_true.to(cuda), max_iter=j)
+        assert len(stopped) == j + 1
+        assert float(stopped[-1][0]) == pytest.approx(float(errors[j][0]), rel=1e-7)
+        assert float(stopped[-1][1]) == float(errors[j][1])
+    zero_errors, _ = dp.conjugate_gradient(ops["A"], p.b.to(cuda), max_iter=3000)  # no x_true: the column is zeros (cg.py:28)
+    assert all(float(e) == 0.0 for e, _ in zero_errors)
 
 
 def test_benchmark_suite_on_the_reference_disk_layout(cuda, tmp_path):
@@ -701,7 +759,11 @@ def test_pcg_at_baseline_sizes(cuda, case):
         assert abs(result.iterations - lo) <= 1
         if result.iterations == oracle.iterations:
             assert torch.linalg.vector_norm(x - xo) <= 1e-8 * torch.linalg.vector_norm(xo)
-            assert abs(result.res - oracle.res) <= 1e-8 * oracle.res
+            # final relative residual ||r|| / ||b|| = sqrt(criterion): equal within 1e-8 of the residual's scale (||b||),
+            # and to 1e-6 of its own size - after ~200 bodies the two dot-product orders have drifted ~1e-8 apart
+            # relative to a residual that has itself dropped by 1e-4 (measured: 316^2 IC(0), 195 bodies, 1.0e-8)
+            assert abs(np.sqrt(result.res) - np.sqrt(oracle.res)) <= 1e-8
+            assert abs(result.res - oracle.res) <= 1e-6 * oracle.res
     a = osp.to_scipy(*p.A)
     bn = p.b.numpy()
     true_rel = np.linalg.norm(a @ x.numpy() - bn) / np.linalg.norm(bn)
@@ -758,3 +820,40 @@ def test_pcg_mixed_level_stream_directions(cuda):
         ref = dp.pcg_solve_batch([(ops["A"], b, plain), extra], 1e-8, 3000)
         for g, w in zip(got, ref):
             assert g.iterations == w.iterations and torch.equal(g.x_hat, w.x_hat)
+
+
+# ---- training losses on the COO SpMV kernel --------------------------------------------------------------
+def test_sparse_losses_match_the_reference(cuda):
+    """metrics.frobenius_loss / inverse_loss / hutchinson_trace through dp_coo_spmv_batch_f32 against the dense oracle and
+    the golden values the unmodified reference module produced (tests/golden/metrics_golden.json); gradients of
+    frobenius_loss with respect to the CNN output against autograd through the dense form."""
+    from deeppreconditioning_b200 import metrics
+    from oracle import metrics as om
+    from test_oracle import _loss_batch
+
+    golden = json.loads((Path(__file__).parent / "golden" / "metrics_golden.json").read_text())
+    st, learned, solution, rhs = _loss_batch()
+    lower, tril = learned.dense()[:, 0], st.dense()[:, 0]
+    st_d, ln_d = helpers.to_device(st, cuda), helpers.to_device(learned, cuda)
+    fro = metrics.frobenius_loss(ln_d, solution.to(cuda), rhs.to(cuda))
+    assert float(fro) == pytest.approx(float(om.frobenius_loss(lower, solution, rhs)), rel=1e-5)
+    assert float(fro) == pytest.approx(golden["frobenius_loss"], rel=1e-5)
+    inv = metrics.inverse_loss(st_d, ln_d)  # all unit vectors: the exact Frobenius norm
+    assert float(inv) == pytest.approx(float(om.inverse_loss(tril, lower)), rel=1e-4)
+    assert float(inv) == pytest.approx(golden["inverse_loss"], rel=1e-4)
+    torch.manual_seed(7)
+    vector = torch.randn(tril.shape[:2])
+    hut = metrics.hutchinson_trace(st_d, ln_d, vector.to(cuda))
+    assert float(hut) == pytest.approx(float(om.hutchinson_trace(tril, lower, vector)), rel=1e-5)
+    assert float(hut) == pytest.approx(golden["hutchinson_trace_seed7"], rel=1e-5)
+    gen = torch.Generator(device=cuda).manual_seed(1)
+    est = metrics.inverse_loss(st_d, ln_d, probes=256, generator=gen)  # Hutchinson estimate of the same norm
+    assert float(est) == pytest.approx(float(inv), rel=0.1)
+    # gradient with respect to the factor's features (what training back-propagates, train.py:59)
+    feats = ln_d.features.clone().requires_grad_(True)
+    loss = metrics.frobenius_loss(ln_d.replace_feature(feats), solution.to(cuda), rhs.to(cuda))
+    loss.backward()
+    dense_l = lower.clone().requires_grad_(True)
+    om.frobenius_loss(dense_l, solution, rhs).backward()
+    idx = learned.indices.long()
+    torch.testing.assert_close(feats.grad[:, 0].cpu(), dense_l.grad[idx[:, 0], idx[:, 1], idx[:, 2]], rtol=1e-4, atol=1e-4)

@@ -201,3 +201,62 @@ def test_sludge_pattern_data_set_reads_the_reference_layout(tmp_path):
     assert pair[3] == (16, 36) and pair[0].batch_size == 2 and set(pair[0].indices[:, 0].tolist()) == {0, 1}
     with pytest.raises(AssertionError):
         SludgePatternDataSet("validation", 1, root=root, device="cpu")
+
+
+# ---- the CNN side: sparse convolution against the dense one, reference checkpoint layout ----------------
+@pytest.mark.parametrize("k,padding", [(1, (0, 0)), (2, (1, 0)), (2, (0, 1)), (3, (1, 1))])
+def test_sparse_conv_is_the_dense_conv(k, padding):
+    """SparseConv2d == torch's dense conv2d on the densified input, at exactly the sites whose window holds an active
+    input (spconv's regular, pattern-dilating convolution, model.py:27-40); everything else stays inactive."""
+    from deeppreconditioning_b200 import model as models
+
+    torch.manual_seed(3)
+    cin, cout, h, w, batch = 5, 7, 19, 23, 2
+    dense = torch.randn(batch, h, w, cin) * (torch.rand(batch, h, w, 1) < 0.15)
+    x = models.SparseConvTensor.from_dense(dense)
+    conv = models.SparseConv2d(cin, cout, k, padding=padding)
+    out = conv(x)
+    want = torch.nn.functional.conv2d(dense.permute(0, 3, 1, 2), conv.weight.permute(0, 3, 1, 2), conv.bias, padding=padding)
+    active = torch.nn.functional.conv2d((dense != 0).any(-1, keepdim=True).permute(0, 3, 1, 2).float(),
+                                        torch.ones(1, 1, k, k), padding=padding) > 0
+    assert list(want.shape[2:]) == out.spatial_shape
+    idx = out.indices.long()
+    got_mask = torch.zeros_like(active[:, 0])
+    got_mask[idx[:, 0], idx[:, 1], idx[:, 2]] = True
+    assert torch.equal(got_mask, active[:, 0]) and out.indices.shape[0] == int(active.sum())  # no duplicates, no extras
+    torch.testing.assert_close(out.features, want.permute(0, 2, 3, 1)[idx[:, 0], idx[:, 1], idx[:, 2]], rtol=1e-5, atol=1e-5)
+
+
+def test_reference_checkpoint_layout_loads():
+    """A state dict with the reference's names and spconv 2.x shapes (spconv.SparseSequential of SparseConv2d [out,k,k,in]
+    and nn.PReLU, model.py:27-40; 20 678 parameters = the 87 844-byte best.pt of dvc.lock:51-55) loads strictly, and the
+    weights land where the forward pass reads them."""
+    from deeppreconditioning_b200 import model as models
+
+    channels = models.DEFAULT_CHANNELS
+    torch.manual_seed(11)
+    state, index = {}, 0
+    specs = [(channels[0], channels[1], 1)] + [(a, b, 2) for a, b in zip(channels[1:-2], channels[2:-1])] + [(channels[-2], channels[-1], 1)]
+    for n_layer, (cin, cout, k) in enumerate(specs):
+        state[f"layers.{index}.weight"] = 0.2 * torch.randn(cout, k, k, cin)
+        state[f"layers.{index}.bias"] = 0.2 * torch.randn(cout)
+        index += 1
+        if n_layer < len(specs) - 1:
+            state[f"layers.{index}.weight"] = torch.rand(1)  # nn.PReLU
+            index += 1
+    assert sum(t.numel() for t in state.values()) == 20678
+    net = models.PreconditionerNet(channels)
+    assert set(net.state_dict()) == set(state)
+    net.load_state_dict(state, strict=True)
+    # a 2x2 layer evaluated by hand: out = sum_taps in[y + ky - ph, x + kx - pw] @ W[:, ky, kx, :].T + bias
+    layer = net.layers[2]
+    x = models.SparseConvTensor(torch.randn(1, 16), torch.tensor([[0, 4, 6]], dtype=torch.int32), [9, 9], 1)
+    out = layer(x)
+    for site, feat in zip(out.indices.tolist(), out.features):
+        ky, kx = 4 - site[1] + layer.padding[0], 6 - site[2] + layer.padding[1]
+        torch.testing.assert_close(feat, x.features[0] @ state["layers.2.weight"][:, ky, kx, :].T + state["layers.2.bias"])
+    st, _, _, _ = helpers.problem("poisson2d", 16).systems_tril, None, None, None
+    with torch.no_grad():
+        lower = net(st)
+    assert (lower.features[lower.indices[:, 1] < lower.indices[:, 2]] == 0).all()
+    assert (lower.features[lower.indices[:, 1] == lower.indices[:, 2]] > 0).all()

@@ -256,3 +256,125 @@ def test_level_ordering_commutes_with_the_path_on_the_oracle(kind, side):
     x_back = torch.empty_like(lvl.x_hat)
     x_back[torch.from_numpy(perm).long()] = lvl.x_hat
     assert torch.linalg.vector_norm(x_back - nat.x_hat) <= 1e-8 * torch.linalg.vector_norm(nat.x_hat)
+
+
+# ---- threshold incomplete Cholesky (stands in for ilupp.icholt, test.py:86): host routine vs its restatement ------------
+def _icholt_host(rowptr, col, val, fill_in, threshold):
+    """dp_icholt_host through ctypes: host pointers only, no GPU needed."""
+    from deeppreconditioning_b200 import _lib, build
+
+    build.build()
+    n = len(rowptr) - 1
+    rowptr, col, val = (np.ascontiguousarray(a) for a in (np.asarray(rowptr, np.int32), np.asarray(col, np.int32), np.asarray(val, np.float64)))
+    cap = len(col) + n * fill_in + 1
+    rp, c, v, nnz = np.empty(n + 1, np.int32), np.empty(cap, np.int32), np.empty(cap, np.float64), np.zeros(1, np.int64)
+    status = _lib.lib().dp_icholt_host(n, rowptr.ctypes.data, col.ctypes.data, val.ctypes.data, fill_in, threshold,
+                                       rp.ctypes.data, c.ctypes.data, v.ctypes.data, cap, nnz.ctypes.data)
+    return status, rp, c[: int(nnz[0])], v[: int(nnz[0])]
+
+
+@pytest.mark.parametrize("kind,side", [("poisson2d", 16), ("poisson3d", 6), ("poisson2d", 33)])
+@pytest.mark.parametrize("fill_in,threshold", [(1, 0.1), (0, 0.0), (3, 0.01), (1000, 0.0)])
+def test_icholt_host_is_its_restatement(kind, side, fill_in, threshold):
+    """csrc/icholt.cu == oracle/icholt.py bit for bit (same operations, same order), for the reference's default
+    arguments (1, 0.1), the no-fill corner, a generous setting and the complete factorisation."""
+    from oracle import icholt as oict
+
+    p = helpers.problem(kind, side, 0, 0.5, None)
+    status, rp, c, v = _icholt_host(*p.T, fill_in, threshold)
+    assert status == 0
+    want = oict.icholt(*p.T, fill_in, threshold)
+    assert np.array_equal(rp, want[0]) and np.array_equal(c, want[1])
+    assert np.array_equal(v.view(np.int64), want[2].view(np.int64))
+    L = osp.to_scipy(rp, c, v)
+    assert (L.diagonal() > 0).all() and sp.triu(L, 1).nnz == 0
+    assert np.all(np.diff(rp) - 1 <= np.diff(p.T[0]) - 1 + fill_in)  # rule 2: at most nnz(A_i) + fill_in off-diagonals
+    a = osp.to_scipy(*p.A)
+    if fill_in == 1000 and threshold == 0.0:  # nothing dropped: the complete Cholesky factor
+        assert abs(L @ L.T - a).max() < 1e-12 * abs(a).max()
+    # a usable preconditioner: fewer PCG iterations than Jacobi through the oracle loop
+    jac = pcg.preconditioned_conjugate_gradient(osp.to_torch_csr(*p.A), p.b, operators.Jacobi(a.diagonal()), max_iter=3000)
+    ict = pcg.preconditioned_conjugate_gradient(osp.to_torch_csr(*p.A), p.b, operators.FactoredSolve(rp, c, v), max_iter=3000)
+    assert ict.iterations < jac.iterations and ict.res < 1e-8
+
+
+def test_icholt_host_rejects_bad_structure():
+    p = helpers.problem("poisson2d", 8, 0, 0.5, None)
+    rp, c, v = (np.array(a) for a in p.T)
+    assert _icholt_host(rp, c, -v, 1, 0.1)[0] == 5            # negative definite: non-positive pivot
+    c_bad = c.copy()
+    c_bad[rp[3 + 1] - 1] = 2                                  # row 3 without its diagonal in last place
+    assert _icholt_host(rp, c_bad, v, 1, 0.1)[0] == 5
+    from deeppreconditioning_b200 import _lib
+    assert _lib.lib().dp_icholt_host(-1, None, None, None, 0, 0.0, None, None, None, 0, None) == 1
+
+
+def test_a_norm_error_history_from_cg_coefficients():
+    """conjugate_gradient's error column (cg.py:28-30,42-44) from the final error and a_k <r_k, r_k> (the identity the
+    CUDA drop-in uses instead of an SpMV per iteration) against the reference's literal evaluation."""
+    p = helpers.problem("poisson2d", 32, 0, 0.5, None)
+    A = osp.to_torch_csr(*p.A)
+    x_true = torch.from_numpy(spla.spsolve(osp.to_scipy(*p.A).tocsc(), p.b.numpy()))
+    errors, x = pcg.conjugate_gradient(A, p.b, x_true=x_true, max_iter=3000)
+    run = pcg.preconditioned_conjugate_gradient(A, p.b, operators.Identity(), max_iter=3000)
+    assert len(run.history) == len(errors)
+    bb = float(torch.inner(p.b, p.b))
+    e = x - x_true
+    tail = np.zeros(len(errors))
+    tail[:-1] = np.cumsum([a * r * bb for a, r in zip(run.alphas, run.history[:-1])][::-1])[::-1]
+    tail += float(torch.inner(e, A @ e))
+    np.testing.assert_allclose(tail, [float(err) for err, _ in errors], rtol=1e-9)
+
+
+# ---- training losses (SURVEY §8f-3): the dense restatement against the reference module itself --------------------------
+def _loss_batch():
+    from deeppreconditioning_b200 import model as models, synthetic
+
+    st, sol, rhs, sizes = synthetic.make_batch("poisson2d", 9, [0, 1, 2])
+    torch.manual_seed(69)
+    with torch.no_grad():
+        learned = models.PreconditionerNet(models.DEFAULT_CHANNELS)(st)
+    torch.manual_seed(5)
+    return st, learned, torch.randn_like(rhs), rhs
+
+
+@pytest.mark.skipif(not reference.available(), reason="reference checkout not present (GPU box)")
+def test_metrics_oracle_is_the_reference():
+    """oracle/metrics.py == uibk/deep_preconditioning/metrics.py (imported unmodified; it only needs SparseConvTensor
+    objects with dense()/replace_feature, which the stand-in provides), and the golden values of tests/golden."""
+    import importlib
+    import sys
+
+    from oracle import metrics as om
+
+    sys.path.insert(0, str(reference.REFERENCE_ROOT))
+    try:
+        ref = importlib.import_module("uibk.deep_preconditioning.metrics")
+    finally:
+        sys.path.remove(str(reference.REFERENCE_ROOT))
+    st, learned, solution, rhs = _loss_batch()
+    lower, tril = learned.dense()[:, 0], st.dense()[:, 0]
+    torch.testing.assert_close(om.frobenius_loss(lower, solution, rhs), ref.frobenius_loss(learned, solution, rhs), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(om.inverse_loss(tril, lower), ref.inverse_loss(st, learned), rtol=1e-5, atol=1e-5)
+    torch.manual_seed(7)
+    want = ref.hutchinson_trace(st, learned)  # draws randn(systems.shape[:2]) from the global generator
+    torch.manual_seed(7)
+    vector = torch.randn(tril.shape[:2])
+    torch.testing.assert_close(om.hutchinson_trace(tril, lower, vector), want, rtol=1e-5, atol=1e-5)
+    golden = json.loads((Path(__file__).parent / "golden" / "metrics_golden.json").read_text())
+    assert golden["frobenius_loss"] == pytest.approx(float(ref.frobenius_loss(learned, solution, rhs)), rel=1e-5)
+    assert golden["inverse_loss"] == pytest.approx(float(ref.inverse_loss(st, learned)), rel=1e-5)
+    assert golden["hutchinson_trace_seed7"] == pytest.approx(float(want), rel=1e-5)
+
+
+def test_metrics_oracle_matches_golden():
+    from oracle import metrics as om
+
+    golden = json.loads((Path(__file__).parent / "golden" / "metrics_golden.json").read_text())
+    st, learned, solution, rhs = _loss_batch()
+    lower, tril = learned.dense()[:, 0], st.dense()[:, 0]
+    assert float(om.frobenius_loss(lower, solution, rhs)) == pytest.approx(golden["frobenius_loss"], rel=1e-5)
+    assert float(om.inverse_loss(tril, lower)) == pytest.approx(golden["inverse_loss"], rel=1e-5)
+    torch.manual_seed(7)
+    vector = torch.randn(tril.shape[:2])
+    assert float(om.hutchinson_trace(tril, lower, vector)) == pytest.approx(golden["hutchinson_trace_seed7"], rel=1e-5)

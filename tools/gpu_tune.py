@@ -115,7 +115,7 @@ if "single" not in skip:
         p.ls = copy.copy(fplan.ls)
         for name in ("rowptr", "col", "val", "level_sorted"):
             setattr(p.ls, name, getattr(fplan.ls, name).clone())
-        p.ls.source = f.val.data_ptr()
+        p.ls.source = type(p.ls).key(f)
         return (f, p, r0.clone())
 
     pool = [clone_system() for _ in range(592)]

@@ -37,7 +37,7 @@ K = 1024
 out = np.zeros(2 * K * 8, np.int64)
 h = _lib.lib(); h.dp_debug_ts_trace.argtypes = [ctypes.c_void_p]; h.dp_debug_ts_trace(out.ctypes.data)
 t = out.reshape(2, K, 8)
-names = ["wait for the stage's bytes", "stage -> registers", "release (+ re-arm by the last warp)", "issue polls + first look", "wait for a level"]
+names = ["wait for the stage's bytes", "stage -> registers", "release", "loads issued, next tile's bytes awaited, first try", "wait for a level"]
 for cta in (0, 1):
     used = int((t[cta, :, 0] > 0).sum())
     if used < 8:
