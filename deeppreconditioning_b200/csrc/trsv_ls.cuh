@@ -15,9 +15,11 @@
 //     kPending NaN pattern - the protocol of the sync-free solve (data is its own flag, one 8-byte store per row), with a
 //     shared-memory round trip (~30 cycles) in place of the L2 hop. There is no level barrier: a row is solved as soon as
 //     ITS dependencies are, warps of the CTA work on different levels (and tiles) at the same time.
-//     Round 1 ordered the levels by a ring of mbarriers, one phase per level step: every warp arrived at every step
-//     whether it had rows in the level or not, and a step cost ~690 cycles (profiles/README.md); the per-level cost now
-//     is the dependency chain itself (shared-memory store -> load, two multiply-adds).
+//     Round 1 ordered the levels by a ring of mbarriers, one phase per level step, every warp arriving at every step
+//     whether it had rows in the level or not. Both forms take ~0.45 us per level of a 316^2 factor (profiles/r2/README.md:
+//     neither a gate word before the polls, nor four producer warps, nor a one-tile lookahead of the row fetch, nor
+//     per-chunk mbarriers in place of the polls moved that number); this one needs no level array, takes its vectors by
+//     position (bulk copies) and is the faster one inside PCG on level-ordered systems.
 //   * a solved value also goes to global memory (original numbering through `perm`, or by position when the caller keeps
 //     its vectors in level order: perm == nullptr, coalesced).
 // The window. Tile t's slots are armed by the producer warp right before it issues tile t's bulk copies, i.e. after
@@ -217,8 +219,6 @@ __device__ __forceinline__ void trsv_level_stream(const LsFactor& F, const doubl
             const int tm = t % kWt, tp = (t + kWt - 1) % kWt;  // window tile of this tile / of the previous one
             double rcp = 0.0, v[kDeps];
             int w[kDeps];
-            int gate = -1;  // the highest dependency position outside this warp's own rows
-            const int warp_first = t * kTileRows + (tid & ~31);
 #pragma unroll
             for (int u = 0; u < kDeps; ++u) {
                 w[u] = 0, v[u] = 0.0;
@@ -226,23 +226,11 @@ __device__ __forceinline__ void trsv_level_stream(const LsFactor& F, const doubl
                     const int q = sc[e + u];  // position of the dependency: in this tile or the one before
                     w[u] = ((q >> 9) == t ? tm : tp) * kTileRows + (q & (kTileRows - 1));
                     v[u] = sv[e + u];
-                    if (q < warp_first) gate = max(gate, q);
                 }
             }
             if (valid) rcp = sv[(kUpper ? rs : re - 1) - as];  // the copy stores 1 / diagonal (dp_sptrsv_permute)
             pipe.release();  // the stage goes back before any waiting
             LS_TRACE(t, 2);
-            // Sixteen warps polling three slots per lane saturate the shared-memory pipe and every store and poll of the
-            // rows that ARE being solved queues behind them (measured: 900 cycles per level). Rows are solved roughly in
-            // position order, so the warp first waits on ONE word - the slot of its highest outside dependency, the same
-            // address in every lane: one broadcast wavefront per poll - and only then looks at its own slots.
-            gate = __reduce_max_sync(kFull, gate);
-            if (gate >= 0) {
-                const unsigned long long* gslot = win + ((gate >> 9) == t ? tm : tp) * kTileRows + (gate & (kTileRows - 1));
-                for (unsigned spins = 0; lds_volatile_u64(gslot) == kPending && spins < kLsSpinBudget; ++spins) {
-                }
-            }
-            LS_TRACE(t, 3);
             unsigned long long* mine = win + (size_t)tm * kTileRows + tid;
             bool done = !valid;
             unsigned long long uu[kDeps];

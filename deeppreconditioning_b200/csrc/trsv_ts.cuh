@@ -138,7 +138,13 @@ __device__ __forceinline__ int ts_blocks(const TsTile& d) { return d.rowptr ? (d
 // warp that paid them was late for its next tile, hence last again, and its serial path - bytes, stage -> registers, issue,
 // poll - became the period of the whole CTA (4700 cycles per 512 rows). The producer warp takes the issue off every
 // consumer's path. Items are numbered since kernel start: item i lives in stage i % kTsStages, its (i / kTsStages)-th use.
-constexpr int kTsThreads = kBlock + kWarp;  // 16 consumer warps (one thread per row of a tile) + the producer warp
+// ... and FOUR of them, one per array of an item: in steady state every mbarrier.arrive.expect_tx and every cp.async.bulk
+// costs its issuing thread ~255 ns whatever the size of the copy (tools/microbench/tma_stream.cu,
+// profiles/r2/tma_stream.log: an item of 1 / 2 / 4 copies takes 510 / 765 / 1280 ns from one thread, with 3 or 7 stages
+// alike), so one producer could not issue a 4-array item faster than every 1.28 us - 24 KB per 1.28 us and CTA is below
+// the HBM share of an SM. Issued from four warps the four copies overlap.
+constexpr int kTsProducers = 4;
+constexpr int kTsThreads = kBlock + kTsProducers * kWarp;  // 16 consumer warps (one thread per row of a tile) + producers
 
 struct TsPipe {
     TsSmem* sm;
@@ -151,7 +157,7 @@ struct TsPipe {
         if (threadIdx.x == 0) {
 #pragma unroll
             for (int k = 0; k < kTsStages; ++k) {
-                mbar_init(&sm->full[k], 1u);
+                mbar_init(&sm->full[k], (unsigned)kTsProducers);
                 mbar_init(&sm->empty[k], (unsigned)kWarpsPerBlock);
             }
             mbar_fence_init();
@@ -164,47 +170,56 @@ struct TsPipe {
         while (t < ntiles && j >= ts_blocks(sm->tab[t])) ++t, j = 0;
         return t < ntiles;
     }
-    // The producer warp (all lanes): arm `stage` (free: every consumer warp has released its previous item) with block j
-    // of tile t. Under load a bulk copy blocks its issuing thread for ~400 cycles whatever its size, so the item's four
-    // copies go out from four lanes at once; lane 0 arms the barrier with the total first.
-    __device__ __forceinline__ void issue(unsigned stage, int t, int j) {
-        const int lane = threadIdx.x & 31;
+    // Producer warp `role` (0..3 = values, columns, row pointers, right-hand sides; lane 0 acts): arm `stage` (free: every
+    // consumer warp has released its previous item) with this role's array of block j of tile t. The stage's `full`
+    // barrier counts kTsProducers arrivals: a role without a copy for this item (blocks j > 0 carry no metadata) just
+    // arrives.
+    __device__ __forceinline__ void issue(int role, unsigned stage, int t, int j) {
         const TsTile& d = sm->tab[t];
         TsStage& st = sm->stage[stage];
         const int bs = d.cs + j * kTsCap;
         const int be = min(d.ce, bs + kTsCap);
         const int as = bs & ~3;
-        const unsigned ncol = (unsigned)(((be + 3) & ~3) - as), nval = (unsigned)(((be + 1) & ~1) - as);
-        unsigned bytes = ncol * 4u + nval * 8u;
-        const int r0 = d.ltile * kTileRows;
-        const unsigned nr = (unsigned)min(kTileRows, d.n - r0);
-        const unsigned rp_bytes = ((nr + 1u) * 4u + 15u) & ~15u;
-        // right-hand sides of the tile: rows [r0, r0 + nr), or - reversed - rows [n - r0 - nr, n - r0) from the even row below
-        const int b0 = d.rev ? (d.n - r0 - (int)nr) & ~1 : r0;
-        const unsigned b_bytes = ((unsigned)((d.rev ? d.n - r0 : r0 + (int)nr) - b0) * 8u + 15u) & ~15u;
-        if (j == 0) bytes += rp_bytes + b_bytes;
         unsigned long long* bar = &sm->full[stage];
         const unsigned long long pol = l2_policy_stream();
-        if (lane == 0) mbar_arrive_expect_tx(bar, bytes);
-        __syncwarp();
-        if (lane == 0) bulk_g2s(st.val, d.val + as, nval * 8u, bar, pol);
-        if (lane == 1) bulk_g2s(st.col, d.col + as, ncol * 4u, bar, pol);
-        if (lane == 2 && j == 0) bulk_g2s(st.rowptr, d.rowptr + r0, rp_bytes, bar, pol);
-        if (lane == 3 && j == 0) bulk_g2s(st.b, d.b + b0, b_bytes, bar, pol);
+        if (role == 0) {
+            const unsigned nval = (unsigned)(((be + 1) & ~1) - as);
+            mbar_arrive_expect_tx(bar, nval * 8u);
+            bulk_g2s(st.val, d.val + as, nval * 8u, bar, pol);
+        } else if (role == 1) {
+            const unsigned ncol = (unsigned)(((be + 3) & ~3) - as);
+            mbar_arrive_expect_tx(bar, ncol * 4u);
+            bulk_g2s(st.col, d.col + as, ncol * 4u, bar, pol);
+        } else if (j > 0) {
+            mbar_arrive(bar);
+        } else {
+            const int r0 = d.ltile * kTileRows;
+            const unsigned nr = (unsigned)min(kTileRows, d.n - r0);
+            if (role == 2) {
+                const unsigned rp_bytes = ((nr + 1u) * 4u + 15u) & ~15u;
+                mbar_arrive_expect_tx(bar, rp_bytes);
+                bulk_g2s(st.rowptr, d.rowptr + r0, rp_bytes, bar, pol);
+            } else {
+                // rows [r0, r0 + nr), or - reversed - rows [n - r0 - nr, n - r0) from the even row below
+                const int b0 = d.rev ? (d.n - r0 - (int)nr) & ~1 : r0;
+                const unsigned b_bytes = ((unsigned)((d.rev ? d.n - r0 : r0 + (int)nr) - b0) * 8u + 15u) & ~15u;
+                mbar_arrive_expect_tx(bar, b_bytes);
+                bulk_g2s(st.b, d.b + b0, b_bytes, bar, pol);
+            }
+        }
     }
-    // Producer warp, once per round (after the round's table is complete and visible): every item of the round, in
-    // order, each as soon as its stage has been released by all consumer warps.
-    __device__ __forceinline__ void produce(int count) {
+    // Lane 0 of producer warp `role`, once per round (after the round's table is complete and visible): this role's part
+    // of every item of the round, in order, each as soon as its stage has been released by all consumer warps.
+    __device__ __forceinline__ void produce(int role, int count) {
         ntiles = count;
         int t = 0, j = -1;
         while (next_item(t, j)) {
             const unsigned stage = c_count % kTsStages, use = c_count / kTsStages;
-            if (use > 0 && (threadIdx.x & 31) == 0) {
+            if (use > 0) {
                 while (!mbar_try_wait_hint(&sm->empty[stage], (use - 1u) & 1u, 2000u)) {
                 }
             }
-            __syncwarp();
-            issue(stage, t, j);
+            issue(role, stage, t, j);
             ++c_count;
         }
     }
@@ -426,7 +441,7 @@ __device__ __forceinline__ void trsv_tile_stream(const TsSysDev* __restrict__ sy
     TsPipe pipe;
     pipe.init(&sm);
     const int tid = threadIdx.x;
-    const bool producer = tid >= kBlock;  // the last warp
+    const bool producer = tid >= kBlock;  // the last kTsProducers warps
     const int G = gridDim.x;
     const int items = max_tiles * nsys;  // < 2^31: checked by the host
     const int mine = items > (int)blockIdx.x ? (items - (int)blockIdx.x + G - 1) / G : 0;
@@ -451,7 +466,7 @@ __device__ __forceinline__ void trsv_tile_stream(const TsSysDev* __restrict__ sy
         }
         __syncthreads();
         if (producer) {
-            pipe.produce(cnt);
+            if ((tid & 31) == 0) pipe.produce((tid - kBlock) >> 5, cnt);
             continue;
         }
         pipe.begin(cnt);
