@@ -80,6 +80,8 @@ _SIGNATURES = {
     "dp_sptrsv_analyse_workspace_bytes": (C.c_size_t, [_i32]),
     "dp_sptrsv_analyse": (C.c_int, [_i32, _p, _p, _i32, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
     "dp_sptrsv_plan_chunks": (_i64, [_i32, _p]),
+    "dp_sptrsv_plan_sizes_workspace_bytes": (C.c_size_t, [_i32]),
+    "dp_sptrsv_plan_sizes": (C.c_int, [_i32, _p, _p, _p, _p, _p, C.c_size_t, _p]),
     "dp_sptrsv_plan_build": (C.c_int, [_i32, _i32, _p, _p, _p, _p, _i64, _p]),
     "dp_sptrsv_workspace_bytes": (C.c_size_t, []),
     "dp_sptrsv_solve_f64": (C.c_int, [_i32, _p, _p, _p, _i32, _p, _i64, _i32, _p, _p, _p, _p, C.c_size_t, _p]),

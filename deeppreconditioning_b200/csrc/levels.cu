@@ -230,6 +230,26 @@ __global__ void perm_stats_kernel(int n, const int* __restrict__ rowptr_p, const
     }
 }
 
+// chunks[l] = ceil(size(l) / 32) for l < *nlevels, 0 beyond (the scan below runs over n + 1 entries: nlevels is only
+// known on the device); summary[2] = widest level in chunks.
+__global__ void level_chunks_kernel(int n, const int* __restrict__ nlevels, const int* __restrict__ level_ptr,
+                                    int* __restrict__ chunks, int* __restrict__ summary) {
+    const int nl = *nlevels;
+    int widest = 0;
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l <= n; l += gridDim.x * blockDim.x) {
+        const int c = l < nl ? (level_ptr[l + 1] - level_ptr[l] + 31) / 32 : 0;
+        chunks[l] = c;
+        widest = max(widest, c);
+    }
+    widest = __reduce_max_sync(kFull, widest);
+    if ((threadIdx.x & 31) == 0 && widest > 0) atomicMax(summary + 2, widest);
+}
+__global__ void plan_summary_kernel(int n, const int* __restrict__ nlevels, const int* __restrict__ chunk_ptr,
+                                    int* __restrict__ summary) {
+    summary[0] = *nlevels;
+    summary[1] = chunk_ptr[min(*nlevels, n)];  // exclusive scan: entry nlevels is the total
+}
+
 static int grid_for(long long items, int threads) {
     long long b = (items + threads - 1) / threads;
     long long cap = (long long)sm_count() * 16;
@@ -350,6 +370,28 @@ int dp_sptrsv_permute(int32_t n, int32_t upper, const int32_t* rowptr, const int
     perm_fill_kernel<<<grid_for(32ll * n, 256), 256, 0, s>>>(n, upper ? 1 : 0, rowptr, col, val, perm, inv, rowptr_p, col_p, val_p);
     DP_LAUNCH_CHECK();
     perm_stats_kernel<<<grid_for(n, 256), 256, 0, s>>>(n, rowptr_p, col_p, stats_out);
+    DP_LAUNCH_CHECK();
+    return DP_OK;
+}
+
+size_t dp_sptrsv_plan_sizes_workspace_bytes(int32_t n) {
+    const long long m = (long long)(n < 0 ? 0 : n) + 1;
+    return align_up(sizeof(int) * (size_t)m, 256) + scan_workspace_bytes(m);
+}
+
+int dp_sptrsv_plan_sizes(int32_t n, const int32_t* nlevels, const int32_t* level_ptr, int32_t* chunk_ptr,
+                         int32_t* summary_out, void* workspace, size_t workspace_bytes, void* stream) {
+    if (n < 0 || !nlevels || !level_ptr || !chunk_ptr || !summary_out || !workspace) return DP_ERR_INVALID;
+    if (workspace_bytes < dp_sptrsv_plan_sizes_workspace_bytes(n)) return DP_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    int* chunks = static_cast<int*>(workspace);
+    void* scan_ws = static_cast<char*>(workspace) + align_up(sizeof(int) * ((size_t)n + 1), 256);
+    DP_CUDA(cudaMemsetAsync(summary_out, 0, 3 * sizeof(int), s));
+    level_chunks_kernel<<<grid_for((long long)n + 1, 256), 256, 0, s>>>(n, nlevels, level_ptr, chunks, summary_out);
+    DP_LAUNCH_CHECK();
+    const int st = exclusive_scan_i32(chunks, chunk_ptr, (long long)n + 1, scan_ws, s);
+    if (st != DP_OK) return st;
+    plan_summary_kernel<<<1, 1, 0, s>>>(n, nlevels, chunk_ptr, summary_out);
     DP_LAUNCH_CHECK();
     return DP_OK;
 }

@@ -155,20 +155,19 @@ def analyse(matrix: CsrMatrix, upper: bool, level_stream: bool = True) -> Triang
         _lib.check(lib.dp_sptrsv_analyse(n, _lib.ptr(matrix.rowptr), _lib.ptr(matrix.col), int(upper), _lib.ptr(level),
                                          _lib.ptr(perm), _lib.ptr(level_ptr), _lib.ptr(nlev), _lib.ptr(flag),
                                          _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "dp_sptrsv_analyse")
-    nlevels = int(nlev.item())  # once per matrix
+    # plan sizes on the device (chunk prefix over the levels, total, widest level); ONE 12-byte read-back per matrix
+    chunk_ptr, summary = torch.empty(n + 1, **i32), torch.empty(3, **i32)
+    ws2 = _workspace(lib.dp_sptrsv_plan_sizes_workspace_bytes(n), dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.dp_sptrsv_plan_sizes(n, _lib.ptr(nlev), _lib.ptr(level_ptr), _lib.ptr(chunk_ptr), _lib.ptr(summary),
+                                            _lib.ptr(ws2), ws2.numel(), _lib.stream_ptr(dev)), "dp_sptrsv_plan_sizes")
+    nlevels, nchunks, widest_chunks = (int(v) for v in summary.tolist())
     _lib.raise_on_flag(flag, "dp_sptrsv_analyse (not triangular, or diagonal not first/last in its row)")
-    lp_host = np.ascontiguousarray(level_ptr[: nlevels + 1].cpu().numpy(), dtype=np.int32)
-    chunks = (np.diff(lp_host) + 31) // 32
-    chunk_ptr_host = np.concatenate([[0], np.cumsum(chunks)]).astype(np.int32)
-    nchunks = int(lib.dp_sptrsv_plan_chunks(nlevels, lp_host.ctypes.data))
-    assert nchunks == int(chunk_ptr_host[-1])
-    chunk_ptr = torch.from_numpy(chunk_ptr_host).to(dev)
     plan = torch.empty(max(nchunks * 32, 1), **i32)
     with torch.cuda.device(dev):
         _lib.check(lib.dp_sptrsv_plan_build(n, nlevels, _lib.ptr(perm), _lib.ptr(level_ptr), _lib.ptr(chunk_ptr),
                                             _lib.ptr(plan), nchunks, _lib.stream_ptr(dev)), "dp_sptrsv_plan_build")
-    out = TriangularPlan(level, perm, level_ptr[: nlevels + 1], nlevels, plan, nchunks,
-                         int(chunks.max()) if nlevels else 0, bool(upper))
+    out = TriangularPlan(level, perm, level_ptr[: nlevels + 1], nlevels, plan, nchunks, widest_chunks, bool(upper))
     if level_stream:
         out.ls = level_ordered(matrix, out)
     return out

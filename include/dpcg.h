@@ -117,6 +117,13 @@ int dp_sptrsv_analyse(int32_t n, const int32_t* rowptr, const int32_t* col, int3
  * The caller reads level_ptr[0..nlevels] back once per matrix (HOST copy), sizes the plan with
  * dp_sptrsv_plan_chunks, and uploads chunk_ptr[l] = sum_{l'<l} ceil(size(l')/32) (nlevels+1 int32, DEVICE). */
 int64_t dp_sptrsv_plan_chunks(int32_t nlevels, const int32_t* level_ptr_host);
+/* The same sizes without a host round trip of level_ptr: chunk_ptr (DEVICE int32[n+1], exclusive prefix of the levels'
+ * chunk counts, entries past nlevels repeat the total) and summary_out (DEVICE int32[3]) = {nlevels, nchunks, chunks of
+ * the widest level}: the caller reads 12 bytes back once per matrix to size the plan. nlevels: the device word written
+ * by dp_sptrsv_analyse. */
+size_t dp_sptrsv_plan_sizes_workspace_bytes(int32_t n);
+int dp_sptrsv_plan_sizes(int32_t n, const int32_t* nlevels, const int32_t* level_ptr, int32_t* chunk_ptr,
+                         int32_t* summary_out, void* workspace, size_t workspace_bytes, void* stream);
 int dp_sptrsv_plan_build(int32_t n, int32_t nlevels, const int32_t* perm, const int32_t* level_ptr,
                          const int32_t* chunk_ptr, int32_t* plan, int64_t nchunks, void* stream);
 

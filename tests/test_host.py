@@ -145,6 +145,18 @@ assert out.shape == (n, 4), out.shape
 assert out[:, 0].tolist() == [float(i) for i in range(n)]
 assert out[:, 1].tolist() == [100.0 + i for i in range(n)]
 assert out[:, 3].tolist() == [float(i) for i in range(n)]
+# the 8-column records of BenchmarkSuite.run (index, kappa, density, iterations, setup, duration, success, residual)
+wide = torch.tensor([[float(i), 2.0 * i, 0.5, 10.0 + i, 0.1, 0.2, 100.0, 1e-9] for i in mine], dtype=torch.float64).reshape(-1, 8)
+table = distributed.gather_records(wide, n)
+assert table.shape == (n, 8) and table[:, 3].tolist() == [10.0 + i for i in range(n)] and table[:, 1].tolist() == [2.0 * i for i in range(n)]
+# the bench's step schedule: every system of a step is solved by exactly one rank, a rank's systems are its shard's
+import argparse, importlib.util
+spec = importlib.util.spec_from_file_location("bench", {root!r} + "/bench.py"); bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
+args = argparse.Namespace(systems_total=32, step_systems=8)
+for step in range(6):
+    both = [bench.step_indices(args, step, r, 2) for r in range(2)]
+    assert sorted(both[0] + both[1]) == list(range((step % 4) * 8, (step % 4) * 8 + 8))
+    assert all(i % 2 == r for r in range(2) for i in both[r])
 dist.barrier(); dist.destroy_process_group()
 print("rank", rank, "ok")
 """

@@ -5,8 +5,9 @@ import deeppreconditioning_b200 as dp
 from deeppreconditioning_b200.sparse import CsrMatrix
 dev = torch.device("cuda", 0); torch.cuda.set_device(0)
 bench.MAX_ITER = 50
-args = argparse.Namespace(systems_per_gpu=32, side=316, net="net")
-mine, host = bench.build_host_systems(args, 0, 1, dev)
+
+args = argparse.Namespace(side=316, net="net", systems_total=32, step_systems=32)
+_, host = bench.build_chunk(args, list(range(32)), bench.make_net(args, dev), dev, keep_host=True)
 def e2e_step():
     systems = []
     for h in host:
