@@ -92,6 +92,10 @@ _SIGNATURES = {
     "dp_sptrsv_ls_limits": (None, [_p]),
     "dp_sptrsv_ls_workspace_bytes": (C.c_size_t, [_i32]),
     "dp_sptrsv_ls_solve_batch_f64": (C.c_int, [C.POINTER(TrsvLsSystem), _i32, _p, C.c_size_t, _p]),
+    "dp_sptrsv_ls_prepare": (C.c_int, [C.POINTER(TrsvLsSystem), _i32, _p, C.c_size_t, _p]),
+    "dp_sptrsv_ls_launch": (C.c_int, [_i32, _p, C.c_size_t, _p]),
+    "dp_sptrsv_ts_prepare": (C.c_int, [C.POINTER(TrsvLsSystem), _i32, _p, C.c_size_t, _p]),
+    "dp_sptrsv_ts_launch": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _p, _p, _p]),
     "dp_sptrsv_ts_limits": (None, [_p]),
     "dp_sptrsv_ts_workspace_bytes": (C.c_size_t, [C.POINTER(TrsvLsSystem), _i32]),
     "dp_sptrsv_ts_solve_batch_f64": (C.c_int, [C.POINTER(TrsvLsSystem), _i32, _p, _p, C.c_size_t, _p]),

@@ -353,8 +353,8 @@ void dp_sptrsv_ls_limits(int32_t* limits_host) {
 
 size_t dp_sptrsv_ls_workspace_bytes(int32_t nsys) { return align_up(sizeof(LsSysDev) * (size_t)(nsys > 0 ? nsys : 0), 256); }
 
-int dp_sptrsv_ls_solve_batch_f64(const dp_trsv_ls_system_t* systems_host, int32_t nsys, void* workspace,
-                                 size_t workspace_bytes, void* stream) {
+int dp_sptrsv_ls_prepare(const dp_trsv_ls_system_t* systems_host, int32_t nsys, void* workspace, size_t workspace_bytes,
+                         void* stream) {
     if (!systems_host || nsys <= 0 || !workspace) return DP_ERR_INVALID;
     if (workspace_bytes < dp_sptrsv_ls_workspace_bytes(nsys)) return DP_ERR_WORKSPACE;
     cudaStream_t s = (cudaStream_t)stream;
@@ -370,14 +370,26 @@ int dp_sptrsv_ls_solve_batch_f64(const dp_trsv_ls_system_t* systems_host, int32_
         d.b = u.b, d.x = u.x, d.upper = u.upper ? 1 : 0;
         dev[(size_t)i] = d;
     }
-    LsSysDev* sys = static_cast<LsSysDev*>(workspace);
-    DP_CUDA(cudaMemcpyAsync(sys, dev.data(), sizeof(LsSysDev) * (size_t)nsys, cudaMemcpyHostToDevice, s));
+    DP_CUDA(cudaMemcpyAsync(workspace, dev.data(), sizeof(LsSysDev) * (size_t)nsys, cudaMemcpyHostToDevice, s));
     DP_CUDA(cudaStreamSynchronize(s));  // `dev` is a stack-lifetime staging buffer
+    return DP_OK;
+}
+
+int dp_sptrsv_ls_launch(int32_t nsys, void* workspace, size_t workspace_bytes, void* stream) {
+    if (nsys <= 0 || !workspace) return DP_ERR_INVALID;
+    if (workspace_bytes < dp_sptrsv_ls_workspace_bytes(nsys)) return DP_ERR_WORKSPACE;
     if (allow_dynamic_smem((const void*)sptrsv_ls_batch_kernel, sizeof(LsSmem)) != DP_OK) return DP_ERR_CUDA;
     const int resident = sm_count();
-    sptrsv_ls_batch_kernel<<<nsys < resident ? nsys : resident, kLsThreads, sizeof(LsSmem), s>>>(sys, nsys);
+    sptrsv_ls_batch_kernel<<<nsys < resident ? nsys : resident, kLsThreads, sizeof(LsSmem), (cudaStream_t)stream>>>(
+        static_cast<const LsSysDev*>(workspace), nsys);
     DP_LAUNCH_CHECK();
     return DP_OK;
+}
+
+int dp_sptrsv_ls_solve_batch_f64(const dp_trsv_ls_system_t* systems_host, int32_t nsys, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+    const int st = dp_sptrsv_ls_prepare(systems_host, nsys, workspace, workspace_bytes, stream);
+    return st != DP_OK ? st : dp_sptrsv_ls_launch(nsys, workspace, workspace_bytes, stream);
 }
 
 /* ---- tile-stream batch solve ---------------------------------------------------------------------------------- */
@@ -395,26 +407,33 @@ size_t dp_sptrsv_ts_workspace_bytes(const dp_trsv_ls_system_t* systems_host, int
     return bytes;
 }
 
-int dp_sptrsv_ts_solve_batch_f64(const dp_trsv_ls_system_t* systems_host, int32_t nsys, int32_t* flag_out, void* workspace,
-                                 size_t workspace_bytes, void* stream) {
-    if (!systems_host || nsys <= 0 || !flag_out || !workspace) return DP_ERR_INVALID;
+// What dp_sptrsv_ts_launch needs to know about a prepared batch: kept in the first 256 bytes of the workspace, behind
+// the abort word.
+struct TsPrepared {
+    unsigned long long word;  // abort bit of the solve (zeroed by every launch)
+    int nsys, max_tiles, nmax, short_rows, nperm, pad;
+};
+static_assert(sizeof(TsPrepared) <= 256, "workspace header");
+
+int dp_sptrsv_ts_prepare(const dp_trsv_ls_system_t* systems_host, int32_t nsys, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+    if (!systems_host || nsys <= 0 || !workspace) return DP_ERR_INVALID;
     if (workspace_bytes < dp_sptrsv_ts_workspace_bytes(systems_host, nsys)) return DP_ERR_WORKSPACE;
     if (!aligned16(workspace)) return DP_ERR_ALIGNMENT;
     cudaStream_t s = (cudaStream_t)stream;
     char* ws = static_cast<char*>(workspace);
-    unsigned long long* word = reinterpret_cast<unsigned long long*>(ws);
     TsSysDev* sys = reinterpret_cast<TsSysDev*>(ws + 256);
     size_t off = ts_header_bytes(nsys);
     TsPermDev* perm_sys = reinterpret_cast<TsPermDev*>(ws + off);
     off += align_up(sizeof(TsPermDev) * (size_t)nsys, 256);
     std::vector<TsSysDev> dev((size_t)nsys);
     std::vector<TsPermDev> perms;
-    int max_tiles = 0, nmax = 0;
-    bool short_rows = true;
+    TsPrepared head{};
+    head.nsys = nsys, head.short_rows = 1;
     for (int i = 0; i < nsys; ++i) {
         const dp_trsv_ls_system_t& u = systems_host[i];
         if (u.n <= 0 || !u.rowptr_p || !u.col_p || !u.val_p || !u.b || !u.x || u.b == u.x) return DP_ERR_INVALID;
-        short_rows = short_rows && (u.flags & DP_TRSV_SHORT_ROWS) != 0;
+        if (!(u.flags & DP_TRSV_SHORT_ROWS)) head.short_rows = 0;
         if (!aligned16(u.col_p) || !aligned16(u.val_p) || !aligned16(u.rowptr_p) || (!u.perm && !aligned16(u.b)))
             return DP_ERR_ALIGNMENT;  // spans of all four arrays are moved by 16-byte granular bulk copies
         TsSysDev d{};
@@ -430,27 +449,59 @@ int dp_sptrsv_ts_solve_batch_f64(const dp_trsv_ls_system_t* systems_host, int32_
             perms.push_back(g);
         }
         d.ntiles = (u.n + kTileRows - 1) / kTileRows;
-        if (d.ntiles > max_tiles) max_tiles = d.ntiles;
-        if (u.n > nmax) nmax = u.n;
+        if (d.ntiles > head.max_tiles) head.max_tiles = d.ntiles;
+        if (u.n > head.nmax) head.nmax = u.n;
         dev[(size_t)i] = d;
     }
-    DP_CUDA(cudaMemsetAsync(word, 0, sizeof(unsigned long long), s));
-    // pageable sources: the calls return once the bytes are staged, the vectors may go out of scope
+    head.nperm = (int)perms.size();
+    if ((long long)head.max_tiles * nsys >= (1ll << 31) - 1024) return DP_ERR_INVALID;  // the kernel counts items in 32 bits
+    DP_CUDA(cudaMemcpyAsync(ws, &head, sizeof(head), cudaMemcpyHostToDevice, s));
     DP_CUDA(cudaMemcpyAsync(sys, dev.data(), sizeof(TsSysDev) * (size_t)nsys, cudaMemcpyHostToDevice, s));
-    const int np = (int)perms.size();
+    if (head.nperm)
+        DP_CUDA(cudaMemcpyAsync(perm_sys, perms.data(), sizeof(TsPermDev) * perms.size(), cudaMemcpyHostToDevice, s));
+    DP_CUDA(cudaStreamSynchronize(s));  // staging buffers are about to go out of scope
+    return DP_OK;
+}
+
+// `prepared_host`: the five integers dp_sptrsv_ts_prepare derived (the caller keeps them; nothing is read back).
+int dp_sptrsv_ts_launch(int32_t nsys, int32_t max_tiles, int32_t nmax, int32_t short_rows, int32_t nperm, int32_t* flag_out,
+                        void* workspace, void* stream) {
+    if (nsys <= 0 || max_tiles <= 0 || !flag_out || !workspace) return DP_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    char* ws = static_cast<char*>(workspace);
+    unsigned long long* word = reinterpret_cast<unsigned long long*>(ws);
+    TsSysDev* sys = reinterpret_cast<TsSysDev*>(ws + 256);
+    TsPermDev* perm_sys = reinterpret_cast<TsPermDev*>(ws + ts_header_bytes(nsys));
+    DP_CUDA(cudaMemsetAsync(word, 0, sizeof(unsigned long long), s));
     const int pass_grid = (nmax + 255) / 256 < sm_count() * 8 ? (nmax + 255) / 256 : sm_count() * 8;
-    if (np) {
-        DP_CUDA(cudaMemcpyAsync(perm_sys, perms.data(), sizeof(TsPermDev) * (size_t)np, cudaMemcpyHostToDevice, s));
-        ts_gather_kernel<<<pass_grid, 256, 0, s>>>(perm_sys, np);
+    if (nperm) {
+        ts_gather_kernel<<<pass_grid, 256, 0, s>>>(perm_sys, nperm);
         DP_LAUNCH_CHECK();
     }
-    const int st = ts_solve_launch(sys, nsys, max_tiles, nmax, short_rows, true, word, flag_out, s);
+    const int st = ts_solve_launch(sys, nsys, max_tiles, nmax, short_rows != 0, true, word, flag_out, s);
     if (st != DP_OK) return st;
-    if (np) {
-        ts_scatter_kernel<<<pass_grid, 256, 0, s>>>(perm_sys, np);
+    if (nperm) {
+        ts_scatter_kernel<<<pass_grid, 256, 0, s>>>(perm_sys, nperm);
         DP_LAUNCH_CHECK();
     }
     return DP_OK;
+}
+
+int dp_sptrsv_ts_solve_batch_f64(const dp_trsv_ls_system_t* systems_host, int32_t nsys, int32_t* flag_out, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+    if (!flag_out) return DP_ERR_INVALID;
+    int st = dp_sptrsv_ts_prepare(systems_host, nsys, workspace, workspace_bytes, stream);
+    if (st != DP_OK) return st;
+    int max_tiles = 0, nmax = 0, short_rows = 1, nperm = 0;
+    for (int i = 0; i < nsys; ++i) {
+        const dp_trsv_ls_system_t& u = systems_host[i];
+        const int nt = (u.n + kTileRows - 1) / kTileRows;
+        if (nt > max_tiles) max_tiles = nt;
+        if (u.n > nmax) nmax = u.n;
+        if (!(u.flags & DP_TRSV_SHORT_ROWS)) short_rows = 0;
+        if (u.perm) ++nperm;
+    }
+    return dp_sptrsv_ts_launch(nsys, max_tiles, nmax, short_rows, nperm, flag_out, workspace, stream);
 }
 
 int dp_ic0_f64(int32_t n, const int32_t* rowptr, const int32_t* col, const double* a_val, double* l_val,

@@ -37,6 +37,9 @@
 #ifndef DPCG_PIPE_EVICT_FIRST
 #define DPCG_PIPE_EVICT_FIRST 1
 #endif
+#ifndef DPCG_PIPE_WAIT_HINT
+#define DPCG_PIPE_WAIT_HINT 1000  // ns a consumer warp may sleep in try_wait on a stage's `full` barrier (0: spin)
+#endif
 
 namespace dp {
 
@@ -61,6 +64,19 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned 
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// try_wait with a suspend-time hint (ns): a warp that waits for bytes sleeps in hardware instead of taking issue slots
+// from the warps that work.
+__device__ __forceinline__ bool mbar_try_wait_hint(unsigned long long* bar, unsigned parity, unsigned ns) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
         : "memory");
     return ok != 0;
 }
@@ -323,8 +339,14 @@ struct PipeT {
         }
         const unsigned stage = c_count % kStages;
         const unsigned par = (c_count / kStages) & 1u;
+#if DPCG_PIPE_WAIT_HINT
+        // (ncu, round 2: the plain try_wait spin was 13.5 % of the fused kernel's executed instructions)
+        while (!mbar_try_wait_hint(&full[stage], par, DPCG_PIPE_WAIT_HINT)) {
+        }
+#else
         while (!mbar_try_wait(&full[stage], par)) {
         }
+#endif
         return stage;
     }
     __device__ __forceinline__ void release() {

@@ -83,18 +83,6 @@ constexpr int kTsFast = DPCG_TS_FAST;      // register path: rows with at most t
 constexpr int kTsSlots = kTsCap + 8;       // up to 3 lead-in entries (16-byte alignment) + tail rounding
 static_assert(kTsCap % 4 == 0 && kTsCap >= 64, "stage capacity");
 
-__device__ __forceinline__ bool mbar_try_wait_hint(unsigned long long* bar, unsigned parity, unsigned ns) {
-    unsigned ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
-        : "memory");
-    return ok != 0;
-}
-
 struct TsSysDev {
     LsFactor F;       // level-ordered copy (perm / lvl unused here)
     const double* b;  // position space

