@@ -309,6 +309,50 @@ def test_pcg_tile_stream_batch_drops_finished_systems(cuda):
         assert got.iterations == want.iterations and got.res == want.res and torch.equal(got.x_hat, want.x_hat)
 
 
+def test_prepared_triangular_batches_repeat_with_new_right_hand_sides(cuda):
+    """PreparedTriangularBatch (dp_sptrsv_ls_prepare/launch, dp_sptrsv_ts_prepare/launch): descriptors uploaded once,
+    solve() repeated with new right-hand sides written into the same buffers; every solve bit-identical to plain
+    substitution, for the level-stream kernel (natural order = gather through perm, and level order = vectors by position)
+    and the tile-stream kernel (original numbering and position space)."""
+    rng = np.random.default_rng(11)
+    p2 = helpers.problem("poisson2d", 48, 2, 0.5, None)
+    lr, lc, lv = helpers.ic0_factor(p2)
+    lower = CsrMatrix.from_arrays(lr, lc, lv, device=cuda)
+    plan = precond.analyse(lower, False)
+    assert plan.ls is not None and not plan.perm_is_identity
+    # the same factor on the level-ordered system: perm == identity -> vectors by position
+    st = helpers.to_device(p2.systems_tril, cuda)
+    order = precond.level_ordering(CsrMatrix.from_spconv(st, p2.n, "tril"))
+    lower_lo = precond.incomplete_cholesky0(CsrMatrix.from_spconv(order.renumber(st), p2.n, "tril"))
+    plan_lo = precond.analyse(lower_lo, False)
+    assert plan_lo.ls is not None and plan_lo.perm_is_identity
+    host_lo = tuple(a for a in lower_lo.to_host())
+    p3 = helpers.problem("poisson3d", 12, 1, 0.5, None)
+    t3 = CsrMatrix.from_arrays(*p3.T, device=cuda)
+    plan3 = precond.analyse(t3, False, level_stream=False)
+    cases = [("ls", lower, plan, (lr, lc, lv), False), ("ls", lower_lo, plan_lo, host_lo, False),
+             ("ts", t3, plan3, p3.T, False), ("ts", t3, plan3, p3.T, True)]
+    for algorithm, matrix, pl, host, position_space in cases:
+        bs = [torch.zeros(matrix.n, dtype=torch.float64, device=cuda) for _ in range(3)]
+        xs = [torch.empty(matrix.n, dtype=torch.float64, device=cuda) for _ in range(3)]
+        prepared = precond.PreparedTriangularBatch([(matrix, pl, b) for b in bs], xs, algorithm, None, position_space)
+        for _ in range(3):
+            rhs = [rng.standard_normal(matrix.n) for _ in bs]
+            for b, r in zip(bs, rhs):
+                b.copy_(torch.from_numpy(r))
+            got = prepared.solve()
+            prepared.check()
+            perm = pl.perm.cpu().numpy().astype(np.int64)
+            for x, r in zip(got, rhs):
+                if position_space:  # b and x indexed by position: x_pos[k] = x[perm[k]] of the system with b[perm[k]] = r[k]
+                    b_orig = np.empty_like(r)
+                    b_orig[perm] = r
+                    want = ckernels.sptrsv_lower(*host, b_orig)[perm]
+                else:
+                    want = ckernels.sptrsv_lower(*host, r)
+                assert np.array_equal(x.cpu().numpy(), want), (algorithm, position_space)
+
+
 def test_level_stream_eligibility(cuda):
     """Factors the level-stream solve cannot take (a dependency further back than its shared-memory window, rows too
     long for registers, tiles larger than a pipeline stage) are refused at analysis and solved sync-free; a chain of
