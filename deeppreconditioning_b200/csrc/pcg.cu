@@ -690,6 +690,127 @@ __global__ void __launch_bounds__(kBlock, 2) pcg_phase_kernel(Ctx ctx, int k) {
     }
 }
 
+// ---- lean element-wise kernels of the stepped engine for batches whose systems are all SOLVE-mode (tile-stream) --------
+// In SOLVE mode PH_APPLY1 streams no matrix (r_new = r_old - a Ap, x += a p, <r,r>) and PH_DOTRZ is <r,z> plus re-arming y:
+// pure vector passes. Through pcg_phase_kernel they run two 512-thread CTAs per SM (its shared-memory pipeline and 64
+// registers), one tile per CTA in flight and a dependent load round per tile: 0.53 / 0.41 of the HBM peak on 8 x 256^3
+// (tools/c5_timeline.py), a quarter of a config-5 iteration. These kernels do the same arithmetic in the same order -
+// same per-tile partial sums (lane butterfly -> 16 warp sums -> half-warp butterfly), same scalars, same bits - with
+// three CTAs per SM and nothing but registers.
+__device__ __forceinline__ double tile_sum(double v, double (*scratch)[kWarpsPerBlock], int& flip) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* sc = scratch[flip];
+    flip ^= 1;
+    v = warp_sum(v);
+    if (lane == 0) sc[warp] = v;
+    __syncthreads();
+    return half_warp_sum(sc[lane & (kWarpsPerBlock - 1)]);
+}
+
+struct LeanCursor {  // walks the static list of all systems' tiles: contiguous range of this CTA
+    int g, g1, s, lo, hi;
+    __device__ __forceinline__ void init(const Ctx& ctx) {
+        const int total = ctx.total_tiles;
+        const int quot = total / (int)gridDim.x, rem = total % (int)gridDim.x;
+        g = (int)blockIdx.x * quot + min((int)blockIdx.x, rem);
+        g1 = g + quot + ((int)blockIdx.x < rem ? 1 : 0);
+        s = g < g1 ? find_segment(ctx.tile_ofs, ctx.nsys, g) : 0;
+        lo = __ldg(ctx.tile_ofs + s), hi = __ldg(ctx.tile_ofs + s + 1);
+    }
+    __device__ __forceinline__ bool advance(const Ctx& ctx) {  // true when the system changed
+        bool changed = false;
+        while (g >= hi) ++s, lo = hi, hi = __ldg(ctx.tile_ofs + s + 1), changed = true;
+        return changed;
+    }
+};
+
+template <bool kInit>
+__global__ void __launch_bounds__(kBlock, 3) solve_apply1_kernel(Ctx ctx, int k) {
+    __shared__ double scratch[2][kWarpsPerBlock];
+    __shared__ double scratch2[kWarpsPerBlock];
+    int flip = 0;
+    LeanCursor cur;
+    cur.init(ctx);
+    bool fresh = true, active = false;
+    double a = 0.0;
+    const double *ro = nullptr, *ap = nullptr, *pn = nullptr;
+    double *rnw = nullptr, *x = nullptr, *part_rr = nullptr;
+    int n = 0;
+    for (; cur.g < cur.g1; ++cur.g) {
+        if (cur.advance(ctx) || fresh) {
+            fresh = false;
+            const SysDev* S = ctx.sys + cur.s;
+            n = S->n;
+            ro = S->r[k & 1], rnw = S->r[(k + 1) & 1], pn = S->p[(k + 1) & 1], ap = S->ap, x = S->x, part_rr = S->part_rr;
+            active = kInit || ld_relaxed_s32(ctx.state + cur.s) == 0;  // written before the previous launch ended: uniform
+            a = 0.0;
+            if (!kInit && active) a = __ldcg(S->scal + (k & 1)) / block_reduce_array(S->part_pap, S->ntiles, scratch2);  // cg.py:78
+        }
+        const int tile = cur.g - cur.lo;
+        if (!active) continue;
+        const int row = tile * kTileRows + threadIdx.x;
+        double rn = 0.0;
+        if (row < n) {
+            const double r_old = ro[row];
+            if (kInit) {
+                rn = r_old;
+            } else {
+                const double ap_i = ap[row], x_i = x[row], p_i = pn[row];
+                rn = __dsub_rn(r_old, __dmul_rn(a, ap_i));   // cg.py:80
+                x[row] = __dadd_rn(x_i, __dmul_rn(a, p_i));  // cg.py:79
+            }
+            rnw[row] = rn;
+        }
+        if (!kInit) {
+            const double rr = tile_sum(__dmul_rn(rn, rn), scratch, flip);  // cg.py:86
+            if (threadIdx.x == 0) part_rr[tile] = rr;
+        }
+        if (tile == 0) {  // one CTA per system and launch
+            const SysDev* S = ctx.sys + cur.s;
+            if (!kInit && threadIdx.x == 0 && S->coef) S->coef[2 * k] = a;
+            if (kInit) {  // publish <b,b> once (all part_bb were written by the previous launch)
+                const double bb = block_reduce_array(S->part_bb, S->ntiles, scratch2);
+                if (threadIdx.x == 0) S->scal[2] = bb;
+            }
+        }
+    }
+}
+
+template <bool kInit>
+__global__ void __launch_bounds__(kBlock, 3) solve_dotrz_kernel(Ctx ctx, int k) {
+    __shared__ double scratch[2][kWarpsPerBlock];
+    int flip = 0;
+    LeanCursor cur;
+    cur.init(ctx);
+    bool fresh = true, active = false;
+    const double *rn = nullptr, *zn = nullptr;
+    double *t = nullptr, *part_rz = nullptr, *part_rr = nullptr;
+    int n = 0, rearm = 0;
+    for (; cur.g < cur.g1; ++cur.g) {
+        if (cur.advance(ctx) || fresh) {
+            fresh = false;
+            const SysDev* S = ctx.sys + cur.s;
+            n = S->n, rearm = S->rearm_t;
+            rn = S->r[(k + 1) & 1], zn = S->z[(k + 1) & 1], t = S->t, part_rz = S->part_rz[(k + 1) & 1], part_rr = S->part_rr;
+            active = kInit || ld_relaxed_s32(ctx.state + cur.s) == 0;
+        }
+        const int tile = cur.g - cur.lo;
+        if (!active) continue;
+        const int row = tile * kTileRows + threadIdx.x;
+        double ri = 0.0, zi = 0.0;
+        if (row < n) {
+            ri = rn[row], zi = zn[row];
+            if (rearm) st_relaxed_u64(t + row, kPending);  // y for the next forward solve
+        }
+        const double rz = tile_sum(__dmul_rn(ri, zi), scratch, flip);  // cg.py:76,82
+        if (threadIdx.x == 0) part_rz[tile] = rz;
+        if (kInit) {  // iteration 0 checks <z0,z0> (cg.py:66)
+            const double zz = tile_sum(__dmul_rn(zi, zi), scratch, flip);
+            if (threadIdx.x == 0) part_rr[tile] = zz;
+        }
+    }
+}
+
 // ---- host side -----------------------------------------------------------------------------------------------
 static inline int64_t pad32(int64_t v) { return (v + 31) / 32 * 32; }
 static inline int ntiles_of(int n) { return (n + kTileRows - 1) / kTileRows; }
@@ -748,13 +869,30 @@ struct TsPhases {
     const TsSysDev* bwd[2];
     int nsys, max_tiles, nmax;
     bool short_rows;  // every system promises DP_TRSV_SHORT_ROWS (solve_algorithm bit 1)
+    bool all_solve;   // the batch holds nothing but tile-stream SOLVE systems: APPLY1 / DOTRZ are pure vector passes
     unsigned long long* word;
 };
 
 template <bool kInit>
+static int launch_lean(bool dotrz, const Ctx& ctx, int k, cudaStream_t s) {
+    const void* kernel = dotrz ? (const void*)solve_dotrz_kernel<kInit> : (const void*)solve_apply1_kernel<kInit>;
+    int grid = coop_grid(kernel, kBlock, 0);  // resident CTAs (cached per device): one contiguous tile range each
+    if (grid > ctx.total_tiles) grid = ctx.total_tiles;
+    if (dotrz)
+        solve_dotrz_kernel<kInit><<<grid, kBlock, 0, s>>>(ctx, k);
+    else
+        solve_apply1_kernel<kInit><<<grid, kBlock, 0, s>>>(ctx, k);
+    DP_LAUNCH_CHECK();
+    return DP_OK;
+}
+
+template <bool kInit>
 static int launch_apply(const Ctx& ctx, int k, int tile_grid, int coop, const TsPhases* ts, cudaStream_t s) {
     int st;
-    if ((st = launch_phase<PH_APPLY1, kInit>(ctx, k, tile_grid, false, s)) != DP_OK) return st;
+    const bool lean = ts != nullptr && ts->all_solve;  // every system is a tile-stream SOLVE system: pure vector passes
+    if (lean) {
+        if ((st = launch_lean<kInit>(false, ctx, k, s)) != DP_OK) return st;
+    } else if ((st = launch_phase<PH_APPLY1, kInit>(ctx, k, tile_grid, false, s)) != DP_OK) return st;
     if (ctx.has_multiply && (st = launch_phase<PH_APPLY2, kInit>(ctx, k, tile_grid, false, s)) != DP_OK) return st;
     if (ctx.has_solve) {
         if (ts) {  // finished systems are solved along (their vectors are scratch by then): no host round trip
@@ -767,7 +905,9 @@ static int launch_apply(const Ctx& ctx, int k, int tile_grid, int coop, const Ts
             if ((st = launch_phase<PH_FWD, kInit>(ctx, k, coop, true, s)) != DP_OK) return st;
             if ((st = launch_phase<PH_BWD, kInit>(ctx, k, coop, true, s)) != DP_OK) return st;
         }
-        if ((st = launch_phase<PH_DOTRZ, kInit>(ctx, k, tile_grid, false, s)) != DP_OK) return st;
+        if (lean) {
+            if ((st = launch_lean<kInit>(true, ctx, k, s)) != DP_OK) return st;
+        } else if ((st = launch_phase<PH_DOTRZ, kInit>(ctx, k, tile_grid, false, s)) != DP_OK) return st;
     }
     return DP_OK;
 }
@@ -1043,6 +1183,7 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
             ts_phases.bwd[par] = reinterpret_cast<const TsSysDev*>(ws + lay.ts_sys[2 + par]);
         }
         ts_phases.short_rows = ts_short;
+        ts_phases.all_solve = n_ts == nsys;
         ts_phases.word = reinterpret_cast<unsigned long long*>(ws + lay.ts_word);
         ts = &ts_phases;
     }
