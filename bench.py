@@ -20,8 +20,10 @@ e2e     : the same through the reference-facing call with HOST operands (c3: pin
           preconditioned_conjugate_gradient receives from test.py:138; c5: the pinned COO lower triangle and b - what
           the data set yields): H2D copies, L^T assembly / analysis, workspace setup, solve, D2H of x/iterations inside
           the timed region.
-roofline: the solve kernels, algorithmic bytes per launch (12 nnzA + 24 nnzL + 132 N + 12 per iteration and system,
-          SURVEY §8d) / CUDA-event duration, against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
+roofline: the solve kernels, algorithmic bytes per launch (E nnzA + 2 E nnzL + 132 N + 12 per iteration and system,
+          SURVEY §8d; E = bytes the kernel streams per stored entry: 6 from the lossless packed copies the fused engine
+          uses when they exist - config 3 -, else 12) / CUDA-event duration, against the measured HBM copy bandwidth
+          (MEASURED_PEAKS.json).
 cpu_baseline / --impl reference: the CPU restatement of the reference loop (oracle/pcg.py, `as_is`: including the second
           `A @` of cg.py:87), torch CPU CSR operands built on the CPU by oracle/sparse.py (the process never loads
           libdpcg.so), all host threads, on a bounded sample of the same workload. The reference itself is Python and
@@ -84,10 +86,19 @@ def workload_name(args):
             f"rtol=1e-8 (squared), max_iter={MAX_ITER}; step = next {args.step_systems} systems of the set")
 
 
-def iter_bytes(n, nnz_a, nnz_l):
-    """Algorithmic bytes of one PCG iteration: SpMV(A) + SpMV(L^T) + SpMV(L) + 72 N."""
-    spmv = lambda nnz: 12 * nnz + 4 * (n + 1) + 16 * n
+def iter_bytes(n, nnz_a, nnz_l, entry_bytes=12):
+    """Algorithmic bytes of one PCG iteration: SpMV(A) + SpMV(L^T) + SpMV(L) + 72 N. `entry_bytes`: what the
+    kernel streams per stored entry - 12 (fp64 value + int32 column) or 6 from the packed copies (fp32 + uint16)."""
+    spmv = lambda nnz: entry_bytes * nnz + 4 * (n + 1) + 16 * n
     return spmv(nnz_a) + 2 * spmv(nnz_l) + 72 * n
+
+
+def entry_bytes_of(batch):
+    """6 when the fused engine streams the packed copies of this batch (every streamed matrix has one), else 12."""
+    if os.environ.get("DPCG_NO_PACK", "0")[:1] == "1":
+        return 12
+    mats = [m for e in batch.entries for m in [e["A"], *e["M"].stream_matrices()]]
+    return 6 if all(m._packed for m in mats) else 12
 
 
 # ---- clocks ------------------------------------------------------------------------------------------------------------
@@ -754,7 +765,8 @@ def run_c3(args, rank, world, device):
     solved = sorted({s % nchunks for s in range(nsteps)})
     results = {c: batches[c].results() for c in solved}
     kernel_ms = [k0.elapsed_time(k1) for _, k0, k1 in launches]
-    chunk_bytes = {c: sum(iter_bytes(e["A"].n, e["A"].nnz, e["M"].L.nnz) * r.iterations
+    entry_bytes = {c: entry_bytes_of(batches[c]) for c in solved}
+    chunk_bytes = {c: sum(iter_bytes(e["A"].n, e["A"].nnz, e["M"].L.nnz, entry_bytes[c]) * r.iterations
                           for e, r in zip(batches[c].entries, results[c])) for c in solved}
     local_bytes = float(sum(chunk_bytes[c] for c, _, _ in launches))
     local_gbs = local_bytes / (sum(kernel_ms) / 1e3) / 1e9
@@ -820,11 +832,13 @@ def run_c3(args, rank, world, device):
     tpath = ROOT / "profiles" / "traffic.json"
     if tpath.exists():
         tj = json.loads(tpath.read_text())
-        per_iter = tj.get("pcg_fused_kernel_dram_bytes_per_system_iteration")
+        packed_run = all(v == 6 for v in entry_bytes.values())
+        per_iter = tj.get("pcg_fused_kernel_packed_dram_bytes_per_system_iteration" if packed_run
+                          else "pcg_fused_kernel_dram_bytes_per_system_iteration")
         if per_iter:
             its = [sum(r.iterations for r in results[c]) for c, _, _ in launches]
             traffic = float(per_iter) * float(np.mean(its))
-            traffic_source = tj.get("source", "profiles/traffic.json (ncu --set full capture of a short launch, scaled by iterations)")
+            traffic_source = tj.get("source_packed" if packed_run else "source", "profiles/traffic.json (ncu --set full capture of a short launch, scaled by iterations)")
     per_gpu = args.step_systems // world
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -836,7 +850,12 @@ def run_c3(args, rank, world, device):
                          f"{resident_gb:.0f} GB resident per GPU",
                    "iterations_mean": float(iterations.mean()), "iterations_min": int(iterations.min()),
                    "iterations_max": int(iterations.max()), "systems_measured": int(len(iterations)),
-                   "engine": "fused persistent cooperative kernel", "setup_s_untimed": setup_s},
+                   "engine": "fused persistent cooperative kernel", "setup_s_untimed": setup_s,
+                   "matrix_stream": ("packed copies (dp_csr_pack, lossless: fp32 value + uint16 tile-relative column = 6 B per "
+                                     "entry, widened on load, same fp64 arithmetic and bits)" if all(v == 6 for v in entry_bytes.values())
+                                     else "fp64 value + int32 column = 12 B per entry"),
+                   "bytes_per_system_iteration": float(np.mean([iter_bytes(e["A"].n, e["A"].nnz, e["M"].L.nnz, entry_bytes[c])
+                                                                for c in solved for e in batches[c].entries]))},
         "ms_to_tol_per_system": elapsed_ms / args.steps / per_gpu,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all, "steps": e2e_steps},

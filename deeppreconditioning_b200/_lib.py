@@ -37,7 +37,9 @@ class PcgSystem(C.Structure):
             "dinv", "fwd_plan", "bwd_plan",
             "fwd_ls_rowptr", "fwd_ls_col", "fwd_ls_val", "fwd_ls_perm", "fwd_ls_level",
             "bwd_ls_rowptr", "bwd_ls_col", "bwd_ls_val", "bwd_ls_perm", "bwd_ls_level",
-            "b", "x", "work", "iters_out", "res_out", "history", "coef")]
+            "b", "x", "work", "iters_out", "res_out", "history", "coef",
+            "a_col16", "a_val32", "a_tile_base", "m_col16", "m_val32", "m_tile_base",
+            "mt_col16", "mt_val32", "mt_tile_base")]
 
 
 class TrsvSystem(C.Structure):
@@ -76,6 +78,9 @@ _SIGNATURES = {
     "dp_csr_inv_diagonal": (C.c_int, [_i32, _p, _p, _p, _p, _p, _p]),
     "dp_csr_aat_nnz": (C.c_int, [_i32, _p, _p, _p, _p, _p, _p]),
     "dp_spmv_csr_f64": (C.c_int, [_i32, _i32, _p, _p, _p, _p, _p, _p]),
+    "dp_csr_pack_tile_rows": (_i32, []),
+    "dp_csr_pack": (C.c_int, [_i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "dp_spmv_csr_packed_f64": (C.c_int, [_i32, _i32, _p, _p, _p, _p, _p, _p, _p]),
     "dp_coo_spmv_batch_f32": (C.c_int, [_p, _p, _i64, _i32, _i32, _p, _i32, _p, _p]),
     "dp_sptrsv_analyse_workspace_bytes": (C.c_size_t, [_i32]),
     "dp_sptrsv_analyse": (C.c_int, [_i32, _p, _p, _i32, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),

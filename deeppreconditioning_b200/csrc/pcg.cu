@@ -169,8 +169,9 @@ struct Scal {
 };
 
 // ---- PH_INIT: r0 = b - A x0 (cg.py:60), <b,b>, p = 0, arm the sync-free buffers -------------------------------
+template <class P>
 __device__ __forceinline__ void phase_init(const Ctx& ctx, const SysDev& S, const TileDesc& d, int rs, int re,
-                                           Smem& sm, Pipe& pipe) {
+                                           Smem& sm, P& pipe) {
     const int tile = d.ltile;
     const int row = tile * kTileRows + threadIdx.x;
     const double ax = pipe.tile_spmv(d, rs, re, GatherPlain{S.x}, true);
@@ -200,9 +201,9 @@ __device__ __forceinline__ void phase_init(const Ctx& ctx, const SysDev& S, cons
 // kCheckState: the static schedule (stepped engine) still visits finished systems and must skip them; the flag is
 // written by another CTA in this very phase, so it is read once per CTA and broadcast (a per-thread read could
 // split the CTA around a barrier). The fused engine's active list never contains a finished system.
-template <bool kCheckState>
+template <bool kCheckState, class P>
 __device__ __forceinline__ void phase_a(const Ctx& ctx, const SysDev& S, const TileDesc& d, int rs, int re, int k,
-                                        Smem& sm, Scal& sc, Pipe& pipe) {
+                                        Smem& sm, Scal& sc, P& pipe) {
     const int s = d.sys, tile = d.ltile;
     const int row = tile * kTileRows + threadIdx.x;
     const bool valid = row < S.n;
@@ -271,9 +272,9 @@ __device__ __forceinline__ void phase_a(const Ctx& ctx, const SysDev& S, const T
 }
 
 // ---- PH_APPLY1 ----------------------------------------------------------------------------------------------
-template <bool kInit>
+template <bool kInit, class P>
 __device__ __forceinline__ void phase_apply1(const Ctx& ctx, const SysDev& S, const TileDesc& d, int rs, int re, int k,
-                                             Smem& sm, Scal& sc, Pipe& pipe) {
+                                             Smem& sm, Scal& sc, P& pipe) {
     const int s = d.sys, tile = d.ltile;
     const int row = tile * kTileRows + threadIdx.x;
     const bool valid = row < S.n;
@@ -359,9 +360,9 @@ __device__ __forceinline__ void phase_apply1(const Ctx& ctx, const SysDev& S, co
 }
 
 // ---- PH_APPLY2 (MULTIPLY): z = L t ---------------------------------------------------------------------------
-template <bool kInit>
+template <bool kInit, class P>
 __device__ __forceinline__ void phase_apply2(const Ctx& ctx, const SysDev& S, const TileDesc& d, int rs, int re, int k,
-                                             Smem& sm, Scal& sc, Pipe& pipe) {
+                                             Smem& sm, Scal& sc, P& pipe) {
     const int s = d.sys, tile = d.ltile;
     if (sc.sys != s) {
         sc.sys = s;
@@ -392,9 +393,9 @@ __device__ __forceinline__ void phase_apply2(const Ctx& ctx, const SysDev& S, co
 }
 
 // ---- PH_DOTRZ (SOLVE): <r,z> after the backward solve -----------------------------------------------------------
-template <bool kInit>
+template <bool kInit, class P>
 __device__ __forceinline__ void phase_dotrz(const Ctx& ctx, const SysDev& S, const TileDesc& d, int k, Smem& sm, Scal& sc,
-                                            Pipe& pipe) {
+                                            P& pipe) {
     const int s = d.sys, tile = d.ltile;
     if (sc.sys != s) {
         sc.sys = s;
@@ -473,9 +474,9 @@ __device__ __forceinline__ bool phase_trsv(const Ctx& ctx, int k, const Smem& sm
 }
 
 // ---- tile schedule ---------------------------------------------------------------------------------------------
-template <int kPhase, bool kInit, bool kCheckState>
+template <int kPhase, bool kInit, bool kCheckState, class P>
 __device__ __forceinline__ void run_tile(const Ctx& ctx, const SysDev& S, const TileDesc& d, int rs, int re, int k,
-                                         Smem& sm, Scal& sc, Pipe& pipe) {
+                                         Smem& sm, Scal& sc, P& pipe) {
     if (kPhase == PH_INIT) phase_init(ctx, S, d, rs, re, sm, pipe);
     if (kPhase == PH_A) phase_a<kCheckState>(ctx, S, d, rs, re, k, sm, sc, pipe);
     if (kPhase == PH_APPLY1) phase_apply1<kInit>(ctx, S, d, rs, re, k, sm, sc, pipe);
@@ -484,7 +485,7 @@ __device__ __forceinline__ void run_tile(const Ctx& ctx, const SysDev& S, const 
 }
 
 // Describe tiles [ga, gb) of list `cur` for table kTab: which system / local tile, and what the phase streams.
-template <int kTab>
+template <int kTab, bool kPacked>
 __device__ __forceinline__ void build_table(const Ctx& ctx, int cur, int ga, int gb, Smem& sm) {
     const int count = __ldcg(ctx.act_meta + 2 * cur);
     const int* asys = ctx.act_sys[cur];
@@ -502,17 +503,17 @@ __device__ __forceinline__ void build_table(const Ctx& ctx, int cur, int ga, int
         if (kTab == TAB_P1 && precond == DP_PRECOND_CSR) M = S->M;
         if (kTab == TAB_P2 && precond == DP_PRECOND_MULTIPLY) M = S->M;
         TileDesc d;
-        tile_desc_fill(d, M, lt);
+        tile_desc_fill<kPacked>(d, M, lt);
         d.sys = s;
         sm.tab[kTab][i] = d;
     }
 }
 
-template <int kTab>
+template <int kTab, bool kPacked>
 __device__ __forceinline__ void ensure_table(const Ctx& ctx, int cur, int ver, int ga, int gb, Smem& sm) {
     if (sm.tab_ver[kTab] == ver && sm.tab_ga[kTab] == ga && sm.tab_gb[kTab] == gb) return;  // CTA-uniform
     __syncthreads();  // every thread has compared the keys / left the old table
-    build_table<kTab>(ctx, cur, ga, gb, sm);
+    build_table<kTab, kPacked>(ctx, cur, ga, gb, sm);
     if (threadIdx.x == 0) sm.tab_ver[kTab] = ver, sm.tab_ga[kTab] = ga, sm.tab_gb[kTab] = gb;
     __syncthreads();
 }
@@ -521,8 +522,8 @@ __device__ __forceinline__ void ensure_table(const Ctx& ctx, int cur, int ver, i
 // fused engine: `cur` = the active list (unfinished systems); stepped engine: list 0 = all systems, kCheckState.
 // `next_tab` (fused engine only, -1 = none): the table the NEXT phase will stream; when it is still valid for this
 // CTA's range its first items are issued before the grid barrier (Pipe::begin_early).
-template <int kPhase, bool kInit, bool kCheckState>
-__device__ __forceinline__ void run_tiles(const Ctx& ctx, int k, int cur, int ver, int total, Smem& sm, Pipe& pipe,
+template <int kPhase, bool kInit, bool kCheckState, class P>
+__device__ __forceinline__ void run_tiles(const Ctx& ctx, int k, int cur, int ver, int total, Smem& sm, P& pipe,
                                           int next_tab = -1) {
     constexpr int kTab = kPhase == PH_APPLY1 ? TAB_P1 : kPhase == PH_APPLY2 ? TAB_P2 : TAB_A;
     constexpr bool kStream = kPhase != PH_DOTRZ;
@@ -534,7 +535,7 @@ __device__ __forceinline__ void run_tiles(const Ctx& ctx, int k, int cur, int ve
     Scal sc;
     for (int ga = g0; ga < g1; ga += kMaxRoundTiles) {
         const int gb = min(g1, ga + kMaxRoundTiles);
-        ensure_table<kTab>(ctx, cur, ver, ga, gb, sm);
+        ensure_table<kTab, P::kIsPacked>(ctx, cur, ver, ga, gb, sm);
         const TileDesc* tab = sm.tab[kTab];
         if (kStream) {
             if (!pipe.begin_resume(tab, gb - ga, kTab)) {
@@ -592,9 +593,9 @@ __device__ __forceinline__ void rebuild_active(const Ctx& ctx, int cur, Smem& sm
 
 // Returns false on abort. `done` = finished count of the last barrier.
 // `list_stays`: the active list (hence every table) survives this iteration, so the last phase may start table A early.
-template <bool kInit, bool kSolve>
+template <bool kInit, bool kSolve, class P>
 __device__ __forceinline__ bool apply_preconditioner(const Ctx& ctx, int k, int cur, int ver, int total, GridBarrier& bar,
-                                                     Smem& sm, Pipe& pipe, bool list_stays) {
+                                                     Smem& sm, P& pipe, bool list_stays) {
     const int tab_a = list_stays ? (int)TAB_A : -1;
     run_tiles<PH_APPLY1, kInit, false>(ctx, k, cur, ver, total, sm, pipe,
                                        ctx.has_multiply ? (int)TAB_P2 : (kSolve ? -1 : tab_a));
@@ -620,7 +621,8 @@ __device__ __forceinline__ bool apply_preconditioner(const Ctx& ctx, int k, int 
     return true;
 }
 
-__device__ __forceinline__ Smem& smem_init(unsigned char* raw, Pipe& pipe) {
+template <class P>
+__device__ __forceinline__ Smem& smem_init(unsigned char* raw, P& pipe) {
     Smem& sm = *reinterpret_cast<Smem*>(raw);
     if (threadIdx.x == 0) {
         sm.sys_id = -1, sm.trace_pos = 0;
@@ -636,10 +638,12 @@ __device__ __forceinline__ Smem& smem_init(unsigned char* raw, Pipe& pipe) {
 // kSolve: the batch holds SOLVE-mode systems. Two instantiations, so that the triangular-solve code (two inlined sync-free
 // streams, the level-stream call) does not weigh on the register allocation of the batches that never run it - the
 // benchmarked multiply-mode batches among them.
-template <bool kSolve>
+// kPacked: every matrix the batch streams comes with its packed copy (dp_csr_pack): 6 instead of 12 bytes per entry through
+// the same pipeline, same bits.
+template <bool kSolve, bool kPacked>
 __global__ void __launch_bounds__(kBlock, 2) pcg_fused_kernel(Ctx ctx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Pipe pipe;
+    typename std::conditional<kPacked, PipePacked, Pipe>::type pipe;
     Smem& sm = smem_init(smem_raw, pipe);
     pipe.keep_l2 = ctx.keep_l2;
     GridBarrier bar{ctx.word, ctx.flag, &sm.bcast, 0u, gridDim.x};
@@ -933,8 +937,8 @@ int dp_device_info(int* sm_count_host, int* pcg_ctas_per_sm_host, int* l2_bytes_
     if (sm_count_host) *sm_count_host = sms;
     if (l2_bytes_host) *l2_bytes_host = l2;
     if (pcg_ctas_per_sm_host) {
-        if (allow_smem(pcg_fused_kernel<false>) != DP_OK) return DP_ERR_CUDA;
-        *pcg_ctas_per_sm_host = coop_grid((const void*)pcg_fused_kernel<false>, kBlock, sizeof(Smem)) / (sms > 0 ? sms : 1);
+        if (allow_smem(pcg_fused_kernel<false, false>) != DP_OK) return DP_ERR_CUDA;
+        *pcg_ctas_per_sm_host = coop_grid((const void*)pcg_fused_kernel<false, false>, kBlock, sizeof(Smem)) / (sms > 0 ? sms : 1);
     }
     return DP_OK;
 }
@@ -962,7 +966,8 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
     std::vector<int> tile_ofs((size_t)nsys + 1, 0), fwd_ofs((size_t)nsys + 1, 0), bwd_ofs((size_t)nsys + 1, 0);
     std::vector<int> ident((size_t)nsys + 1, 0);
     int has_multiply = 0, has_solve = 0, has_ls = 0, n_solve = 0, n_ts = 0;
-    long long working_set_bytes = 0;
+    bool packed = true;  // every streamed matrix of every system comes with its packed copy
+    long long working_set_bytes = 0, matrix_entries = 0;
     long long sum_fwd_lvl = 0, sum_bwd_lvl = 0;
     std::vector<TsSysDev> ts_sys[4];
     std::vector<int> ts_owner;  // system index of each tile-stream descriptor
@@ -976,9 +981,16 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
         d.n = u.n;
         d.precond = u.precond;
         d.ntiles = ntiles_of(u.n);
-        d.A = CsrView{u.a_rowptr, u.a_col, u.a_val, u.n, u.a_nnz};
-        d.M = CsrView{u.m_rowptr, u.m_col, u.m_val, u.n, u.m_nnz};
-        d.Mt = CsrView{u.mt_rowptr, u.mt_col, u.mt_val, u.n, u.mt_nnz};
+        d.A = CsrView{u.a_rowptr, u.a_col, u.a_val, u.n, u.a_nnz, u.a_col16, u.a_val32, u.a_tile_base};
+        d.M = CsrView{u.m_rowptr, u.m_col, u.m_val, u.n, u.m_nnz, u.m_col16, u.m_val32, u.m_tile_base};
+        d.Mt = CsrView{u.mt_rowptr, u.mt_col, u.mt_val, u.n, u.mt_nnz, u.mt_col16, u.mt_val32, u.mt_tile_base};
+        {
+            auto has_pack = [](const CsrView& V) { return V.col16 && V.val32 && V.tbase && aligned16(V.col16) && aligned16(V.val32); };
+            if (!has_pack(d.A)) packed = false;
+            if ((u.precond == DP_PRECOND_MULTIPLY || u.precond == DP_PRECOND_CSR) && !has_pack(d.M)) packed = false;
+            if (u.precond == DP_PRECOND_MULTIPLY && !has_pack(d.Mt)) packed = false;
+            if (u.precond == DP_PRECOND_SOLVE) packed = false;
+        }
         d.dinv = u.dinv;
         d.fwd_plan = u.fwd_plan;
         d.bwd_plan = u.bwd_plan;
@@ -1039,9 +1051,10 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
         }
         d.b = u.b;
         d.x = u.x;
-        working_set_bytes += 12ll * ((long long)u.a_nnz + (u.precond >= DP_PRECOND_MULTIPLY ? u.m_nnz : 0) +
-                                     (u.precond == DP_PRECOND_MULTIPLY || u.precond == DP_PRECOND_SOLVE ? u.mt_nnz : 0)) +
-                             8ll * 10 * u.n;
+        const long long entries = (long long)u.a_nnz + (u.precond >= DP_PRECOND_MULTIPLY ? u.m_nnz : 0) +
+                                  (u.precond == DP_PRECOND_MULTIPLY || u.precond == DP_PRECOND_SOLVE ? u.mt_nnz : 0);
+        matrix_entries += entries;
+        working_set_bytes += 12ll * entries + 8ll * 10 * u.n;
         const int64_t np = pad32(u.n), tp = pad32(d.ntiles);
         double* w = u.work;
         d.r[0] = w; d.r[1] = w + np; d.p[0] = w + 2 * np; d.p[1] = w + 3 * np;
@@ -1077,7 +1090,13 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
 
     // the tile-stream solves replace the FWD/BWD phases of the stepped engine for ALL solve-mode systems of the batch
     if (n_ts && (n_ts != n_solve || params_host->engine != DP_ENGINE_STEPPED)) return DP_ERR_INVALID;
-    const void* fused = has_solve ? (const void*)pcg_fused_kernel<true> : (const void*)pcg_fused_kernel<false>;
+    {
+        const char* e = getenv("DPCG_NO_PACK");  // experiments / A-B runs: ignore the packed copies
+        if ((e && e[0] == '1') || params_host->engine != DP_ENGINE_FUSED) packed = false;
+    }
+    const void* fused = has_solve ? (const void*)pcg_fused_kernel<true, false>
+                        : packed  ? (const void*)pcg_fused_kernel<false, true>
+                                  : (const void*)pcg_fused_kernel<false, false>;
     if (allow_dynamic_smem(fused, sizeof(Smem)) != DP_OK || allow_smem(pcg_phase_kernel<PH_FWD, false>) != DP_OK) return DP_ERR_CUDA;
     const int coop = coop_grid(fused, kBlock, sizeof(Smem));
     const int coop_phase = coop_grid((const void*)pcg_phase_kernel<PH_FWD, false>, kBlock, sizeof(Smem));
@@ -1111,6 +1130,7 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
         DP_CUDA(cudaGetDevice(&dev));
         DP_CUDA(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev));
         const char* e = getenv("DPCG_KEEP_L2");  // experiments: 0 / 1 forces the policy
+        if (packed) working_set_bytes -= matrix_entries * 6;
         ctx.keep_l2 = e ? (e[0] == '1') : (working_set_bytes * 10 < (long long)l2 * 6);
     }
     ctx.rtol = params_host->rtol;

@@ -27,11 +27,12 @@ struct SpmvSmem {
     TileDesc tab[kSpmvRound];
 };
 
+template <bool kPacked>
 __global__ void __launch_bounds__(kBlock, 2)
 spmv_csr_kernel(CsrView A, const double* __restrict__ x, double* __restrict__ y) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SpmvSmem& sm = *reinterpret_cast<SpmvSmem*>(smem_raw);
-    Pipe pipe;
+    typename std::conditional<kPacked, PipePacked, Pipe>::type pipe;
     pipe.init(sm.pipe.bytes, &sm.pipe.bar);
     const int ntiles = (A.n + kTileRows - 1) / kTileRows;
     const int quot = ntiles / (int)gridDim.x, rem = ntiles % (int)gridDim.x;  // ranges differ by at most one tile
@@ -42,7 +43,7 @@ spmv_csr_kernel(CsrView A, const double* __restrict__ x, double* __restrict__ y)
         __syncthreads();  // the previous round's table is no longer read
         for (int i = threadIdx.x; i < cnt; i += kBlock) {
             TileDesc d;
-            tile_desc_fill(d, A, ga + i);
+            tile_desc_fill<kPacked>(d, A, ga + i);
             d.sys = 0;
             sm.tab[i] = d;
         }
@@ -54,11 +55,48 @@ spmv_csr_kernel(CsrView A, const double* __restrict__ x, double* __restrict__ y)
             const TileDesc& d = sm.tab[i];
             const int rs = rs_n, re = re_n;
             if (i + 1 < cnt) tile_row_extent(sm.tab[i + 1], rs_n, re_n);  // one tile ahead
-            const double s = pipe.tile_spmv<DPCG_SPMV_UNROLL>(d, rs, re, gx, true);
+            const double s = pipe.template tile_spmv<DPCG_SPMV_UNROLL>(d, rs, re, gx, true);
             const int row = d.ltile * kTileRows + (int)threadIdx.x;
             if (row < A.n) y[row] = s;
         }
     }
+}
+
+// dp_csr_pack: one CTA per 512-row tile. Pass 1 finds the tile's column range, pass 2 writes the 6-byte entries and checks
+// that nothing was lost (values bit for bit through fp32, columns within 16 bits of the tile's smallest).
+__global__ void __launch_bounds__(kBlock)
+csr_pack_kernel(int n, const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val,
+                unsigned short* __restrict__ col16, float* __restrict__ val32, int* __restrict__ tile_base,
+                int* __restrict__ status) {
+    __shared__ int s_lo[kWarpsPerBlock], s_hi[kWarpsPerBlock];
+    const int tile = blockIdx.x;
+    const int cs = __ldg(rowptr + min(tile * kTileRows, n)), ce = __ldg(rowptr + min((tile + 1) * kTileRows, n));
+    int lo = 0x7fffffff, hi = -1;
+    for (int q = cs + (int)threadIdx.x; q < ce; q += kBlock) {
+        const int c = __ldg(col + q);
+        lo = min(lo, c), hi = max(hi, c);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(kFull, lo, o));
+        hi = max(hi, __shfl_xor_sync(kFull, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) s_lo[threadIdx.x >> 5] = lo, s_hi[threadIdx.x >> 5] = hi;
+    __syncthreads();
+    lo = s_lo[0], hi = s_hi[0];
+#pragma unroll
+    for (int w = 1; w < kWarpsPerBlock; ++w) lo = min(lo, s_lo[w]), hi = max(hi, s_hi[w]);
+    if (ce == cs) lo = 0, hi = 0;
+    int bad = (hi - lo > 65535 || lo < 0) ? 2 : 0;
+    if (threadIdx.x == 0) tile_base[tile] = lo;
+    for (int q = cs + (int)threadIdx.x; q < ce; q += kBlock) {
+        const double v = val[q];
+        const float f = (float)v;
+        if (as_bits((double)f) != as_bits(v)) bad |= 1;
+        val32[q] = f;
+        col16[q] = (unsigned short)(__ldg(col + q) - lo);
+    }
+    if (bad) atomicOr(status, bad);
 }
 
 // utils.py:15-43 — batched COO SpMV in fp32. Accumulation order is unspecified in the reference
@@ -163,12 +201,41 @@ int dp_spmv_csr_f64(int32_t n, int32_t nnz, const int32_t* rowptr, const int32_t
     if (n < 0 || nnz < 0 || !rowptr || !y || (nnz > 0 && (!col || !val || !x))) return DP_ERR_INVALID;
     if (!aligned16(col) || !aligned16(val)) return DP_ERR_ALIGNMENT;
     if (n == 0) return DP_OK;
-    if (allow_dynamic_smem((const void*)spmv_csr_kernel, sizeof(SpmvSmem)) != DP_OK) return DP_ERR_CUDA;
+    if (allow_dynamic_smem((const void*)spmv_csr_kernel<false>, sizeof(SpmvSmem)) != DP_OK) return DP_ERR_CUDA;
     const int tiles = (n + kTileRows - 1) / kTileRows;
     const int resident = 2 * sm_count();
     const int grid = tiles < resident ? tiles : resident;
     CsrView A{rowptr, col, val, n, nnz};
-    spmv_csr_kernel<<<grid, kBlock, sizeof(SpmvSmem), (cudaStream_t)stream>>>(A, x, y);
+    spmv_csr_kernel<false><<<grid, kBlock, sizeof(SpmvSmem), (cudaStream_t)stream>>>(A, x, y);
+    DP_LAUNCH_CHECK();
+    return DP_OK;
+}
+
+int32_t dp_csr_pack_tile_rows(void) { return kTileRows; }
+
+int dp_csr_pack(int32_t n, int32_t nnz, const int32_t* rowptr, const int32_t* col, const double* val, uint16_t* col16,
+                float* val32, int32_t* tile_base, int32_t* status_out, void* stream) {
+    if (n < 0 || nnz < 0 || !rowptr || !tile_base || !status_out || (nnz > 0 && (!col || !val || !col16 || !val32)))
+        return DP_ERR_INVALID;
+    if (!aligned16(col16) || !aligned16(val32)) return DP_ERR_ALIGNMENT;
+    if (n == 0) return DP_OK;
+    const int tiles = (n + kTileRows - 1) / kTileRows;
+    csr_pack_kernel<<<tiles, kBlock, 0, (cudaStream_t)stream>>>(n, rowptr, col, val, col16, val32, tile_base, status_out);
+    DP_LAUNCH_CHECK();
+    return DP_OK;
+}
+
+int dp_spmv_csr_packed_f64(int32_t n, int32_t nnz, const int32_t* rowptr, const uint16_t* col16, const float* val32,
+                           const int32_t* tile_base, const double* x, double* y, void* stream) {
+    if (n < 0 || nnz < 0 || !rowptr || !y || !tile_base || (nnz > 0 && (!col16 || !val32 || !x))) return DP_ERR_INVALID;
+    if (!aligned16(col16) || !aligned16(val32)) return DP_ERR_ALIGNMENT;
+    if (n == 0) return DP_OK;
+    if (allow_dynamic_smem((const void*)spmv_csr_kernel<true>, sizeof(SpmvSmem)) != DP_OK) return DP_ERR_CUDA;
+    const int tiles = (n + kTileRows - 1) / kTileRows;
+    const int resident = 2 * sm_count();
+    const int grid = tiles < resident ? tiles : resident;
+    CsrView A{rowptr, nullptr, nullptr, n, nnz, col16, val32, tile_base};
+    spmv_csr_kernel<true><<<grid, kBlock, sizeof(SpmvSmem), (cudaStream_t)stream>>>(A, x, y);
     DP_LAUNCH_CHECK();
     return DP_OK;
 }

@@ -14,6 +14,10 @@ struct CsrView {
     const double* __restrict__ val;
     int n;
     int nnz;
+    // optional packed stream copy (dp_csr_pack): fp32 values, 16-bit columns relative to the tile's smallest column
+    const unsigned short* __restrict__ col16;
+    const float* __restrict__ val32;
+    const int* __restrict__ tbase;
 };
 
 // Gather functors: what "x[c]" means for a phase. Vectors written earlier in the same persistent kernel are read

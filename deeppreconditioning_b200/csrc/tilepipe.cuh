@@ -20,7 +20,13 @@
 // Bulk copies need 16-byte aligned addresses and sizes: a block's copy starts at the 16-byte boundary at or below its
 // first entry and ends at the one at or above its last. The few bytes read beyond the matrix's last entry stay inside
 // the 16-byte unit that holds that entry (arrays are 16-byte aligned, dpcg.h), so they can never touch another page.
+//
+// Packed stream (kPacked): the same pipeline over the lossless 6-byte copy of a matrix (dp_csr_pack: fp32 values, 16-bit
+// columns relative to the tile's smallest column). A stage of the same size holds twice the entries, the lanes widen on
+// load (exact) and run the identical fp64 recurrence: same bits, half the matrix bytes from HBM.
 #pragma once
+
+#include <type_traits>
 
 #include "common.cuh"
 #include "spmv.cuh"
@@ -133,16 +139,19 @@ struct TileDesc {
     int cs, ce;  // entries of the tile
     int ltile;   // tile index inside its matrix
     int sys;     // system id (PCG), unused by the standalone kernel
+    int base;    // packed stream: smallest column of the tile (col = base + col16); col / val then point at col16 / val32
 };
 
 // Shared memory of a pipeline of geometry (kCap entries per stage, kStages stages): the stages' bytes (values first,
 // then column indices) and one full/empty mbarrier pair per stage. Several geometries may be laid over the same bytes
 // (each with its own barriers) as long as only one of them has items in flight at a time.
-template <int kCap, int kStages>
+template <int kCap, int kStages, bool kPacked = false>
 struct PipeGeom {
-    static constexpr int kSlots = kCap + 8;  // up to 3 lead-in entries (16-byte alignment) + tail rounding
-    static constexpr size_t kBytes = (size_t)kStages * kSlots * 12;
-    static_assert(kCap % 4 == 0 && kCap >= 64, "stage capacity");
+    // lead-in entries down to the 16-byte boundary of the span's first entry (3, packed: 7) + tail rounding
+    static constexpr int kSlots = kCap + (kPacked ? 16 : 8);
+    static constexpr int kEntryBytes = kPacked ? 6 : 12;
+    static constexpr size_t kBytes = (size_t)kStages * kSlots * kEntryBytes;
+    static_assert(kCap % 8 == 0 && kCap >= 64, "stage capacity");
 };
 template <int kStages>
 struct PipeBarriers {
@@ -163,13 +172,15 @@ struct PipeShared {
 
 // Fill the stream part of a descriptor for tile `ltile` of matrix M (one dependent load pair; CTA-parallel in the
 // table builders).
+template <bool kPacked = false>
 __device__ __forceinline__ void tile_desc_fill(TileDesc& d, const CsrView& M, int ltile) {
     d.rowptr = M.rowptr;
-    d.col = M.col;
-    d.val = M.val;
+    d.col = kPacked ? reinterpret_cast<const int*>(M.col16) : M.col;
+    d.val = kPacked ? reinterpret_cast<const double*>(M.val32) : M.val;
     d.n = M.n;
     d.nnz = M.nnz;
     d.ltile = ltile;
+    d.base = (kPacked && M.rowptr) ? __ldg(M.tbase + ltile) : 0;
     if (M.rowptr) {
         d.cs = __ldg(M.rowptr + min(ltile * kTileRows, M.n));
         d.ce = __ldg(M.rowptr + min((ltile + 1) * kTileRows, M.n));
@@ -181,11 +192,17 @@ __device__ __forceinline__ void tile_desc_fill(TileDesc& d, const CsrView& M, in
 // Register state of a pipeline; lives for the whole kernel (or is saved/restored through `counts()`/`resume()`).
 // Items are numbered since kernel start: item i lives in stage i % kStages and is the (i / kStages)-th use of that
 // stage, which fixes the mbarrier parities.
-template <int kCap, int kStages>
+template <int kCap, int kStages, bool kPacked = false>
 struct PipeT {
-    static constexpr int kSlots = PipeGeom<kCap, kStages>::kSlots;
-    double* val0;  // stage s: val0 + s * kSlots, col0 + s * kSlots
-    int* col0;
+    static constexpr int kSlots = PipeGeom<kCap, kStages, kPacked>::kSlots;
+    static constexpr bool kIsPacked = kPacked;
+    using ValT = typename std::conditional<kPacked, float, double>::type;
+    using ColT = typename std::conditional<kPacked, unsigned short, int>::type;
+    static constexpr int kValUnit = 16 / (int)sizeof(ValT);  // entries per 16-byte unit of the bulk copies
+    static constexpr int kColUnit = 16 / (int)sizeof(ColT);
+    static constexpr int kAlign = kColUnit > kValUnit ? kColUnit : kValUnit;  // a block's copies start at this entry boundary
+    ValT* val0;  // stage s: val0 + s * kSlots, col0 + s * kSlots
+    ColT* col0;
     unsigned long long* full;
     unsigned long long* empty;
     const TileDesc* tab;
@@ -199,13 +216,22 @@ struct PipeT {
     int keep_l2;        // the matrices fit the L2 together with the vectors: do not mark their lines evict-first
 
     static __device__ __forceinline__ int blocks(const TileDesc& d) { return (d.ce - d.cs + kCap - 1) / kCap; }
-    __device__ __forceinline__ const double* stage_val(unsigned s) const { return val0 + (size_t)s * kSlots; }
-    __device__ __forceinline__ const int* stage_col(unsigned s) const { return col0 + (size_t)s * kSlots; }
+    __device__ __forceinline__ const ValT* stage_val(unsigned s) const { return val0 + (size_t)s * kSlots; }
+    __device__ __forceinline__ const ColT* stage_col(unsigned s) const { return col0 + (size_t)s * kSlots; }
+    // the 16-byte aligned copies that bring entries [as, be) of a tile's arrays into a stage (as = bs & ~(kAlign - 1))
+    __device__ __forceinline__ void issue_copies(const TileDesc& d, unsigned stage, int as, int be, unsigned long long pol) {
+        const unsigned ncol = (unsigned)(((be + kColUnit - 1) & ~(kColUnit - 1)) - as);
+        const unsigned nval = (unsigned)(((be + kValUnit - 1) & ~(kValUnit - 1)) - as);
+        unsigned long long* bar = &full[stage];
+        mbar_arrive_expect_tx(bar, ncol * (unsigned)sizeof(ColT) + nval * (unsigned)sizeof(ValT));
+        bulk_g2s(val0 + (size_t)stage * kSlots, reinterpret_cast<const ValT*>(d.val) + as, nval * (unsigned)sizeof(ValT), bar, pol);
+        bulk_g2s(col0 + (size_t)stage * kSlots, reinterpret_cast<const ColT*>(d.col) + as, ncol * (unsigned)sizeof(ColT), bar, pol);
+    }
 
     // Bind to shared memory. `fresh`: initialise the barriers (once per kernel and geometry); ends with a CTA barrier.
     __device__ __forceinline__ void init(unsigned char* bytes, PipeBarriers<kStages>* bar, bool fresh = true) {
-        val0 = reinterpret_cast<double*>(bytes);
-        col0 = reinterpret_cast<int*>(bytes + (size_t)kStages * kSlots * 8);
+        val0 = reinterpret_cast<ValT*>(bytes);
+        col0 = reinterpret_cast<ColT*>(bytes + (size_t)kStages * kSlots * sizeof(ValT));
         full = bar->full, empty = bar->empty;
         tab = nullptr;
         ntiles = 0;
@@ -248,13 +274,7 @@ struct PipeT {
         const TileDesc& d = tab[p_tile];
         const int bs = d.cs + p_blk * kCap;
         const int be = min(d.ce, bs + kCap);
-        const int as = bs & ~3;
-        const unsigned ncol = (unsigned)(((be + 3) & ~3) - as), nval = (unsigned)(((be + 1) & ~1) - as);
-        unsigned long long* bar = &full[stage];
-        const unsigned long long pol = keep_l2 ? l2_policy_keep() : l2_policy_stream();
-        mbar_arrive_expect_tx(bar, ncol * 4u + nval * 8u);
-        bulk_g2s(val0 + (size_t)stage * kSlots, d.val + as, nval * 8u, bar, pol);
-        bulk_g2s(col0 + (size_t)stage * kSlots, d.col + as, ncol * 4u, bar, pol);
+        issue_copies(d, stage, bs & ~(kAlign - 1), be, keep_l2 ? l2_policy_keep() : l2_policy_stream());
         ++p_blk, ++p_count;
         return true;
     }
@@ -280,13 +300,7 @@ struct PipeT {
             }
         }
         const TileDesc& d = tab[t];
-        const int as = d.cs & ~3;
-        const unsigned ncol = (unsigned)(((d.ce + 3) & ~3) - as), nval = (unsigned)(((d.ce + 1) & ~1) - as);
-        unsigned long long* bar = &full[stage];
-        const unsigned long long pol = l2_policy_stream();
-        mbar_arrive_expect_tx(bar, ncol * 4u + nval * 8u);
-        bulk_g2s(val0 + (size_t)stage * kSlots, d.val + as, nval * 8u, bar, pol);
-        bulk_g2s(col0 + (size_t)stage * kSlots, d.col + as, ncol * 4u, bar, pol);
+        issue_copies(d, stage, d.cs & ~(kAlign - 1), d.ce, l2_policy_stream());
         ++p_count;
     }
     // ... and its consumer side: wait for the next item without any producer duty.
@@ -364,11 +378,12 @@ struct PipeT {
         for (int j = 0; j < nb; ++j) {
             const int bs = d.cs + j * kCap;
             const int be = min(d.ce, bs + kCap);
-            const int as = bs & ~3;
+            const int as = bs & ~(kAlign - 1);
             const unsigned stage = acquire();
             if (compute) {
-                const double* __restrict__ sv = stage_val(stage);
-                const int* __restrict__ sc = stage_col(stage);
+                const ValT* __restrict__ sv = stage_val(stage);
+                const ColT* __restrict__ sc = stage_col(stage);
+                const int base = kPacked ? d.base : 0;
                 const int qe = min(re, be) - as;
                 for (int q = max(rs, bs) - as; q < qe; q += kUnroll) {
                     int c[kUnroll];
@@ -376,8 +391,8 @@ struct PipeT {
 #pragma unroll
                     for (int u = 0; u < kUnroll; ++u) {
                         const bool on = q + u < qe;
-                        c[u] = on ? sc[q + u] : 0;
-                        v[u] = on ? sv[q + u] : 0.0;
+                        c[u] = on ? base + (int)sc[q + u] : 0;
+                        v[u] = on ? (double)sv[q + u] : 0.0;  // packed: fp32 -> fp64 is exact
                     }
 #pragma unroll
                     for (int u = 0; u < kUnroll; ++u) xv[u] = (q + u < qe) ? x(c[u]) : 0.0;
@@ -396,6 +411,9 @@ struct PipeT {
 };
 
 using Pipe = PipeT<kPipeCap, kPipeStages>;  // the SpMV geometry: whole tiles per stage
+// ... and the packed stream over the same bytes: twice the entries per stage (the CNN factor's 7680-entry tile is one item)
+using PipePacked = PipeT<2 * kPipeCap, kPipeStages, true>;
+static_assert(PipeGeom<2 * kPipeCap, kPipeStages, true>::kBytes <= PipeGeom<kPipeCap, kPipeStages>::kBytes, "packed stages fit");
 
 // Row extent of this thread's row in tile d (coalesced; issue one tile ahead to hide the latency).
 __device__ __forceinline__ void tile_row_extent(const TileDesc& d, int& rs, int& re) {
@@ -411,8 +429,8 @@ __device__ __forceinline__ void tile_row_extent(const TileDesc& d, int& rs, int&
 // Per value bit-identical to block_sum (lane butterfly -> 16 warp sums -> 16-wide butterfly).
 constexpr int kReduceSlots = 3 * kWarpsPerBlock;
 
-template <int kN>
-__device__ __forceinline__ void tile_reduce(double (&v)[kN], double (*scratch2x)[kReduceSlots], Pipe& pipe) {
+template <int kN, class P>
+__device__ __forceinline__ void tile_reduce(double (&v)[kN], double (*scratch2x)[kReduceSlots], P& pipe) {
     static_assert(kN <= 3, "scratch holds 3 values per warp");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* scratch = scratch2x[pipe.flip];
@@ -441,8 +459,8 @@ struct TileRed {
     int count[kRedRing];
 };
 
-template <int kN, class Write>
-__device__ __forceinline__ void tile_reduce_async(double (&v)[kN], TileRed& red, Pipe& pipe, const Write& write) {
+template <int kN, class P, class Write>
+__device__ __forceinline__ void tile_reduce_async(double (&v)[kN], TileRed& red, P& pipe, const Write& write) {
     static_assert(kN <= 3, "ring slots hold 3 values per warp");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned r = pipe.t_count % kRedRing;

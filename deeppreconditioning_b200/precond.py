@@ -418,8 +418,19 @@ class _Operator:
         """Write this operator's arrays into a ``dp_pcg_system_t``."""
         system.precond = self.precond
 
+    def stream_matrices(self) -> list:
+        """The CSR matrices a PCG iteration streams for this operator (candidates for packed copies)."""
+        return []
+
     def nnz_explicit(self) -> int | None:
         return None
+
+
+def fill_packed(system: _lib.PcgSystem, tag: str, matrix: CsrMatrix) -> None:
+    """Hand the packed stream copy of ``matrix`` (if it has been made and is exact) to the descriptor."""
+    pk = matrix._packed or None
+    for name in ("col16", "val32", "tile_base"):
+        setattr(system, f"{tag}_{name}", _lib.ptr(getattr(pk, name)) if pk is not None else None)
 
 
 class Identity(_Operator):
@@ -458,6 +469,10 @@ class CsrOperator(_Operator):
         system.precond = self.precond
         system.m_rowptr, system.m_col, system.m_val = _lib.ptr(self.M.rowptr), _lib.ptr(self.M.col), _lib.ptr(self.M.val)
         system.m_nnz = self.M.nnz
+        fill_packed(system, "m", self.M)
+
+    def stream_matrices(self):
+        return [self.M]
 
 
 class FactoredMultiply(_Operator):
@@ -478,6 +493,11 @@ class FactoredMultiply(_Operator):
         system.mt_rowptr, system.mt_col, system.mt_val = (_lib.ptr(self.Lt.rowptr), _lib.ptr(self.Lt.col),
                                                           _lib.ptr(self.Lt.val))
         system.m_nnz, system.mt_nnz = self.L.nnz, self.Lt.nnz
+        fill_packed(system, "m", self.L)
+        fill_packed(system, "mt", self.Lt)
+
+    def stream_matrices(self):
+        return [self.L, self.Lt]
 
 
 class FactoredSolve(FactoredMultiply):

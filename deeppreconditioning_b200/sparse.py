@@ -42,6 +42,8 @@ class CsrMatrix:
         self.rowptr, self.col, self.val, self.n = rowptr.contiguous(), col.contiguous(), val.contiguous(), int(n)
         self._t: CsrMatrix | None = None
         self._dinv: torch.Tensor | None = None
+        self._packed = None        # None: not tried; False: no exact packed copy exists; else PackedCsr
+        self._packed_key = None    # (col, val) tensor versions the verdict belongs to
 
     # ---- construction ----------------------------------------------------------------------------------------
     @classmethod
@@ -159,11 +161,27 @@ class CsrMatrix:
         rowptr[1:] = torch.cumsum(per_row, 0).to(torch.int32)
         return CsrMatrix(rowptr, self.col[keep].contiguous(), self.val[keep].contiguous(), self.n)
 
-    def matvec(self, x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
-        """``y = A x`` on the device (``dp_spmv_csr_f64``)."""
+    def packed(self) -> "PackedCsr | None":
+        """The lossless 6-byte-per-entry stream copy (``dp_csr_pack``: fp32 values, 16-bit tile-relative columns) or
+        ``None`` when the matrix has no exact one. Cached; in-place changes of ``col`` / ``val`` invalidate it."""
+        pack_many([self])
+        return self._packed or None
+
+    def matvec(self, x: torch.Tensor, out: torch.Tensor | None = None, packed: bool = False) -> torch.Tensor:
+        """``y = A x`` on the device (``dp_spmv_csr_f64``; ``packed``: from the packed copy, same bits, must exist)."""
         assert x.is_cuda and x.dtype == torch.float64 and x.shape == (self.n,)
         x = x.contiguous()
         y = out if out is not None else torch.empty(self.n, dtype=torch.float64, device=self.device)
+        if packed:
+            pk = self.packed()
+            if pk is None:
+                raise _lib.DpcgError("matrix has no exact packed copy (values beyond fp32 or a tile wider than 65535 columns)")
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().dp_spmv_csr_packed_f64(self.n, self.nnz, _lib.ptr(self.rowptr), _lib.ptr(pk.col16),
+                                                             _lib.ptr(pk.val32), _lib.ptr(pk.tile_base), _lib.ptr(x),
+                                                             _lib.ptr(y), _lib.stream_ptr(self.device)),
+                           "dp_spmv_csr_packed_f64")
+            return y
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().dp_spmv_csr_f64(self.n, self.nnz, _lib.ptr(self.rowptr), _lib.ptr(self.col),
                                                   _lib.ptr(self.val), _lib.ptr(x), _lib.ptr(y),
@@ -195,6 +213,50 @@ class CsrMatrix:
     def to_torch_csr(self, device="cpu") -> torch.Tensor:
         return torch.sparse_csr_tensor(self.rowptr.to(device).long(), self.col.to(device).long(), self.val.to(device),
                                        size=self.shape)
+
+
+class PackedCsr:
+    """Packed stream copy of a :class:`CsrMatrix` (shares its ``rowptr``): ``col16 uint16[nnz]``, ``val32 float32[nnz]``,
+    ``tile_base int32[ceil(n / 512)]`` with ``col = tile_base[row // 512] + col16``."""
+
+    def __init__(self, col16: torch.Tensor, val32: torch.Tensor, tile_base: torch.Tensor) -> None:
+        self.col16, self.val32, self.tile_base = col16, val32, tile_base
+
+
+def pack_many(matrices) -> None:
+    """Give every matrix of ``matrices`` its packed-copy verdict (``CsrMatrix._packed``) with ONE device synchronisation:
+    all ``dp_csr_pack`` launches first, then one read of the status words. Matrices whose verdict is current are skipped."""
+    todo, seen = [], set()
+    for m in matrices:
+        key = (m.col._version, m.val._version, m.col.data_ptr(), m.val.data_ptr())
+        if id(m) in seen or (m._packed is not None and m._packed_key == key):
+            continue
+        seen.add(id(m))
+        m._packed, m._packed_key = None, key
+        todo.append(m)
+    if not todo:
+        return
+    lib = _lib.lib()
+    tile_rows = int(lib.dp_csr_pack_tile_rows())
+    by_device = {}
+    for m in todo:
+        by_device.setdefault(m.device, []).append(m)
+    for dev, ms in by_device.items():
+        status = torch.zeros(len(ms), dtype=torch.int32, device=dev)
+        copies = []
+        with torch.cuda.device(dev):
+            for i, m in enumerate(ms):
+                nnz = m.nnz
+                col16 = torch.empty(max((nnz + 7) // 8 * 8, 8), dtype=torch.uint16, device=dev)
+                val32 = torch.empty(max((nnz + 3) // 4 * 4, 4), dtype=torch.float32, device=dev)
+                tile_base = torch.empty(max((m.n + tile_rows - 1) // tile_rows, 1), dtype=torch.int32, device=dev)
+                _lib.check(lib.dp_csr_pack(m.n, nnz, _lib.ptr(m.rowptr), _lib.ptr(m.col), _lib.ptr(m.val), _lib.ptr(col16),
+                                           _lib.ptr(val32), _lib.ptr(tile_base), status.data_ptr() + 4 * i,
+                                           _lib.stream_ptr(dev)), "dp_csr_pack")
+                copies.append(PackedCsr(col16, val32, tile_base))
+        verdicts = status.cpu().tolist()  # the one synchronisation
+        for m, pk, bad in zip(ms, copies, verdicts):
+            m._packed = pk if bad == 0 else False
 
 
 def as_csr(matrix, device=None) -> CsrMatrix:

@@ -91,6 +91,25 @@ int dp_csr_inv_diagonal(int32_t n, const int32_t* rowptr, const int32_t* col, co
 int dp_csr_aat_nnz(int32_t n, const int32_t* rowptr, const int32_t* col, const int32_t* rowptr_t, const int32_t* col_t,
                    int64_t* nnz_out, void* stream);
 
+/* ---- packed stream copy of a CSR matrix (lossless) -----------------------------------------------------------
+ * The operands of this path are fp32 data widened to fp64 (the CNN output and the data set's matrices are fp32,
+ * test.py:100-105, data_set.py:121-125) on banded patterns, so the 12 bytes per stored entry of the fp64/int32 CSR
+ * are mostly zeros. dp_csr_pack writes the same matrix as 6 bytes per entry: val32[q] = (float)val[q] and
+ * col16[q] = col[q] - tile_base[t], t = the 512-row tile (dp_csr_pack_tile_rows()) that holds entry q, tile_base[t] =
+ * the smallest column of the tile. The copy exists only if it is EXACT: *status_out (device int32, OR-ed bits) is 0
+ * when every value survives the fp32 round trip bit for bit and every tile spans fewer than 65536 columns; otherwise
+ * bit 0 (a value is not an fp32 number) and / or bit 1 (a tile is too wide) is set and the copy must not be used.
+ * The kernels that accept a packed copy (dp_spmv_csr_packed_f64, dp_pcg_solve_f64) widen on load and do the same fp64
+ * arithmetic in the same order: results are bit-identical to the unpacked path, HBM traffic per entry is halved.
+ * col16 / val32 need room for nnz entries rounded up to a multiple of 16 bytes, 16-byte aligned;
+ * tile_base int32[ceil(n / 512)]. */
+int32_t dp_csr_pack_tile_rows(void);
+int dp_csr_pack(int32_t n, int32_t nnz, const int32_t* rowptr, const int32_t* col, const double* val, uint16_t* col16,
+                float* val32, int32_t* tile_base, int32_t* status_out, void* stream);
+/* y = A x from the packed copy; same bits as dp_spmv_csr_f64. */
+int dp_spmv_csr_packed_f64(int32_t n, int32_t nnz, const int32_t* rowptr, const uint16_t* col16, const float* val32,
+                           const int32_t* tile_base, const double* x, double* y, void* stream);
+
 /* ---- K2: CSR SpMV fp64 ---------------------------------------------------------------------------------
  * y = A x. Replaces `A @ p` / `M @ r` (cg.py:60,61,75,81). Row sums are sequential in column order with
  * separately rounded products and sums, i.e. bit-identical to scipy's csr_matvec. */
@@ -286,6 +305,13 @@ typedef struct dp_pcg_system {
                            * built p for body k (cg.py:82 of body k-1; 0 for k = 0). The CG coefficients are the Lanczos
                            * tridiagonal of M*A: the host turns them into the condition-number estimate that replaces
                            * the dense torch.linalg.cond of test.py:111-113. */
+    /* Optional packed stream copies (dp_csr_pack, status 0) of A, of L / M and of L^T. When EVERY system of a batch
+     * without SOLVE-mode systems brings the copies of all the matrices its phases stream, the FUSED engine streams
+     * those (6 instead of 12 bytes per entry, same bits); otherwise they are ignored. The unpacked arrays above stay
+     * mandatory. */
+    const uint16_t* a_col16; const float* a_val32; const int32_t* a_tile_base;
+    const uint16_t* m_col16; const float* m_val32; const int32_t* m_tile_base;
+    const uint16_t* mt_col16; const float* mt_val32; const int32_t* mt_tile_base;
 } dp_pcg_system_t;
 
 #define DP_SOLVE_TILE_STREAM 1

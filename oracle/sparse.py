@@ -79,3 +79,27 @@ def explicit_product(l_rowptr, l_col, l_val):
 def sparse_matvec_mul(indices, features, vector_batch, transpose: bool):
     """``utils.py:15-43`` on plain arrays: ``[B, N]`` fp32 result."""
     return ckernels.coo_spmv_batch(np.asarray(indices), np.asarray(features), np.asarray(vector_batch), transpose)
+
+
+def pack_csr(rowptr, col, val, tile_rows: int = 512):
+    """Restatement of ``dp_csr_pack`` (no reference counterpart: a lossless storage format of this implementation):
+    per tile of ``tile_rows`` rows the smallest column, 16-bit offsets from it, fp32 values. Returns
+    ``(col16, val32, tile_base, status)`` with ``status`` bit 0 = a value is not an fp32 number, bit 1 = a tile spans
+    65536 columns or more."""
+    rowptr, col, val = np.asarray(rowptr), np.asarray(col), np.asarray(val, dtype=np.float64)
+    n = len(rowptr) - 1
+    ntiles = (n + tile_rows - 1) // tile_rows
+    col16 = np.zeros(len(col), np.uint16)
+    with np.errstate(over="ignore", invalid="ignore"):
+        val32 = val.astype(np.float32)
+    tile_base = np.zeros(max(ntiles, 1), np.int32)
+    status = 0 if np.array_equal(val32.astype(np.float64).view(np.int64), val.view(np.int64)) else 1
+    for t in range(ntiles):
+        cs, ce = rowptr[min(t * tile_rows, n)], rowptr[min((t + 1) * tile_rows, n)]
+        if ce > cs:
+            lo, hi = int(col[cs:ce].min()), int(col[cs:ce].max())
+            tile_base[t] = lo
+            if hi - lo > 65535:
+                status |= 2
+            col16[cs:ce] = ((col[cs:ce] - lo) & 0xFFFF).astype(np.uint16)
+    return col16, val32, tile_base, status

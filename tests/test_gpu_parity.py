@@ -122,6 +122,105 @@ def test_spmv_long_and_empty_rows(cuda):
     assert one.matvec(torch.tensor([2.0], dtype=torch.float64, device=cuda)).item() == 5.0
 
 
+@pytest.mark.parametrize("kind,side,net", CASES)
+def test_packed_copy_bit_exact(cuda, kind, side, net):
+    """dp_csr_pack against its restatement, and the SpMV from the packed copy against scipy: same bits as the fp64 stream."""
+    p = helpers.problem(kind, side, 0, 0.5, net)
+    ops = gpu_operands(p, cuda)
+    x = np.random.default_rng(7).standard_normal(p.n)
+    xd = torch.from_numpy(x).to(cuda)
+    for key, want in [("A", p.A), ("L", p.L), ("Lt", osp.transpose_csr(*p.L))]:
+        pk = ops[key].packed()
+        assert pk is not None, key
+        col16, val32, base, status = osp.pack_csr(*want)
+        assert status == 0
+        nnz = len(want[1])
+        assert np.array_equal(pk.col16[:nnz].cpu().numpy(), col16), key
+        assert np.array_equal(pk.val32[:nnz].cpu().numpy().view(np.int32), val32.view(np.int32)), key
+        assert np.array_equal(pk.tile_base.cpu().numpy()[: len(base)], base), key
+        y = ops[key].matvec(xd, packed=True).cpu().numpy()
+        assert np.array_equal(y, osp.to_scipy(*want) @ x), key
+
+
+def test_packed_copy_limits_and_block_boundaries(cuda):
+    """Matrices without an exact packed copy are reported (and PCG falls back to the fp64 stream); tiles that straddle
+    the packed stage capacity (7680 entries), rows cut by a block boundary, nnz not a multiple of 8, empty rows."""
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(3)
+    for n, per_row in [(512, 7), (513, 8), (1500, 9), (2048, 16), (700, 23), (5000, 4), (1200, 40)]:
+        rows = np.repeat(np.arange(n), per_row)
+        cols = rng.integers(0, n, size=n * per_row)
+        vals = rng.standard_normal(n * per_row).astype(np.float32).astype(np.float64)
+        m = sp.csr_matrix((vals, (rows, cols)), shape=(n, n))
+        m.sum_duplicates()
+        m.data = m.data.astype(np.float32).astype(np.float64)
+        m.sort_indices()
+        if n == 1500:
+            m = m.tolil(); m[10, :] = 0; m[n - 1, :] = 0; m = m.tocsr(); m.eliminate_zeros(); m.sort_indices()
+        x = rng.standard_normal(n)
+        M = CsrMatrix.from_scipy(m, cuda)
+        y = M.matvec(torch.from_numpy(x).to(cuda), packed=True).cpu().numpy()
+        assert np.array_equal(y, ckernels.spmv_csr(m.indptr, m.indices, m.data, x)), (n, per_row, m.nnz)
+    # a value that is not an fp32 number
+    p = helpers.problem("poisson2d", 37, 0, 0.5, "net")
+    rowptr, col, val = p.A
+    bad = np.array(val)
+    bad[5] *= 1.0 + 2.0 ** -40
+    B = CsrMatrix.from_arrays(rowptr, col, bad, cuda)
+    assert B.packed() is None
+    with pytest.raises(dp_lib.DpcgError):
+        B.matvec(torch.zeros(p.n, dtype=torch.float64, device=cuda), packed=True)
+    got = dp.pcg_solve(B, p.b.to(cuda), dp.Jacobi(B), max_iter=2000)
+    want = dp.pcg_solve(B, p.b.to(cuda), dp.Jacobi(B), max_iter=2000, pack=False)
+    assert got.iterations == want.iterations and torch.equal(got.x_hat, want.x_hat)
+    # a tile wider than 65535 columns
+    n = 70000
+    wide = sp.identity(n, format="lil")
+    wide[0, n - 1] = 2.0
+    W = CsrMatrix.from_scipy(wide.tocsr(), cuda)
+    assert W.packed() is None
+    # in-place changes invalidate the cached verdict
+    A = CsrMatrix.from_arrays(*p.A, cuda)
+    assert A.packed() is not None
+    A.val[5] *= 1.0 + 2.0 ** -40
+    assert A.packed() is None
+
+
+@pytest.mark.parametrize("kind,side,net,name", [("poisson2d", 64, "net", "multiply"), ("poisson2d", 100, "tril", "multiply"),
+                                                ("poisson3d", 12, "net", "multiply"), ("poisson2d", 64, "net", "jacobi"),
+                                                ("poisson2d", 37, "net", "identity"), ("poisson2d", 16, "net", "explicit")])
+def test_pcg_from_packed_copies_is_bitwise_the_fp64_stream(cuda, kind, side, net, name):
+    """The fused engine on the packed copies (6 bytes per entry) gives exactly the bits of the fp64 / int32 stream:
+    iteration counts, criterion history, CG coefficients and solution."""
+    p = helpers.problem(kind, side, 0, 0.5, net)
+    ops = gpu_operands(p, cuda)
+    M = gpu_operator(name, ops, p, cuda)
+    b = p.b.to(cuda)
+    got = dp.pcg_solve(ops["A"], b, M, max_iter=3000, history=True)
+    assert ops["A"]._packed, "the packed path did not run"
+    want = dp.pcg_solve(ops["A"], b, M, max_iter=3000, history=True, pack=False)
+    assert got.iterations == want.iterations and got.res == want.res
+    assert got.history == want.history and got.alphas == want.alphas
+    assert torch.equal(got.x_hat, want.x_hat)
+
+
+def test_pcg_packed_batch_is_bitwise_the_fp64_batch(cuda):
+    """A mixed batch (sizes, preconditioners) from packed copies against the same batch from the fp64 stream."""
+    systems = []
+    for kind, side, net, name in [("poisson2d", 16, "net", "multiply"), ("poisson2d", 64, "net", "jacobi"),
+                                  ("poisson2d", 37, "net", "multiply"), ("poisson2d", 100, "tril", "identity"),
+                                  ("poisson2d", 16, "net", "explicit"), ("poisson3d", 12, "tril", "multiply")]:
+        p = helpers.problem(kind, side, 0, 0.5, net)
+        ops = gpu_operands(p, cuda)
+        systems.append((ops["A"], p.b.to(cuda), gpu_operator(name, ops, p, cuda)))
+    got = dp.pcg_solve_batch(systems, max_iter=3000)
+    want = dp.pcg_solve_batch(systems, max_iter=3000, pack=False)
+    for g, w in zip(got, want):
+        assert g.iterations == w.iterations and g.res == w.res and torch.equal(g.x_hat, w.x_hat)
+    assert len({r.iterations for r in got}) > 3
+
+
 def test_sparse_matvec_mul_known_answer(cuda):
     """tests/test_utils.py:11-41 through the CUDA kernel."""
     indices = torch.tensor([[0, 0, 0], [0, 0, 1], [0, 1, 0], [0, 1, 1], [0, 2, 2],

@@ -36,7 +36,9 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_descriptor_layout_and_size_queries(lib):
-    assert ctypes.sizeof(_lib.PcgSystem) == 10 * 4 + 29 * 8
+    assert ctypes.sizeof(_lib.PcgSystem) == 10 * 4 + 38 * 8
+    assert _lib.PcgSystem.a_col16.offset == 40 + 29 * 8 and _lib.PcgSystem.mt_tile_base.offset == 40 + 37 * 8
+    assert lib.dp_csr_pack_tile_rows() == 512
     assert ctypes.sizeof(_lib.PcgParams) == 24
     assert _lib.PcgSystem.a_rowptr.offset == 40 and _lib.PcgSystem.history.offset == 40 + 27 * 8 and _lib.PcgSystem.coef.offset == 40 + 28 * 8
     for n in (1, 31, 32, 33, 511, 512, 513, 99856):
@@ -54,6 +56,9 @@ def test_argument_validation_without_a_gpu(lib):
     assert lib.dp_spmv_csr_f64(-1, 0, None, None, None, None, None, None) == 1
     assert lib.dp_spmv_csr_f64(4, 4, 16, 20, 32, 48, 64, None) == 2  # col pointer 20 is not 16-byte aligned
     assert lib.dp_csr_from_coo(None, None, 5, 0, 4, 0, None, None, None, None, None, None, 0, None) == 1
+    assert lib.dp_csr_pack(4, 4, 16, 32, 48, 64, 80, None, 96, None) == 1  # no tile_base
+    assert lib.dp_csr_pack(4, 4, 16, 32, 48, 66, 80, 96, 112, None) == 2   # col16 pointer 66 is not 16-byte aligned
+    assert lib.dp_spmv_csr_packed_f64(4, 4, 16, 32, 48, None, 64, 80, None) == 1
     params = _lib.PcgParams(1e-8, 10, 0, 1, 0)
     assert lib.dp_pcg_solve_f64(None, 1, ctypes.byref(params), None, None, 0, None) == 1
 

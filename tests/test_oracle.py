@@ -378,3 +378,21 @@ def test_metrics_oracle_matches_golden():
     torch.manual_seed(7)
     vector = torch.randn(tril.shape[:2])
     assert float(om.hutchinson_trace(tril, lower, vector)) == pytest.approx(golden["hutchinson_trace_seed7"], rel=1e-5)
+
+
+def test_pack_oracle_round_trip():
+    """The packed stream format is lossless where it says so: columns and values rebuild bit for bit; a value beyond fp32
+    or a tile wider than 16 bits of columns is reported."""
+    p = helpers.problem("poisson2d", 37, 0, 0.5, "net")
+    for rowptr, col, val in (p.A, p.L, osp.transpose_csr(*p.L)):
+        col16, val32, base, status = osp.pack_csr(rowptr, col, val)
+        assert status == 0
+        rows = np.repeat(np.arange(len(rowptr) - 1), np.diff(rowptr))
+        assert np.array_equal(base[rows // 512] + col16.astype(np.int64), col)
+        assert np.array_equal(val32.astype(np.float64).view(np.int64), np.asarray(val).view(np.int64))
+    rowptr, col, val = p.A
+    bad = np.array(val, dtype=np.float64)
+    bad[5] = 0.1
+    assert osp.pack_csr(rowptr, col, bad)[3] == 1
+    wide = (np.array([0, 2, 3], np.int32), np.array([0, 70000, 1], np.int32), np.array([1.0, 2.0, 3.0]))
+    assert osp.pack_csr(*wide)[3] == 2
