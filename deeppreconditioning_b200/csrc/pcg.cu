@@ -93,7 +93,10 @@ struct Ctx {
 // Tile tables: the stream descriptors of the tiles of this CTA's range, one table per SpMV-shaped phase. They
 // survive across iterations (the range only changes when the active list is rebuilt), so the producer thread finds
 // the next item's addresses in shared memory instead of chasing rowptr through L2.
-constexpr int kMaxRoundTiles = 64;
+#ifndef DPCG_ROUND_TILES
+#define DPCG_ROUND_TILES 64
+#endif
+constexpr int kMaxRoundTiles = DPCG_ROUND_TILES;
 #ifndef DPCG_APPLY2_UNROLL
 #define DPCG_APPLY2_UNROLL kPipeUnroll
 #endif
@@ -252,7 +255,7 @@ __device__ __forceinline__ void phase_a(const Ctx& ctx, const SysDev& S, const T
         return;
     }
     double* pn = S.p[(k + 1) & 1];
-    const double ap = pipe.tile_spmv<kPhaseAUnroll>(d, rs, re, GatherZBetaP{z, po, sc.v}, true);  // cg.py:75
+    const double ap = pipe.template tile_spmv<kPhaseAUnroll>(d, rs, re, GatherZBetaP{z, po, sc.v}, true);  // cg.py:75
     double pap[1] = {0.0};
     if (valid) {
         const double pi = __dadd_rn(zr, __dmul_rn(sc.v, pr));  // cg.py:83
@@ -305,6 +308,9 @@ __device__ __forceinline__ void phase_apply1(const Ctx& ctx, const SysDev& S, co
     }
     const double a = sc.v;
 
+    // (Streaming the matrix first and updating r / x afterwards, so that this row's loads fly under the stream instead of
+    // stalling the head of the tile, was measured and is slower: the row loop then waits for them on the same scoreboard -
+    // APPLY1 head 1.0 -> 0.4 us, row loop 2.1 -> 3.2 us, profiles/r2/pack_experiments.md.)
     double rn = 0.0;
     if (valid) {
         rn = kInit ? r_old : __dsub_rn(r_old, __dmul_rn(a, ap_i));      // cg.py:80
@@ -321,12 +327,12 @@ __device__ __forceinline__ void phase_apply1(const Ctx& ctx, const SysDev& S, co
             zi = __dmul_rn(dinv_i, rn);
             break;
         case DP_PRECOND_CSR:  // table P1 streams M
-            zi = kInit ? pipe.tile_spmv(d, rs, re, GatherPlain{ro}, true)
-                       : pipe.tile_spmv<kApply1Unroll>(d, rs, re, GatherRMinusAAp{ro, S.ap, a}, true);
+            zi = kInit ? pipe.tile_spmv(d, rs, re, GatherWork{ro}, true)
+                       : pipe.template tile_spmv<kApply1Unroll>(d, rs, re, GatherRMinusAAp{ro, S.ap, a}, true);
             break;
         case DP_PRECOND_MULTIPLY: {  // table P1 streams L^T
-            const double ti = kInit ? pipe.tile_spmv(d, rs, re, GatherPlain{ro}, true)
-                                    : pipe.tile_spmv<kApply1Unroll>(d, rs, re, GatherRMinusAAp{ro, S.ap, a}, true);
+            const double ti = kInit ? pipe.tile_spmv(d, rs, re, GatherWork{ro}, true)
+                                    : pipe.template tile_spmv<kApply1Unroll>(d, rs, re, GatherRMinusAAp{ro, S.ap, a}, true);
             if (valid) S.t[row] = ti;
             have_z = false;
             break;
@@ -375,7 +381,7 @@ __device__ __forceinline__ void phase_apply2(const Ctx& ctx, const SysDev& S, co
     const int row = tile * kTileRows + threadIdx.x;
     double rn = 0.0;
     if (row < S.n) rn = S.r[(k + 1) & 1][row];
-    const double zi = pipe.tile_spmv<kApply2Unroll>(d, rs, re, GatherPlain{S.t}, true);
+    const double zi = pipe.template tile_spmv<kApply2Unroll>(d, rs, re, GatherWork{S.t}, true);
     if (row < S.n) S.z[(k + 1) & 1][row] = zi;
     double v[2] = {__dmul_rn(rn, zi), __dmul_rn(zi, zi)};
     double* part_rr = S.part_rr;
@@ -533,6 +539,9 @@ __device__ __forceinline__ void run_tiles(const Ctx& ctx, int k, int cur, int ve
     const int quot = total / (int)gridDim.x, rem = total % (int)gridDim.x;
     const int g0 = (int)blockIdx.x * quot + min((int)blockIdx.x, rem), g1 = g0 + quot + ((int)blockIdx.x < rem ? 1 : 0);
     Scal sc;
+#ifdef DPCG_PIPE_TRACE
+    pipe.tr_phase = kPhase;
+#endif
     for (int ga = g0; ga < g1; ga += kMaxRoundTiles) {
         const int gb = min(g1, ga + kMaxRoundTiles);
         ensure_table<kTab, P::kIsPacked>(ctx, cur, ver, ga, gb, sm);
@@ -551,6 +560,9 @@ __device__ __forceinline__ void run_tiles(const Ctx& ctx, int k, int cur, int ve
             int rs = 0, re = 0;
             if (kStream) tile_row_extent(d, rs, re);
             run_tile<kPhase, kInit, kCheckState>(ctx, S, d, rs, re, k, sm, sc, pipe);
+#ifdef DPCG_PIPE_TRACE
+            pipe.tr_mark(5);
+#endif
         }
     }
     if (next_tab >= 0 && g1 > g0 && g1 - g0 <= kMaxRoundTiles && sm.tab_ver[next_tab] == ver &&
@@ -950,6 +962,20 @@ int dp_debug_pcg_trace(const void* workspace, int32_t nsys, int64_t* out_host, i
     DP_CUDA(cudaMemcpy(out_host, static_cast<const char*>(workspace) + lay.trace, sizeof(long long) * 2 * (size_t)cap,
                        cudaMemcpyDeviceToHost));
     return DP_OK;
+}
+
+int dp_debug_pipe_trace(uint64_t* out_host, int32_t capacity) {
+#ifdef DPCG_PIPE_TRACE
+    if (!out_host || capacity <= 0) return DP_ERR_INVALID;
+    const int cap = capacity < kPipeTraceCap ? capacity : kPipeTraceCap;
+    for (int w = 0; w < 2; ++w)
+        DP_CUDA(cudaMemcpyFromSymbol(out_host + (size_t)w * capacity, g_pipe_trace, sizeof(unsigned long long) * (size_t)cap,
+                                     sizeof(unsigned long long) * (size_t)w * kPipeTraceCap, cudaMemcpyDeviceToHost));
+    return DP_OK;
+#else
+    (void)out_host, (void)capacity;
+    return DP_ERR_INVALID;  // built without -DDPCG_PIPE_TRACE
+#endif
 }
 
 int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp_pcg_params_t* params_host,

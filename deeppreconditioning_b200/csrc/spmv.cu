@@ -1,5 +1,6 @@
 // spmv.cu — library plumbing + standalone K2 entry points (dp_spmv_csr_f64, dp_coo_spmv_batch_f32).
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -88,7 +89,7 @@ csr_pack_kernel(int n, const int* __restrict__ rowptr, const int* __restrict__ c
     for (int w = 1; w < kWarpsPerBlock; ++w) lo = min(lo, s_lo[w]), hi = max(hi, s_hi[w]);
     if (ce == cs) lo = 0, hi = 0;
     int bad = (hi - lo > 65535 || lo < 0) ? 2 : 0;
-    if (threadIdx.x == 0) tile_base[tile] = lo;
+    if (threadIdx.x == 0) tile_base[2 * tile] = lo, tile_base[2 * tile + 1] = ce > cs ? hi - lo + 1 : 0;
     for (int q = cs + (int)threadIdx.x; q < ce; q += kBlock) {
         const double v = val[q];
         const float f = (float)v;
@@ -154,6 +155,8 @@ int allow_dynamic_smem(const void* kernel, size_t bytes) {
     KernelEntry& e = kernel_entry(dev, kernel);
     if (e.smem >= bytes && e.smem > 0) return DP_OK;
     DP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (const char* c = getenv("DPCG_CARVEOUT"))  // experiments: shared-memory share of the L1 / shared-memory array, percent
+        DP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(c)));
     e.smem = bytes;
     e.threads = 0;  // occupancy depends on the attribute
     return DP_OK;

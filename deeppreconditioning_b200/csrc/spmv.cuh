@@ -22,27 +22,45 @@ struct CsrView {
 
 // Gather functors: what "x[c]" means for a phase. Vectors written earlier in the same persistent kernel are read
 // with plain (coherent after the grid barrier's fence) loads; matrix data goes through the read-only path.
+// kVecs > 0: the functor reads kVecs vectors of the solve's own work block (16-byte aligned, padded to 32 entries) and may
+// be served from a shared-memory WINDOW of those vectors instead (tilepipe.cuh, packed stream): vec(i) names the vectors,
+// combine() is the same arithmetic on the two loaded values, so both routes give the same bits.
 struct GatherPlain {
+    static constexpr int kVecs = 0;
     const double* x;
     __device__ __forceinline__ double operator()(int c) const { return x[c]; }
 };
 struct GatherReadOnly {  // standalone kernels: x is immutable for the whole launch
+    static constexpr int kVecs = 0;
     const double* __restrict__ x;
     __device__ __forceinline__ double operator()(int c) const { return __ldg(x + c); }
 };
+struct GatherWork {  // a plain gather from one of the work vectors
+    static constexpr int kVecs = 1;
+    const double* x;
+    __device__ __forceinline__ const double* vec(int) const { return x; }
+    __device__ __forceinline__ double combine(double a, double) const { return a; }
+    __device__ __forceinline__ double operator()(int c) const { return x[c]; }
+};
 // p_new[c] = z[c] + beta * p_old[c]   (cg.py:83), evaluated on the fly so the p-update needs no pass of its own.
 struct GatherZBetaP {
+    static constexpr int kVecs = 2;
     const double* z;
     const double* p;
     double beta;
-    __device__ __forceinline__ double operator()(int c) const { return __dadd_rn(z[c], __dmul_rn(beta, p[c])); }
+    __device__ __forceinline__ const double* vec(int i) const { return i ? p : z; }
+    __device__ __forceinline__ double combine(double zc, double pc) const { return __dadd_rn(zc, __dmul_rn(beta, pc)); }
+    __device__ __forceinline__ double operator()(int c) const { return combine(z[c], p[c]); }
 };
 // r_new[c] = r_old[c] - a * Ap[c]     (cg.py:80), evaluated on the fly for the gather of L^T r / M r.
 struct GatherRMinusAAp {
+    static constexpr int kVecs = 2;
     const double* r;
     const double* ap;
     double a;
-    __device__ __forceinline__ double operator()(int c) const { return __dsub_rn(r[c], __dmul_rn(a, ap[c])); }
+    __device__ __forceinline__ const double* vec(int i) const { return i ? ap : r; }
+    __device__ __forceinline__ double combine(double rc, double apc) const { return __dsub_rn(rc, __dmul_rn(a, apc)); }
+    __device__ __forceinline__ double operator()(int c) const { return combine(r[c], ap[c]); }
 };
 
 }  // namespace dp

@@ -22,8 +22,13 @@
 // the 16-byte unit that holds that entry (arrays are 16-byte aligned, dpcg.h), so they can never touch another page.
 //
 // Packed stream (kPacked): the same pipeline over the lossless 6-byte copy of a matrix (dp_csr_pack: fp32 values, 16-bit
-// columns relative to the tile's smallest column). A stage of the same size holds twice the entries, the lanes widen on
-// load (exact) and run the identical fp64 recurrence: same bits, half the matrix bytes from HBM.
+// columns relative to the tile's smallest column). The lanes widen on load (exact) and run the identical fp64 recurrence:
+// same bits, half the matrix bytes from HBM. The stages take half the bytes, and the other half holds gather WINDOWS:
+// a banded tile (512 rows of a 2-D stencil factor touch ~1150 consecutive columns) reads every gathered vector entry
+// 5..15 times, and with 2 x 113 KB of shared memory per SM the L1 that should catch those re-reads is 28 KB - the
+// gathers were L2 round trips (long_scoreboard 42 % of the warp samples, ncu round 2). So the columns [base, base + span)
+// of the phase's work vectors are copied once per tile into shared memory (bulk copies, one tile ahead, completion on an
+// mbarrier) and the gathers become shared-memory loads. Same values, same arithmetic, same bits.
 #pragma once
 
 #include <type_traits>
@@ -43,15 +48,48 @@
 #ifndef DPCG_PIPE_EVICT_FIRST
 #define DPCG_PIPE_EVICT_FIRST 1
 #endif
+#ifndef DPCG_PACK_WINDOWS
+#define DPCG_PACK_WINDOWS 0  // experiment: gather windows in shared memory behind (half-size) packed stages
+#endif
+#ifndef DPCG_PACK_CAP
+#if DPCG_PACK_WINDOWS
+#define DPCG_PACK_CAP DPCG_PIPE_CAP        // entries per stage of the packed stream: half the bytes, the rest holds the windows
+#else
+#define DPCG_PACK_CAP (2 * DPCG_PIPE_CAP)  // ... the same bytes per stage as the fp64 stream: twice the entries
+#endif
+#endif
+#ifndef DPCG_PACK_STAGES
+#define DPCG_PACK_STAGES DPCG_PIPE_STAGES
+#endif
+#ifndef DPCG_PIPE_SPLIT_ISSUE
+#define DPCG_PIPE_SPLIT_ISSUE 0  // experiment: the three async operations of an item issued by three threads of different warps
+#endif
+#ifndef DPCG_PIPE_TOPUP_AT_RELEASE
+#define DPCG_PIPE_TOPUP_AT_RELEASE 0  // experiment: a second look for the next item when a stage is handed back
+#endif
 #ifndef DPCG_PIPE_WAIT_HINT
 #define DPCG_PIPE_WAIT_HINT 1000  // ns a consumer warp may sleep in try_wait on a stage's `full` barrier (0: spin)
 #endif
 
 namespace dp {
 
+// -DDPCG_PIPE_TRACE: timeline of two warps of CTA 0 through the tile pipeline (label << 48 | clock), read back with
+// dp_debug_pipe_trace. Not compiled into the shipped library.
+#ifdef DPCG_PIPE_TRACE
+constexpr int kPipeTraceCap = 1 << 15;
+__device__ unsigned long long g_pipe_trace[2][kPipeTraceCap];
+#define DP_PIPE_MARK(label) tr_mark(label)
+#else
+#define DP_PIPE_MARK(label) ((void)0)
+#endif
+
 constexpr int kPipeCap = DPCG_PIPE_CAP;        // entries per stage (multiple of 4)
 constexpr int kPipeStages = DPCG_PIPE_STAGES;
 constexpr int kPipeUnroll = DPCG_PIPE_UNROLL;  // gathers in flight per thread
+constexpr int kPackCap = DPCG_PACK_CAP;
+constexpr int kPackStages = DPCG_PACK_STAGES;
+constexpr bool kPackWindows = DPCG_PACK_WINDOWS != 0;
+constexpr int kMaxStages = kPipeStages > kPackStages ? kPipeStages : kPackStages;
 
 // ---- PTX wrappers (sm_90+/sm_100a) ---------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -130,6 +168,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                  : "memory");
 #endif
 }
+// 16-byte asynchronous copy global -> shared (LDGSTS) and its completion hook: the mbarrier receives one arrival from this
+// thread once all its earlier cp.async have landed (.noinc: the arrival is part of the barrier's initial count).
+__device__ __forceinline__ void cp_async_16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(unsigned long long* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // ---- descriptors ------------------------------------------------------------------------------------------------
 struct TileDesc {
     const int* rowptr;  // nullptr: this tile streams nothing in this phase
@@ -140,7 +186,11 @@ struct TileDesc {
     int ltile;   // tile index inside its matrix
     int sys;     // system id (PCG), unused by the standalone kernel
     int base;    // packed stream: smallest column of the tile (col = base + col16); col / val then point at col16 / val32
+    int span;    // packed stream: doubles of the tile's gather window [base & ~1, ...) if it fits kWinCap, else 0 (no window)
 };
+constexpr int kWinCap = 1408;  // doubles per gather window (a 512-row tile of a 316-wide 2-D factor spans 1146 columns)
+constexpr int kWinBufs = 2;    // the tile being consumed and the next one
+constexpr int kWinVecs = 2;    // vectors a gather functor may combine
 
 // Shared memory of a pipeline of geometry (kCap entries per stage, kStages stages): the stages' bytes (values first,
 // then column indices) and one full/empty mbarrier pair per stage. Several geometries may be laid over the same bytes
@@ -150,24 +200,29 @@ struct PipeGeom {
     // lead-in entries down to the 16-byte boundary of the span's first entry (3, packed: 7) + tail rounding
     static constexpr int kSlots = kCap + (kPacked ? 16 : 8);
     static constexpr int kEntryBytes = kPacked ? 6 : 12;
-    static constexpr size_t kBytes = (size_t)kStages * kSlots * kEntryBytes;
+    static constexpr size_t kStageBytes = (size_t)kStages * kSlots * kEntryBytes;
+    static constexpr size_t kWinBytes = (kPacked && kPackWindows) ? (size_t)kWinBufs * kWinVecs * kWinCap * 8 : 0;  // behind the stages
+    static constexpr size_t kBytes = kStageBytes + kWinBytes;
+    static_assert(kStageBytes % 16 == 0, "windows start 16-byte aligned");
     static_assert(kCap % 8 == 0 && kCap >= 64, "stage capacity");
 };
 template <int kStages>
 struct PipeBarriers {
     alignas(8) unsigned long long full[kStages];   // producer -> consumers: bytes have landed
     alignas(8) unsigned long long empty[kStages];  // consumers -> producer: all 16 warps are done with the stage
+    alignas(8) unsigned long long wfull[kWinBufs];   // gather windows (packed stream): every thread's copies have landed
+    alignas(8) unsigned long long wempty[kWinBufs];  // ... all 16 warps are done with the window
 };
 // The level-stream triangular solve (trsv_ls.cuh) lays a finer geometry (stages of kLsCap entries: a stencil factor has 3
 // entries per row) plus its shared-memory solution window over the same bytes (checked there).
 constexpr int kLsCap = 1536;
 // (3 level-stream stages: matrix 3 * 18 528, row pointers 3 * 2 080, right-hand sides 3 * 4 096, a window of 5 tiles)
 constexpr size_t kLsFusedBytes = 3 * ((size_t)(kLsCap + 8) * 12 + (kTileRows + 8) * 4 + kTileRows * 8) + 5 * kTileRows * 8;
-constexpr size_t kPipeRawBytes = PipeGeom<kPipeCap, kPipeStages>::kBytes > kLsFusedBytes ? PipeGeom<kPipeCap, kPipeStages>::kBytes
-                                                                                          : kLsFusedBytes;
+constexpr size_t max3(size_t a, size_t b, size_t c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
+constexpr size_t kPipeRawBytes = max3(PipeGeom<kPipeCap, kPipeStages>::kBytes, PipeGeom<kPackCap, kPackStages, true>::kBytes, kLsFusedBytes);
 struct PipeShared {
     alignas(16) unsigned char bytes[kPipeRawBytes];
-    PipeBarriers<kPipeStages> bar;
+    PipeBarriers<kMaxStages> bar;
 };
 
 // Fill the stream part of a descriptor for tile `ltile` of matrix M (one dependent load pair; CTA-parallel in the
@@ -180,7 +235,13 @@ __device__ __forceinline__ void tile_desc_fill(TileDesc& d, const CsrView& M, in
     d.n = M.n;
     d.nnz = M.nnz;
     d.ltile = ltile;
-    d.base = (kPacked && M.rowptr) ? __ldg(M.tbase + ltile) : 0;
+    d.base = 0, d.span = 0;
+    if (kPacked && M.rowptr) {
+        const int2 info = __ldg(reinterpret_cast<const int2*>(M.tbase) + ltile);  // (smallest column, columns spanned)
+        d.base = info.x;
+        const int wlen = ((info.x + info.y + 1) & ~1) - (info.x & ~1);
+        d.span = (info.y > 0 && wlen <= kWinCap) ? wlen : 0;
+    }
     if (M.rowptr) {
         d.cs = __ldg(M.rowptr + min(ltile * kTileRows, M.n));
         d.ce = __ldg(M.rowptr + min((ltile + 1) * kTileRows, M.n));
@@ -208,12 +269,31 @@ struct PipeT {
     const TileDesc* tab;
     int ntiles;
     unsigned c_count;   // items this warp has consumed
-    unsigned p_count;   // items issued (meaningful in lane 0 of warp 0 only, like the cursor below)
+    int role;           // issuer role of this thread: 0 arms the stage's barrier, 1 copies the values, 2 the columns; -1 none
+    unsigned p_count;   // items issued (meaningful in the issuer threads only, like the cursor below)
     int p_tile, p_blk;  // next item of the round to issue
     unsigned t_count;   // streaming tiles this warp has reduced (ring index of tile_reduce_async)
     int flip;           // tile_reduce scratch buffer in use next
     int early;          // 1 + id of the table whose first items are already in flight (begin_early), else 0
     int keep_l2;        // the matrices fit the L2 together with the vectors: do not mark their lines evict-first
+    // gather windows (packed stream): buffer b, vector v at win0 + (b * kWinVecs + v) * kWinCap. Counters are CTA-uniform
+    // (every thread walks the same tiles): windows filled / consumed since kernel start, buffer = count % kWinBufs.
+#ifdef DPCG_PIPE_TRACE
+    int tr_pos = 0;
+    unsigned long long tr_phase = 0;
+    __device__ __forceinline__ void tr_mark(unsigned long long label) {
+        label += 8 * tr_phase;
+        if (blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 160) && tr_pos < kPipeTraceCap) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            g_pipe_trace[threadIdx.x ? 1 : 0][tr_pos++] = (label << 48) | (t & 0xFFFFFFFFFFFFull);
+        }
+    }
+#endif
+    double* win0;
+    unsigned long long* wfull;
+    unsigned long long* wempty;
+    unsigned w_issued, w_count;
 
     static __device__ __forceinline__ int blocks(const TileDesc& d) { return (d.ce - d.cs + kCap - 1) / kCap; }
     __device__ __forceinline__ const ValT* stage_val(unsigned s) const { return val0 + (size_t)s * kSlots; }
@@ -229,19 +309,35 @@ struct PipeT {
     }
 
     // Bind to shared memory. `fresh`: initialise the barriers (once per kernel and geometry); ends with a CTA barrier.
-    __device__ __forceinline__ void init(unsigned char* bytes, PipeBarriers<kStages>* bar, bool fresh = true) {
+    template <class Bars>
+    __device__ __forceinline__ void init(unsigned char* bytes, Bars* bar, bool fresh = true) {
         val0 = reinterpret_cast<ValT*>(bytes);
         col0 = reinterpret_cast<ColT*>(bytes + (size_t)kStages * kSlots * sizeof(ValT));
         full = bar->full, empty = bar->empty;
         tab = nullptr;
         ntiles = 0;
         c_count = 0u, p_count = 0u, p_tile = 0, p_blk = 0, t_count = 0u, flip = 0, early = 0, keep_l2 = 0;
+#if DPCG_PIPE_SPLIT_ISSUE
+        role = threadIdx.x == 0 ? 0 : threadIdx.x == 5 * kWarp ? 1 : threadIdx.x == 10 * kWarp ? 2 : -1;
+#else
+        role = threadIdx.x == 0 ? 0 : -1;
+#endif
+        win0 = reinterpret_cast<double*>(bytes + PipeGeom<kCap, kStages, kPacked>::kStageBytes);
+        wfull = bar->wfull, wempty = bar->wempty;
+        w_issued = 0u, w_count = 0u;
         if (fresh) {
             if (threadIdx.x == 0) {
 #pragma unroll
                 for (int s = 0; s < kStages; ++s) {
                     mbar_init(&full[s], 1u);
                     mbar_init(&empty[s], (unsigned)kWarpsPerBlock);
+                }
+                if (kPacked) {
+#pragma unroll
+                    for (int b = 0; b < kWinBufs; ++b) {
+                        mbar_init(&wfull[b], 1u);
+                        mbar_init(&wempty[b], (unsigned)kWarpsPerBlock);
+                    }
                 }
                 mbar_fence_init();
             }
@@ -252,8 +348,15 @@ struct PipeT {
     // (all items consumed, producer and consumers agree): resume(count) after init(..., false).
     __device__ __forceinline__ void resume(unsigned items) { c_count = p_count = items; }
 
-    // Lane 0 of warp 0: issue the next item of the round if its stage is free. `blocking`: wait for the stage
+    // Issuer threads: issue the next item of the round if its stage is free. `blocking`: wait for the stage
     // (only legal when this warp has itself consumed the stage's previous item). Returns true if an item went out.
+    // An item is three asynchronous operations - arm the stage's `full` barrier with the byte count, bulk copy of the
+    // values, bulk copy of the columns - and each costs the thread that issues it ~250-290 ns whatever its size
+    // (profiles/r2/tma_stream.log; tools/trace_pipe.py: 860 ns per item on thread 0's path, a third of a phase-A tile).
+    // They are therefore dealt to lane 0 of three different warps (roles 0, 1, 2): every issuer walks the same item
+    // sequence with its own cursor and performs its own operation as soon as the stage's previous tenant has been
+    // released by all warps. A copy may complete before the barrier is armed: the transaction count goes negative for a
+    // moment, the phase cannot complete before the arming arrival.
     __device__ __forceinline__ bool issue_one(bool blocking) {
         while (p_tile < ntiles) {
             if (p_blk < blocks(tab[p_tile])) break;
@@ -274,7 +377,24 @@ struct PipeT {
         const TileDesc& d = tab[p_tile];
         const int bs = d.cs + p_blk * kCap;
         const int be = min(d.ce, bs + kCap);
-        issue_copies(d, stage, bs & ~(kAlign - 1), be, keep_l2 ? l2_policy_keep() : l2_policy_stream());
+        const int as = bs & ~(kAlign - 1);
+#if DPCG_PIPE_SPLIT_ISSUE
+        const unsigned ncol = (unsigned)(((be + kColUnit - 1) & ~(kColUnit - 1)) - as);
+        const unsigned nval = (unsigned)(((be + kValUnit - 1) & ~(kValUnit - 1)) - as);
+        unsigned long long* bar = &full[stage];
+        if (role == 0) {
+            mbar_arrive_expect_tx(bar, ncol * (unsigned)sizeof(ColT) + nval * (unsigned)sizeof(ValT));
+        } else if (role == 1) {
+            bulk_g2s(val0 + (size_t)stage * kSlots, reinterpret_cast<const ValT*>(d.val) + as, nval * (unsigned)sizeof(ValT), bar,
+                     keep_l2 ? l2_policy_keep() : l2_policy_stream());
+        } else {
+            bulk_g2s(col0 + (size_t)stage * kSlots, reinterpret_cast<const ColT*>(d.col) + as, ncol * (unsigned)sizeof(ColT), bar,
+                     keep_l2 ? l2_policy_keep() : l2_policy_stream());
+        }
+#else
+        issue_copies(d, stage, as, be, keep_l2 ? l2_policy_keep() : l2_policy_stream());
+#endif
+        DP_PIPE_MARK(7);
         ++p_blk, ++p_count;
         return true;
     }
@@ -285,7 +405,7 @@ struct PipeT {
         tab = t;
         ntiles = count;
         p_tile = 0, p_blk = 0;
-        if (threadIdx.x == 0) {
+        if (role >= 0) {
             while (issue_one(true)) {
             }
         }
@@ -333,24 +453,25 @@ struct PipeT {
         int issued = 0;
         for (int t = 0; t < ntiles && issued < kStages; ++t) issued += blocks(tab[t]);
         issued = min(issued, kStages);
+        if (role >= 0) p_tile = ntiles;  // nothing more to issue from that table
         for (int j = 0; j < issued; ++j) {
             const unsigned stage = c_count % kStages;
             while (!mbar_try_wait(&full[stage], (c_count / kStages) & 1u)) {
             }
             release();
         }
-        if (threadIdx.x == 0) p_tile = ntiles;  // nothing more to issue from that table
     }
 
     // Consumer side of one item: acquire() waits until the item's bytes have landed and returns its stage; release()
     // hands the stage back once this warp has read what it needs. Every warp acquires and releases every item of the
     // round, in order. Thread 0 doubles as the producer: the item about to be consumed must be out, then it tops up.
     __device__ __forceinline__ unsigned acquire() {
-        if (threadIdx.x == 0) {
+        if (role >= 0) {
             while (p_count <= c_count) issue_one(true);
             while (issue_one(false)) {
             }
         }
+        DP_PIPE_MARK(6);
         const unsigned stage = c_count % kStages;
         const unsigned par = (c_count / kStages) & 1u;
 #if DPCG_PIPE_WAIT_HINT
@@ -367,12 +488,67 @@ struct PipeT {
         __syncwarp();
         if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[c_count % kStages]);
         ++c_count;
+#if DPCG_PIPE_TOPUP_AT_RELEASE
+        // a second chance to send the next item ahead of time: at acquire() the slowest warps may not have released the
+        // stage's previous tenant yet, and the next look would only come when this warp needs the item itself
+        if (role >= 0) {
+            while (issue_one(false)) {
+            }
+        }
+#endif
     }
 
-    // Row sum of this thread's row (entries [rs, re) of the matrix, empty for rows >= n) of tile d.
-    // Every warp of the CTA must call it for every tile of the round, in order (`compute == false` only drains).
-    template <int kUnroll = kPipeUnroll, class Gather>
-    __device__ __forceinline__ double tile_spmv(const TileDesc& d, int rs, int re, const Gather& x, bool compute) {
+    // ---- gather windows (packed stream) -----------------------------------------------------------------------------
+    // Copy the window of tile `t` (columns [t.base & ~1, + t.span) of the functor's vectors) into the next buffer: two bulk
+    // copies issued by ONE thread (lane 0 of warp kWinWarp - not thread 0, which feeds the matrix stages). The buffer's
+    // previous tenant must have been released by all 16 warps first; the issuing warp has itself left that tile and thread 0
+    // had issued all of its items by then, so nobody waits in a circle. Every thread counts the window (CTA-uniform).
+    static constexpr int kWinWarp = kWarpsPerBlock / 2;
+    template <class Gather>
+    __device__ __forceinline__ void window_issue(const TileDesc& t, const Gather& x) {
+        if (threadIdx.x == kWinWarp * 32) {
+            const unsigned buf = w_issued % kWinBufs, fill = w_issued / kWinBufs;
+            if (fill > 0) {
+                while (!mbar_try_wait_hint(&wempty[buf], (fill - 1u) & 1u, 1000u)) {
+                }
+            }
+            const int off = t.base & ~1;
+            const unsigned bytes = (unsigned)t.span * 8u;  // span is even: a multiple of 16 bytes
+            const unsigned long long pol = l2_policy_keep();
+            // the vectors were written with ordinary stores (by other CTAs, before the last grid barrier): order those
+            // generic-proxy writes before the async-proxy reads of the bulk copies
+            asm volatile("fence.proxy.async;" ::: "memory");
+            mbar_arrive_expect_tx(&wfull[buf], bytes * (unsigned)Gather::kVecs);
+#pragma unroll
+            for (int v = 0; v < Gather::kVecs; ++v)
+                bulk_g2s(win0 + (size_t)(buf * kWinVecs + v) * kWinCap, x.vec(v) + off, bytes, &wfull[buf], pol);
+        }
+        ++w_issued;
+    }
+    // Start of a windowed tile: make sure its window is on its way, send the next tile's after it (same system: the
+    // functor's vectors are that system's), wait for this one. Returns the window of vector 0 (vector v: + v * kWinCap).
+    template <class Gather>
+    __device__ __forceinline__ const double* window_acquire(const TileDesc& d, const Gather& x) {
+        if (w_issued == w_count) window_issue(d, x);
+        const int next = (int)(&d - tab) + 1;
+        if (next < ntiles && w_issued == w_count + 1u) {
+            const TileDesc& nx = tab[next];
+            if (nx.span > 0 && nx.sys == d.sys) window_issue(nx, x);
+        }
+        const unsigned buf = w_count % kWinBufs;
+        while (!mbar_try_wait_hint(&wfull[buf], (w_count / kWinBufs) & 1u, 1000u)) {
+        }
+        return win0 + (size_t)buf * kWinVecs * kWinCap;
+    }
+    __device__ __forceinline__ void window_release() {
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&wempty[w_count % kWinBufs]);
+        ++w_count;
+    }
+
+    // The items of tile d: every warp acquires and releases each of them; `load(c)` yields the gathered value of column c.
+    template <int kUnroll, class Load>
+    __device__ __forceinline__ double consume_items(const TileDesc& d, int rs, int re, bool compute, const Load& load) {
         double sum = 0.0;
         const int nb = blocks(d);
         for (int j = 0; j < nb; ++j) {
@@ -380,10 +556,10 @@ struct PipeT {
             const int be = min(d.ce, bs + kCap);
             const int as = bs & ~(kAlign - 1);
             const unsigned stage = acquire();
+            DP_PIPE_MARK(2);
             if (compute) {
                 const ValT* __restrict__ sv = stage_val(stage);
                 const ColT* __restrict__ sc = stage_col(stage);
-                const int base = kPacked ? d.base : 0;
                 const int qe = min(re, be) - as;
                 for (int q = max(rs, bs) - as; q < qe; q += kUnroll) {
                     int c[kUnroll];
@@ -391,29 +567,63 @@ struct PipeT {
 #pragma unroll
                     for (int u = 0; u < kUnroll; ++u) {
                         const bool on = q + u < qe;
-                        c[u] = on ? base + (int)sc[q + u] : 0;
+                        c[u] = on ? (int)sc[q + u] : 0;
                         v[u] = on ? (double)sv[q + u] : 0.0;  // packed: fp32 -> fp64 is exact
                     }
 #pragma unroll
-                    for (int u = 0; u < kUnroll; ++u) xv[u] = (q + u < qe) ? x(c[u]) : 0.0;
+                    for (int u = 0; u < kUnroll; ++u) xv[u] = (q + u < qe) ? load(c[u]) : 0.0;
 #pragma unroll
                     for (int u = 0; u < kUnroll; ++u)
                         if (q + u < qe) sum = __dadd_rn(sum, __dmul_rn(v[u], xv[u]));
                 }
             }
+            DP_PIPE_MARK(3);
             release();
         }
         return sum;
     }
 
-    // Drain the items of a tile whose result is not wanted (its system finished in this very iteration).
-    __device__ __forceinline__ void tile_skip(const TileDesc& d) { tile_spmv<1>(d, 0, 0, GatherPlain{nullptr}, false); }
+    // Row sum of this thread's row (entries [rs, re) of the matrix, empty for rows >= n) of tile d.
+    // Every warp of the CTA must call it for every tile of the round, in order (`compute == false` only drains).
+    template <int kUnroll = kPipeUnroll, class Gather>
+    __device__ __forceinline__ double tile_spmv(const TileDesc& d, int rs, int re, const Gather& x, bool compute) {
+        if constexpr (kPacked && kPackWindows && Gather::kVecs > 0) {
+            if (d.span > 0) {  // CTA-uniform: the gathers of this tile are served from its shared-memory window
+                DP_PIPE_MARK(0);
+                const double* w = window_acquire(d, x);
+                DP_PIPE_MARK(1);
+                const int shift = d.base & 1;  // the window starts at the even column at or below base
+                const double sum = consume_items<kUnroll>(d, rs, re, compute, [&](int c16) {
+                    return x.combine(w[c16 + shift], Gather::kVecs > 1 ? w[kWinCap + c16 + shift] : 0.0);
+                });
+                window_release();
+                DP_PIPE_MARK(4);
+                return sum;
+            }
+        }
+        const int base = kPacked ? d.base : 0;
+        DP_PIPE_MARK(0);
+        const double sum = consume_items<kUnroll>(d, rs, re, compute, [&](int c) { return x(base + c); });
+        DP_PIPE_MARK(4);
+        return sum;
+    }
+
+    // Drain the items of a tile whose result is not wanted (its system finished in this very iteration). A window that was
+    // already sent for it (never the case today: windows are only sent ahead inside one system) is consumed as well.
+    __device__ __forceinline__ void tile_skip(const TileDesc& d) {
+        if (kPacked && kPackWindows && d.span > 0 && w_issued > w_count) {
+            const unsigned buf = w_count % kWinBufs;
+            while (!mbar_try_wait(&wfull[buf], (w_count / kWinBufs) & 1u)) {
+            }
+            window_release();
+        }
+        consume_items<1>(d, 0, 0, false, [](int) { return 0.0; });
+    }
 };
 
 using Pipe = PipeT<kPipeCap, kPipeStages>;  // the SpMV geometry: whole tiles per stage
-// ... and the packed stream over the same bytes: twice the entries per stage (the CNN factor's 7680-entry tile is one item)
-using PipePacked = PipeT<2 * kPipeCap, kPipeStages, true>;
-static_assert(PipeGeom<2 * kPipeCap, kPipeStages, true>::kBytes <= PipeGeom<kPipeCap, kPipeStages>::kBytes, "packed stages fit");
+// ... and the packed stream over the same bytes: stages of the same entry count (half the bytes) + the gather windows
+using PipePacked = PipeT<kPackCap, kPackStages, true>;
 
 // Row extent of this thread's row in tile d (coalesced; issue one tile ahead to hide the latency).
 __device__ __forceinline__ void tile_row_extent(const TileDesc& d, int& rs, int& re) {
@@ -451,8 +661,8 @@ __device__ __forceinline__ void tile_reduce(double (&v)[kN], double (*scratch2x)
 // ring slot and bumps the slot's counter; the warp that arrives last folds the 16 warp sums (same fixed order, same
 // bits as tile_reduce) and hands them to `write` in its lane 0. Warps are at most kPipeStages streaming tiles apart
 // (a stage is re-armed only after all 16 warps passed it), so a ring of kRedRing slots is never overrun.
-constexpr int kRedRing = 4;
-static_assert(kPipeStages < kRedRing, "reduction ring must outlast the warps' maximum distance");
+constexpr int kRedRing = 8;
+static_assert(kMaxStages < kRedRing, "reduction ring must outlast the warps' maximum distance");
 
 struct TileRed {
     double slot[kRedRing][3][kWarpsPerBlock];

@@ -217,7 +217,7 @@ class CsrMatrix:
 
 class PackedCsr:
     """Packed stream copy of a :class:`CsrMatrix` (shares its ``rowptr``): ``col16 uint16[nnz]``, ``val32 float32[nnz]``,
-    ``tile_base int32[ceil(n / 512)]`` with ``col = tile_base[row // 512] + col16``."""
+    ``tile_base int32[ceil(n / 512), 2]`` = (smallest column, columns spanned) per tile, ``col = tile_base[row // 512, 0] + col16``."""
 
     def __init__(self, col16: torch.Tensor, val32: torch.Tensor, tile_base: torch.Tensor) -> None:
         self.col16, self.val32, self.tile_base = col16, val32, tile_base
@@ -249,7 +249,7 @@ def pack_many(matrices) -> None:
                 nnz = m.nnz
                 col16 = torch.empty(max((nnz + 7) // 8 * 8, 8), dtype=torch.uint16, device=dev)
                 val32 = torch.empty(max((nnz + 3) // 4 * 4, 4), dtype=torch.float32, device=dev)
-                tile_base = torch.empty(max((m.n + tile_rows - 1) // tile_rows, 1), dtype=torch.int32, device=dev)
+                tile_base = torch.empty((max((m.n + tile_rows - 1) // tile_rows, 1), 2), dtype=torch.int32, device=dev)
                 _lib.check(lib.dp_csr_pack(m.n, nnz, _lib.ptr(m.rowptr), _lib.ptr(m.col), _lib.ptr(m.val), _lib.ptr(col16),
                                            _lib.ptr(val32), _lib.ptr(tile_base), status.data_ptr() + 4 * i,
                                            _lib.stream_ptr(dev)), "dp_csr_pack")

@@ -95,14 +95,15 @@ int dp_csr_aat_nnz(int32_t n, const int32_t* rowptr, const int32_t* col, const i
  * The operands of this path are fp32 data widened to fp64 (the CNN output and the data set's matrices are fp32,
  * test.py:100-105, data_set.py:121-125) on banded patterns, so the 12 bytes per stored entry of the fp64/int32 CSR
  * are mostly zeros. dp_csr_pack writes the same matrix as 6 bytes per entry: val32[q] = (float)val[q] and
- * col16[q] = col[q] - tile_base[t], t = the 512-row tile (dp_csr_pack_tile_rows()) that holds entry q, tile_base[t] =
- * the smallest column of the tile. The copy exists only if it is EXACT: *status_out (device int32, OR-ed bits) is 0
+ * col16[q] = col[q] - tile_base[2t], t = the 512-row tile (dp_csr_pack_tile_rows()) that holds entry q; tile_base holds
+ * one pair per tile: {smallest column of the tile, number of columns it spans (largest - smallest + 1; 0: empty tile)}. The copy exists only if it is EXACT: *status_out (device int32, OR-ed bits) is 0
  * when every value survives the fp32 round trip bit for bit and every tile spans fewer than 65536 columns; otherwise
  * bit 0 (a value is not an fp32 number) and / or bit 1 (a tile is too wide) is set and the copy must not be used.
  * The kernels that accept a packed copy (dp_spmv_csr_packed_f64, dp_pcg_solve_f64) widen on load and do the same fp64
  * arithmetic in the same order: results are bit-identical to the unpacked path, HBM traffic per entry is halved.
  * col16 / val32 need room for nnz entries rounded up to a multiple of 16 bytes, 16-byte aligned;
- * tile_base int32[ceil(n / 512)]. */
+ * tile_base int32[2 * ceil(n / 512)], 8-byte aligned. Tiles that span few columns (banded matrices: 2-D stencil factors)
+ * let dp_pcg_solve_f64 serve a phase's gathers from a shared-memory window of the vectors instead of L2. */
 int32_t dp_csr_pack_tile_rows(void);
 int dp_csr_pack(int32_t n, int32_t nnz, const int32_t* rowptr, const int32_t* col, const double* val, uint16_t* col16,
                 float* val32, int32_t* tile_base, int32_t* status_out, void* stream);
@@ -336,6 +337,9 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
 /* Diagnostics: with DPCG_TRACE=1 in the environment the fused engine records (label, clock64) pairs of CTA 0 into the
  * workspace; this copies up to `capacity` pairs to out_host[2*capacity] (label = 8*phase + point). Synchronous. */
 int dp_debug_pcg_trace(const void* workspace, int32_t nsys, int64_t* out_host, int32_t capacity);
+/* Tuning builds only (-DDPCG_PIPE_TRACE; DP_ERR_INVALID otherwise): per-tile timeline of two warps of CTA 0 through the tile
+ * pipeline of the last PCG launch, out_host[2 * capacity] words of (label << 48 | globaltimer ns). Synchronous. */
+int dp_debug_pipe_trace(uint64_t* out_host, int32_t capacity);
 
 #ifdef __cplusplus
 }

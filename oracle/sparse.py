@@ -83,7 +83,7 @@ def sparse_matvec_mul(indices, features, vector_batch, transpose: bool):
 
 def pack_csr(rowptr, col, val, tile_rows: int = 512):
     """Restatement of ``dp_csr_pack`` (no reference counterpart: a lossless storage format of this implementation):
-    per tile of ``tile_rows`` rows the smallest column, 16-bit offsets from it, fp32 values. Returns
+    per tile of ``tile_rows`` rows the smallest column and the number of columns spanned, 16-bit offsets, fp32 values. Returns
     ``(col16, val32, tile_base, status)`` with ``status`` bit 0 = a value is not an fp32 number, bit 1 = a tile spans
     65536 columns or more."""
     rowptr, col, val = np.asarray(rowptr), np.asarray(col), np.asarray(val, dtype=np.float64)
@@ -92,13 +92,13 @@ def pack_csr(rowptr, col, val, tile_rows: int = 512):
     col16 = np.zeros(len(col), np.uint16)
     with np.errstate(over="ignore", invalid="ignore"):
         val32 = val.astype(np.float32)
-    tile_base = np.zeros(max(ntiles, 1), np.int32)
+    tile_base = np.zeros((max(ntiles, 1), 2), np.int32)
     status = 0 if np.array_equal(val32.astype(np.float64).view(np.int64), val.view(np.int64)) else 1
     for t in range(ntiles):
         cs, ce = rowptr[min(t * tile_rows, n)], rowptr[min((t + 1) * tile_rows, n)]
         if ce > cs:
             lo, hi = int(col[cs:ce].min()), int(col[cs:ce].max())
-            tile_base[t] = lo
+            tile_base[t] = (lo, hi - lo + 1)
             if hi - lo > 65535:
                 status |= 2
             col16[cs:ce] = ((col[cs:ce] - lo) & 0xFFFF).astype(np.uint16)

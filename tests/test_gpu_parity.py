@@ -137,7 +137,7 @@ def test_packed_copy_bit_exact(cuda, kind, side, net):
         nnz = len(want[1])
         assert np.array_equal(pk.col16[:nnz].cpu().numpy(), col16), key
         assert np.array_equal(pk.val32[:nnz].cpu().numpy().view(np.int32), val32.view(np.int32)), key
-        assert np.array_equal(pk.tile_base.cpu().numpy()[: len(base)], base), key
+        assert np.array_equal(pk.tile_base.cpu().numpy()[: len(base)], base), key  # (smallest column, span) per tile
         y = ops[key].matvec(xd, packed=True).cpu().numpy()
         assert np.array_equal(y, osp.to_scipy(*want) @ x), key
 

@@ -388,7 +388,8 @@ def test_pack_oracle_round_trip():
         col16, val32, base, status = osp.pack_csr(rowptr, col, val)
         assert status == 0
         rows = np.repeat(np.arange(len(rowptr) - 1), np.diff(rowptr))
-        assert np.array_equal(base[rows // 512] + col16.astype(np.int64), col)
+        assert np.array_equal(base[rows // 512, 0] + col16.astype(np.int64), col)
+        assert all(col[rowptr[t * 512]:rowptr[min((t + 1) * 512, len(rowptr) - 1)]].max() == b0 + sp - 1 for t, (b0, sp) in enumerate(base))
         assert np.array_equal(val32.astype(np.float64).view(np.int64), np.asarray(val).view(np.int64))
     rowptr, col, val = p.A
     bad = np.array(val, dtype=np.float64)

@@ -26,5 +26,5 @@ for r in rows:
         agg[k][2] = r[ti].strip()[:90]
 ti_, ts_ = sum(v[0] for v in agg.values()) or 1, sum(v[1] for v in agg.values()) or 1
 print(f"total warp instructions {ti_:.3g}, samples {ts_:.0f}")
-for (p, l), (ins, smp, txt) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+for (p, l), (ins, smp, txt) in sorted(agg.items(), key=lambda kv: -kv[1][int(__import__("os").environ.get("BY_SAMPLES", "0"))])[:top]:
     print(f"{100 * ins / ti_:5.1f}% inst {100 * smp / ts_:5.1f}% smp  {p}:{l:<4d} {txt}")
