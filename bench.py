@@ -408,7 +408,8 @@ def extras(device, host0):
         r = batch.results()[0]
         nnz_l = L.nnz if name == "cnn_multiply" else (T.nnz if name.startswith("ic0_solve") else 0)
         single[name] = {"ms_to_tol": ms, "iterations": r.iterations, "us_per_iteration": 1e3 * ms / max(r.iterations, 1),
-                        "res": r.res, "algorithmic_gbs": iter_bytes(n, A.nnz, nnz_l) * r.iterations / ms / 1e6}
+                        "res": r.res, "bytes_per_matrix_entry": entry_bytes_of(batch),
+                        "algorithmic_gbs": iter_bytes(n, A.nnz, nnz_l, entry_bytes_of(batch)) * r.iterations / ms / 1e6}
     single["ic0_solve"]["setup_ms_analysis_plus_factorisation"] = ic_setup_ms
     single["ic0_solve"]["levels"] = fwd.nlevels
     single["ic0_solve"]["triangular_solves"] = "level-stream (one CTA, dependencies polled in a shared-memory window)"
@@ -524,6 +525,11 @@ def extras(device, host0):
     ms = timed(lambda: A3.matvec(x, y), reps=10)
     spmv_bytes = 12 * A3.nnz + 4 * (n3 + 1) + 16 * n3
     out["spmv_128^3"] = {"ms": ms, "algorithmic_gbs": spmv_bytes / ms / 1e6, "frac_of_hbm_peak": spmv_bytes / ms / 1e6 / peak}
+    if A3.packed() is not None:  # the same product from the lossless 6-byte copy (same bits): half the matrix bytes
+        ms = timed(lambda: A3.matvec(x, y, packed=True), reps=10)
+        pbytes = 6 * A3.nnz + 4 * (n3 + 1) + 16 * n3
+        out["spmv_128^3_packed"] = {"ms": ms, "algorithmic_gbs": pbytes / ms / 1e6, "frac_of_hbm_peak": pbytes / ms / 1e6 / peak,
+                                    "speedup_vs_fp64_stream": out["spmv_128^3"]["ms"] / ms}
     fwd3 = precond.analyse(T3, False)
     ms = timed(lambda: precond.triangular_solve(T3, fwd3, x, y), reps=5)
     trsv_bytes = 12 * T3.nnz + 4 * (n3 + 1) + 16 * n3
@@ -569,9 +575,10 @@ def extras(device, host0):
 
         ms = timed(go3, reps=2)
         r = batch3.results()[0]
-        gbs = iter_bytes(n3, A3.nnz, nnz_l) * r.iterations / ms / 1e6
+        eb = entry_bytes_of(batch3)
+        gbs = iter_bytes(n3, A3.nnz, nnz_l, eb) * r.iterations / ms / 1e6
         pcg3[name] = {"ms_to_tol": ms, "iterations": r.iterations, "us_per_iteration": 1e3 * ms / max(r.iterations, 1),
-                      "res": r.res, "algorithmic_gbs": gbs, "frac_of_hbm_peak": gbs / peak}
+                      "res": r.res, "bytes_per_matrix_entry": eb, "algorithmic_gbs": gbs, "frac_of_hbm_peak": gbs / peak}
         del batch3
     pcg3["ic0_solve"]["triangular_solves"] = "sync-free (levels of up to 12 k rows: not level-stream material)"
     out["pcg_single_system_128^3"] = pcg3
@@ -768,6 +775,9 @@ def run_c3(args, rank, world, device):
     entry_bytes = {c: entry_bytes_of(batches[c]) for c in solved}
     chunk_bytes = {c: sum(iter_bytes(e["A"].n, e["A"].nnz, e["M"].L.nnz, entry_bytes[c]) * r.iterations
                           for e, r in zip(batches[c].entries, results[c])) for c in solved}
+    packed_run = all(v == 6 for v in entry_bytes.values())
+    bytes_per_sysit = float(np.mean([iter_bytes(e["A"].n, e["A"].nnz, e["M"].L.nnz, entry_bytes[c])
+                                     for c in solved for e in batches[c].entries]))
     local_bytes = float(sum(chunk_bytes[c] for c, _, _ in launches))
     local_gbs = local_bytes / (sum(kernel_ms) / 1e3) / 1e9
     peak, peak_source = peaks()
@@ -832,7 +842,6 @@ def run_c3(args, rank, world, device):
     tpath = ROOT / "profiles" / "traffic.json"
     if tpath.exists():
         tj = json.loads(tpath.read_text())
-        packed_run = all(v == 6 for v in entry_bytes.values())
         per_iter = tj.get("pcg_fused_kernel_packed_dram_bytes_per_system_iteration" if packed_run
                           else "pcg_fused_kernel_dram_bytes_per_system_iteration")
         if per_iter:
@@ -852,10 +861,9 @@ def run_c3(args, rank, world, device):
                    "iterations_max": int(iterations.max()), "systems_measured": int(len(iterations)),
                    "engine": "fused persistent cooperative kernel", "setup_s_untimed": setup_s,
                    "matrix_stream": ("packed copies (dp_csr_pack, lossless: fp32 value + uint16 tile-relative column = 6 B per "
-                                     "entry, widened on load, same fp64 arithmetic and bits)" if all(v == 6 for v in entry_bytes.values())
+                                     "entry, widened on load, same fp64 arithmetic and bits)" if packed_run
                                      else "fp64 value + int32 column = 12 B per entry"),
-                   "bytes_per_system_iteration": float(np.mean([iter_bytes(e["A"].n, e["A"].nnz, e["M"].L.nnz, entry_bytes[c])
-                                                                for c in solved for e in batches[c].entries]))},
+                   "bytes_per_system_iteration": bytes_per_sysit},
         "ms_to_tol_per_system": elapsed_ms / args.steps / per_gpu,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all, "steps": e2e_steps},
