@@ -109,7 +109,7 @@ _SIGNATURES = {
     "dp_pcg_work_doubles": (_i64, [_i32]),
     "dp_pcg_workspace_bytes": (C.c_size_t, [_i32]),
     "dp_debug_pcg_trace": (C.c_int, [_p, _i32, _p, _i32]),
-    "dp_debug_pipe_trace": (C.c_int, [_p, _i32]),
+    "dp_debug_pipe_trace": (C.c_int, [_p, _i32, _i32]),
     "dp_pcg_solve_f64": (C.c_int, [C.POINTER(PcgSystem), _i32, C.POINTER(PcgParams), _p, _p, C.c_size_t, _p]),
 }
 

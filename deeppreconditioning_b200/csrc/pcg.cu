@@ -40,6 +40,7 @@
 namespace dp {
 
 int trsv_lookahead();                                          // sptrsv.cu
+int pipe_trace_read_spmv(uint64_t* out_host, int capacity);    // spmv.cu (trace builds)
 
 struct SysDev {
     int n, precond, ntiles;
@@ -964,16 +965,17 @@ int dp_debug_pcg_trace(const void* workspace, int32_t nsys, int64_t* out_host, i
     return DP_OK;
 }
 
-int dp_debug_pipe_trace(uint64_t* out_host, int32_t capacity) {
+int dp_debug_pipe_trace(uint64_t* out_host, int32_t capacity, int32_t unit) {
 #ifdef DPCG_PIPE_TRACE
     if (!out_host || capacity <= 0) return DP_ERR_INVALID;
+    if (unit == 1) return dp::pipe_trace_read_spmv(out_host, capacity);  // (every translation unit has its own trace buffer)
     const int cap = capacity < kPipeTraceCap ? capacity : kPipeTraceCap;
     for (int w = 0; w < 2; ++w)
         DP_CUDA(cudaMemcpyFromSymbol(out_host + (size_t)w * capacity, g_pipe_trace, sizeof(unsigned long long) * (size_t)cap,
                                      sizeof(unsigned long long) * (size_t)w * kPipeTraceCap, cudaMemcpyDeviceToHost));
     return DP_OK;
 #else
-    (void)out_host, (void)capacity;
+    (void)out_host, (void)capacity, (void)unit;
     return DP_ERR_INVALID;  // built without -DDPCG_PIPE_TRACE
 #endif
 }

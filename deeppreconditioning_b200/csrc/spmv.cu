@@ -139,6 +139,19 @@ KernelEntry& kernel_entry(int dev, const void* kernel) {  // caller holds g_cach
 }
 }  // namespace
 
+int pipe_trace_read_spmv(uint64_t* out_host, int capacity) {
+#ifdef DPCG_PIPE_TRACE
+    const int cap = capacity < kPipeTraceCap ? capacity : kPipeTraceCap;
+    for (int w = 0; w < 2; ++w)
+        DP_CUDA(cudaMemcpyFromSymbol(out_host + (size_t)w * capacity, g_pipe_trace, sizeof(unsigned long long) * (size_t)cap,
+                                     sizeof(unsigned long long) * (size_t)w * kPipeTraceCap, cudaMemcpyDeviceToHost));
+    return DP_OK;
+#else
+    (void)out_host, (void)capacity;
+    return DP_ERR_INVALID;
+#endif
+}
+
 int sm_count() {
     const int dev = current_device();
     const bool cacheable = dev >= 0 && dev < kMaxDevices;

@@ -65,7 +65,7 @@
 #define DPCG_PIPE_SPLIT_ISSUE 0  // experiment: the three async operations of an item issued by three threads of different warps
 #endif
 #ifndef DPCG_PIPE_ROUND_ROBIN
-#define DPCG_PIPE_ROUND_ROBIN 0  // items are issued by lane 0 of warp (item index mod 16) instead of thread 0
+#define DPCG_PIPE_ROUND_ROBIN 0  // K > 0: item j is issued by lane 0 of warp (j mod K) * (16 / K) instead of thread 0
 #endif
 #ifndef DPCG_PIPE_TOPUP_AT_RELEASE
 #define DPCG_PIPE_TOPUP_AT_RELEASE 0  // experiment: a second look for the next item when a stage is handed back
@@ -321,7 +321,7 @@ struct PipeT {
         ntiles = 0;
         c_count = 0u, p_count = 0u, p_tile = 0, p_blk = 0, t_count = 0u, flip = 0, early = 0, keep_l2 = 0;
 #if DPCG_PIPE_ROUND_ROBIN
-        role = (threadIdx.x & 31) == 0 ? 0 : -1;
+        role = ((threadIdx.x & 31) == 0 && (threadIdx.x >> 5) % (kWarpsPerBlock / DPCG_PIPE_ROUND_ROBIN) == 0) ? 0 : -1;
 #elif DPCG_PIPE_SPLIT_ISSUE
         role = threadIdx.x == 0 ? 0 : threadIdx.x == 5 * kWarp ? 1 : threadIdx.x == 10 * kWarp ? 2 : -1;
 #else
@@ -373,7 +373,7 @@ struct PipeT {
         // Issuing an item costs its thread ~0.8 us inside the busy kernel (tools/trace_pipe.py), and on thread 0 alone that
         // is added to every tile of warp 0 - the warp the other fifteen then wait for. Dealt round robin, every warp pays
         // it once in sixteen items. Each lane 0 walks the whole item sequence with its own cursor and skips the others' items.
-        if ((p_count % kWarpsPerBlock) != (threadIdx.x >> 5)) {
+        if ((p_count % DPCG_PIPE_ROUND_ROBIN) * (kWarpsPerBlock / DPCG_PIPE_ROUND_ROBIN) != (threadIdx.x >> 5)) {
             ++p_blk, ++p_count;
             return true;
         }

@@ -338,8 +338,8 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
  * workspace; this copies up to `capacity` pairs to out_host[2*capacity] (label = 8*phase + point). Synchronous. */
 int dp_debug_pcg_trace(const void* workspace, int32_t nsys, int64_t* out_host, int32_t capacity);
 /* Tuning builds only (-DDPCG_PIPE_TRACE; DP_ERR_INVALID otherwise): per-tile timeline of two warps of CTA 0 through the tile
- * pipeline of the last PCG launch, out_host[2 * capacity] words of (label << 48 | globaltimer ns). Synchronous. */
-int dp_debug_pipe_trace(uint64_t* out_host, int32_t capacity);
+ * pipeline of the last launch, out_host[2 * capacity] words of (label << 48 | globaltimer ns). Synchronous. */
+int dp_debug_pipe_trace(uint64_t* out_host, int32_t capacity, int32_t unit /* 0: PCG kernels, 1: standalone SpMV */);
 
 #ifdef __cplusplus
 }

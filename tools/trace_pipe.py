@@ -23,7 +23,7 @@ batch = dp.PcgBatch(systems, 1e-8, a.max_iter, pack=not a.unpacked)
 batch.solve(); torch.cuda.synchronize()
 cap = 1 << 15
 buf = np.zeros(2 * cap, np.uint64)
-_lib.check(_lib.lib().dp_debug_pipe_trace(buf.ctypes.data, cap), "dp_debug_pipe_trace")
+_lib.check(_lib.lib().dp_debug_pipe_trace(buf.ctypes.data, cap, 0), "dp_debug_pipe_trace")
 names = {(0, 1): "wait window", (0, 2): "wait bytes (1st item)", (1, 2): "wait bytes (1st item)", (2, 3): "row loop", (3, 2): "release + wait bytes (next item)",
          (3, 4): "release (+ window)", (4, 5): "tile tail: stores, reduce", (5, 0): "next tile head: loads, scalars", (4, 0): "between tiles", (5, 5): "tile without stream"}
 phases = {1: "A", 2: "APPLY1", 3: "APPLY2"}
