@@ -15,6 +15,8 @@ Workload c5 (BASELINE config 5): 64 systems 256^3 (7-point, N = 16 777 216) on 8
 systems kept in the level order of the factor, tile-stream triangular solves. A step = one PCG solve of the GPU's 8
 systems; "scaling": "weak" (8 per GPU at any N: 64 systems need the HBM of 8 GPUs).
 
+config  : names the workload, identical in both arms; what a run found (iteration statistics, engine, matrix stream format,
+          resident bytes, untimed set-up) is in `details`.
 value   : solves/s with operands resident in HBM (CUDA events, max over ranks).
 e2e     : the same through the reference-facing call with HOST operands (c3: pinned CSR of A and L, b - what
           preconditioned_conjugate_gradient receives from test.py:138; c5: the pinned COO lower triangle and b - what
@@ -84,6 +86,17 @@ def workload_name(args):
     return (f"{args.systems_total} x poisson2d {args.side}x{args.side} (N={args.side ** 2}) test set sharded over the GPUs, "
             f"random-init Preconditioner{'Net' if args.net == 'net' else 'TrilNet'} L, multiply mode, "
             f"rtol=1e-8 (squared), max_iter={MAX_ITER}; step = next {args.step_systems} systems of the set")
+
+
+def workload_config(args):
+    """`config` of the JSON line: the same dictionary in both arms (the driver compares them). What a run found out about
+    the workload (iteration counts, engine, resident bytes, set-up time) goes into `details`."""
+    world = max(1, args.gpus)
+    if args.config == "c5":
+        return {"workload": workload_name(args), "systems_total": args.c5_per_gpu * world, "systems_per_gpu": args.c5_per_gpu,
+                "l2": "5.2 GB per system-iteration >> 126 MB L2: no flush between timed steps"}
+    return {"workload": workload_name(args), "systems_total": args.systems_total, "systems_per_step": args.step_systems,
+            "l2": f"a step streams {args.step_systems // world} x 34-55 MB per GPU and iteration >> 126 MB L2: no flush between timed steps"}
 
 
 def iter_bytes(n, nnz_a, nnz_l, entry_bytes=12):
@@ -309,7 +322,7 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": workload_name(args)},
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -351,7 +364,7 @@ def run_reference_c5(args, threads):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": workload_name(args)},
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                          "ms_per_iteration": 1e3 * per_iter},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -853,10 +866,9 @@ def run_c3(args, rank, world, device):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args), "systems_total": args.systems_total, "systems_per_step": args.step_systems,
-                   "systems_per_gpu_per_step": per_gpu, "systems_resident_per_gpu": nchunks * per_gpu,
-                   "l2": f"per-GPU working set of a step {per_gpu * 0.057:.1f} GB >> 126 MB L2 (no flush needed); "
-                         f"{resident_gb:.0f} GB resident per GPU",
+        "config": workload_config(args),
+        "details": {"systems_per_gpu_per_step": per_gpu, "systems_resident_per_gpu": nchunks * per_gpu,
+                   "resident_gb_per_gpu": resident_gb,
                    "iterations_mean": float(iterations.mean()), "iterations_min": int(iterations.min()),
                    "iterations_max": int(iterations.max()), "systems_measured": int(len(iterations)),
                    "engine": "fused persistent cooperative kernel", "setup_s_untimed": setup_s,
@@ -973,8 +985,8 @@ def run_c5(args, rank, world, device):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args), "systems_total": per_gpu * world, "systems_per_gpu": per_gpu,
-                   "l2": f"{resident_gb:.0f} GB resident per GPU, 5.2 GB per system-iteration >> 126 MB L2 (no flush needed)",
+        "config": workload_config(args),
+        "details": {"resident_gb_per_gpu": resident_gb,
                    "iterations": its, "iterations_mean_all_ranks": all_its / (per_gpu * world),
                    "engine": "stepped (tile-stream SpTRSV launches between the fused phases)", "setup_s_untimed": setup_s},
         "ms_to_tol_per_system": elapsed_ms / args.steps / per_gpu,
