@@ -13,6 +13,10 @@ constexpr int kBlock = 512;                  // threads per CTA of every row-par
 constexpr int kWarpsPerBlock = kBlock / kWarp;
 constexpr int kTileRows = kBlock;            // one CTA pass covers 512 consecutive rows (16 chunks of 32)
 constexpr unsigned kFull = 0xffffffffu;
+// A kernel may carry warps beyond the kBlock row threads (the producer warp of the packed PCG engine, tilepipe.cuh): they
+// walk the same control flow - every CTA barrier - and read the results of the CTA-wide reductions, but own no row and
+// never contribute to a sum or a scan.
+__device__ __forceinline__ bool row_thread() { return threadIdx.x < (unsigned)kBlock; }
 
 // "Not yet produced" marker for sync-free dependency resolution: a quiet NaN with a payload that IEEE
 // arithmetic on this GPU never generates (computed NaNs are canonical 0x7ff8000000000000).
@@ -99,7 +103,7 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     v = warp_sum(v);
     __syncthreads();  // scratch may still be read by a previous call
-    if (lane == 0) scratch[warp] = v;
+    if (lane == 0 && warp < kWarpsPerBlock) scratch[warp] = v;
     __syncthreads();
     double w = scratch[lane & (kWarpsPerBlock - 1)];
     return half_warp_sum(w);
@@ -113,7 +117,7 @@ __device__ __forceinline__ void block_sum_n(double (&v)[kN], double* scratch) {
 #pragma unroll
     for (int i = 0; i < kN; ++i) v[i] = warp_sum(v[i]);
     __syncthreads();
-    if (lane == 0) {
+    if (lane == 0 && warp < kWarpsPerBlock) {
 #pragma unroll
         for (int i = 0; i < kN; ++i) scratch[i * kWarpsPerBlock + warp] = v[i];
     }
@@ -132,7 +136,7 @@ __device__ __forceinline__ int block_exclusive_scan_int(int v, int* total, int* 
         if (lane >= o) inc += t;
     }
     __syncthreads();
-    if (lane == 31) sh[warp] = inc;
+    if (lane == 31 && warp < kWarpsPerBlock) sh[warp] = inc;
     __syncthreads();
     if (warp == 0) {
         const int w = lane < kWarpsPerBlock ? sh[lane] : 0;
@@ -147,14 +151,15 @@ __device__ __forceinline__ int block_exclusive_scan_int(int v, int* total, int* 
     }
     __syncthreads();
     *total = sh[kWarpsPerBlock];
-    return sh[warp] + inc - v;
+    return sh[warp & (kWarpsPerBlock - 1)] + inc - v;  // (warps beyond the row threads: value unused)
 }
 
 // Sum of `count` doubles stored at `p` (global, produced before the last grid-wide barrier): thread t adds
 // p[t], p[t+kBlock], ... in that order, then block_sum. Same bits in every CTA.
 __device__ __forceinline__ double block_reduce_array(const double* p, int count, double* scratch) {
     double v = 0.0;
-    for (int i = threadIdx.x; i < count; i += kBlock) v = __dadd_rn(v, __ldcg(p + i));
+    if (row_thread())
+        for (int i = threadIdx.x; i < count; i += kBlock) v = __dadd_rn(v, __ldcg(p + i));
     return block_sum(v, scratch);
 }
 

@@ -180,7 +180,7 @@ __device__ __forceinline__ void phase_init(const Ctx& ctx, const SysDev& S, cons
     const int row = tile * kTileRows + threadIdx.x;
     const double ax = pipe.tile_spmv(d, rs, re, GatherPlain{S.x}, true);
     double bb[1] = {0.0};
-    if (row < S.n) {
+    if (row < S.n && row_thread()) {
         const double bi = S.b[row];
         S.r[1][row] = __dsub_rn(bi, ax);
         S.p[0][row] = 0.0;
@@ -210,7 +210,7 @@ __device__ __forceinline__ void phase_a(const Ctx& ctx, const SysDev& S, const T
                                         Smem& sm, Scal& sc, P& pipe) {
     const int s = d.sys, tile = d.ltile;
     const int row = tile * kTileRows + threadIdx.x;
-    const bool valid = row < S.n;
+    const bool valid = row < S.n && row_thread();
     const double* z = S.z[k & 1];
     const double* po = S.p[k & 1];
     // loads that do not depend on this phase's scalars go first
@@ -225,9 +225,11 @@ __device__ __forceinline__ void phase_a(const Ctx& ctx, const SysDev& S, const T
             double v[2] = {0.0, 0.0};
             const double* prr = S.part_rr;
             const double* prz = S.part_rz[k & 1];
-            for (int i = threadIdx.x; i < S.ntiles; i += kBlock) {
-                v[0] = __dadd_rn(v[0], __ldcg(prr + i));
-                v[1] = __dadd_rn(v[1], __ldcg(prz + i));
+            if (row_thread()) {
+                for (int i = threadIdx.x; i < S.ntiles; i += kBlock) {
+                    v[0] = __dadd_rn(v[0], __ldcg(prr + i));
+                    v[1] = __dadd_rn(v[1], __ldcg(prz + i));
+                }
             }
             const double bb = __ldcg(S.scal + 2);
             const double rz_prev = k > 0 ? __ldcg(S.scal + ((k - 1) & 1)) : 1.0;
@@ -281,7 +283,7 @@ __device__ __forceinline__ void phase_apply1(const Ctx& ctx, const SysDev& S, co
                                              Smem& sm, Scal& sc, P& pipe) {
     const int s = d.sys, tile = d.ltile;
     const int row = tile * kTileRows + threadIdx.x;
-    const bool valid = row < S.n;
+    const bool valid = row < S.n && row_thread();
     const double* ro = S.r[k & 1];
     double* rnw = S.r[(k + 1) & 1];
     const double* pn = S.p[(k + 1) & 1];
@@ -380,10 +382,11 @@ __device__ __forceinline__ void phase_apply2(const Ctx& ctx, const SysDev& S, co
         return;
     }
     const int row = tile * kTileRows + threadIdx.x;
+    const bool valid = row < S.n && row_thread();
     double rn = 0.0;
-    if (row < S.n) rn = S.r[(k + 1) & 1][row];
+    if (valid) rn = S.r[(k + 1) & 1][row];
     const double zi = pipe.template tile_spmv<kApply2Unroll>(d, rs, re, GatherWork{S.t}, true);
-    if (row < S.n) S.z[(k + 1) & 1][row] = zi;
+    if (valid) S.z[(k + 1) & 1][row] = zi;
     double v[2] = {__dmul_rn(rn, zi), __dmul_rn(zi, zi)};
     double* part_rr = S.part_rr;
     double* part_rz = S.part_rz[(k + 1) & 1];
@@ -411,7 +414,7 @@ __device__ __forceinline__ void phase_dotrz(const Ctx& ctx, const SysDev& S, con
     if (!sc.active) return;
     const int row = tile * kTileRows + threadIdx.x;
     double rn = 0.0, zi = 0.0;
-    if (row < S.n) {
+    if (row < S.n && row_thread()) {
         rn = S.r[(k + 1) & 1][row];
         zi = S.z[(k + 1) & 1][row];
         // a sync-free forward solve polls y and needs it armed before every application; the sync-free backward solve
@@ -582,7 +585,7 @@ __device__ __forceinline__ void rebuild_active(const Ctx& ctx, int cur, Smem& sm
     for (int i0 = 0; i0 < count; i0 += kBlock) {
         const int i = i0 + threadIdx.x;
         int s = -1, alive = 0, nt = 0;
-        if (i < count) {
+        if (i < count && row_thread()) {
             s = __ldcg(asys + i);
             alive = ld_relaxed_s32(ctx.state + s) == 0;
             nt = alive ? __ldcg(aofs + i + 1) - __ldcg(aofs + i) : 0;
@@ -653,8 +656,13 @@ __device__ __forceinline__ Smem& smem_init(unsigned char* raw, P& pipe) {
 // benchmarked multiply-mode batches among them.
 // kPacked: every matrix the batch streams comes with its packed copy (dp_csr_pack): 6 instead of 12 bytes per entry through
 // the same pipeline, same bits.
+// The packed engine runs kBlock + 32 threads: warp 16 is the PRODUCER warp. It walks the same control flow as the row warps
+// (every CTA and grid barrier), owns no row, contributes to no sum, and its lane 0 issues every item of the tile pipeline as
+// soon as the item's stage has been handed back - up to kStages items ahead of the rows, instead of 0.86 us per item on the
+// path of warp 0 (profiles/r2/pack_experiments.md). At 544 threads the kernel must fit 56 registers; this instantiation does.
+constexpr int kFusedThreadsPacked = kPackProducerWarp ? kBlock + kWarp : kBlock;
 template <bool kSolve, bool kPacked>
-__global__ void __launch_bounds__(kBlock, 2) pcg_fused_kernel(Ctx ctx) {
+__global__ void __launch_bounds__(kPacked ? kFusedThreadsPacked : kBlock, 2) pcg_fused_kernel(Ctx ctx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typename std::conditional<kPacked, PipePacked, Pipe>::type pipe;
     Smem& sm = smem_init(smem_raw, pipe);
@@ -1126,7 +1134,8 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
                         : packed  ? (const void*)pcg_fused_kernel<false, true>
                                   : (const void*)pcg_fused_kernel<false, false>;
     if (allow_dynamic_smem(fused, sizeof(Smem)) != DP_OK || allow_smem(pcg_phase_kernel<PH_FWD, false>) != DP_OK) return DP_ERR_CUDA;
-    const int coop = coop_grid(fused, kBlock, sizeof(Smem));
+    const int fused_threads = (!has_solve && packed) ? kFusedThreadsPacked : kBlock;
+    const int coop = coop_grid(fused, fused_threads, sizeof(Smem));
     const int coop_phase = coop_grid((const void*)pcg_phase_kernel<PH_FWD, false>, kBlock, sizeof(Smem));
     auto clamp_pw = [](long long lvl_chunks, int grid) {
         long long pw = (long long)trsv_lookahead() * lvl_chunks;
@@ -1196,7 +1205,7 @@ int dp_pcg_solve_f64(const dp_pcg_system_t* systems_host, int32_t nsys, const dp
         ctx.pw_fwd = clamp_pw(sum_fwd_lvl, grid);
         ctx.pw_bwd = clamp_pw(sum_bwd_lvl, grid);
         void* args[] = {&ctx};
-        DP_CUDA(cudaLaunchCooperativeKernel(fused, dim3(grid), dim3(kBlock), args, sizeof(Smem), s));
+        DP_CUDA(cudaLaunchCooperativeKernel(fused, dim3(grid), dim3(fused_threads), args, sizeof(Smem), s));
         return DP_OK;
     }
     if (params_host->engine != DP_ENGINE_STEPPED) return DP_ERR_INVALID;

@@ -64,6 +64,9 @@
 #ifndef DPCG_PIPE_SPLIT_ISSUE
 #define DPCG_PIPE_SPLIT_ISSUE 0  // experiment: the three async operations of an item issued by three threads of different warps
 #endif
+#ifndef DPCG_PACK_PRODUCER_WARP
+#define DPCG_PACK_PRODUCER_WARP 1  // the packed PCG engine runs a 17th warp that only issues the stages' copies
+#endif
 #ifndef DPCG_PIPE_ROUND_ROBIN
 #define DPCG_PIPE_ROUND_ROBIN 0  // K > 0: item j is issued by lane 0 of warp (j mod K) * (16 / K) instead of thread 0
 #endif
@@ -92,6 +95,7 @@ constexpr int kPipeUnroll = DPCG_PIPE_UNROLL;  // gathers in flight per thread
 constexpr int kPackCap = DPCG_PACK_CAP;
 constexpr int kPackStages = DPCG_PACK_STAGES;
 constexpr bool kPackWindows = DPCG_PACK_WINDOWS != 0;
+constexpr bool kPackProducerWarp = DPCG_PACK_PRODUCER_WARP != 0;
 constexpr int kMaxStages = kPipeStages > kPackStages ? kPipeStages : kPackStages;
 
 // ---- PTX wrappers (sm_90+/sm_100a) ---------------------------------------------------------------------------
@@ -272,6 +276,8 @@ struct PipeT {
     const TileDesc* tab;
     int ntiles;
     unsigned c_count;   // items this warp has consumed
+    bool ghost;         // this thread belongs to the producer warp (beyond the kBlock row threads): it owns no row, issues the
+                        // items as early as their stages allow and neither waits for bytes nor hands stages back
     int role;           // issuer role of this thread: 0 arms the stage's barrier, 1 copies the values, 2 the columns; -1 none
     unsigned p_count;   // items issued (meaningful in the issuer threads only, like the cursor below)
     int p_tile, p_blk;  // next item of the round to issue
@@ -320,6 +326,10 @@ struct PipeT {
         tab = nullptr;
         ntiles = 0;
         c_count = 0u, p_count = 0u, p_tile = 0, p_blk = 0, t_count = 0u, flip = 0, early = 0, keep_l2 = 0;
+        ghost = threadIdx.x >= (unsigned)kBlock;
+        if (blockDim.x > (unsigned)kBlock) {  // a producer warp of its own: its lane 0 is the only issuer
+            role = threadIdx.x == (unsigned)kBlock ? 0 : -1;
+        } else
 #if DPCG_PIPE_ROUND_ROBIN
         role = ((threadIdx.x & 31) == 0 && (threadIdx.x >> 5) % (kWarpsPerBlock / DPCG_PIPE_ROUND_ROBIN) == 0) ? 0 : -1;
 #elif DPCG_PIPE_SPLIT_ISSUE
@@ -470,7 +480,7 @@ struct PipeT {
         if (role >= 0) p_tile = ntiles;  // nothing more to issue from that table
         for (int j = 0; j < issued; ++j) {
             const unsigned stage = c_count % kStages;
-            while (!mbar_try_wait(&full[stage], (c_count / kStages) & 1u)) {
+            while (!ghost && !mbar_try_wait(&full[stage], (c_count / kStages) & 1u)) {
             }
             release();
         }
@@ -488,6 +498,7 @@ struct PipeT {
         DP_PIPE_MARK(6);
         const unsigned stage = c_count % kStages;
         const unsigned par = (c_count / kStages) & 1u;
+        if (ghost) return stage;  // the producer warp reads nothing
 #if DPCG_PIPE_WAIT_HINT
         // (ncu, round 2: the plain try_wait spin was 13.5 % of the fused kernel's executed instructions)
         while (!mbar_try_wait_hint(&full[stage], par, DPCG_PIPE_WAIT_HINT)) {
@@ -500,7 +511,7 @@ struct PipeT {
     }
     __device__ __forceinline__ void release() {
         __syncwarp();
-        if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[c_count % kStages]);
+        if ((threadIdx.x & 31) == 0 && !ghost) mbar_arrive(&empty[c_count % kStages]);
         ++c_count;
 #if DPCG_PIPE_TOPUP_AT_RELEASE
         // a second chance to send the next item ahead of time: at acquire() the slowest warps may not have released the
@@ -520,7 +531,8 @@ struct PipeT {
     static constexpr int kWinWarp = kWarpsPerBlock / 2;
     template <class Gather>
     __device__ __forceinline__ void window_issue(const TileDesc& t, const Gather& x) {
-        if (threadIdx.x == kWinWarp * 32) {
+        // (with a producer warp in the CTA its lane 0 issues the windows as well, tiles ahead of the rows)
+        if (blockDim.x > (unsigned)kBlock ? threadIdx.x == (unsigned)kBlock : threadIdx.x == kWinWarp * 32) {
             const unsigned buf = w_issued % kWinBufs, fill = w_issued / kWinBufs;
             if (fill > 0) {
                 while (!mbar_try_wait_hint(&wempty[buf], (fill - 1u) & 1u, 1000u)) {
@@ -550,13 +562,13 @@ struct PipeT {
             if (nx.span > 0 && nx.sys == d.sys) window_issue(nx, x);
         }
         const unsigned buf = w_count % kWinBufs;
-        while (!mbar_try_wait_hint(&wfull[buf], (w_count / kWinBufs) & 1u, 1000u)) {
+        while (!ghost && !mbar_try_wait_hint(&wfull[buf], (w_count / kWinBufs) & 1u, 1000u)) {
         }
         return win0 + (size_t)buf * kWinVecs * kWinCap;
     }
     __device__ __forceinline__ void window_release() {
         __syncwarp();
-        if ((threadIdx.x & 31) == 0) mbar_arrive(&wempty[w_count % kWinBufs]);
+        if ((threadIdx.x & 31) == 0 && !ghost) mbar_arrive(&wempty[w_count % kWinBufs]);
         ++w_count;
     }
 
@@ -571,7 +583,7 @@ struct PipeT {
             const int as = bs & ~(kAlign - 1);
             const unsigned stage = acquire();
             DP_PIPE_MARK(2);
-            if (compute) {
+            if (compute && !ghost) {
                 const ValT* __restrict__ sv = stage_val(stage);
                 const ColT* __restrict__ sc = stage_col(stage);
                 const int qe = min(re, be) - as;
@@ -627,7 +639,7 @@ struct PipeT {
     __device__ __forceinline__ void tile_skip(const TileDesc& d) {
         if (kPacked && kPackWindows && d.span > 0 && w_issued > w_count) {
             const unsigned buf = w_count % kWinBufs;
-            while (!mbar_try_wait(&wfull[buf], (w_count / kWinBufs) & 1u)) {
+            while (!ghost && !mbar_try_wait(&wfull[buf], (w_count / kWinBufs) & 1u)) {
             }
             window_release();
         }
@@ -661,7 +673,7 @@ __device__ __forceinline__ void tile_reduce(double (&v)[kN], double (*scratch2x)
     pipe.flip ^= 1;
 #pragma unroll
     for (int i = 0; i < kN; ++i) v[i] = warp_sum(v[i]);
-    if (lane == 0) {
+    if (lane == 0 && warp < kWarpsPerBlock) {
 #pragma unroll
         for (int i = 0; i < kN; ++i) scratch[i * kWarpsPerBlock + warp] = v[i];
     }
@@ -689,6 +701,7 @@ __device__ __forceinline__ void tile_reduce_async(double (&v)[kN], TileRed& red,
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned r = pipe.t_count % kRedRing;
     ++pipe.t_count;
+    if (pipe.ghost) return;  // the producer warp owns no row
 #pragma unroll
     for (int i = 0; i < kN; ++i) v[i] = warp_sum(v[i]);
     int old = 0;

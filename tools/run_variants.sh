@@ -1,4 +1,6 @@
 cd /root/repo
 L=deeppreconditioning_b200/lib
-echo "== default"; python tools/time_spmv.py 128 2>&1 | grep "\^3"
-for v in s4 rr2s4 rr4s4 rr8s4 rr4; do echo "== $v"; DPCG_LIB=$PWD/$L/libdpcg_$v.so python tools/time_spmv.py 128 2>&1 | grep "\^3"; done
+run() { echo "== $1 $2"; env $2 DPCG_LIB=$PWD/$L/libdpcg_$1.so timeout 300 python tools/gpu_pack_ab.py --systems 64 --reps 1 $3 2>&1 | grep -v Warning | grep "solves/s\|bitwise\|Error\|error"; }
+run pw "" 
+run pw4 "" --packed-only
+echo "=== trace"; DPCG_LIB=$PWD/$L/libdpcg_tr_pw.so timeout 200 python tools/trace_pipe.py 2>&1 | grep -v Warn
