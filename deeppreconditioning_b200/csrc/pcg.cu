@@ -216,6 +216,10 @@ __device__ __forceinline__ void phase_a(const Ctx& ctx, const SysDev& S, const T
     // loads that do not depend on this phase's scalars go first
     double zr = 0.0, pr = 0.0;
     if (valid) zr = z[row], pr = po[row];
+    if (pipe.ghost) {
+        if (d.span > 0) prefetch_columns(z, d.base, d.span), prefetch_columns(po, d.base, d.span);  // (covers the rows' own lines)
+        else prefetch_tile_rows(z, tile, S.n), prefetch_tile_rows(po, tile, S.n);
+    }
     if (sc.sys != s) {
         sc.sys = s;
         sc.active = false;
@@ -291,6 +295,14 @@ __device__ __forceinline__ void phase_apply1(const Ctx& ctx, const SysDev& S, co
     const int precond = S.precond;
     // scalar-independent loads first
     double r_old = 0.0, ap_i = 0.0, x_i = 0.0, p_i = 0.0, dinv_i = 0.0;
+    if (pipe.ghost) {
+        if (d.span > 0) {  // the gather of L^T r / M r reaches beyond this tile's rows
+            prefetch_columns(ro, d.base, d.span);
+            if (!kInit) prefetch_columns(S.ap, d.base, d.span);
+        }
+        prefetch_tile_rows(ro, tile, S.n);
+        if (!kInit) prefetch_tile_rows(S.ap, tile, S.n), prefetch_tile_rows(S.x, tile, S.n), prefetch_tile_rows(pn, tile, S.n);
+    }
     if (valid) {
         r_old = ro[row];
         if (!kInit) ap_i = S.ap[row], x_i = S.x[row], p_i = pn[row];
@@ -385,6 +397,10 @@ __device__ __forceinline__ void phase_apply2(const Ctx& ctx, const SysDev& S, co
     const bool valid = row < S.n && row_thread();
     double rn = 0.0;
     if (valid) rn = S.r[(k + 1) & 1][row];
+    if (pipe.ghost) {
+        prefetch_tile_rows(S.r[(k + 1) & 1], tile, S.n);
+        if (d.span > 0) prefetch_columns(S.t, d.base, d.span);
+    }
     const double zi = pipe.template tile_spmv<kApply2Unroll>(d, rs, re, GatherWork{S.t}, true);
     if (valid) S.z[(k + 1) & 1][row] = zi;
     double v[2] = {__dmul_rn(rn, zi), __dmul_rn(zi, zi)};

@@ -67,6 +67,12 @@
 #ifndef DPCG_PACK_PRODUCER_WARP
 #define DPCG_PACK_PRODUCER_WARP 1  // the packed PCG engine runs a 17th warp that only issues the stages' copies
 #endif
+#ifndef DPCG_GHOST_PREFETCH
+#define DPCG_GHOST_PREFETCH 1  // the producer warp prefetches the rows' own vector lines of the tiles it passes: 0 off, 1 L2, 2 L1
+#endif
+#ifndef DPCG_GHOST_PREFETCH_GATHER
+#define DPCG_GHOST_PREFETCH_GATHER 1  // ... and the lines of the columns a banded tile gathers from (TileDesc base / span)
+#endif
 #ifndef DPCG_PIPE_ROUND_ROBIN
 #define DPCG_PIPE_ROUND_ROBIN 0  // K > 0: item j is issued by lane 0 of warp (j mod K) * (16 / K) instead of thread 0
 #endif
@@ -182,6 +188,37 @@ __device__ __forceinline__ void cp_async_16(void* dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(unsigned long long* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// The producer warp runs up to kStages tiles ahead of the row warps: it asks for the 32 lines that hold the 512 rows of a
+// vector in tile `tile` (one line per lane), so that the row warps' loads at the head of that tile find them in cache instead of
+// paying an HBM round trip (tools/trace_pipe.py: 1.1 us at the head of every APPLY1 tile).
+__device__ __forceinline__ void prefetch_tile_rows(const double* v, int tile, int n) {
+#if DPCG_GHOST_PREFETCH
+    const int row = tile * kTileRows + (int)(threadIdx.x & 31) * 16;
+    if (row < n) {
+#if DPCG_GHOST_PREFETCH == 1
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(v + row));
+#else
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(v + row));
+#endif
+    }
+#else
+    (void)v, (void)tile, (void)n;
+#endif
+}
+// ... and for the columns [base, base + span) a banded tile gathers from (span <= kWinCap doubles = 88 lines: three rounds).
+__device__ __forceinline__ void prefetch_columns(const double* v, int base, int span) {
+#if DPCG_GHOST_PREFETCH && DPCG_GHOST_PREFETCH_GATHER
+    for (int c = (int)(threadIdx.x & 31) * 16; c < span; c += 32 * 16) {
+#if DPCG_GHOST_PREFETCH == 1
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(v + (base & ~15) + c));
+#else
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(v + (base & ~15) + c));
+#endif
+    }
+#else
+    (void)v, (void)base, (void)span;
+#endif
 }
 // ---- descriptors ------------------------------------------------------------------------------------------------
 struct TileDesc {
