@@ -23,12 +23,13 @@
 //
 // Packed stream (kPacked): the same pipeline over the lossless 6-byte copy of a matrix (dp_csr_pack: fp32 values, 16-bit
 // columns relative to the tile's smallest column). The lanes widen on load (exact) and run the identical fp64 recurrence:
-// same bits, half the matrix bytes from HBM. The stages take half the bytes, and the other half holds gather WINDOWS:
-// a banded tile (512 rows of a 2-D stencil factor touch ~1150 consecutive columns) reads every gathered vector entry
-// 5..15 times, and with 2 x 113 KB of shared memory per SM the L1 that should catch those re-reads is 28 KB - the
-// gathers were L2 round trips (long_scoreboard 42 % of the warp samples, ncu round 2). So the columns [base, base + span)
-// of the phase's work vectors are copied once per tile into shared memory (bulk copies, one tile ahead, completion on an
-// mbarrier) and the gathers become shared-memory loads. Same values, same arithmetic, same bits.
+// same bits, half the matrix bytes from HBM; a stage of the same bytes holds twice the entries (the CNN factor's tile is one
+// item). When the CTA carries a warp beyond its kBlock row threads, that PRODUCER warp is the issuer: it walks the same
+// tiles, reads nothing, and sends every item the moment its stage has been handed back (pcg.cu, packed engine).
+// Experiment (DPCG_PACK_WINDOWS=1, off): half of the stage bytes hold gather WINDOWS - the columns [base, base + span) a
+// banded tile touches (~1150 for 512 rows of a 316-wide 2-D factor), copied once per tile into shared memory by bulk copies,
+// one tile ahead, so that the gathers become shared-memory loads. Same values, same arithmetic, same bits; the row loops
+// halve, but the stages do too, and the time comes back as waiting for bytes (profiles/r2/pack_experiments.md).
 #pragma once
 
 #include <type_traits>
@@ -61,9 +62,6 @@
 #ifndef DPCG_PACK_STAGES
 #define DPCG_PACK_STAGES DPCG_PIPE_STAGES
 #endif
-#ifndef DPCG_PIPE_SPLIT_ISSUE
-#define DPCG_PIPE_SPLIT_ISSUE 0  // experiment: the three async operations of an item issued by three threads of different warps
-#endif
 #ifndef DPCG_PACK_PRODUCER_WARP
 #define DPCG_PACK_PRODUCER_WARP 1  // the packed PCG engine runs a 17th warp that only issues the stages' copies
 #endif
@@ -72,12 +70,6 @@
 #endif
 #ifndef DPCG_GHOST_PREFETCH_GATHER
 #define DPCG_GHOST_PREFETCH_GATHER 1  // ... and the lines of the columns a banded tile gathers from (TileDesc base / span)
-#endif
-#ifndef DPCG_PIPE_ROUND_ROBIN
-#define DPCG_PIPE_ROUND_ROBIN 0  // K > 0: item j is issued by lane 0 of warp (j mod K) * (16 / K) instead of thread 0
-#endif
-#ifndef DPCG_PIPE_TOPUP_AT_RELEASE
-#define DPCG_PIPE_TOPUP_AT_RELEASE 0  // experiment: a second look for the next item when a stage is handed back
 #endif
 #ifndef DPCG_PIPE_WAIT_HINT
 #define DPCG_PIPE_WAIT_HINT 1000  // ns a consumer warp may sleep in try_wait on a stage's `full` barrier (0: spin)
@@ -315,7 +307,7 @@ struct PipeT {
     unsigned c_count;   // items this warp has consumed
     bool ghost;         // this thread belongs to the producer warp (beyond the kBlock row threads): it owns no row, issues the
                         // items as early as their stages allow and neither waits for bytes nor hands stages back
-    int role;           // issuer role of this thread: 0 arms the stage's barrier, 1 copies the values, 2 the columns; -1 none
+    int role;           // 0: this thread issues the items, -1: it does not
     unsigned p_count;   // items issued (meaningful in the issuer threads only, like the cursor below)
     int p_tile, p_blk;  // next item of the round to issue
     unsigned t_count;   // streaming tiles this warp has reduced (ring index of tile_reduce_async)
@@ -364,16 +356,8 @@ struct PipeT {
         ntiles = 0;
         c_count = 0u, p_count = 0u, p_tile = 0, p_blk = 0, t_count = 0u, flip = 0, early = 0, keep_l2 = 0;
         ghost = threadIdx.x >= (unsigned)kBlock;
-        if (blockDim.x > (unsigned)kBlock) {  // a producer warp of its own: its lane 0 is the only issuer
-            role = threadIdx.x == (unsigned)kBlock ? 0 : -1;
-        } else
-#if DPCG_PIPE_ROUND_ROBIN
-        role = ((threadIdx.x & 31) == 0 && (threadIdx.x >> 5) % (kWarpsPerBlock / DPCG_PIPE_ROUND_ROBIN) == 0) ? 0 : -1;
-#elif DPCG_PIPE_SPLIT_ISSUE
-        role = threadIdx.x == 0 ? 0 : threadIdx.x == 5 * kWarp ? 1 : threadIdx.x == 10 * kWarp ? 2 : -1;
-#else
-        role = threadIdx.x == 0 ? 0 : -1;
-#endif
+        // the issuer: lane 0 of the producer warp when the CTA has one, else thread 0 (which then also does its rows)
+        role = threadIdx.x == (blockDim.x > (unsigned)kBlock ? (unsigned)kBlock : 0u) ? 0 : -1;
         win0 = reinterpret_cast<double*>(bytes + PipeGeom<kCap, kStages, kPacked>::kStageBytes);
         wfull = bar->wfull, wempty = bar->wempty;
         w_issued = 0u, w_count = 0u;
@@ -402,13 +386,11 @@ struct PipeT {
 
     // Issuer threads: issue the next item of the round if its stage is free. `blocking`: wait for the stage
     // (only legal when this warp has itself consumed the stage's previous item). Returns true if an item went out.
-    // An item is three asynchronous operations - arm the stage's `full` barrier with the byte count, bulk copy of the
-    // values, bulk copy of the columns - and each costs the thread that issues it ~250-290 ns whatever its size
-    // (profiles/r2/tma_stream.log; tools/trace_pipe.py: 860 ns per item on thread 0's path, a third of a phase-A tile).
-    // They are therefore dealt to lane 0 of three different warps (roles 0, 1, 2): every issuer walks the same item
-    // sequence with its own cursor and performs its own operation as soon as the stage's previous tenant has been
-    // released by all warps. A copy may complete before the barrier is armed: the transaction count goes negative for a
-    // moment, the phase cannot complete before the arming arrival.
+    // An item is three asynchronous operations - arm the stage's `full` barrier with the byte count, bulk copy of the values,
+    // bulk copy of the columns. Inside the busy kernel this one-lane chain costs its warp ~0.86 us per item
+    // (tools/trace_pipe.py), which is why the packed PCG engine gives it to a producer warp of its own; splitting the three
+    // operations over three warps or dealing the items round robin among the row warps was measured and does not help
+    // (profiles/r2/pack_experiments.md).
     __device__ __forceinline__ bool issue_one(bool blocking) {
         while (p_tile < ntiles) {
             if (p_blk < blocks(tab[p_tile])) break;
@@ -416,15 +398,6 @@ struct PipeT {
         }
         if (p_tile >= ntiles) return false;
         if (p_count - c_count >= (unsigned)kStages) return false;  // this warp still owns the stage's previous item
-#if DPCG_PIPE_ROUND_ROBIN
-        // Issuing an item costs its thread ~0.8 us inside the busy kernel (tools/trace_pipe.py), and on thread 0 alone that
-        // is added to every tile of warp 0 - the warp the other fifteen then wait for. Dealt round robin, every warp pays
-        // it once in sixteen items. Each lane 0 walks the whole item sequence with its own cursor and skips the others' items.
-        if ((p_count % DPCG_PIPE_ROUND_ROBIN) * (kWarpsPerBlock / DPCG_PIPE_ROUND_ROBIN) != (threadIdx.x >> 5)) {
-            ++p_blk, ++p_count;
-            return true;
-        }
-#endif
         const unsigned stage = p_count % kStages, use = p_count / kStages;
         if (use > 0) {
             const unsigned par = (use - 1u) & 1u;
@@ -439,22 +412,7 @@ struct PipeT {
         const int bs = d.cs + p_blk * kCap;
         const int be = min(d.ce, bs + kCap);
         const int as = bs & ~(kAlign - 1);
-#if DPCG_PIPE_SPLIT_ISSUE
-        const unsigned ncol = (unsigned)(((be + kColUnit - 1) & ~(kColUnit - 1)) - as);
-        const unsigned nval = (unsigned)(((be + kValUnit - 1) & ~(kValUnit - 1)) - as);
-        unsigned long long* bar = &full[stage];
-        if (role == 0) {
-            mbar_arrive_expect_tx(bar, ncol * (unsigned)sizeof(ColT) + nval * (unsigned)sizeof(ValT));
-        } else if (role == 1) {
-            bulk_g2s(val0 + (size_t)stage * kSlots, reinterpret_cast<const ValT*>(d.val) + as, nval * (unsigned)sizeof(ValT), bar,
-                     keep_l2 ? l2_policy_keep() : l2_policy_stream());
-        } else {
-            bulk_g2s(col0 + (size_t)stage * kSlots, reinterpret_cast<const ColT*>(d.col) + as, ncol * (unsigned)sizeof(ColT), bar,
-                     keep_l2 ? l2_policy_keep() : l2_policy_stream());
-        }
-#else
         issue_copies(d, stage, as, be, keep_l2 ? l2_policy_keep() : l2_policy_stream());
-#endif
         DP_PIPE_MARK(7);
         ++p_blk, ++p_count;
         return true;
@@ -550,14 +508,6 @@ struct PipeT {
         __syncwarp();
         if ((threadIdx.x & 31) == 0 && !ghost) mbar_arrive(&empty[c_count % kStages]);
         ++c_count;
-#if DPCG_PIPE_TOPUP_AT_RELEASE
-        // a second chance to send the next item ahead of time: at acquire() the slowest warps may not have released the
-        // stage's previous tenant yet, and the next look would only come when this warp needs the item itself
-        if (role >= 0) {
-            while (issue_one(false)) {
-            }
-        }
-#endif
     }
 
     // ---- gather windows (packed stream) -----------------------------------------------------------------------------
