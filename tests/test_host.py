@@ -277,3 +277,25 @@ def test_reference_checkpoint_layout_loads():
         lower = net(st)
     assert (lower.features[lower.indices[:, 1] < lower.indices[:, 2]] == 0).all()
     assert (lower.features[lower.indices[:, 1] == lower.indices[:, 2]] > 0).all()
+
+
+def test_bench_line_helpers():
+    """bench.py: both arms print the same `config` dictionary (the driver compares them), and the algorithmic byte count
+    follows the bytes per stored entry of the stream the engine used (6 from packed copies, 12 from the fp64 CSR)."""
+    import argparse
+    import sys
+
+    sys.path.insert(0, str(ROOT))
+    import bench
+
+    for cfg, gpus in (("c3", 1), ("c3", 8), ("c5", 8)):
+        args = argparse.Namespace(config=cfg, gpus=gpus, systems_total=1024, step_systems=128, side=316, net="net",
+                                  c5_side=256, c5_per_gpu=8)
+        config = bench.workload_config(args)
+        assert config == bench.workload_config(args) and "workload" in config and "l2" in config
+        assert all(isinstance(v, (str, int)) for v in config.values()), "static values only: no run findings in config"
+    assert "1024 x poisson2d 316x316" in bench.workload_config(argparse.Namespace(
+        config="c3", gpus=1, systems_total=1024, step_systems=128, side=316, net="net", c5_side=256, c5_per_gpu=8))["workload"]
+    n, nnz_a, nnz_l = 99856, 498016, 1494660
+    assert bench.iter_bytes(n, nnz_a, nnz_l) == 12 * nnz_a + 24 * nnz_l + 132 * n + 12
+    assert bench.iter_bytes(n, nnz_a, nnz_l) - bench.iter_bytes(n, nnz_a, nnz_l, 6) == 6 * (nnz_a + 2 * nnz_l)
